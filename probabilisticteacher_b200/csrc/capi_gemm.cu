@@ -1,0 +1,42 @@
+// C ABI: dense contractions (see include/ptb200.h for the contract of every entry point).
+#include "gemm_tn.h"
+#include "../../include/ptb200.h"
+
+using namespace ptb;
+
+extern "C" int ptb200_gemm_tn_f16(const void* A, int batch, int rows, int k_per_tap, int64_t lda,
+                                  int64_t a_batch_stride, int taps, const int* shifts, const void* B,
+                                  int n_total, int bn, int epi, const float* bias, int n_bias, void* D,
+                                  int64_t ldd, int64_t d_batch_stride, const void* aux, int w_valid,
+                                  int wp, float* d0, int ld0, float* d1, int ld1, int split,
+                                  int n_valid, int max_ctas, void* stream) {
+  GemmTnArgs a;
+  a.A = A;
+  a.batch = batch;
+  a.rows = rows;
+  a.k_per_tap = k_per_tap;
+  a.lda = lda;
+  a.a_batch_stride = a_batch_stride;
+  a.taps = taps;
+  for (int i = 0; i < 9; ++i) a.shifts[i] = (shifts != nullptr && i < taps) ? shifts[i] : 0;
+  a.B = B;
+  a.n_total = n_total;
+  a.bn = bn;
+  a.epi = epi;
+  a.bias = bias;
+  a.n_bias = n_bias;
+  a.D = D;
+  a.ldd = ldd;
+  a.d_batch_stride = d_batch_stride;
+  a.aux = aux;
+  a.w_valid = w_valid;
+  a.wp = wp;
+  a.d0 = d0;
+  a.ld0 = ld0;
+  a.d1 = d1;
+  a.ld1 = ld1;
+  a.split = split;
+  a.n_valid = n_valid;
+  a.max_ctas = max_ctas;
+  return gemm_tn_launch(a, static_cast<cudaStream_t>(stream));
+}

@@ -1,0 +1,413 @@
+// Implicit-GEMM "TN" kernel for sm_100a: D[b][p][n] = sum_t sum_k A[b][p + shift_t][k] * B[n][t*K + k]
+//
+// One kernel covers every dense contraction on the Probabilistic Teacher hot path whose
+// operands are K-major:
+//   * 3x3 conv forward over NHWC activations stored as flattened, right-padded rows
+//     ([N][H*Wp][C], Wp = W+1, pad column kept at zero) -- the 9 taps are 9 row shifts of
+//     the same TMA box, top/bottom padding comes from TMA out-of-bounds zero fill
+//     (reference: pt/modeling/backbone/vgg.py:45-53,65-72 via detectron2 Conv2d -> cuDNN);
+//   * 3x3 conv data-gradient (same kernel, weights pre-flipped/transposed);
+//   * RPN 3x3 conv + 1x1 objectness/(mu,sigma) heads (pt/modeling/proposal_generator/rpn.py:44-55,96);
+//   * box head fc1/fc2/predictor and their data-gradients (taps = 1)
+//     (pt/modeling/roi_heads/roi_heads.py:127-128, fast_rcnn.py:157-169).
+//
+// Structure: persistent CTAs (one per SM), warp-specialised:
+//   warp 0    : TMA producer (A tile 128 rows x 64 k, B tile BN rows x 64 k, SWIZZLE_128B)
+//   warp 1    : tcgen05.mma issuer (M=128, N=BN, K=16 per instruction, fp32 accumulators in TMEM,
+//               two accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1)
+//   warps 2-5 : epilogue (tcgen05.ld -> bias/ReLU/pad-mask -> fp16 -> swizzled smem -> TMA store,
+//               or fp32 direct stores for the narrow head outputs)
+#include "ptx.cuh"
+#include "gemm_tn.h"
+
+namespace ptb {
+
+static constexpr int BM = 128;
+static constexpr int BK = 64;
+static constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
+static constexpr int STAGING_BYTES = BM * 128;     // one 128 x 64 fp16 output chunk
+static constexpr int NUM_THREADS = 192;
+static constexpr int EPI_THREADS = 128;
+
+struct SmemCtl {
+  uint64_t full[8];
+  uint64_t empty[8];
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
+  uint64_t aux_full[2];
+  uint32_t tmem_base;
+  uint32_t pad;
+};
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+               const __grid_constant__ CUtensorMap map_d, const __grid_constant__ CUtensorMap map_aux,
+               const GemmTnParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve: [stages x (A | B)] [2 x staging] [bias BN floats] [ctl]
+  const int bn = p.bn;
+  const int stages = p.stages;
+  const int b_stage_bytes = bn * BK * 2;
+  const int stage_bytes = A_STAGE_BYTES + b_stage_bytes;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* staging = smem + stages * stage_bytes;
+  float* bias_s = reinterpret_cast<float*>(staging + 2 * STAGING_BYTES);
+  SmemCtl* ctl = reinterpret_cast<SmemCtl*>(bias_s + 256);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int m_tiles = (p.rows + BM - 1) / BM;
+  const int n_tiles = p.n_total / bn;
+  const int tiles_per_batch = m_tiles * n_tiles;
+  const int num_tiles = tiles_per_batch * p.batch;
+  const int k_chunks = p.k_per_tap / BK;
+  const int k_iters = k_chunks * p.taps;
+
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < static_cast<uint32_t>(2 * bn)) tmem_cols <<= 1;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+    if (p.epi != EPI_F32_SPLIT) tma_prefetch_desc(&map_d);
+    for (int i = 0; i < stages; ++i) {
+      mbar_init(&ctl->full[i], 1);
+      mbar_init(&ctl->empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&ctl->tmem_full[i], 1);
+      mbar_init(&ctl->tmem_empty[i], EPI_THREADS / 32);
+      mbar_init(&ctl->aux_full[i], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(&ctl->tmem_base, tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = ctl->tmem_base;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int b = tile / tiles_per_batch;
+        const int rem = tile - b * tiles_per_batch;
+        const int mt = rem / n_tiles;
+        const int nt = rem - mt * n_tiles;
+        const int row0 = mt * BM;
+        const int n0 = nt * bn;
+        for (int t = 0; t < p.taps; ++t) {
+          const int arow = row0 + p.shifts[t];
+          for (int kc = 0; kc < k_chunks; ++kc) {
+            mbar_wait(&ctl->empty[s], ph ^ 1);
+            uint8_t* sa = smem + s * stage_bytes;
+            uint8_t* sb = sa + A_STAGE_BYTES;
+            mbar_arrive_expect_tx(&ctl->full[s], A_STAGE_BYTES + b_stage_bytes);
+            tma_load_3d(sa, &map_a, &ctl->full[s], kc * BK, arow, b);
+            tma_load_2d(sb, &map_b, &ctl->full[s], t * p.k_per_tap + kc * BK, n0);
+            if (++s == stages) {
+              s = 0;
+              ph ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    const uint32_t idesc = umma_idesc_f16(BM, bn, 0, 0);
+    int s = 0;
+    uint32_t ph = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      const uint32_t aph = (it >> 1) & 1;
+      mbar_wait(&ctl->tmem_empty[as], aph ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + as * bn;
+      for (int ki = 0; ki < k_iters; ++ki) {
+        mbar_wait(&ctl->full[s], ph);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
+          const uint32_t b_addr = a_addr + A_STAGE_BYTES;
+          const uint64_t da = umma_desc_sw128(a_addr, 16, 1024);
+          const uint64_t db = umma_desc_sw128(b_addr, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // advancing 16 fp16 (32 B) along K inside the 128 B swizzle row = +2 in the >>4 field
+            umma_f16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (ki > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&ctl->empty[s]);
+          if (ki == k_iters - 1) umma_commit(&ctl->tmem_full[as]);
+        }
+        __syncwarp();
+        if (++s == stages) {
+          s = 0;
+          ph ^= 1;
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    const int q = warp & 3;            // TMEM lane quarter this warp may access
+    const int r = q * 32 + lane;       // row of the 128-row tile owned by this thread
+    const int et = threadIdx.x - 64;   // 0..127 index among epilogue threads
+    int it = 0;
+    int st_buf = 0;
+    uint32_t aux_ph[2] = {0, 0};
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int b = tile / tiles_per_batch;
+      const int rem = tile - b * tiles_per_batch;
+      const int mt = rem / n_tiles;
+      const int nt = rem - mt * n_tiles;
+      const int row0 = mt * BM;
+      const int n0 = nt * bn;
+      const int as = it & 1;
+      const uint32_t aph = (it >> 1) & 1;
+
+      // stage the bias slice (previous tile's readers are past the barrier below)
+      named_bar_sync(1, EPI_THREADS);
+      for (int i = et; i < bn; i += EPI_THREADS)
+        bias_s[i] = (p.bias != nullptr && n0 + i < p.n_bias) ? p.bias[n0 + i] : 0.f;
+      named_bar_sync(1, EPI_THREADS);
+
+      mbar_wait(&ctl->tmem_full[as], aph);
+      tc_fence_after();
+
+      const int row = row0 + r;
+      bool row_live = row < p.rows;
+      if (p.wp > 0) row_live = row_live && ((row % p.wp) < p.w_valid);
+      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * bn;
+
+      if (p.epi == EPI_F32_SPLIT) {
+        for (int c0 = 0; c0 < bn; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld_32x16(t_addr + c0, v);
+          tmem_ld_wait();
+          if (row < p.rows) {
+            const size_t grow = static_cast<size_t>(b) * p.rows + row;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int n = n0 + c0 + j;
+              if (n < p.n_valid) {
+                const float x = __uint_as_float(v[j]) + bias_s[c0 + j];
+                if (n < p.split)
+                  p.d0[grow * p.ld0 + n] = x;
+                else
+                  p.d1[grow * p.ld1 + (n - p.split)] = x;
+              }
+            }
+          }
+        }
+      } else {
+        for (int c0 = 0; c0 < bn; c0 += 64) {
+          uint8_t* stg = staging + st_buf * STAGING_BYTES;
+          uint8_t* auxb = stg;  // aux tile is loaded into the staging buffer itself
+          // the TMA store that last read this staging buffer must have drained
+          if (et == 0) tma_store_wait_read<1>();
+          named_bar_sync(1, EPI_THREADS);
+          if (p.epi == EPI_MASK_F16) {
+            if (et == 0) {
+              mbar_arrive_expect_tx(&ctl->aux_full[st_buf], STAGING_BYTES);
+              tma_load_3d(auxb, &map_aux, &ctl->aux_full[st_buf], n0 + c0, row0, b);
+            }
+          }
+          uint32_t v[64];
+          tmem_ld_32x32(t_addr + c0, v);
+          tmem_ld_32x32(t_addr + c0 + 32, v + 32);
+          tmem_ld_wait();
+          if (p.epi == EPI_MASK_F16) {
+            mbar_wait(&ctl->aux_full[st_buf], aux_ph[st_buf]);
+            aux_ph[st_buf] ^= 1;
+          }
+          uint8_t* rowp = stg + r * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            uint4* dst = reinterpret_cast<uint4*>(rowp + ((j ^ (r & 7)) << 4));
+            float f[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[j * 8 + e]) + bias_s[c0 + j * 8 + e];
+            if (p.epi == EPI_BIAS_RELU_F16) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
+            } else if (p.epi == EPI_MASK_F16) {
+              // keep the gradient only where the forward activation (aux tile) was positive
+              const uint4 a = *dst;
+              const __half2* ah = reinterpret_cast<const __half2*>(&a);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 af = __half22float2(ah[e]);
+                if (!(af.x > 0.f)) f[2 * e] = 0.f;
+                if (!(af.y > 0.f)) f[2 * e + 1] = 0.f;
+              }
+            }
+            if (!row_live) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] = 0.f;
+            }
+            uint4 o;
+            __half2 h0 = __floats2half2_rn(f[0], f[1]);
+            __half2 h1 = __floats2half2_rn(f[2], f[3]);
+            __half2 h2 = __floats2half2_rn(f[4], f[5]);
+            __half2 h3 = __floats2half2_rn(f[6], f[7]);
+            o.x = *reinterpret_cast<uint32_t*>(&h0);
+            o.y = *reinterpret_cast<uint32_t*>(&h1);
+            o.z = *reinterpret_cast<uint32_t*>(&h2);
+            o.w = *reinterpret_cast<uint32_t*>(&h3);
+            *dst = o;
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(1, EPI_THREADS);
+          if (et == 0) {
+            tma_store_3d(&map_d, stg, n0 + c0, row0, b);
+            tma_store_commit();
+          }
+          st_buf ^= 1;
+        }
+      }
+      // this accumulator stage may now be overwritten by the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ctl->tmem_empty[as]);
+    }
+    if (et == 0) tma_store_wait_all<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 0) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess) return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+// fp16 tensor map with up to 3 dims, innermost contiguous; box inner dim = 64 elements (128 B).
+int make_tmap_f16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
+                  const uint64_t* strides_bytes /* rank-1 entries */, const uint32_t* box) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) return -1;
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[5];
+  cuuint32_t bx[5];
+  cuuint32_t es[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+    if (i + 1 < rank) gstr[i] = strides_bytes[i];
+  }
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<void*>(base), gdim, gstr,
+                  bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -2;
+}
+
+static int g_num_sms = 0;
+
+int gemm_tn_launch(const GemmTnArgs& a, cudaStream_t stream) {
+  if (a.k_per_tap % BK != 0 || a.bn % 16 != 0 || a.bn > 256 || a.bn < 16) return 1001;
+  if (a.n_total % a.bn != 0) return 1002;
+  if (a.epi != EPI_F32_SPLIT && a.bn % 64 != 0) return 1003;
+  if (a.taps < 1 || a.taps > 9) return 1004;
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  CUtensorMap ma, mb, md, mx;
+  {
+    uint64_t dims[3] = {(uint64_t)a.k_per_tap, (uint64_t)a.rows, (uint64_t)a.batch};
+    uint64_t str[2] = {(uint64_t)a.lda * 2, (uint64_t)a.a_batch_stride * 2};
+    uint32_t box[3] = {BK, BM, 1};
+    if (make_tmap_f16(&ma, a.A, 3, dims, str, box)) return 1010;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)a.k_per_tap * a.taps, (uint64_t)a.n_total};
+    uint64_t str[1] = {(uint64_t)a.k_per_tap * a.taps * 2};
+    uint32_t box[2] = {BK, (uint32_t)a.bn};
+    if (make_tmap_f16(&mb, a.B, 2, dims, str, box)) return 1011;
+  }
+  if (a.epi != EPI_F32_SPLIT) {
+    uint64_t dims[3] = {(uint64_t)a.n_total, (uint64_t)a.rows, (uint64_t)a.batch};
+    uint64_t str[2] = {(uint64_t)a.ldd * 2, (uint64_t)a.d_batch_stride * 2};
+    uint32_t box[3] = {64, BM, 1};
+    if (make_tmap_f16(&md, a.D, 3, dims, str, box)) return 1012;
+    if (a.epi == EPI_MASK_F16) {
+      if (make_tmap_f16(&mx, a.aux, 3, dims, str, box)) return 1013;
+    } else {
+      mx = md;
+    }
+  } else {
+    md = ma;
+    mx = ma;
+  }
+  GemmTnParams p;
+  p.batch = a.batch;
+  p.rows = a.rows;
+  p.k_per_tap = a.k_per_tap;
+  p.taps = a.taps;
+  for (int i = 0; i < 9; ++i) p.shifts[i] = i < a.taps ? a.shifts[i] : 0;
+  p.n_total = a.n_total;
+  p.bn = a.bn;
+  p.w_valid = a.w_valid;
+  p.wp = a.wp;
+  p.epi = a.epi;
+  p.bias = a.bias;
+  p.n_bias = a.n_bias;
+  p.d0 = a.d0;
+  p.ld0 = a.ld0;
+  p.d1 = a.d1;
+  p.ld1 = a.ld1;
+  p.split = a.split;
+  p.n_valid = a.n_valid;
+  const int stage_bytes = A_STAGE_BYTES + a.bn * BK * 2;
+  const int fixed = 2 * STAGING_BYTES + 256 * 4 + (int)sizeof(SmemCtl) + 1024;
+  int stages = (232448 - fixed) / stage_bytes;
+  if (stages > 8) stages = 8;
+  if (stages < 2) return 1005;
+  p.stages = stages;
+  const int smem_bytes = stages * stage_bytes + fixed;
+  static int configured = 0;
+  if (configured < smem_bytes) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         232448);
+    if (e != cudaSuccess) return (int)e;
+    configured = 232448;
+  }
+  const int m_tiles = (a.rows + BM - 1) / BM;
+  const int num_tiles = m_tiles * (a.n_total / a.bn) * a.batch;
+  int grid = num_tiles < g_num_sms ? num_tiles : g_num_sms;
+  if (a.max_ctas > 0 && grid > a.max_ctas) grid = a.max_ctas;
+  if (grid < 1) return 0;
+  gemm_tn_kernel<<<grid, NUM_THREADS, smem_bytes, stream>>>(ma, mb, md, mx, p);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace ptb

@@ -1,0 +1,60 @@
+// Internal (C++) interface of the tcgen05 implicit-GEMM kernels. The public C ABI is include/ptb200.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ptb {
+
+enum GemmEpilogue {
+  EPI_BIAS_RELU_F16 = 0,  // D = relu(acc + bias) -> fp16 via TMA store (pad column forced to 0)
+  EPI_BIAS_F16 = 1,       // D = acc + bias -> fp16
+  EPI_F32_SPLIT = 2,      // acc + bias -> fp32, columns [0,split) to d0, [split,n_valid) to d1
+  EPI_MASK_F16 = 3,       // D = (aux > 0) ? acc : 0 -> fp16 (ReLU backward fused into dgrad)
+};
+
+struct GemmTnParams {
+  int batch, rows, k_per_tap, taps;
+  int shifts[9];
+  int n_total, bn;
+  int w_valid, wp;
+  int epi;
+  int stages;
+  const float* bias;
+  int n_bias;
+  float* d0;
+  int ld0;
+  float* d1;
+  int ld1;
+  int split;
+  int n_valid;
+};
+
+struct GemmTnArgs {
+  // A: fp16 [batch][rows][lda] (k_per_tap <= lda), row shift per tap
+  const void* A;
+  int batch, rows, k_per_tap;
+  int64_t lda, a_batch_stride;  // in elements
+  int taps;
+  int shifts[9];
+  // B: fp16 [n_total][taps * k_per_tap]
+  const void* B;
+  int n_total, bn;
+  // epilogue
+  int epi;
+  const float* bias;
+  int n_bias;
+  void* D;  // fp16 [batch][rows][ldd]
+  int64_t ldd, d_batch_stride;
+  const void* aux;  // fp16, same geometry as D (EPI_MASK_F16)
+  int w_valid, wp;  // wp > 0: rows with (row % wp) >= w_valid are written as zero
+  float* d0;
+  int ld0;
+  float* d1;
+  int ld1;
+  int split, n_valid;
+  int max_ctas;  // 0 = one per SM
+};
+
+int gemm_tn_launch(const GemmTnArgs& a, cudaStream_t stream);
+
+}  // namespace ptb
