@@ -32,6 +32,16 @@ int ptb200_gemm_tn_f16(const void* A, int batch, int rows, int k_per_tap, int64_
                        float* d0, int ld0, float* d1, int ld1, int split, int n_valid, int max_ctas,
                        void* stream);
 
+/* Weight gradient  out[m][t*n_total + n] += scale * sum_b sum_p G[b][p][m] * X[b][p + shifts[t]][n]
+ * (fp16 operands, fp32 accumulation, split-K with fp32 atomic accumulation into `out`).
+ * Replaces the cuDNN wgrad / cuBLAS calls autograd issues for the layers listed above
+ * (pt/engine/trainer.py:384 `losses.backward()`). m_total % 128 == 0, n_total % 64 == 0.
+ * ksplit <= 0 selects the split automatically. */
+int ptb200_gemm_wgrad_f16(const void* G, int64_t ldg, int64_t g_batch_stride, const void* X,
+                          int64_t ldx, int64_t x_batch_stride, int batch, int rows, int m_total,
+                          int n_total, int taps, const int* shifts, float* out, int64_t ld_out,
+                          float scale, int ksplit, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

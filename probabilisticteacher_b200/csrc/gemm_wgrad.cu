@@ -1,0 +1,251 @@
+// Weight-gradient contraction on tcgen05 (sm_100a):
+//   dW[m][t*n_total + n] += sum_b sum_p  G[b][p][m] * X[b][p + shift_t][n]
+// G = gradient w.r.t. the layer output (fp16, [batch][rows][m_total]), X = layer input (fp16,
+// [batch][rows][n_total]); both are "MN-major" operands (the reduction index p is the slow axis),
+// so the UMMA descriptors use the MN-major SWIZZLE_128B canonical layout and TMA loads
+// [64 k-rows][64 channels] boxes. Covers
+//   * 3x3 conv weight gradients of VGG blocks 3-5 and the RPN conv (9 taps = 9 row shifts of X;
+//     reference: autograd of pt/modeling/backbone/vgg.py:65-72 through cuDNN wgrad),
+//   * fc1 / fc2 / predictor weight gradients (taps = 1).
+// The reduction over (batch, rows) is split across CTAs (split-K); partial tiles are accumulated
+// into the fp32 gradient arena with vectorised red.global.add (gradients of the two student
+// forward passes of one step accumulate into the same arena, as autograd does for the reference).
+#include "ptx.cuh"
+#include "gemm_tn.h"
+
+namespace ptb {
+
+static constexpr int WG_BM = 128;   // output-channel tile (UMMA M)
+static constexpr int WG_BK = 64;    // reduction rows per stage
+static constexpr int WG_THREADS = 192;
+static constexpr int WG_BLK_BYTES = WG_BK * 128;  // one [64 rows][64 ch] box
+
+struct WgCtl {
+  uint64_t full[8];
+  uint64_t empty[8];
+  uint64_t acc_full;
+  uint32_t tmem_base;
+  uint32_t pad;
+};
+
+struct WgParams {
+  int batch, rows, m_total, n_total, bn, taps;
+  int shifts[9];
+  int ksplit, stages;
+  float* out;
+  int64_t ld_out;
+  float scale;
+};
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c),
+               "f"(d)
+               : "memory");
+}
+
+__device__ __forceinline__ void tma_load_4d(void* smem, const CUtensorMap* m, uint64_t* bar, int c0,
+                                            int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_u32(smem)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(WG_THREADS, 1)
+gemm_wgrad_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant__ CUtensorMap map_x,
+                  const WgParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  const int bn = p.bn;
+  const int a_bytes = (WG_BM / 64) * WG_BLK_BYTES;  // 16 KB
+  const int b_bytes = (bn / 64) * WG_BLK_BYTES;
+  const int stage_bytes = a_bytes + b_bytes;
+  WgCtl* ctl = reinterpret_cast<WgCtl*>(smem + p.stages * stage_bytes);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // tile decode: blockIdx.x = ((tap * m_tiles + mt) * n_tiles + nt) * ksplit + ks
+  const int m_tiles = p.m_total / WG_BM;
+  const int n_tiles = p.n_total / bn;
+  int id = blockIdx.x;
+  const int ks = id % p.ksplit;
+  id /= p.ksplit;
+  const int nt = id % n_tiles;
+  id /= n_tiles;
+  const int mt = id % m_tiles;
+  const int tap = id / m_tiles;
+
+  const int chunks_per_img = (p.rows + WG_BK - 1) / WG_BK;
+  const int total_chunks = chunks_per_img * p.batch;
+  const int c_begin = static_cast<int>((static_cast<int64_t>(total_chunks) * ks) / p.ksplit);
+  const int c_end = static_cast<int>((static_cast<int64_t>(total_chunks) * (ks + 1)) / p.ksplit);
+  const int k_iters = c_end - c_begin;
+
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < static_cast<uint32_t>(bn)) tmem_cols <<= 1;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&map_g);
+    tma_prefetch_desc(&map_x);
+    for (int i = 0; i < p.stages; ++i) {
+      mbar_init(&ctl->full[i], 1);
+      mbar_init(&ctl->empty[i], 1);
+    }
+    mbar_init(&ctl->acc_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(&ctl->tmem_base, tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = ctl->tmem_base;
+
+  if (k_iters > 0) {
+    if (warp == 0) {
+      if (lane == 0) {
+        int s = 0;
+        uint32_t ph = 0;
+        const int shift = p.shifts[tap];
+        for (int c = c_begin; c < c_end; ++c) {
+          const int b = c / chunks_per_img;
+          const int r0 = (c - b * chunks_per_img) * WG_BK;
+          mbar_wait(&ctl->empty[s], ph ^ 1);
+          uint8_t* sa = smem + s * stage_bytes;
+          uint8_t* sb = sa + a_bytes;
+          mbar_arrive_expect_tx(&ctl->full[s], stage_bytes);
+          tma_load_4d(sa, &map_g, &ctl->full[s], 0, r0, mt * (WG_BM / 64), b);
+          tma_load_4d(sb, &map_x, &ctl->full[s], 0, r0 + shift, nt * (bn / 64), b);
+          if (++s == p.stages) {
+            s = 0;
+            ph ^= 1;
+          }
+        }
+      }
+    } else if (warp == 1) {
+      const uint32_t idesc = umma_idesc_f16(WG_BM, bn, 1, 1);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int ki = 0; ki < k_iters; ++ki) {
+        mbar_wait(&ctl->full[s], ph);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
+          const uint32_t b_addr = a_addr + a_bytes;
+          // MN-major SW128: LBO = stride between 64-channel blocks, SBO = stride between 8-row groups
+          const uint64_t da = umma_desc_sw128(a_addr, WG_BLK_BYTES, 1024);
+          const uint64_t db = umma_desc_sw128(b_addr, WG_BLK_BYTES, 1024);
+#pragma unroll
+          for (int k = 0; k < WG_BK / 16; ++k) {
+            // 16 reduction rows = 2048 B further into each block
+            umma_f16_ss(tmem_base, da + (2048 >> 4) * k, db + (2048 >> 4) * k, idesc,
+                        (ki > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&ctl->empty[s]);
+          if (ki == k_iters - 1) umma_commit(&ctl->acc_full);
+        }
+        __syncwarp();
+        if (++s == p.stages) {
+          s = 0;
+          ph ^= 1;
+        }
+      }
+    } else {
+      const int q = warp & 3;
+      const int r = q * 32 + lane;
+      mbar_wait(&ctl->acc_full, 0);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+      float* orow = p.out + static_cast<int64_t>(mt * WG_BM + r) * p.ld_out +
+                    static_cast<int64_t>(tap) * p.n_total + nt * bn;
+      for (int c0 = 0; c0 < bn; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(t_addr + c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          red_add_v4(orow + c0 + 4 * j, __uint_as_float(v[4 * j]) * p.scale,
+                     __uint_as_float(v[4 * j + 1]) * p.scale, __uint_as_float(v[4 * j + 2]) * p.scale,
+                     __uint_as_float(v[4 * j + 3]) * p.scale);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 0) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+int make_tmap_f16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
+                  const uint64_t* strides_bytes, const uint32_t* box);
+
+static int g_wg_sms = 0;
+
+// G: [batch][rows][ldg] fp16 (m_total channels used), X: [batch][rows][ldx] fp16 (n_total used)
+int gemm_wgrad_launch(const void* G, int64_t ldg, int64_t g_batch_stride, const void* X, int64_t ldx,
+                      int64_t x_batch_stride, int batch, int rows, int m_total, int n_total, int taps,
+                      const int* shifts, float* out, int64_t ld_out, float scale, int ksplit,
+                      cudaStream_t stream) {
+  if (m_total % WG_BM != 0 || n_total % 64 != 0 || taps < 1 || taps > 9) return 1101;
+  int bn = 256;
+  while (n_total % bn != 0) bn >>= 1;
+  if (bn < 64) return 1102;
+  if (g_wg_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_wg_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  CUtensorMap mg, mx;
+  {
+    uint64_t dims[4] = {64, (uint64_t)rows, (uint64_t)(m_total / 64), (uint64_t)batch};
+    uint64_t str[3] = {(uint64_t)ldg * 2, 128, (uint64_t)g_batch_stride * 2};
+    uint32_t box[4] = {64, WG_BK, (uint32_t)(WG_BM / 64), 1};
+    if (make_tmap_f16(&mg, G, 4, dims, str, box)) return 1110;
+  }
+  {
+    uint64_t dims[4] = {64, (uint64_t)rows, (uint64_t)(n_total / 64), (uint64_t)batch};
+    uint64_t str[3] = {(uint64_t)ldx * 2, 128, (uint64_t)x_batch_stride * 2};
+    uint32_t box[4] = {64, WG_BK, (uint32_t)(bn / 64), 1};
+    if (make_tmap_f16(&mx, X, 4, dims, str, box)) return 1111;
+  }
+  WgParams p;
+  p.batch = batch;
+  p.rows = rows;
+  p.m_total = m_total;
+  p.n_total = n_total;
+  p.bn = bn;
+  p.taps = taps;
+  for (int i = 0; i < 9; ++i) p.shifts[i] = (shifts != nullptr && i < taps) ? shifts[i] : 0;
+  p.out = out;
+  p.ld_out = ld_out;
+  p.scale = scale;
+  const int tiles = taps * (m_total / WG_BM) * (n_total / bn);
+  const int total_chunks = ((rows + WG_BK - 1) / WG_BK) * batch;
+  if (ksplit <= 0) {
+    ksplit = (2 * g_wg_sms + tiles - 1) / tiles;   // ~2 waves of CTAs
+    const int max_split = (total_chunks + 15) / 16;  // at least 16 k-iterations per CTA
+    if (ksplit > max_split) ksplit = max_split;
+    if (ksplit < 1) ksplit = 1;
+  }
+  p.ksplit = ksplit;
+  const int stage_bytes = (WG_BM / 64 + bn / 64) * WG_BLK_BYTES;
+  int stages = (232448 - 2048) / stage_bytes;
+  if (stages > 8) stages = 8;
+  p.stages = stages;
+  const int smem_bytes = stages * stage_bytes + (int)sizeof(WgCtl) + 1024;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_wgrad_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  gemm_wgrad_kernel<<<tiles * ksplit, WG_THREADS, smem_bytes, stream>>>(mg, mx, p);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace ptb
