@@ -1,9 +1,14 @@
-/* ptb200 -- C ABI of the B200-native Probabilistic Teacher hot path.
+/* ptb200 -- C ABI of the B200-native Probabilistic Teacher hot path (libptb200.so).
  *
- * Every entry point takes plain device pointers, sizes and a cudaStream_t (as void*), returns 0 on
- * success or a non-zero error code (cudaError_t values < 1000, argument errors >= 1000), and never
- * synchronises the stream. Each declaration cites the reference interface it replaces
- * (paths relative to the reference checkout of hikvision-research/ProbabilisticTeacher).
+ * Conventions
+ *  - Every entry point takes plain device pointers, sizes and a cudaStream_t (as void*), returns 0 on
+ *    success or a non-zero error code (cudaError_t values < 1000, argument errors >= 1000), and never
+ *    synchronises the stream. Pointers are DEVICE pointers unless the parameter name ends in `_host`.
+ *  - Activations are fp16 "NHWC-flat": [N][H][Wp][C] with Wp = W + 1; the pad column x = W is kept at
+ *    zero so that the 3x3 taps of a convolution are plain row shifts of the flattened [H*Wp] axis.
+ *  - Variable-length results live in fixed-capacity buffers with a device-side count per image.
+ *  - Each declaration cites the reference interface it replaces (paths relative to the reference
+ *    checkout of hikvision-research/ProbabilisticTeacher; "d2" = detectron2 v0.5, un-vendored).
  */
 #ifndef PTB200_H
 #define PTB200_H
@@ -18,29 +23,208 @@ extern "C" {
 #define PTB200_EPI_F32_SPLIT 2
 #define PTB200_EPI_MASK_F16 3
 
+/* ---- dense contractions (tcgen05 tensor cores, TMA-staged tiles) ------------------------------ */
+
 /* Implicit GEMM  D[b][p][n] = sum_t sum_k A[b][p + shifts[t]][k] * B[n][t*k_per_tap + k]  (+ epilogue).
- * fp16 operands, fp32 accumulation on tcgen05 tensor cores, TMA-staged tiles.
- * Replaces the cuDNN / cuBLAS calls behind detectron2 Conv2d and nn.Linear on the hot path:
+ * fp16 operands, fp32 accumulation. Replaces the cuDNN / cuBLAS calls behind d2 Conv2d and nn.Linear:
  *   pt/modeling/backbone/vgg.py:45-53,65-72 (3x3 conv + bias + ReLU),
  *   pt/modeling/proposal_generator/rpn.py:96 (RPN head), pt/modeling/roi_heads/roi_heads.py:127-128
  *   (box head), pt/modeling/roi_heads/fast_rcnn.py:157-169 (predictor), and their data-gradients.
- * Rows outside [0, rows) read as zero (conv zero padding); `shifts` is a HOST array of `taps` ints. */
+ * Rows outside [0, rows) read as zero (conv zero padding). */
 int ptb200_gemm_tn_f16(const void* A, int batch, int rows, int k_per_tap, int64_t lda,
-                       int64_t a_batch_stride, int taps, const int* shifts, const void* B,
+                       int64_t a_batch_stride, int taps, const int* shifts_host, const void* B,
                        int n_total, int bn, int epi, const float* bias, int n_bias, void* D,
                        int64_t ldd, int64_t d_batch_stride, const void* aux, int w_valid, int wp,
                        float* d0, int ld0, float* d1, int ld1, int split, int n_valid, int max_ctas,
                        void* stream);
 
 /* Weight gradient  out[m][t*n_total + n] += scale * sum_b sum_p G[b][p][m] * X[b][p + shifts[t]][n]
- * (fp16 operands, fp32 accumulation, split-K with fp32 atomic accumulation into `out`).
- * Replaces the cuDNN wgrad / cuBLAS calls autograd issues for the layers listed above
- * (pt/engine/trainer.py:384 `losses.backward()`). m_total % 128 == 0, n_total % 64 == 0.
- * ksplit <= 0 selects the split automatically. */
+ * (split-K, fp32 atomic accumulation). Replaces the wgrad kernels autograd issues at
+ * pt/engine/trainer.py:384 (`losses.backward()`). m_total % 128 == 0, n_total % 64 == 0. */
 int ptb200_gemm_wgrad_f16(const void* G, int64_t ldg, int64_t g_batch_stride, const void* X,
                           int64_t ldx, int64_t x_batch_stride, int batch, int rows, int m_total,
-                          int n_total, int taps, const int* shifts, float* out, int64_t ld_out,
+                          int n_total, int taps, const int* shifts_host, float* out, int64_t ld_out,
                           float scale, int ksplit, void* stream);
+
+/* ---- image / activation helpers ---------------------------------------------------------------- */
+
+/* d2 GeneralizedRCNN.preprocess_image (called at pt/modeling/meta_arch/rcnn.py:38-43): uint8 CHW
+ * images -> (x - mean) / std, zero-padded to the batch max size, emitted directly as the im2col
+ * operand [n][hmax*(wmax+1)][64] (27 live columns, order (ky*3+kx)*3+c) of the first VGG conv. */
+int ptb200_preprocess_im2col(const uint8_t* images, const int* hw_dev, int n, int hmax, int wmax,
+                             int64_t image_stride, const float* mean3_host, const float* std3_host,
+                             void* out_f16, void* stream);
+
+/* F.max_pool2d(2, 2) of pt/modeling/backbone/vgg.py:59,71 (floor mode). */
+int ptb200_maxpool2x2_f16(const void* in, void* out, int n, int h, int w, int c, void* stream);
+
+/* Backward of ReLU followed by the 2x2 max pool (autograd of vgg.py:65-72). */
+int ptb200_maxpool2x2_relu_bwd_f16(const void* x, const void* dpooled, void* dz, int n, int h, int w,
+                                   int c, void* stream);
+
+/* fp32 master weights -> fp16 GEMM operands. */
+int ptb200_cast_f32_f16(const float* src, void* dst, int64_t n, void* stream);
+int ptb200_transpose_pack_f16(const float* src, void* dst, int rows, int cols, int taps, int flip,
+                              int64_t ld_dst, void* stream);
+int ptb200_cast_pad_rows_f16(const float* src, void* dst, int rows, int cols, int ld_dst, void* stream);
+
+/* Bias gradient: out[c] += scale * sum_rows in[row][c]. */
+int ptb200_colsum_f16(const void* in, int64_t rows, int c, int64_t ld, float scale, float* out,
+                      void* stream);
+
+/* Packs the unit gradients of two loss terms (n0 and n1 columns) scaled by the upstream gradients
+ * g0[0], g1[0] and the loss scale into the fp16 [rows][ld] operand of the backward GEMMs. */
+int ptb200_pack_grad2_f16(const float* d0, int n0, const float* d1, int n1, const float* g0,
+                          const float* g1, float lscale, int64_t rows, int ld, void* out, void* stream);
+
+int ptb200_add_f32_to_f16(const void* a, const float* b, float scale, void* out, int64_t n,
+                          void* stream);
+
+/* out = (aux > 0) ? a + scale * b : 0  (sums the two gradient paths into the backbone output). */
+int ptb200_add_mask_f16(const void* a, const float* b, float scale, const void* aux, void* out,
+                        int64_t n, void* stream);
+
+/* ---- sorting ----------------------------------------------------------------------------------- */
+
+/* Segmented stable radix sort, ascending uint32 keys with uint32 payload; replaces torch.sort at
+ * pt/modeling/proposal_generator/proposal_utils.py:87, the sort inside torchvision nms and
+ * torch.randperm in d2 subsample_labels. (end_bit - begin_bit) must be a multiple of 16. */
+int ptb200_segmented_sort_u32(uint32_t* keys, uint32_t* vals, uint32_t* keys_tmp, uint32_t* vals_tmp,
+                              int segments, int64_t seg_stride, const int* seg_len_dev, int max_len,
+                              int begin_bit, int end_bit, void* stream);
+
+/* ---- anchors / proposals / NMS ------------------------------------------------------------------ */
+
+/* pt/modeling/anchor_generator.py:145-148 (cell anchors from the learnable (w,h)) and :108-122 (grid). */
+int ptb200_cell_anchors_from_wh(const float* wh, int num_cell, float* cell, void* stream);
+int ptb200_anchor_grid(const float* cell, int num_cell, int h, int w, float stride, float offset,
+                       float* anchors, void* stream);
+
+/* Sort keys (descending logit, stable) for proposal_utils.py:87. */
+int ptb200_rpn_make_keys(const float* logits, int ld, int n, int h, int w, int num_cell,
+                         uint32_t* keys, uint32_t* vals, void* stream);
+
+/* proposal_utils.py:92-138 for the k best anchors of every image: decode (box_regression.py:101-139),
+ * finite check, clip, non-empty filter, sigma re-scoring (sigma read at the UNSORTED index, :94). */
+int ptb200_rpn_topk_decode(const uint32_t* sorted_idx, int64_t idx_stride, const float* logits,
+                           int ld_logit, const float* deltas, int ld_delta, const float* anchors, int n,
+                           int h, int w, int num_cell, int k, const float* img_hw, float min_size,
+                           float* boxes, float* scores, uint32_t* keys2, uint32_t* vals2,
+                           int* valid_count, int* nonfinite_flag, void* stream);
+
+/* d2 batched_nms -> torchvision nms (proposal_utils.py:140, fast_rcnn.py:104): greedy NMS over the
+ * candidates in `order` (descending score); class_mod > 0 restricts suppression to candidates with
+ * equal (order value % class_mod). keep_idx holds positions in `order`. */
+int ptb200_nms(const float* boxes, int64_t box_stride, const uint32_t* order, int64_t order_stride,
+               const int* counts, int n, int cap, float thresh, int class_mod, int max_keep,
+               unsigned long long* mask_scratch, int* keep_idx, int* keep_count, void* stream);
+
+int ptb200_rpn_gather(const float* boxes, const float* scores, int k, const uint32_t* order,
+                      int64_t order_stride, const int* keep_idx, const int* keep_count, int max_keep,
+                      int n, float* out_boxes, float* out_scores, void* stream);
+
+/* Teacher pseudo-label filter, pt/modeling/roi_heads/fast_rcnn.py:34-120,338-409. */
+int ptb200_roi_infer_candidates(const float* scores, const float* deltas, const float* props,
+                                const int* prop_count, int n, int cap, int num_classes,
+                                const float* img_hw, float score_thresh, const float* weights4_host,
+                                float* cboxes, float* cscores, uint32_t* keys, uint32_t* vals,
+                                int* cand_count, void* stream);
+int ptb200_roi_infer_gather(const float* cboxes, const float* cscores, const float* scores,
+                            const float* deltas, const uint32_t* order, const int* keep_idx,
+                            const int* keep_count, int n, int cap, int num_classes, int topk,
+                            float* out_boxes, float* out_scores, int64_t* out_classes, float* out_logits,
+                            float* out_sigma, int* out_src_roi, void* stream);
+
+/* ---- matching / sampling ------------------------------------------------------------------------ */
+
+/* d2 pairwise_iou + Matcher([lo, hi], [0,-1,1], allow_low_quality_matches=True), as called at
+ * pt/modeling/proposal_generator/rpn.py:414-415. labels in {-1, 0, 1} (before sub-sampling). */
+int ptb200_rpn_match(const float* gt_boxes, const int* gt_count, int gt_cap, const float* anchors,
+                     int num_anchors, int n, float iou_lo, float iou_hi, float* max_iou_scratch,
+                     int* best_per_gt_scratch, int* matched_idx, int* labels, void* stream);
+
+/* d2 subsample_labels building blocks (rpn.py:433, roi_heads.py:223-225). */
+int ptb200_compact_pos_neg(const int* labels, int64_t stride, const int* seg_len, int fixed_len,
+                           int segments, int bg_label, int* pos_list, int* neg_list, int* counts,
+                           void* stream);
+int ptb200_prio_keys(const float* prio_pos, const float* prio_neg, int64_t stride, const int* counts,
+                     int n, uint32_t* keys, uint32_t* vals, void* stream);
+int ptb200_rpn_sample_apply(const int* pos_list, const int* neg_list, const uint32_t* perm,
+                            int64_t stride, const int* counts, int n, int num_anchors,
+                            int batch_per_image, int max_pos, signed char* labels_out, void* stream);
+
+/* pt/modeling/roi_heads/roi_heads.py:192-255 (supervised) with add_ground_truth_to_proposals
+ * (proposal_utils.py:157-224) and d2 _sample_proposals. */
+int ptb200_roi_label(const float* gt_boxes, const int* gt_classes, const int* gt_count, int gt_cap,
+                     const float* props, const int* prop_count, int prop_cap, int n, int num_classes,
+                     float iou_thr, int* cls, int* matched, int* cand_count, void* stream);
+int ptb200_roi_sample_apply(const int* pos_list, const int* neg_list, const uint32_t* perm,
+                            int64_t stride, const int* counts, const int* cls, const int* matched,
+                            const float* gt_boxes, const int* gt_count, int gt_cap, const float* props,
+                            const int* prop_count, int prop_cap, int n, int batch_per_image, int max_fg,
+                            int num_classes, float* out_rois, int* out_cls, float* out_gt,
+                            int* out_count, int* out_src, void* stream);
+
+/* pt/modeling/roi_heads/roi_heads.py:257-291 (_sample_proposals_unsup). */
+int ptb200_roi_match_unsup(const float* pseudo_boxes, const float* pseudo_logits,
+                           const float* pseudo_sigma, const int* pseudo_count, int pseudo_cap,
+                           const float* props, const int* prop_count, int prop_cap, int n,
+                           int num_classes_plus1, float iou_thr, float* out_rois, float* out_pseudo,
+                           float* out_logits, float* out_sigma, int* out_count, void* stream);
+
+/* ---- ROIAlign ------------------------------------------------------------------------------------ */
+
+/* d2 ROIPooler -> torchvision roi_align(aligned=True, sampling_ratio=0), roi_heads.py:68-73,126.
+ * out: fp16 [n*cap][pooled*pooled][c] (the K-major fc1 operand); bwd accumulates into fp32 dfeat. */
+int ptb200_roi_align_fwd_f16(const void* feat, int n, int h, int w, int c, const float* rois,
+                             const int* roi_count, int cap, float spatial_scale, int pooled, void* out,
+                             void* stream);
+int ptb200_roi_align_bwd_f16(const void* dout, int n, int h, int w, int c, const float* rois,
+                             const int* roi_count, int cap, float spatial_scale, int pooled,
+                             float* dfeat, void* stream);
+
+/* ---- losses (fused forward + unit-gradient backward) --------------------------------------------- */
+
+/* pt/modeling/proposal_generator/rpn.py:191-255 (+ box_regression.py:33-35,142-176). loss2 = {cls, loc}. */
+int ptb200_rpn_loss_sup(const float* logits, int ld_logit, const float* deltas, int ld_delta,
+                        const signed char* labels, const int* matched, const float* gt_boxes, int gt_cap,
+                        const float* anchors, int n, int h, int w, int num_cell, float norm, float* loss2,
+                        float* dlogits, float* ddeltas, void* stream);
+
+/* pt/modeling/proposal_generator/rpn.py:257-361; danchor_wh (may be NULL) receives d(loss_loc)/d(anchor w,h). */
+int ptb200_rpn_loss_unsup(const float* logits, int ld_logit, const float* deltas, int ld_delta,
+                          const int* labels, const int* matched, const float* pseudo_boxes,
+                          const float* pseudo_logits, const float* pseudo_sigma, int pseudo_cap,
+                          const float* anchors, int n, int h, int w, int num_cell, int num_classes_plus1,
+                          int efl, float lam0, float lam1, float tau0, float tau1, float norm,
+                          float* loss2, float* dlogits, float* ddeltas, float* danchor_wh, void* stream);
+
+/* d2 FastRCNNOutputLayers.losses (mean cross-entropy) + pt/modeling/roi_heads/fast_rcnn.py:265-336. */
+int ptb200_roi_loss_sup(const float* scores, const float* deltas, const int* gt_classes,
+                        const float* props, const float* gt_boxes, const int* counts, int n, int cap,
+                        int num_classes, const float* weights4_host, float* loss2, float* dscores,
+                        float* ddeltas, void* stream);
+
+/* pt/modeling/roi_heads/fast_rcnn.py:179-263 + roi_heads.py:131-172. */
+int ptb200_roi_loss_unsup(const float* scores, const float* deltas, const float* soft_logits,
+                          const float* sigma_t, const float* props, const float* pseudo_boxes,
+                          const int* counts, int n, int cap, int num_classes, int efl, float lam0,
+                          float lam1, float tau0, float tau1, const float* weights4_host, int* totals2,
+                          float* loss2, float* dscores, float* ddeltas, void* stream);
+
+int ptb200_axpy_dev(const float* alpha_dev, float scale, const float* x, float* y, int n, void* stream);
+
+/* ---- optimiser arena ------------------------------------------------------------------------------ */
+
+/* pt/engine/trainer.py:431-449: teacher = keep * teacher + (1 - keep) * student over the flat arena. */
+int ptb200_ema_update(float* teacher, const float* student, int64_t n, float keep_rate, void* stream);
+
+/* pt/engine/trainer.py:592-603 (global L2 norm) and torch.optim.SGD(momentum, weight_decay) step
+ * (trainer.py:386) fused; the clip coefficient clip/max(norm, clip) is evaluated on device. */
+int ptb200_grad_sumsq(const float* grads, int64_t n, float pre_scale, float* sumsq_out, void* stream);
+int ptb200_clip_sgd_step(float* params, const float* grads, float* momentum_buf, int64_t n, float lr,
+                         float momentum, float weight_decay, float clip_norm, float pre_scale,
+                         const float* sumsq_dev, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,19 +1,52 @@
-"""ctypes binding of libptb200.so (the C ABI in include/ptb200.h).
+"""ctypes binding of libptb200.so (the C ABI declared in include/ptb200.h).
 
-The product path has no CPU fallback: if the shared library is missing or a symbol is absent the
-import fails loudly.
+The prototypes are parsed from the header, so the header is the single source of truth for the
+boundary. The product path has no CPU fallback: if the shared library is missing or a declared
+symbol is absent, loading fails loudly.
 """
 import ctypes
 import os
+import re
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libptb200.so")
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "ptb200.h")
 
 _lib = None
+_protos = None
 
 
 class PTB200Error(RuntimeError):
     pass
+
+
+def parse_header(path=HEADER_PATH):
+    """Returns {name: [(ctype_str, param_name), ...]} for every `int ptb200_*(...)` prototype."""
+    text = open(path).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"\bint\s+(ptb200_\w+)\s*\(([^;]*?)\)\s*;", text, flags=re.S):
+        name, args = m.group(1), m.group(2)
+        params = []
+        for a in args.split(","):
+            a = " ".join(a.split())
+            mm = re.match(r"(.*?)(\w+)$", a)
+            params.append((mm.group(1).strip(), mm.group(2)))
+        protos[name] = params
+    return protos
+
+
+def _ctype(t):
+    if "*" in t:
+        return ctypes.c_void_p
+    return {"int": ctypes.c_int, "int64_t": ctypes.c_int64, "float": ctypes.c_float}[t]
+
+
+def protos():
+    global _protos
+    if _protos is None:
+        _protos = parse_header()
+    return _protos
 
 
 def lib():
@@ -23,7 +56,15 @@ def lib():
             raise PTB200Error(
                 f"{LIB_PATH} is missing: run `python -m probabilisticteacher_b200.build` "
                 "(there is no CPU fallback for the hot path)")
-        _lib = ctypes.CDLL(LIB_PATH)
+        L = ctypes.CDLL(LIB_PATH)
+        for name, params in protos().items():
+            try:
+                fn = getattr(L, name)
+            except AttributeError:
+                raise PTB200Error(f"{LIB_PATH} does not export {name} declared in {HEADER_PATH}")
+            fn.restype = ctypes.c_int
+            fn.argtypes = [_ctype(t) for t, _ in params]
+        _lib = L
     return _lib
 
 
@@ -42,3 +83,41 @@ def ptr(t):
 def stream_ptr():
     import torch
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+_keepalive = []
+
+
+def call(name, *args):
+    """Calls an entry point: tensors -> data pointers, None -> NULL, python lists for `*_host`
+    parameters -> temporary C arrays; the trailing `stream` argument is filled in automatically
+    when omitted. Raises PTB200Error on a non-zero return code."""
+    L = lib()
+    params = protos()[name]
+    if len(args) == len(params) - 1:
+        args = args + (stream_ptr(),)
+    if len(args) != len(params):
+        raise TypeError(f"{name} expects {len(params)} arguments, got {len(args)}")
+    conv = []
+    for (ctype, pname), a in zip(params, args):
+        if "*" in ctype:
+            if a is None:
+                conv.append(None)
+            elif isinstance(a, (list, tuple)):
+                arr_t = ctypes.c_float if "float" in ctype else ctypes.c_int
+                arr = (arr_t * len(a))(*a)
+                conv.append(ctypes.cast(arr, ctypes.c_void_p))
+                _keepalive.append(arr)
+                if len(_keepalive) > 64:
+                    del _keepalive[:32]
+            elif isinstance(a, ctypes.c_void_p):
+                conv.append(a)
+            elif isinstance(a, int):
+                conv.append(ctypes.c_void_p(a))
+            else:
+                conv.append(ctypes.c_void_p(a.data_ptr()))
+        else:
+            conv.append(a)
+    rc = getattr(L, name)(*conv)
+    if rc != 0:
+        raise PTB200Error(f"{name} failed with code {rc}")

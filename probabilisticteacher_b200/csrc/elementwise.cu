@@ -1,0 +1,329 @@
+// HBM-bound helpers of the hot path: image pre-processing, max-pool forward/backward, weight
+// packing (fp32 master arena -> fp16 GEMM operands), bias-gradient column sums, gradient packing.
+// Activations are fp16 [N][H][Wp][C] with Wp = W + 1 and the pad column x = W kept at zero.
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include "../../include/ptb200.h"
+
+namespace {
+
+constexpr int kThreads = 256;
+
+inline int grid_for(int64_t n, int per_block = kThreads) {
+  int64_t g = (n + per_block - 1) / per_block;
+  if (g < 1) g = 1;
+  if (g > 148 * 32) g = 148 * 32;
+  return static_cast<int>(g);
+}
+
+// ------------------------------------------------------------------------------------------
+// preprocess: uint8 CHW images -> normalised, im2col'd fp16 rows for conv1_1 as a K=64 GEMM.
+// column (ky*3+kx)*3 + c holds ((img[c][y+ky-1][x+kx-1] - mean[c]) / std[c]) (0 outside the image,
+// matching zero padding of the normalised, zero-padded ImageList), columns 27..63 are zero.
+// One thread per (row, 8-column group).
+__global__ void preprocess_im2col_kernel(const uint8_t* __restrict__ img, const int* __restrict__ hw,
+                                         int N, int Hmax, int Wmax, int64_t img_stride, float m0,
+                                         float m1, float m2, float is0, float is1, float is2,
+                                         __half* __restrict__ out) {
+  const int Wp = Wmax + 1;
+  const int64_t total = static_cast<int64_t>(N) * Hmax * Wp * 8;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int grp = static_cast<int>(i & 7);
+    int64_t row = i >> 3;
+    const int x = static_cast<int>(row % Wp);
+    row /= Wp;
+    const int y = static_cast<int>(row % Hmax);
+    const int n = static_cast<int>(row / Hmax);
+    const int h = hw[2 * n], w = hw[2 * n + 1];
+    __align__(16) __half v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int col = grp * 8 + e;
+      float val = 0.f;
+      if (col < 27 && x < Wmax) {
+        const int t = col / 3, c = col - t * 3;
+        const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
+        if (yy >= 0 && yy < h && xx >= 0 && xx < w) {
+          const float px = static_cast<float>(img[n * img_stride + (static_cast<int64_t>(c) * h + yy) * w + xx]);
+          const float mean = c == 0 ? m0 : (c == 1 ? m1 : m2);
+          const float istd = c == 0 ? is0 : (c == 1 ? is1 : is2);
+          val = (px - mean) * istd;
+        }
+      }
+      v[e] = __float2half_rn(val);
+    }
+    *reinterpret_cast<uint4*>(out + i * 8) = *reinterpret_cast<const uint4*>(v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// 2x2 stride-2 max pool (floor), fp16 NHWC-flat in/out. One thread per (out pixel, 8 channels).
+__global__ void maxpool2x2_kernel(const __half* __restrict__ in, __half* __restrict__ out, int N, int H,
+                                  int W, int C) {
+  const int Wp = W + 1, Ho = H / 2, Wo = W / 2, Wop = Wo + 1, C8 = C / 8;
+  const int64_t total = static_cast<int64_t>(N) * Ho * Wop * C8;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int c8 = static_cast<int>(i % C8);
+    int64_t r = i / C8;
+    const int xo = static_cast<int>(r % Wop);
+    r /= Wop;
+    const int yo = static_cast<int>(r % Ho);
+    const int n = static_cast<int>(r / Ho);
+    uint4 o = make_uint4(0, 0, 0, 0);
+    if (xo < Wo) {
+      const __half* base = in + ((static_cast<int64_t>(n) * H + 2 * yo) * Wp + 2 * xo) * C + c8 * 8;
+      const uint4 a = *reinterpret_cast<const uint4*>(base);
+      const uint4 b = *reinterpret_cast<const uint4*>(base + C);
+      const uint4 c = *reinterpret_cast<const uint4*>(base + static_cast<int64_t>(Wp) * C);
+      const uint4 d = *reinterpret_cast<const uint4*>(base + static_cast<int64_t>(Wp) * C + C);
+      const __half2* ah = reinterpret_cast<const __half2*>(&a);
+      const __half2* bh = reinterpret_cast<const __half2*>(&b);
+      const __half2* ch = reinterpret_cast<const __half2*>(&c);
+      const __half2* dh = reinterpret_cast<const __half2*>(&d);
+      __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) oh[e] = __hmax2(__hmax2(ah[e], bh[e]), __hmax2(ch[e], dh[e]));
+    }
+    *reinterpret_cast<uint4*>(out + i * 8) = o;
+  }
+}
+
+// Backward of (ReLU -> 2x2 max pool): dZ[pos] = dP[pooled] if pos is the first arg-max of its
+// window (row-major scan order, as ATen's max_pool2d) and X[pos] > 0, else 0. X is the pre-pool
+// (post-ReLU) activation, dP the gradient w.r.t. the pooled map. One thread per (out pixel, 8 ch).
+// Rows/cols of X not covered by a window (odd H or W) get zero gradient.
+__global__ void maxpool2x2_relu_bwd_kernel(const __half* __restrict__ x, const __half* __restrict__ dp,
+                                           __half* __restrict__ dz, int N, int H, int W, int C) {
+  const int Wp = W + 1, Ho = H / 2, Wo = W / 2, Wop = Wo + 1, C8 = C / 8;
+  // cover the full input grid in units of 2x2 windows (including the uncovered fringe)
+  const int Hc = (H + 1) / 2, Wc = (Wp + 1) / 2;
+  const int64_t total = static_cast<int64_t>(N) * Hc * Wc * C8;
+  const __half zero = __float2half(0.f);
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int c8 = static_cast<int>(i % C8);
+    int64_t r = i / C8;
+    const int xo = static_cast<int>(r % Wc);
+    r /= Wc;
+    const int yo = static_cast<int>(r % Hc);
+    const int n = static_cast<int>(r / Hc);
+    const bool covered = (yo < Ho) && (xo < Wo);
+    __align__(16) __half g[8];
+    if (covered) {
+      *reinterpret_cast<uint4*>(g) = *reinterpret_cast<const uint4*>(
+          dp + ((static_cast<int64_t>(n) * Ho + yo) * Wop + xo) * C + c8 * 8);
+    }
+    __align__(16) __half xv[4][8];
+    bool live[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int yy = 2 * yo + (k >> 1), xx = 2 * xo + (k & 1);
+      live[k] = (yy < H) && (xx < Wp);
+      if (live[k] && covered)
+        *reinterpret_cast<uint4*>(xv[k]) = *reinterpret_cast<const uint4*>(
+            x + ((static_cast<int64_t>(n) * H + yy) * Wp + xx) * C + c8 * 8);
+    }
+    __align__(16) __half o[4][8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      int best = 0;
+      if (covered) {
+        float bv = __half2float(xv[0][e]);
+#pragma unroll
+        for (int k = 1; k < 4; ++k) {
+          const float v = __half2float(xv[k][e]);
+          if (v > bv) {
+            bv = v;
+            best = k;
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) o[k][e] = (k == best && bv > 0.f) ? g[e] : zero;
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) o[k][e] = zero;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int yy = 2 * yo + (k >> 1), xx = 2 * xo + (k & 1);
+      if (live[k])
+        *reinterpret_cast<uint4*>(dz + ((static_cast<int64_t>(n) * H + yy) * Wp + xx) * C + c8 * 8) =
+            *reinterpret_cast<const uint4*>(o[k]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+__global__ void cast_f32_f16_kernel(const float* __restrict__ src, __half* __restrict__ dst, int64_t n) {
+  const int64_t n4 = n >> 2;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(src)[i];
+    __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
+    uint2 o;
+    o.x = *reinterpret_cast<uint32_t*>(&a);
+    o.y = *reinterpret_cast<uint32_t*>(&b);
+    reinterpret_cast<uint2*>(dst)[i] = o;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) dst[(n4 << 2) + threadIdx.x] = __float2half_rn(src[(n4 << 2) + threadIdx.x]);
+}
+
+// dst[c][r_dst] = src[r][c] (fp32 -> fp16 transpose), dst row length ld_dst >= rows (pad untouched).
+// With taps > 1 the matrices are [rows][taps][cols] -> [cols][taps (flipped)][rows]  (conv dgrad weights).
+__global__ void transpose_pack_kernel(const float* __restrict__ src, __half* __restrict__ dst, int rows,
+                                      int cols, int taps, int flip, int64_t ld_dst) {
+  __shared__ float tile[32][33];
+  const int t = blockIdx.z;
+  const int td = flip ? (taps - 1 - t) : t;
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int r = r0 + j, c = c0 + threadIdx.x;
+    tile[j][threadIdx.x] = (r < rows && c < cols) ? src[(static_cast<int64_t>(r) * taps + t) * cols + c] : 0.f;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int c = c0 + j, r = r0 + threadIdx.x;
+    if (c < cols && r < rows) dst[static_cast<int64_t>(c) * ld_dst + static_cast<int64_t>(td) * rows + r] = __float2half_rn(tile[threadIdx.x][j]);
+  }
+}
+
+// dst[r][0..ld_dst) fp16 = src[r][0..cols) fp32, zero padded (rows x cols -> rows x ld_dst)
+__global__ void cast_pad_rows_kernel(const float* __restrict__ src, __half* __restrict__ dst, int rows,
+                                     int cols, int ld_dst) {
+  const int64_t total = static_cast<int64_t>(rows) * ld_dst;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % ld_dst);
+    const int64_t r = i / ld_dst;
+    dst[i] = __float2half_rn(c < cols ? src[r * cols + c] : 0.f);
+  }
+}
+
+// out[c] += scale * sum_rows in[row][c]   (fp16 in, fp32 atomics). grid.x over row chunks.
+__global__ void colsum_f16_kernel(const __half* __restrict__ in, int64_t rows, int C, int64_t ld,
+                                  float scale, float* __restrict__ out) {
+  const int64_t rows_per_block = (rows + gridDim.x - 1) / gridDim.x;
+  const int64_t r0 = blockIdx.x * rows_per_block;
+  const int64_t r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
+  for (int c = threadIdx.x * 2; c < C; c += blockDim.x * 2) {
+    float a0 = 0.f, a1 = 0.f;
+    for (int64_t r = r0; r < r1; ++r) {
+      const __half2 v = *reinterpret_cast<const __half2*>(in + r * ld + c);
+      const float2 f = __half22float2(v);
+      a0 += f.x;
+      a1 += f.y;
+    }
+    atomicAdd(out + c, a0 * scale);
+    if (c + 1 < C) atomicAdd(out + c + 1, a1 * scale);
+  }
+}
+
+// Pack fp32 unit gradients of two loss terms into the fp16 [rows][ld] GEMM operand:
+// out[r][c] = half(lscale * (c < n0 ? g[0]*d0[r][c] : g[1]*d1[r][c-n0])), zero padded to ld.
+// Optional row map: the source row of packed row r is src_row = r (dense).
+__global__ void pack_grad2_kernel(const float* __restrict__ d0, int n0, const float* __restrict__ d1,
+                                  int n1, const float* __restrict__ g0, const float* __restrict__ g1,
+                                  float lscale, int64_t rows, int ld, __half* __restrict__ out) {
+  const int64_t total = rows * ld;
+  const float w0 = g0 != nullptr ? g0[0] * lscale : lscale;
+  const float w1 = g1 != nullptr ? g1[0] * lscale : lscale;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % ld);
+    const int64_t r = i / ld;
+    float v = 0.f;
+    if (c < n0)
+      v = w0 * d0[r * n0 + c];
+    else if (c < n0 + n1)
+      v = w1 * d1[r * n1 + (c - n0)];
+    out[i] = __float2half_rn(v);
+  }
+}
+
+// out = half(a + scale * b) elementwise over fp16 a (may be null -> 0) and fp32 b.
+__global__ void add_f32_to_f16_kernel(const __half* __restrict__ a, const float* __restrict__ b,
+                                      float scale, __half* __restrict__ out, int64_t n) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float av = a != nullptr ? __half2float(a[i]) : 0.f;
+    out[i] = __float2half_rn(av + scale * b[i]);
+  }
+}
+
+}  // namespace
+
+#define STREAM static_cast<cudaStream_t>(stream)
+#define LAUNCH_OK() static_cast<int>(cudaGetLastError())
+
+extern "C" int ptb200_preprocess_im2col(const uint8_t* images, const int* hw_dev, int n, int hmax, int wmax,
+                                        int64_t image_stride, const float* mean3, const float* std3,
+                                        void* out_f16, void* stream) {
+  const int64_t total = static_cast<int64_t>(n) * hmax * (wmax + 1) * 8;
+  preprocess_im2col_kernel<<<grid_for(total), kThreads, 0, STREAM>>>(
+      images, hw_dev, n, hmax, wmax, image_stride, mean3[0], mean3[1], mean3[2], 1.f / std3[0],
+      1.f / std3[1], 1.f / std3[2], static_cast<__half*>(out_f16));
+  return LAUNCH_OK();
+}
+
+extern "C" int ptb200_maxpool2x2_f16(const void* in, void* out, int n, int h, int w, int c, void* stream) {
+  if (c % 8 != 0) return 1201;
+  const int64_t total = static_cast<int64_t>(n) * (h / 2) * (w / 2 + 1) * (c / 8);
+  maxpool2x2_kernel<<<grid_for(total), kThreads, 0, STREAM>>>(static_cast<const __half*>(in),
+                                                             static_cast<__half*>(out), n, h, w, c);
+  return LAUNCH_OK();
+}
+
+extern "C" int ptb200_maxpool2x2_relu_bwd_f16(const void* x, const void* dpooled, void* dz, int n, int h,
+                                              int w, int c, void* stream) {
+  if (c % 8 != 0) return 1201;
+  const int64_t total = static_cast<int64_t>(n) * ((h + 1) / 2) * ((w + 2) / 2) * (c / 8);
+  maxpool2x2_relu_bwd_kernel<<<grid_for(total), kThreads, 0, STREAM>>>(
+      static_cast<const __half*>(x), static_cast<const __half*>(dpooled), static_cast<__half*>(dz), n, h, w, c);
+  return LAUNCH_OK();
+}
+
+extern "C" int ptb200_cast_f32_f16(const float* src, void* dst, int64_t n, void* stream) {
+  cast_f32_f16_kernel<<<grid_for(n / 4 + 1), kThreads, 0, STREAM>>>(src, static_cast<__half*>(dst), n);
+  return LAUNCH_OK();
+}
+
+extern "C" int ptb200_transpose_pack_f16(const float* src, void* dst, int rows, int cols, int taps, int flip,
+                                         int64_t ld_dst, void* stream) {
+  dim3 grid((cols + 31) / 32, (rows + 31) / 32, taps), block(32, 8);
+  transpose_pack_kernel<<<grid, block, 0, STREAM>>>(src, static_cast<__half*>(dst), rows, cols, taps, flip, ld_dst);
+  return LAUNCH_OK();
+}
+
+extern "C" int ptb200_cast_pad_rows_f16(const float* src, void* dst, int rows, int cols, int ld_dst, void* stream) {
+  cast_pad_rows_kernel<<<grid_for(static_cast<int64_t>(rows) * ld_dst), kThreads, 0, STREAM>>>(
+      src, static_cast<__half*>(dst), rows, cols, ld_dst);
+  return LAUNCH_OK();
+}
+
+extern "C" int ptb200_colsum_f16(const void* in, int64_t rows, int c, int64_t ld, float scale, float* out,
+                                 void* stream) {
+  int blocks = static_cast<int>((rows + 511) / 512);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  colsum_f16_kernel<<<blocks, 256, 0, STREAM>>>(static_cast<const __half*>(in), rows, c, ld, scale, out);
+  return LAUNCH_OK();
+}
+
+extern "C" int ptb200_pack_grad2_f16(const float* d0, int n0, const float* d1, int n1, const float* g0,
+                                     const float* g1, float lscale, int64_t rows, int ld, void* out,
+                                     void* stream) {
+  pack_grad2_kernel<<<grid_for(rows * ld), kThreads, 0, STREAM>>>(d0, n0, d1, n1, g0, g1, lscale, rows, ld,
+                                                                 static_cast<__half*>(out));
+  return LAUNCH_OK();
+}
+
+extern "C" int ptb200_add_f32_to_f16(const void* a, const float* b, float scale, void* out, int64_t n,
+                                     void* stream) {
+  add_f32_to_f16_kernel<<<grid_for(n), kThreads, 0, STREAM>>>(static_cast<const __half*>(a), b, scale,
+                                                             static_cast<__half*>(out), n);
+  return LAUNCH_OK();
+}

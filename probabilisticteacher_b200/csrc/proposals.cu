@@ -1,0 +1,432 @@
+// Proposal path of the Gaussian RPN and the teacher's pseudo-label filter, all on device with
+// fixed-capacity buffers and device-side counts (no host synchronisation):
+//   anchors            pt/modeling/anchor_generator.py:108-122,145-148
+//   decode / clip      pt/modeling/box_regression.py:101-139, detectron2 Boxes.clip / nonempty
+//   top-k + rescoring  pt/modeling/proposal_generator/proposal_utils.py:83-138 (incl. the :94 quirk)
+//   NMS                detectron2 batched_nms -> torchvision nms (IoU > thr suppresses, stable order)
+//   pseudo-label filter pt/modeling/roi_heads/fast_rcnn.py:34-120
+// Head outputs are indexed by "row" = y * (W+1) + x of the flattened, right-padded feature map.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include "../../include/ptb200.h"
+
+namespace {
+
+__device__ __forceinline__ uint32_t order_desc(float f) {
+  // ascending radix order of the returned key == descending float order
+  uint32_t u = __float_as_uint(f);
+  u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+  return ~u;
+}
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+constexpr float kScaleClamp = 4.135166556742356f;  // log(1000/16), box_regression.py:28
+
+__device__ __forceinline__ void decode_box(const float* a, float dx, float dy, float dw, float dh,
+                                           float wx, float wy, float ww, float wh, float* o) {
+  const float w = a[2] - a[0], h = a[3] - a[1];
+  const float cx = a[0] + 0.5f * w, cy = a[1] + 0.5f * h;
+  dx = dx / wx;
+  dy = dy / wy;
+  dw = fminf(dw / ww, kScaleClamp);
+  dh = fminf(dh / wh, kScaleClamp);
+  const float pcx = __fadd_rn(__fmul_rn(dx, w), cx), pcy = __fadd_rn(__fmul_rn(dy, h), cy);
+  const float pw = __fmul_rn(expf(dw), w), ph = __fmul_rn(expf(dh), h);
+  o[0] = __fsub_rn(pcx, __fmul_rn(0.5f, pw));
+  o[1] = __fsub_rn(pcy, __fmul_rn(0.5f, ph));
+  o[2] = __fadd_rn(pcx, __fmul_rn(0.5f, pw));
+  o[3] = __fadd_rn(pcy, __fmul_rn(0.5f, ph));
+}
+
+// ------------------------------------------------------------------------------------------
+__global__ void cell_anchors_from_wh_kernel(const float* __restrict__ wh, int A, float* __restrict__ cell) {
+  const int a = threadIdx.x;
+  if (a < A) {
+    cell[4 * a + 0] = -wh[2 * a] / 2.0f;
+    cell[4 * a + 1] = -wh[2 * a + 1] / 2.0f;
+    cell[4 * a + 2] = wh[2 * a] / 2.0f;
+    cell[4 * a + 3] = wh[2 * a + 1] / 2.0f;
+  }
+}
+
+__global__ void anchor_grid_kernel(const float* __restrict__ cell, int A, int H, int W, float stride,
+                                   float offset, float4* __restrict__ out) {
+  const int total = H * W * A;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int a = i % A;
+    const int loc = i / A;
+    const int x = loc % W, y = loc / W;
+    const float sx = offset * stride + x * stride, sy = offset * stride + y * stride;
+    out[i] = make_float4(sx + cell[4 * a], sy + cell[4 * a + 1], sx + cell[4 * a + 2], sy + cell[4 * a + 3]);
+  }
+}
+
+// keys/vals for the descending sort of objectness logits (one segment per image)
+__global__ void rpn_make_keys_kernel(const float* __restrict__ logits, int ld, int N, int H, int W, int A,
+                                     uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+  const int R = H * W * A, Wp = W + 1;
+  const int64_t total = static_cast<int64_t>(N) * R;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int n = static_cast<int>(i / R);
+    const int r = static_cast<int>(i - static_cast<int64_t>(n) * R);
+    const int a = r % A, loc = r / A;
+    const int x = loc % W, y = loc / W;
+    const int64_t row = static_cast<int64_t>(n) * H * Wp + y * Wp + x;
+    keys[i] = order_desc(logits[row * ld + a]);
+    vals[i] = static_cast<uint32_t>(r);
+  }
+}
+
+// For the j-th best anchor of image n: decode, clip, validity, sigma-rescored score.
+// sigma is read from anchor index j (NOT the sorted index) -- proposal_utils.py:94.
+__global__ void rpn_topk_decode_kernel(const uint32_t* __restrict__ sorted_idx, int64_t idx_stride,
+                                       const float* __restrict__ logits, int ld_logit,
+                                       const float* __restrict__ deltas, int ld_delta,
+                                       const float4* __restrict__ anchors, int N, int H, int W, int A, int k,
+                                       const float* __restrict__ img_hw, float min_size,
+                                       float4* __restrict__ boxes, float* __restrict__ scores,
+                                       uint32_t* __restrict__ keys2, uint32_t* __restrict__ vals2,
+                                       int* __restrict__ valid_count, int* __restrict__ nonfinite_flag) {
+  const int Wp = W + 1;
+  const int total = N * k;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int n = i / k, j = i - n * k;
+    const int r = static_cast<int>(sorted_idx[n * idx_stride + j]);
+    const int a = r % A, loc = r / A;
+    const int64_t row = static_cast<int64_t>(n) * H * Wp + (loc / W) * Wp + (loc % W);
+    const float logit = logits[row * ld_logit + a];
+    const float* d = deltas + row * ld_delta + a * 8;
+    const float4 an = anchors[r];
+    const float av[4] = {an.x, an.y, an.z, an.w};
+    float b[4];
+    decode_box(av, d[0], d[1], d[2], d[3], 1.f, 1.f, 1.f, 1.f, b);
+    bool finite = isfinite(b[0]) && isfinite(b[1]) && isfinite(b[2]) && isfinite(b[3]) && isfinite(logit);
+    if (!finite) atomicOr(nonfinite_flag, 1);
+    const float ih = img_hw[2 * n], iw = img_hw[2 * n + 1];
+    b[0] = fminf(fmaxf(b[0], 0.f), iw);
+    b[1] = fminf(fmaxf(b[1], 0.f), ih);
+    b[2] = fminf(fmaxf(b[2], 0.f), iw);
+    b[3] = fminf(fmaxf(b[3], 0.f), ih);
+    const bool ok = finite && (b[2] - b[0] > min_size) && (b[3] - b[1] > min_size);
+    // sigma of anchor index j (quirk)
+    const int aj = j % A, locj = j / A;
+    const int64_t rowj = static_cast<int64_t>(n) * H * Wp + (locj / W) * Wp + (locj % W);
+    const float* sg = deltas + rowj * ld_delta + aj * 8 + 4;
+    const float ssum = ((sigmoidf_(sg[0]) + sigmoidf_(sg[1])) + sigmoidf_(sg[2])) + sigmoidf_(sg[3]);
+    const float sc = __fmul_rn(logit, 1.f - ssum / 4.0f);
+    boxes[i] = make_float4(b[0], b[1], b[2], b[3]);
+    scores[i] = sc;
+    keys2[i] = ok ? order_desc(sc) : 0xFFFFFFFFu;
+    vals2[i] = static_cast<uint32_t>(j);
+    if (ok) atomicAdd(valid_count + n, 1);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// NMS: 64x64 blocks of the (sorted) candidate list -> suppression bitmask, upper triangle only.
+__global__ void nms_bitmask_kernel(const float4* __restrict__ boxes, int64_t box_stride,
+                                   const uint32_t* __restrict__ order, int64_t order_stride,
+                                   const int* __restrict__ counts, int cap, int words, float thr, int class_mod,
+                                   unsigned long long* __restrict__ mask) {
+  const int cb = blockIdx.x, rb = blockIdx.y, n = blockIdx.z;
+  if (cb < rb) return;
+  int cnt = counts[n];
+  if (cnt > cap) cnt = cap;
+  if (rb * 64 >= cnt) return;
+  __shared__ float4 cbox[64];
+  __shared__ int ccls[64];
+  const int t = threadIdx.x;
+  const int cj = cb * 64 + t;
+  if (cj < cnt) {
+    const uint32_t oj = order[n * order_stride + cj];
+    cbox[t] = boxes[n * box_stride + oj];
+    ccls[t] = class_mod > 0 ? static_cast<int>(oj % class_mod) : 0;
+  }
+  __syncthreads();
+  const int i = rb * 64 + t;
+  if (i >= cnt) return;
+  const uint32_t oi = order[n * order_stride + i];
+  const float4 bi = boxes[n * box_stride + oi];
+  const int ci = class_mod > 0 ? static_cast<int>(oi % class_mod) : 0;
+  const float ai = __fmul_rn(bi.z - bi.x, bi.w - bi.y);
+  unsigned long long bits = 0ull;
+  const int jmax = min(64, cnt - cb * 64);
+  const int j0 = (cb == rb) ? t + 1 : 0;
+  for (int j = j0; j < jmax; ++j) {
+    const float4 bj = cbox[j];
+    const float xx1 = fmaxf(bi.x, bj.x), yy1 = fmaxf(bi.y, bj.y);
+    const float xx2 = fminf(bi.z, bj.z), yy2 = fminf(bi.w, bj.w);
+    const float w = fmaxf(0.f, xx2 - xx1), h = fmaxf(0.f, yy2 - yy1);
+    const float inter = __fmul_rn(w, h);
+    const float aj = __fmul_rn(bj.z - bj.x, bj.w - bj.y);
+    const float iou = __fdiv_rn(inter, __fsub_rn(__fadd_rn(ai, aj), inter));
+    if (iou > thr && ccls[j] == ci) bits |= 1ull << j;
+  }
+  mask[(static_cast<int64_t>(n) * cap + i) * words + cb] = bits;
+}
+
+// Sequential part of NMS, one CTA per image: 64-candidate blocks are resolved by warp 0 with the
+// diagonal mask block, then all threads OR the kept rows into the running `removed` bit vector.
+// Stops after max_keep survivors. keep_idx holds positions in the sorted order.
+__global__ void __launch_bounds__(256, 1)
+nms_scan_kernel(const unsigned long long* __restrict__ mask, const int* __restrict__ counts, int cap, int words,
+                int max_keep, int* __restrict__ keep_idx, int* __restrict__ keep_count) {
+  extern __shared__ unsigned long long removed[];  // [words]
+  __shared__ unsigned long long s_keep;
+  __shared__ int s_total;
+  const int n = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+  int cnt = counts[n];
+  if (cnt > cap) cnt = cap;
+  const unsigned long long* m = mask + static_cast<int64_t>(n) * cap * words;
+  for (int w = tid; w < words; w += blockDim.x) removed[w] = 0ull;
+  if (tid == 0) s_total = 0;
+  __syncthreads();
+  const int nblk = (cnt + 63) / 64;
+  for (int b = 0; b < nblk; ++b) {
+    if (s_total >= max_keep) break;
+    if (tid < 32) {
+      const int r0 = b * 64 + lane, r1 = r0 + 32;
+      const unsigned long long d0 = r0 < cnt ? m[static_cast<int64_t>(r0) * words + b] : 0ull;
+      const unsigned long long d1 = r1 < cnt ? m[static_cast<int64_t>(r1) * words + b] : 0ull;
+      unsigned long long rem = removed[b];
+      const int live = min(64, cnt - b * 64);
+      if (live < 64) rem |= ~0ull << live;
+      unsigned long long keep = 0ull;
+#pragma unroll 4
+      for (int i = 0; i < 64; ++i) {
+        const unsigned long long di = __shfl_sync(0xffffffffu, i < 32 ? d0 : d1, i & 31);
+        if (!((rem >> i) & 1ull)) {
+          keep |= 1ull << i;
+          rem |= di;
+        }
+      }
+      const int total = s_total;
+      // append survivors (lane handles bits lane and lane+32)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int i = lane + 32 * h;
+        if ((keep >> i) & 1ull) {
+          const int pos = total + __popcll(keep & ((1ull << i) - 1ull));
+          if (pos < max_keep) keep_idx[n * max_keep + pos] = b * 64 + i;
+        }
+      }
+      __syncwarp();
+      if (lane == 0) {
+        s_keep = keep;
+        s_total = total + __popcll(keep);
+      }
+    }
+    __syncthreads();
+    const unsigned long long keep = s_keep;
+    for (int w = b + 1 + tid; w < words; w += blockDim.x) {
+      unsigned long long acc = removed[w];
+      unsigned long long kb = keep;
+      while (kb) {
+        const int i = __ffsll(static_cast<long long>(kb)) - 1;
+        kb &= kb - 1ull;
+        acc |= m[static_cast<int64_t>(b * 64 + i) * words + w];
+      }
+      removed[w] = acc;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) keep_count[n] = min(s_total, max_keep);
+}
+
+// proposals[n][i] = boxes[order[keep[i]]], logits likewise; rows >= keep_count zero-filled.
+__global__ void rpn_gather_kernel(const float4* __restrict__ boxes, const float* __restrict__ scores, int k,
+                                  const uint32_t* __restrict__ order, int64_t order_stride,
+                                  const int* __restrict__ keep_idx, const int* __restrict__ keep_count,
+                                  int max_keep, int N, float4* __restrict__ out_boxes, float* __restrict__ out_scores) {
+  const int total = N * max_keep;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int n = i / max_keep, j = i - n * max_keep;
+    if (j < keep_count[n]) {
+      const uint32_t o = order[n * order_stride + keep_idx[i]];
+      out_boxes[i] = boxes[n * k + o];
+      out_scores[i] = scores[n * k + o];
+    } else {
+      out_boxes[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      out_scores[i] = 0.f;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Teacher pseudo-label filter, candidate stage: one thread per (image, roi, class).
+__global__ void roi_infer_candidates_kernel(const float* __restrict__ scores, const float* __restrict__ deltas,
+                                            const float4* __restrict__ props, const int* __restrict__ prop_count,
+                                            int N, int cap, int K, const float* __restrict__ img_hw,
+                                            float score_thresh, float wx, float wy, float ww, float wh,
+                                            float4* __restrict__ cboxes, float* __restrict__ cscores,
+                                            uint32_t* __restrict__ keys, uint32_t* __restrict__ vals,
+                                            int* __restrict__ cand_count) {
+  const int per_img = cap * K;
+  const int total = N * per_img;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int n = i / per_img, rc = i - n * per_img;
+    const int r = rc / K, c = rc - r * K;
+    bool ok = r < prop_count[n];
+    float sc = 0.f;
+    float b[4] = {0.f, 0.f, 0.f, 0.f};
+    if (ok) {
+      const int64_t row = static_cast<int64_t>(n) * cap + r;
+      const float* z = scores + row * (K + 1);
+      float mx = z[0];
+      for (int q = 1; q <= K; ++q) mx = fmaxf(mx, z[q]);
+      float den = 0.f;
+      for (int q = 0; q <= K; ++q) den += expf(z[q] - mx);
+      const float prob = expf(z[c] - mx) / den;
+      const float* d = deltas + row * (8 * K) + c * 8;
+      const float4 p = props[row];
+      const float pv[4] = {p.x, p.y, p.z, p.w};
+      decode_box(pv, d[0], d[1], d[2], d[3], wx, wy, ww, wh, b);
+      // validity of the roi row: every class box and every prob finite (fast_rcnn.py:66-71)
+      bool fin = isfinite(prob);
+      for (int q = 0; q < K && fin; ++q) {
+        float t[4];
+        const float* dq = deltas + row * (8 * K) + q * 8;
+        decode_box(pv, dq[0], dq[1], dq[2], dq[3], wx, wy, ww, wh, t);
+        fin = isfinite(t[0]) && isfinite(t[1]) && isfinite(t[2]) && isfinite(t[3]);
+      }
+      const float ih = img_hw[2 * n], iw = img_hw[2 * n + 1];
+      b[0] = fminf(fmaxf(b[0], 0.f), iw);
+      b[1] = fminf(fmaxf(b[1], 0.f), ih);
+      b[2] = fminf(fmaxf(b[2], 0.f), iw);
+      b[3] = fminf(fmaxf(b[3], 0.f), ih);
+      ok = fin && (prob > score_thresh);
+      const float ssum = ((sigmoidf_(d[4]) + sigmoidf_(d[5])) + sigmoidf_(d[6])) + sigmoidf_(d[7]);
+      sc = __fmul_rn(prob, 1.f - ssum / 4.0f);
+    }
+    cboxes[i] = make_float4(b[0], b[1], b[2], b[3]);
+    cscores[i] = sc;
+    keys[i] = ok ? order_desc(sc) : 0xFFFFFFFFu;
+    vals[i] = static_cast<uint32_t>(rc);
+    if (ok) atomicAdd(cand_count + n, 1);
+  }
+}
+
+__global__ void roi_infer_gather_kernel(const float4* __restrict__ cboxes, const float* __restrict__ cscores,
+                                        const float* __restrict__ scores, const float* __restrict__ deltas,
+                                        const uint32_t* __restrict__ order, const int* __restrict__ keep_idx,
+                                        const int* __restrict__ keep_count, int N, int cap, int K, int topk,
+                                        float4* __restrict__ out_boxes, float* __restrict__ out_scores,
+                                        int64_t* __restrict__ out_classes, float* __restrict__ out_logits,
+                                        float* __restrict__ out_sigma, int* __restrict__ out_src_roi) {
+  const int per_img = cap * K;
+  const int total = N * topk;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int n = i / topk, j = i - n * topk;
+    if (j < keep_count[n]) {
+      const uint32_t rc = order[static_cast<int64_t>(n) * per_img + keep_idx[i]];
+      const int r = rc / K, c = rc - r * K;
+      const int64_t row = static_cast<int64_t>(n) * cap + r;
+      out_boxes[i] = cboxes[static_cast<int64_t>(n) * per_img + rc];
+      out_scores[i] = cscores[static_cast<int64_t>(n) * per_img + rc];
+      out_classes[i] = c;
+      for (int q = 0; q <= K; ++q) out_logits[static_cast<int64_t>(i) * (K + 1) + q] = scores[row * (K + 1) + q];
+      for (int q = 0; q < 4; ++q) out_sigma[i * 4 + q] = deltas[row * (8 * K) + c * 8 + 4 + q];
+      out_src_roi[i] = r;
+    } else {
+      out_boxes[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      out_scores[i] = 0.f;
+      out_classes[i] = 0;
+      for (int q = 0; q <= K; ++q) out_logits[static_cast<int64_t>(i) * (K + 1) + q] = 0.f;
+      for (int q = 0; q < 4; ++q) out_sigma[i * 4 + q] = 0.f;
+      out_src_roi[i] = -1;
+    }
+  }
+}
+
+inline int grid1d(int64_t n) {
+  int64_t g = (n + 255) / 256;
+  if (g > 148 * 16) g = 148 * 16;
+  if (g < 1) g = 1;
+  return static_cast<int>(g);
+}
+
+}  // namespace
+
+#define STREAM static_cast<cudaStream_t>(stream)
+#define LAUNCH_OK() static_cast<int>(cudaGetLastError())
+
+extern "C" int ptb200_cell_anchors_from_wh(const float* wh, int num_cell, float* cell, void* stream) {
+  cell_anchors_from_wh_kernel<<<1, 32, 0, STREAM>>>(wh, num_cell, cell);
+  return LAUNCH_OK();
+}
+
+extern "C" int ptb200_anchor_grid(const float* cell, int num_cell, int h, int w, float stride, float offset,
+                                  float* anchors, void* stream) {
+  anchor_grid_kernel<<<grid1d(static_cast<int64_t>(h) * w * num_cell), 256, 0, STREAM>>>(
+      cell, num_cell, h, w, stride, offset, reinterpret_cast<float4*>(anchors));
+  return LAUNCH_OK();
+}
+
+extern "C" int ptb200_rpn_make_keys(const float* logits, int ld, int n, int h, int w, int num_cell, uint32_t* keys,
+                                    uint32_t* vals, void* stream) {
+  rpn_make_keys_kernel<<<grid1d(static_cast<int64_t>(n) * h * w * num_cell), 256, 0, STREAM>>>(logits, ld, n, h, w,
+                                                                                              num_cell, keys, vals);
+  return LAUNCH_OK();
+}
+
+extern "C" int ptb200_rpn_topk_decode(const uint32_t* sorted_idx, int64_t idx_stride, const float* logits,
+                                      int ld_logit, const float* deltas, int ld_delta, const float* anchors, int n,
+                                      int h, int w, int num_cell, int k, const float* img_hw, float min_size,
+                                      float* boxes, float* scores, uint32_t* keys2, uint32_t* vals2,
+                                      int* valid_count, int* nonfinite_flag, void* stream) {
+  cudaMemsetAsync(valid_count, 0, sizeof(int) * n, STREAM);
+  rpn_topk_decode_kernel<<<grid1d(static_cast<int64_t>(n) * k), 256, 0, STREAM>>>(
+      sorted_idx, idx_stride, logits, ld_logit, deltas, ld_delta, reinterpret_cast<const float4*>(anchors), n, h, w,
+      num_cell, k, img_hw, min_size, reinterpret_cast<float4*>(boxes), scores, keys2, vals2, valid_count,
+      nonfinite_flag);
+  return LAUNCH_OK();
+}
+
+extern "C" int ptb200_nms(const float* boxes, int64_t box_stride, const uint32_t* order, int64_t order_stride,
+                          const int* counts, int n, int cap, float thresh, int class_mod, int max_keep,
+                          unsigned long long* mask_scratch, int* keep_idx, int* keep_count, void* stream) {
+  const int words = (cap + 63) / 64;
+  dim3 grid(words, words, n);
+  nms_bitmask_kernel<<<grid, 64, 0, STREAM>>>(reinterpret_cast<const float4*>(boxes), box_stride, order,
+                                             order_stride, counts, cap, words, thresh, class_mod, mask_scratch);
+  nms_scan_kernel<<<n, 256, words * sizeof(unsigned long long), STREAM>>>(mask_scratch, counts, cap, words, max_keep,
+                                                                         keep_idx, keep_count);
+  return LAUNCH_OK();
+}
+
+extern "C" int ptb200_rpn_gather(const float* boxes, const float* scores, int k, const uint32_t* order,
+                                 int64_t order_stride, const int* keep_idx, const int* keep_count, int max_keep,
+                                 int n, float* out_boxes, float* out_scores, void* stream) {
+  rpn_gather_kernel<<<grid1d(static_cast<int64_t>(n) * max_keep), 256, 0, STREAM>>>(
+      reinterpret_cast<const float4*>(boxes), scores, k, order, order_stride, keep_idx, keep_count, max_keep, n,
+      reinterpret_cast<float4*>(out_boxes), out_scores);
+  return LAUNCH_OK();
+}
+
+extern "C" int ptb200_roi_infer_candidates(const float* scores, const float* deltas, const float* props,
+                                           const int* prop_count, int n, int cap, int num_classes,
+                                           const float* img_hw, float score_thresh, const float* weights4,
+                                           float* cboxes, float* cscores, uint32_t* keys, uint32_t* vals,
+                                           int* cand_count, void* stream) {
+  cudaMemsetAsync(cand_count, 0, sizeof(int) * n, STREAM);
+  roi_infer_candidates_kernel<<<grid1d(static_cast<int64_t>(n) * cap * num_classes), 256, 0, STREAM>>>(
+      scores, deltas, reinterpret_cast<const float4*>(props), prop_count, n, cap, num_classes, img_hw, score_thresh,
+      weights4[0], weights4[1], weights4[2], weights4[3], reinterpret_cast<float4*>(cboxes), cscores, keys, vals,
+      cand_count);
+  return LAUNCH_OK();
+}
+
+extern "C" int ptb200_roi_infer_gather(const float* cboxes, const float* cscores, const float* scores,
+                                       const float* deltas, const uint32_t* order, const int* keep_idx,
+                                       const int* keep_count, int n, int cap, int num_classes, int topk,
+                                       float* out_boxes, float* out_scores, int64_t* out_classes, float* out_logits,
+                                       float* out_sigma, int* out_src_roi, void* stream) {
+  roi_infer_gather_kernel<<<grid1d(static_cast<int64_t>(n) * topk), 256, 0, STREAM>>>(
+      reinterpret_cast<const float4*>(cboxes), cscores, scores, deltas, order, keep_idx, keep_count, n, cap,
+      num_classes, topk, reinterpret_cast<float4*>(out_boxes), out_scores, out_classes, out_logits, out_sigma,
+      out_src_roi);
+  return LAUNCH_OK();
+}

@@ -1,0 +1,203 @@
+// ROIAlign (aligned=True, adaptive sampling grid) over fp16 NHWC-flat features, forward and backward.
+// Semantics follow torchvision.ops.roi_align as called by detectron2's ROIPooler / ROIAlignV2
+// (reference call site: pt/modeling/roi_heads/roi_heads.py:68-73,126). The output is written as
+// fp16 [roi][ph*7+pw][C], i.e. directly in the K-major layout the fc1 GEMM consumes; all 512
+// channels of a sample are read with 16-byte vector loads (one thread = 8 channels).
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include "../../include/ptb200.h"
+
+namespace {
+
+struct Tap {
+  int o1, o2, o3, o4;       // pixel offsets (in pixels, within the image plane)
+  float w1, w2, w3, w4;
+};
+
+__device__ __forceinline__ bool bilinear_taps(float y, float x, int H, int W, int Wp, Tap& t) {
+  if (y < -1.0f || y > H || x < -1.0f || x > W) return false;
+  if (y <= 0.f) y = 0.f;
+  if (x <= 0.f) x = 0.f;
+  int yl = static_cast<int>(y), xl = static_cast<int>(x);
+  int yh, xh;
+  if (yl >= H - 1) {
+    yh = yl = H - 1;
+    y = static_cast<float>(yl);
+  } else {
+    yh = yl + 1;
+  }
+  if (xl >= W - 1) {
+    xh = xl = W - 1;
+    x = static_cast<float>(xl);
+  } else {
+    xh = xl + 1;
+  }
+  const float ly = y - yl, lx = x - xl, hy = 1.f - ly, hx = 1.f - lx;
+  t.w1 = hy * hx;
+  t.w2 = hy * lx;
+  t.w3 = ly * hx;
+  t.w4 = ly * lx;
+  t.o1 = yl * Wp + xl;
+  t.o2 = yl * Wp + xh;
+  t.o3 = yh * Wp + xl;
+  t.o4 = yh * Wp + xh;
+  return true;
+}
+
+struct RoiGeom {
+  float start_w, start_h, bin_w, bin_h;
+  int grid_w, grid_h;
+  float count;
+};
+
+__device__ __forceinline__ RoiGeom roi_geom(const float4 b, float scale, int P) {
+  RoiGeom g;
+  g.start_w = b.x * scale - 0.5f;
+  g.start_h = b.y * scale - 0.5f;
+  const float rw = (b.z * scale - 0.5f) - g.start_w, rh = (b.w * scale - 0.5f) - g.start_h;
+  g.bin_w = rw / P;
+  g.bin_h = rh / P;
+  g.grid_h = static_cast<int>(ceilf(rh / P));
+  g.grid_w = static_cast<int>(ceilf(rw / P));
+  g.count = fmaxf(static_cast<float>(g.grid_h * g.grid_w), 1.f);
+  return g;
+}
+
+// grid: (roi, ph*P+pw) ; block: C/8 threads
+__global__ void roi_align_fwd_kernel(const __half* __restrict__ feat, int H, int W, int C,
+                                     const float4* __restrict__ rois, const int* __restrict__ roi_count,
+                                     int cap, float scale, int P, __half* __restrict__ out) {
+  const int roi = blockIdx.x, bin = blockIdx.y;
+  const int n = roi / cap, j = roi - n * cap;
+  const int c0 = threadIdx.x * 8;
+  const int Wp = W + 1;
+  __half* o = out + (static_cast<int64_t>(roi) * P * P + bin) * C + c0;
+  if (roi_count != nullptr && j >= roi_count[n]) {
+    *reinterpret_cast<uint4*>(o) = make_uint4(0, 0, 0, 0);
+    return;
+  }
+  const RoiGeom g = roi_geom(rois[roi], scale, P);
+  const int ph = bin / P, pw = bin - ph * P;
+  const __half* base = feat + static_cast<int64_t>(n) * H * Wp * C + c0;
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+  for (int iy = 0; iy < g.grid_h; ++iy) {
+    const float y = g.start_h + ph * g.bin_h + (iy + 0.5f) * g.bin_h / g.grid_h;
+    for (int ix = 0; ix < g.grid_w; ++ix) {
+      const float x = g.start_w + pw * g.bin_w + (ix + 0.5f) * g.bin_w / g.grid_w;
+      Tap t;
+      if (!bilinear_taps(y, x, H, W, Wp, t)) continue;
+      const uint4 v1 = *reinterpret_cast<const uint4*>(base + static_cast<int64_t>(t.o1) * C);
+      const uint4 v2 = *reinterpret_cast<const uint4*>(base + static_cast<int64_t>(t.o2) * C);
+      const uint4 v3 = *reinterpret_cast<const uint4*>(base + static_cast<int64_t>(t.o3) * C);
+      const uint4 v4 = *reinterpret_cast<const uint4*>(base + static_cast<int64_t>(t.o4) * C);
+      const __half2* h1 = reinterpret_cast<const __half2*>(&v1);
+      const __half2* h2 = reinterpret_cast<const __half2*>(&v2);
+      const __half2* h3 = reinterpret_cast<const __half2*>(&v3);
+      const __half2* h4 = reinterpret_cast<const __half2*>(&v4);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 a = __half22float2(h1[e]), b = __half22float2(h2[e]), c = __half22float2(h3[e]),
+                     d = __half22float2(h4[e]);
+        acc[2 * e] += t.w1 * a.x + t.w2 * b.x + t.w3 * c.x + t.w4 * d.x;
+        acc[2 * e + 1] += t.w1 * a.y + t.w2 * b.y + t.w3 * c.y + t.w4 * d.y;
+      }
+    }
+  }
+  __align__(16) __half r[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) r[e] = __float2half_rn(acc[e] / g.count);
+  *reinterpret_cast<uint4*>(o) = *reinterpret_cast<const uint4*>(r);
+}
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
+               : "memory");
+}
+
+__global__ void roi_align_bwd_kernel(const __half* __restrict__ dout, int H, int W, int C,
+                                     const float4* __restrict__ rois, const int* __restrict__ roi_count,
+                                     int cap, float scale, int P, float* __restrict__ dfeat) {
+  const int roi = blockIdx.x, bin = blockIdx.y;
+  const int n = roi / cap, j = roi - n * cap;
+  if (roi_count != nullptr && j >= roi_count[n]) return;
+  const int c0 = threadIdx.x * 8;
+  const int Wp = W + 1;
+  const RoiGeom g = roi_geom(rois[roi], scale, P);
+  const int ph = bin / P, pw = bin - ph * P;
+  const uint4 gv = *reinterpret_cast<const uint4*>(dout + (static_cast<int64_t>(roi) * P * P + bin) * C + c0);
+  const __half2* gh = reinterpret_cast<const __half2*>(&gv);
+  float gr[8];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float2 f = __half22float2(gh[e]);
+    gr[2 * e] = f.x / g.count;
+    gr[2 * e + 1] = f.y / g.count;
+  }
+  float* base = dfeat + static_cast<int64_t>(n) * H * Wp * C + c0;
+  for (int iy = 0; iy < g.grid_h; ++iy) {
+    const float y = g.start_h + ph * g.bin_h + (iy + 0.5f) * g.bin_h / g.grid_h;
+    for (int ix = 0; ix < g.grid_w; ++ix) {
+      const float x = g.start_w + pw * g.bin_w + (ix + 0.5f) * g.bin_w / g.grid_w;
+      Tap t;
+      if (!bilinear_taps(y, x, H, W, Wp, t)) continue;
+      const int offs[4] = {t.o1, t.o2, t.o3, t.o4};
+      const float ws[4] = {t.w1, t.w2, t.w3, t.w4};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float* p = base + static_cast<int64_t>(offs[k]) * C;
+        red_add_v4(p, gr[0] * ws[k], gr[1] * ws[k], gr[2] * ws[k], gr[3] * ws[k]);
+        red_add_v4(p + 4, gr[4] * ws[k], gr[5] * ws[k], gr[6] * ws[k], gr[7] * ws[k]);
+      }
+    }
+  }
+}
+
+// out = half(mask ? a + scale * b : 0), mask = aux > 0 (aux optional)
+__global__ void add_mask_kernel(const __half* __restrict__ a, const float* __restrict__ b, float scale,
+                                const __half* __restrict__ aux, __half* __restrict__ out, int64_t n) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float v = (a != nullptr ? __half2float(a[i]) : 0.f) + scale * b[i];
+    if (aux != nullptr && !(__half2float(aux[i]) > 0.f)) v = 0.f;
+    out[i] = __float2half_rn(v);
+  }
+}
+
+}  // namespace
+
+#define STREAM static_cast<cudaStream_t>(stream)
+
+extern "C" int ptb200_roi_align_fwd_f16(const void* feat, int n, int h, int w, int c, const float* rois,
+                                        const int* roi_count, int cap, float spatial_scale, int pooled, void* out,
+                                        void* stream) {
+  if (c % 8 != 0 || c / 8 > 1024) return 1401;
+  dim3 grid(n * cap, pooled * pooled);
+  roi_align_fwd_kernel<<<grid, c / 8, 0, STREAM>>>(static_cast<const __half*>(feat), h, w, c,
+                                                  reinterpret_cast<const float4*>(rois), roi_count, cap,
+                                                  spatial_scale, pooled, static_cast<__half*>(out));
+  return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int ptb200_roi_align_bwd_f16(const void* dout, int n, int h, int w, int c, const float* rois,
+                                        const int* roi_count, int cap, float spatial_scale, int pooled,
+                                        float* dfeat, void* stream) {
+  if (c % 8 != 0 || c / 8 > 1024) return 1401;
+  dim3 grid(n * cap, pooled * pooled);
+  roi_align_bwd_kernel<<<grid, c / 8, 0, STREAM>>>(static_cast<const __half*>(dout), h, w, c,
+                                                  reinterpret_cast<const float4*>(rois), roi_count, cap,
+                                                  spatial_scale, pooled, dfeat);
+  return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int ptb200_add_mask_f16(const void* a, const float* b, float scale, const void* aux, void* out,
+                                   int64_t n, void* stream) {
+  int64_t g = (n + 255) / 256;
+  if (g > 148 * 32) g = 148 * 32;
+  add_mask_kernel<<<static_cast<int>(g), 256, 0, STREAM>>>(static_cast<const __half*>(a), b, scale,
+                                                          static_cast<const __half*>(aux),
+                                                          static_cast<__half*>(out), n);
+  return static_cast<int>(cudaGetLastError());
+}

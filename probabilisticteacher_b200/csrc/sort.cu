@@ -1,0 +1,128 @@
+// Segmented stable LSD radix sort (uint32 keys ascending, uint32 payload), one CTA per segment.
+// Replaces torch.sort / the sort inside torchvision nms / torch.randperm-based sampling on the
+// proposal path (pt/modeling/proposal_generator/proposal_utils.py:87, fast_rcnn.py:104,
+// detectron2 subsample_labels). Segments are a few 10^4 elements, so a single CTA with 1024
+// threads keeps the whole pass structure (histogram -> scan -> stable scatter) in shared memory.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/ptb200.h"
+
+namespace {
+
+constexpr int SORT_THREADS = 1024;
+constexpr int SORT_WARPS = SORT_THREADS / 32;
+constexpr int ITEMS = 4;                       // elements per thread per tile
+constexpr int TILE = SORT_THREADS * ITEMS;     // 4096
+
+__global__ void __launch_bounds__(SORT_THREADS, 1)
+segmented_radix_sort_kernel(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b,
+                            int64_t seg_stride, const int* __restrict__ seg_len, int fixed_len,
+                            int begin_bit, int end_bit) {
+  __shared__ uint32_t bin[256];
+  __shared__ uint32_t tile_base[256];
+  __shared__ uint16_t warp_cnt[SORT_WARPS][256];
+  __shared__ uint32_t scan_tmp[8];
+  const int seg = blockIdx.x;
+  int n = seg_len != nullptr ? seg_len[seg] : fixed_len;
+  if (n > fixed_len) n = fixed_len;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  uint32_t* kin = keys_a + seg * seg_stride;
+  uint32_t* vin = vals_a + seg * seg_stride;
+  uint32_t* kout = keys_b + seg * seg_stride;
+  uint32_t* vout = vals_b + seg * seg_stride;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+
+  for (int shift = begin_bit; shift < end_bit; shift += 8) {
+    if (tid < 256) bin[tid] = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += SORT_THREADS) atomicAdd(&bin[(kin[i] >> shift) & 255u], 1u);
+    __syncthreads();
+    // exclusive scan of the 256 bins (8 warps)
+    uint32_t cnt = 0, incl = 0;
+    if (tid < 256) {
+      cnt = bin[tid];
+      incl = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      if (lane == 31) scan_tmp[warp] = incl;
+    }
+    __syncthreads();
+    if (tid < 256) {
+      uint32_t off = 0;
+      for (int w = 0; w < warp; ++w) off += scan_tmp[w];
+      bin[tid] = off + incl - cnt;
+    }
+    __syncthreads();
+
+    for (int base = 0; base < n; base += TILE) {
+      for (int i = tid; i < SORT_WARPS * 256 / 2; i += SORT_THREADS)
+        reinterpret_cast<uint32_t*>(&warp_cnt[0][0])[i] = 0u;
+      __syncthreads();
+      uint32_t key[ITEMS], val[ITEMS];
+      uint16_t rank[ITEMS];
+#pragma unroll
+      for (int r = 0; r < ITEMS; ++r) {
+        const int idx = base + warp * (32 * ITEMS) + r * 32 + lane;
+        const bool valid = idx < n;
+        key[r] = valid ? kin[idx] : 0u;
+        val[r] = valid ? vin[idx] : 0u;
+        const uint32_t d = (key[r] >> shift) & 255u;
+        const uint32_t peers = __match_any_sync(0xffffffffu, valid ? d : (256u + lane));
+        const uint32_t before = warp_cnt[warp][d];
+        rank[r] = static_cast<uint16_t>(before + __popc(peers & lt_mask));
+        __syncwarp();
+        if (valid && (peers & lt_mask) == 0u) warp_cnt[warp][d] = static_cast<uint16_t>(before + __popc(peers));
+        __syncwarp();
+      }
+      __syncthreads();
+      if (tid < 256) {
+        const uint32_t b0 = bin[tid];
+        uint32_t run = 0;
+#pragma unroll 8
+        for (int w = 0; w < SORT_WARPS; ++w) {
+          const uint32_t c = warp_cnt[w][tid];
+          warp_cnt[w][tid] = static_cast<uint16_t>(run);
+          run += c;
+        }
+        tile_base[tid] = b0;
+        bin[tid] = b0 + run;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int r = 0; r < ITEMS; ++r) {
+        const int idx = base + warp * (32 * ITEMS) + r * 32 + lane;
+        if (idx < n) {
+          const uint32_t d = (key[r] >> shift) & 255u;
+          const uint32_t pos = tile_base[d] + warp_cnt[warp][d] + rank[r];
+          kout[pos] = key[r];
+          vout[pos] = val[r];
+        }
+      }
+      __syncthreads();
+    }
+    uint32_t* t = kin;
+    kin = kout;
+    kout = t;
+    t = vin;
+    vin = vout;
+    vout = t;
+    __syncthreads();
+  }
+}
+
+}  // namespace
+
+// Sorts `segments` segments in place (result in keys/vals when the pass count is even, which the
+// entry point enforces). keys_tmp / vals_tmp are scratch of the same size.
+extern "C" int ptb200_segmented_sort_u32(uint32_t* keys, uint32_t* vals, uint32_t* keys_tmp, uint32_t* vals_tmp,
+                                         int segments, int64_t seg_stride, const int* seg_len_dev, int max_len,
+                                         int begin_bit, int end_bit, void* stream) {
+  if (segments <= 0) return 0;
+  if ((end_bit - begin_bit) % 16 != 0 || begin_bit < 0 || end_bit > 32) return 1301;
+  segmented_radix_sort_kernel<<<segments, SORT_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
+      keys, vals, keys_tmp, vals_tmp, seg_stride, seg_len_dev, max_len, begin_bit, end_bit);
+  return static_cast<int>(cudaGetLastError());
+}

@@ -1,0 +1,158 @@
+"""Torch-tensor wrappers over the C ABI (include/ptb200.h). Tensors only carry device memory; all
+arithmetic happens inside libptb200.so. No CPU fallback: every function needs CUDA tensors."""
+from collections import namedtuple
+
+import torch
+
+from ._lib import call
+
+EPI_BIAS_RELU, EPI_BIAS, EPI_F32_SPLIT, EPI_MASK = 0, 1, 2, 3
+
+# fp16 activation in the flattened right-padded layout: t is [N, H*(W+1), C]
+FlatAct = namedtuple("FlatAct", ["t", "H", "W"])
+
+I32 = torch.int32
+U32 = torch.int32  # uint32 payloads are carried in int32 tensors (bit patterns only)
+
+
+def _shifts(Wp):
+    return [(ky - 1) * Wp + (kx - 1) for ky in range(3) for kx in range(3)]
+
+
+def flat_zeros(N, H, W, C, device):
+    return FlatAct(torch.zeros(N, H * (W + 1), C, dtype=torch.float16, device=device), H, W)
+
+
+def to_flat(x_nchw):
+    """NCHW float tensor -> FlatAct (test helper)."""
+    N, C, H, W = x_nchw.shape
+    t = torch.zeros(N, H, W + 1, C, dtype=torch.float16, device=x_nchw.device)
+    t[:, :, :W] = x_nchw.permute(0, 2, 3, 1).to(torch.float16)
+    return FlatAct(t.reshape(N, H * (W + 1), C), H, W)
+
+
+def from_flat(a):
+    """FlatAct -> NCHW fp16 tensor (test helper)."""
+    N, _, C = a.t.shape
+    return a.t.reshape(N, a.H, a.W + 1, C)[:, :, :a.W].permute(0, 3, 1, 2)
+
+
+# ------------------------------------------------------------------------------------------ GEMMs
+def gemm_tn(A, B, *, taps=1, shifts=None, bn=None, epi=EPI_BIAS, bias=None, out=None, aux=None,
+            w_valid=0, wp=0, d0=None, d1=None, split=0, n_valid=0, n_total=None):
+    """A: [batch, rows, K] fp16; B: [n_rows, taps*K] fp16. Returns out (fp16 [batch, rows, n_total]) or
+    (d0, d1) for the fp32 split epilogue."""
+    batch, rows, lda = A.shape
+    k = B.shape[1] // taps
+    if n_total is None:
+        n_total = B.shape[0]
+    if bn is None:
+        bn = 256
+        while n_total % bn:
+            bn //= 2
+    if epi == EPI_F32_SPLIT:
+        if d0 is None:
+            d0 = torch.empty(batch, rows, split, dtype=torch.float32, device=A.device)
+        if d1 is None:
+            d1 = torch.empty(batch, rows, n_valid - split, dtype=torch.float32, device=A.device)
+        ld_d, dbs = 0, 0
+    else:
+        if out is None:
+            out = torch.empty(batch, rows, n_total, dtype=torch.float16, device=A.device)
+        ld_d, dbs = out.shape[2], out.shape[1] * out.shape[2]
+    call("ptb200_gemm_tn_f16", A, batch, rows, k, lda, rows * lda, taps, shifts, B, n_total, bn, epi, bias,
+         0 if bias is None else bias.numel(), out, ld_d, dbs, aux, w_valid, wp, d0, split, d1,
+         n_valid - split, split, n_valid, 0)
+    return (d0, d1) if epi == EPI_F32_SPLIT else out
+
+
+def conv3x3(x: FlatAct, w_packed, bias, relu=True, aux=None, out=None):
+    """3x3 / stride 1 / pad 1 convolution over a FlatAct. w_packed: fp16 [Cout, 9*Cin] ([co][ky][kx][ci]).
+    aux != None selects the ReLU-mask epilogue (data-gradient path)."""
+    Wp = x.W + 1
+    epi = EPI_MASK if aux is not None else (EPI_BIAS_RELU if relu else EPI_BIAS)
+    o = gemm_tn(x.t, w_packed, taps=9, shifts=_shifts(Wp), epi=epi, bias=bias, aux=aux, w_valid=x.W, wp=Wp,
+                out=out)
+    return FlatAct(o, x.H, x.W)
+
+
+def wgrad(G, X, out, *, taps=1, shifts=None, scale=1.0, ksplit=0, m_total=None, n_total=None):
+    """out[m][t*n + n'] += scale * sum G[b][p][m] X[b][p+shift_t][n']."""
+    batch, rows, ldg = G.shape
+    ldx = X.shape[2]
+    m_total = m_total or ldg
+    n_total = n_total or ldx
+    call("ptb200_gemm_wgrad_f16", G, ldg, rows * ldg, X, ldx, rows * ldx, batch, rows, m_total, n_total, taps,
+         shifts, out, taps * n_total, float(scale), ksplit)
+    return out
+
+
+def conv3x3_wgrad(dy: FlatAct, x: FlatAct, out, scale=1.0):
+    return wgrad(dy.t, x.t, out, taps=9, shifts=_shifts(x.W + 1), scale=scale)
+
+
+# ------------------------------------------------------------------------------------------ elementwise
+def preprocess_im2col(images_u8, hw, hmax, wmax, mean, std):
+    """images_u8: uint8 [N, 3, hmax, wmax] (device) when all images share a size, else a flat buffer with
+    image_stride; hw: int32 [N, 2] device. Returns FlatAct with C = 64."""
+    N = hw.shape[0]
+    out = torch.empty(N, hmax * (wmax + 1), 64, dtype=torch.float16, device=images_u8.device)
+    call("ptb200_preprocess_im2col", images_u8, hw, N, hmax, wmax, images_u8.stride(0), list(mean), list(std), out)
+    return FlatAct(out, hmax, wmax)
+
+
+def maxpool2x2(x: FlatAct):
+    N, _, C = x.t.shape
+    Ho, Wo = x.H // 2, x.W // 2
+    out = torch.empty(N, Ho * (Wo + 1), C, dtype=torch.float16, device=x.t.device)
+    call("ptb200_maxpool2x2_f16", x.t, out, N, x.H, x.W, C)
+    return FlatAct(out, Ho, Wo)
+
+
+def maxpool2x2_relu_bwd(x: FlatAct, dpooled: FlatAct):
+    N, _, C = x.t.shape
+    dz = torch.empty_like(x.t)
+    call("ptb200_maxpool2x2_relu_bwd_f16", x.t, dpooled.t, dz, N, x.H, x.W, C)
+    return FlatAct(dz, x.H, x.W)
+
+
+def colsum(x2d, out, scale=1.0, c=None):
+    rows, ld = x2d.shape
+    call("ptb200_colsum_f16", x2d, rows, c or ld, ld, float(scale), out)
+
+
+def segmented_sort(keys, vals, seg_len=None, max_len=None, begin_bit=0, end_bit=32):
+    """In-place stable ascending sort of each row of keys/vals ([segments, stride] int32 bit patterns)."""
+    segs, stride = keys.shape
+    kt = torch.empty_like(keys)
+    vt = torch.empty_like(vals)
+    call("ptb200_segmented_sort_u32", keys, vals, kt, vt, segs, stride, seg_len, max_len or stride, begin_bit,
+         end_bit)
+
+
+def nms(boxes, order, counts, thresh, max_keep, class_mod=0):
+    """boxes: fp32 [N, nbox, 4]; order: int32 [N, cap] candidate indices in descending-score order;
+    counts: int32 [N]. Returns keep_idx [N, max_keep] (positions in `order`), keep_count [N]."""
+    N, cap = order.shape
+    words = (cap + 63) // 64
+    mask = torch.empty(N * cap * words, dtype=torch.int64, device=boxes.device)
+    keep_idx = torch.zeros(N, max_keep, dtype=I32, device=boxes.device)
+    keep_count = torch.zeros(N, dtype=I32, device=boxes.device)
+    call("ptb200_nms", boxes, boxes.shape[1], order, cap, counts, N, cap, float(thresh), class_mod, max_keep, mask,
+         keep_idx, keep_count)
+    return keep_idx, keep_count
+
+
+def roi_align_fwd(feat: FlatAct, rois, counts, cap, scale, pooled):
+    N, _, C = feat.t.shape
+    out = torch.empty(N * cap, pooled * pooled * C, dtype=torch.float16, device=feat.t.device)
+    call("ptb200_roi_align_fwd_f16", feat.t, N, feat.H, feat.W, C, rois, counts, cap, float(scale), pooled, out)
+    return out
+
+
+def roi_align_bwd(dout, feat_like: FlatAct, rois, counts, cap, scale, pooled):
+    N, rows, C = feat_like.t.shape
+    dfeat = torch.zeros(N, rows, C, dtype=torch.float32, device=dout.device)
+    call("ptb200_roi_align_bwd_f16", dout, N, feat_like.H, feat_like.W, C, rois, counts, cap, float(scale), pooled,
+         dfeat)
+    return dfeat
