@@ -1,0 +1,249 @@
+"""Flat parameter arena of one detector (student or teacher).
+
+All parameters live in ONE contiguous fp32 buffer laid out for the kernels (HBM-resident, 16-byte
+aligned segments), so that the EMA teacher update, the gradient all-reduce, the grad-norm clip and
+the SGD step are single streaming passes (`pt/engine/trainer.py:431-449,592-603,386`), and the fp16
+GEMM operands are produced by one cast pass over the same layout.
+
+Internal layouts (reference layout in brackets; `state_dict()` converts):
+  conv weight   [Cout][ky][kx][Cin]           ([Cout][Cin][3][3])
+  fc1 weight    [1024][ph*7+pw][512]          ([1024][512*49], channel-major flatten of NCHW)
+  RPN 1x1 heads one block [128][512]: rows 0..8 objectness, 9..80 anchor deltas, rest zero padding
+  predictor     one block [128][1024]: rows 0..K cls_score, K+1..K+8K bbox_pred, rest zero padding
+Parameter names are the reference's state_dict keys (checkpoint row).
+"""
+import math
+from collections import OrderedDict
+
+import torch
+
+from ._lib import call
+
+VGG16 = [[64, 64], [128, 128], [256, 256, 256], [512, 512, 512], [512, 512, 512]]
+
+
+def _round8(n):
+    return (n + 7) // 8 * 8
+
+
+class Segment:
+    __slots__ = ("name", "shape", "offset", "numel", "trainable", "kind")
+
+    def __init__(self, name, shape, offset, trainable, kind):
+        self.name, self.shape, self.offset, self.trainable, self.kind = name, tuple(shape), offset, trainable, kind
+        self.numel = int(math.prod(shape))
+
+
+class ParamArena:
+    def __init__(self, num_classes=8, num_cell=9, fc_dim=1024, pooled=7, freeze_at=2,
+                 differentiable_anchors=True, device="cuda", with_grads=True):
+        self.K = num_classes
+        self.A = num_cell
+        self.fc_dim = fc_dim
+        self.pooled = pooled
+        self.device = torch.device(device)
+        segs = []
+        off = 0
+
+        def add(name, shape, trainable, kind):
+            nonlocal off
+            s = Segment(name, shape, off, trainable, kind)
+            segs.append(s)
+            off += _round8(s.numel)
+            return s
+
+        convs = []
+        cin = 3
+        for bi, chans in enumerate(VGG16, start=1):
+            for ci, cout in enumerate(chans, start=1):
+                convs.append((f"backbone.vgg_block{bi}.0.conv{ci}", cin, cout, bi > freeze_at))
+                cin = cout
+        self.conv_specs = convs
+        C = cin
+        for tr in (False, True):  # frozen segments first so that the trainable part is a contiguous suffix
+            for name, ci_, co_, trainable in convs:
+                if trainable == tr:
+                    add(name + ".weight", (co_, 3, 3, ci_), trainable, "conv")
+                    add(name + ".bias", (co_,), trainable, "vec")
+        add("proposal_generator.rpn_head.conv.weight", (C, 3, 3, C), True, "conv")
+        add("proposal_generator.rpn_head.conv.bias", (C,), True, "vec")
+        add("proposal_generator.rpn_head._heads.weight", (128, C), True, "rpn_heads_w")
+        add("proposal_generator.rpn_head._heads.bias", (128,), True, "rpn_heads_b")
+        if differentiable_anchors:
+            add("proposal_generator.anchor_generator.anchor_0", (num_cell, 2), True, "mat")
+        fin = pooled * pooled
+        add("roi_heads.box_head.fc1.weight", (fc_dim, fin, C), True, "fc1")
+        add("roi_heads.box_head.fc1.bias", (fc_dim,), True, "vec")
+        add("roi_heads.box_head.fc2.weight", (fc_dim, fc_dim), True, "mat")
+        add("roi_heads.box_head.fc2.bias", (fc_dim,), True, "vec")
+        add("roi_heads.box_predictor._heads.weight", (128, fc_dim), True, "pred_w")
+        add("roi_heads.box_predictor._heads.bias", (128,), True, "pred_b")
+        self.segments = OrderedDict((s.name, s) for s in segs)
+        self.total = off
+        self.trainable_start = min(s.offset for s in segs if s.trainable)
+        self.C = C
+        self.data = torch.zeros(self.total, dtype=torch.float32, device=self.device)
+        self.half = torch.zeros(self.total, dtype=torch.float16, device=self.device)
+        self.conv1_half = torch.zeros(64, 64, dtype=torch.float16, device=self.device)
+        if with_grads:
+            n = self.total - self.trainable_start
+            self.grads = torch.zeros(n, dtype=torch.float32, device=self.device)
+            self.momentum = torch.zeros(n, dtype=torch.float32, device=self.device)
+            self.dgrad_half = {}
+        else:
+            self.grads = self.momentum = None
+            self.dgrad_half = None
+
+    # ------------------------------------------------------------------ views
+    def view(self, name):
+        s = self.segments[name]
+        return self.data[s.offset:s.offset + s.numel].view(s.shape)
+
+    def hview(self, name):
+        s = self.segments[name]
+        return self.half[s.offset:s.offset + s.numel].view(s.shape)
+
+    def gview(self, name):
+        s = self.segments[name]
+        o = s.offset - self.trainable_start
+        return self.grads[o:o + s.numel].view(s.shape)
+
+    def exposed_parameters(self):
+        """(reference name, data view, grad view or None, trainable) for every reference parameter."""
+        K, A = self.K, self.A
+        out = []
+        for s in self.segments.values():
+            v = self.view(s.name)
+            g = self.gview(s.name) if (s.trainable and self.grads is not None) else None
+            if s.kind == "rpn_heads_w":
+                base = "proposal_generator.rpn_head."
+                out.append((base + "objectness_logits.weight", v[:A], None if g is None else g[:A], True))
+                out.append((base + "anchor_deltas.weight", v[A:A * 9], None if g is None else g[A:A * 9], True))
+            elif s.kind == "rpn_heads_b":
+                base = "proposal_generator.rpn_head."
+                out.append((base + "objectness_logits.bias", v[:A], None if g is None else g[:A], True))
+                out.append((base + "anchor_deltas.bias", v[A:A * 9], None if g is None else g[A:A * 9], True))
+            elif s.kind == "pred_w":
+                base = "roi_heads.box_predictor."
+                out.append((base + "cls_score.weight", v[:K + 1], None if g is None else g[:K + 1], True))
+                out.append((base + "bbox_pred.weight", v[K + 1:9 * K + 1], None if g is None else g[K + 1:9 * K + 1], True))
+            elif s.kind == "pred_b":
+                base = "roi_heads.box_predictor."
+                out.append((base + "cls_score.bias", v[:K + 1], None if g is None else g[:K + 1], True))
+                out.append((base + "bbox_pred.bias", v[K + 1:9 * K + 1], None if g is None else g[K + 1:9 * K + 1], True))
+            else:
+                out.append((s.name, v, g, s.trainable))
+        return out
+
+    # ------------------------------------------------------------------ reference layout <-> internal
+    @staticmethod
+    def _to_ref(kind, t, C, pooled):
+        if kind == "conv":
+            return t.permute(0, 3, 1, 2).contiguous()
+        if kind == "fc1":
+            return t.permute(0, 2, 1).reshape(t.shape[0], -1).contiguous()
+        return t.clone()
+
+    def state_dict(self):
+        sd = OrderedDict()
+        kinds = {}
+        for s in self.segments.values():
+            kinds[s.name] = s.kind
+        for name, v, _, _ in self.exposed_parameters():
+            kind = kinds.get(name, "mat")
+            t = self._to_ref(kind, v, self.C, self.pooled)
+            if name.endswith("objectness_logits.weight") or name.endswith("anchor_deltas.weight"):
+                t = t.reshape(t.shape[0], t.shape[1], 1, 1)
+            sd[name] = t
+        return sd
+
+    def load_state_dict(self, sd):
+        kinds = {s.name: s.kind for s in self.segments.values()}
+        with torch.no_grad():
+            for name, v, _, _ in self.exposed_parameters():
+                if name not in sd:
+                    raise KeyError(f"{name} missing from state_dict")
+                src = sd[name].to(self.device, torch.float32)
+                kind = kinds.get(name, "mat")
+                if kind == "conv":
+                    src = src.permute(0, 2, 3, 1)
+                elif kind == "fc1":
+                    src = src.reshape(src.shape[0], self.C, self.pooled * self.pooled).permute(0, 2, 1)
+                v.copy_(src.reshape(v.shape))
+        self.pack()
+
+    # ------------------------------------------------------------------ fp16 operands
+    def pack(self, dgrad=None):
+        """fp32 masters -> fp16 GEMM operands: one cast pass for the forward operands (same offsets),
+        the K-padded first conv, and (student only) the transposed operands of the data-gradient GEMMs."""
+        call("ptb200_cast_f32_f16", self.data, self.half, self.total)
+        w1 = self.view("backbone.vgg_block1.0.conv1.weight").view(64, 27)
+        call("ptb200_cast_pad_rows_f16", w1, self.conv1_half, 64, 27, 64)
+        if dgrad is None:
+            dgrad = self.dgrad_half is not None
+        if dgrad:
+            self._pack_dgrad()
+
+    def _dg(self, name, shape):
+        t = self.dgrad_half.get(name)
+        if t is None:
+            t = torch.zeros(shape, dtype=torch.float16, device=self.device)
+            self.dgrad_half[name] = t
+        return t
+
+    def _pack_dgrad(self):
+        first_trainable = True
+        for name, cin, cout, trainable in self.conv_specs:
+            if not trainable:
+                continue
+            if first_trainable:  # its input is the frozen part: no data-gradient needed
+                first_trainable = False
+                continue
+            dst = self._dg(name, (cin, 9 * cout))
+            call("ptb200_transpose_pack_f16", self.view(name + ".weight"), dst, cout, cin, 9, 1, 9 * cout)
+        C = self.C
+        dst = self._dg("rpn_conv", (C, 9 * C))
+        call("ptb200_transpose_pack_f16", self.view("proposal_generator.rpn_head.conv.weight"), dst, C, C, 9, 1, 9 * C)
+        dst = self._dg("rpn_heads", (C, 128))
+        call("ptb200_transpose_pack_f16", self.view("proposal_generator.rpn_head._heads.weight"), dst, 128, C, 1, 0, 128)
+        fin = self.pooled * self.pooled * C
+        dst = self._dg("fc1", (fin, self.fc_dim))
+        call("ptb200_transpose_pack_f16", self.view("roi_heads.box_head.fc1.weight"), dst, self.fc_dim, fin, 1, 0, self.fc_dim)
+        dst = self._dg("fc2", (self.fc_dim, self.fc_dim))
+        call("ptb200_transpose_pack_f16", self.view("roi_heads.box_head.fc2.weight"), dst, self.fc_dim, self.fc_dim, 1, 0, self.fc_dim)
+        dst = self._dg("pred", (self.fc_dim, 128))
+        call("ptb200_transpose_pack_f16", self.view("roi_heads.box_predictor._heads.weight"), dst, 128, self.fc_dim, 1, 0, 128)
+
+    # ------------------------------------------------------------------ init (SURVEY 8d synthetic weights)
+    def init_synthetic(self, seed=0):
+        """Random init with the reference's initialisers: c2_msra_fill for VGG convs (vgg.py:61-63; the
+        unconditional vgg16_caffe.pth load of vgg.py:127-152 has no file to read here), N(0,0.01) RPN
+        head, c2_xavier_fill box head, N(0,0.01)/N(0,0.001) predictor (fast_rcnn.py:164-169)."""
+        g = torch.Generator().manual_seed(seed)
+        sd = OrderedDict()
+        for name, cin, cout, _ in self.conv_specs:
+            sd[name + ".weight"] = torch.randn(cout, cin, 3, 3, generator=g) * math.sqrt(2.0 / (cout * 9))
+            sd[name + ".bias"] = torch.zeros(cout)
+        C, A, K = self.C, self.A, self.K
+        p = "proposal_generator.rpn_head."
+        sd[p + "conv.weight"] = torch.randn(C, C, 3, 3, generator=g) * 0.01
+        sd[p + "conv.bias"] = torch.zeros(C)
+        sd[p + "objectness_logits.weight"] = torch.randn(A, C, 1, 1, generator=g) * 0.01
+        sd[p + "objectness_logits.bias"] = torch.zeros(A)
+        sd[p + "anchor_deltas.weight"] = torch.randn(A * 8, C, 1, 1, generator=g) * 0.01
+        sd[p + "anchor_deltas.bias"] = torch.zeros(A * 8)
+        if "proposal_generator.anchor_generator.anchor_0" in self.segments:
+            from .config import get_cfg
+            sd["proposal_generator.anchor_generator.anchor_0"] = torch.tensor(get_cfg().MODEL.ANCHOR_GENERATOR.ANCHOR[0])
+        fin = C * self.pooled ** 2
+        for name, fi, fo in (("roi_heads.box_head.fc1", fin, self.fc_dim), ("roi_heads.box_head.fc2", self.fc_dim, self.fc_dim)):
+            bound = math.sqrt(3.0 / fi)
+            sd[name + ".weight"] = (torch.rand(fo, fi, generator=g) * 2 - 1) * bound
+            sd[name + ".bias"] = torch.zeros(fo)
+        p = "roi_heads.box_predictor."
+        sd[p + "cls_score.weight"] = torch.randn(K + 1, self.fc_dim, generator=g) * 0.01
+        sd[p + "cls_score.bias"] = torch.zeros(K + 1)
+        sd[p + "bbox_pred.weight"] = torch.randn(K * 8, self.fc_dim, generator=g) * 0.001
+        sd[p + "bbox_pred.bias"] = torch.zeros(K * 8)
+        self.load_state_dict(sd)
+        return sd

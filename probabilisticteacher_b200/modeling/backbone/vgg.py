@@ -1,0 +1,74 @@
+"""VGG16 backbone on the B200 path: the counterpart of `pt/modeling/backbone/vgg.py:36-72` (VGGBlock:
+3x3 conv + bias + ReLU, 2x2 max pool after blocks 1-4), `:94-165` (VGG, stride-16 `vgg_block5` output) and
+`:189-230` (build_vgg_backbone, FREEZE_AT). Every conv is one launch of the tcgen05 implicit-GEMM
+kernel over fp16 NHWC-flat activations; backward is explicit (data- and weight-gradient GEMMs)."""
+import torch
+from torch import nn
+
+from ... import ops
+from ..._lib import call
+from ..registry import BACKBONE_REGISTRY
+
+
+class VGG(nn.Module):
+    def __init__(self, arena, loss_scale):
+        super().__init__()
+        self.arena = arena
+        self.loss_scale = loss_scale
+        self._out_features = ["vgg_block5"]
+        self._out_feature_strides = {"vgg_block5": 16}
+        self._out_feature_channels = {"vgg_block5": arena.C}
+
+    def output_shape(self):
+        return {"vgg_block5": dict(channels=self.arena.C, stride=16)}
+
+    def forward(self, im2col: ops.FlatAct, save=False):
+        """im2col: the K=64 operand of conv1_1 produced by ptb200_preprocess_im2col.
+        Returns ({"vgg_block5": FlatAct}, records) where records hold what backward needs."""
+        ar = self.arena
+        specs = ar.conv_specs
+        name0 = specs[0][0]
+        W = im2col.W
+        y = ops.gemm_tn(im2col.t, ar.conv1_half, epi=ops.EPI_BIAS_RELU, bias=ar.view(name0 + ".bias"), w_valid=W,
+                        wp=W + 1)
+        x = ops.FlatAct(y, im2col.H, im2col.W)
+        records = []
+        block = 1
+        for name, cin, cout, trainable in specs[1:]:
+            b = int(name.split("vgg_block")[1][0])
+            pooled = False
+            if b != block:
+                x = ops.maxpool2x2(x)
+                block = b
+                pooled = True
+            w = ar.hview(name + ".weight").view(cout, 9 * cin)
+            y = ops.conv3x3(x, w, ar.view(name + ".bias"), relu=True)
+            if save and trainable:
+                records.append(dict(name=name, x=x, y=y, pooled=pooled, cin=cin, cout=cout))
+            x = y
+        return {"vgg_block5": x}, records
+
+    def backward(self, records, dz: ops.FlatAct):
+        """dz: gradient w.r.t. the pre-ReLU output of the last conv (already ReLU-masked), scaled by
+        the loss scale. Accumulates weight / bias gradients into the arena."""
+        ar = self.arena
+        inv = 1.0 / self.loss_scale
+        for i in range(len(records) - 1, -1, -1):
+            r = records[i]
+            gw = ar.gview(r["name"] + ".weight").view(r["cout"], 9 * r["cin"])
+            ops.conv3x3_wgrad(dz, r["x"], gw, scale=inv)
+            ops.colsum(dz.t.view(-1, r["cout"]), ar.gview(r["name"] + ".bias"), scale=inv)
+            if i == 0:
+                break
+            wd = ar.dgrad_half[r["name"]]
+            if r["pooled"]:
+                dp = ops.conv3x3(dz, wd, None, relu=False)
+                dz = ops.maxpool2x2_relu_bwd(records[i - 1]["y"], dp)
+            else:
+                dz = ops.conv3x3(dz, wd, None, aux=r["x"].t)
+
+
+@BACKBONE_REGISTRY.register()
+def build_vgg_backbone(cfg, arena, loss_scale):
+    assert cfg.MODEL.VGG.DEPTH == 16, "only VGG16 is on the hot path (configs/Guassian-RCNN-VGG.yaml:8)"
+    return VGG(arena, loss_scale)
