@@ -55,6 +55,11 @@ int ptb200_preprocess_im2col(const uint8_t* images, const int* hw_dev, int n, in
                              int64_t image_stride, const float* mean3_host, const float* std3_host,
                              void* out_f16, void* stream);
 
+/* PTrainer.resize (pt/engine/trainer.py:557-590) for one CHW uint8 image: bilinear down-scale to
+ * (dh, dw) pasted at (x1, y1) on a canvas filled with int(pixel_mean). */
+int ptb200_resize_paste_u8(const uint8_t* src, uint8_t* dst, int h, int w, int dh, int dw, int x1, int y1,
+                           int m0, int m1, int m2, void* stream);
+
 /* F.max_pool2d(2, 2) of pt/modeling/backbone/vgg.py:59,71 (floor mode). */
 int ptb200_maxpool2x2_f16(const void* in, void* out, int n, int h, int w, int c, void* stream);
 

@@ -87,6 +87,13 @@ def stream_ptr():
 
 _keepalive = []
 
+# kernels launched per entry point (default 1); `launch_count[0]` counts launches of OUR kernels.
+KERNELS_PER_CALL = {"ptb200_nms": 2, "ptb200_rpn_match": 2, "ptb200_roi_loss_unsup": 2}
+launch_count = [0]
+# optional per-call profiler: set to a callable(name, args) -> context manager (bench.py uses it to
+# time the dominant kernel with CUDA events on the launching stream)
+profiler = [None]
+
 
 def call(name, *args):
     """Calls an entry point: tensors -> data pointers, None -> NULL, python lists for `*_host`
@@ -118,6 +125,13 @@ def call(name, *args):
                 conv.append(ctypes.c_void_p(a.data_ptr()))
         else:
             conv.append(a)
-    rc = getattr(L, name)(*conv)
+    launch_count[0] += KERNELS_PER_CALL.get(name, 1)
+    prof = profiler[0]
+    if prof is not None:
+        tok = prof.begin(name, args)
+        rc = getattr(L, name)(*conv)
+        prof.end(tok)
+    else:
+        rc = getattr(L, name)(*conv)
     if rc != 0:
         raise PTB200Error(f"{name} failed with code {rc}")

@@ -254,6 +254,32 @@ __global__ void add_f32_to_f16_kernel(const __half* __restrict__ a, const float*
   }
 }
 
+// PTrainer.resize (pt/engine/trainer.py:557-590) on device: bilinear down-scale (F.interpolate,
+// align_corners=False) pasted centred on a canvas filled with int(pixel_mean); float -> uint8 truncation.
+__global__ void resize_paste_u8_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int H, int W,
+                                       int dh, int dw, int x1, int y1, int m0, int m1, int m2) {
+  const int total = 3 * H * W;
+  const float sh = static_cast<float>(H) / dh, sw = static_cast<float>(W) / dw;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int x = i % W, y = (i / W) % H, c = i / (W * H);
+    uint8_t v = static_cast<uint8_t>(c == 0 ? m0 : (c == 1 ? m1 : m2));
+    const int yy = y - y1, xx = x - x1;
+    if (yy >= 0 && yy < dh && xx >= 0 && xx < dw) {
+      float fy = sh * (yy + 0.5f) - 0.5f, fx = sw * (xx + 0.5f) - 0.5f;
+      if (fy < 0.f) fy = 0.f;
+      if (fx < 0.f) fx = 0.f;
+      const int y0 = static_cast<int>(fy), x0 = static_cast<int>(fx);
+      const int y1i = y0 + (y0 < H - 1 ? 1 : 0), x1i = x0 + (x0 < W - 1 ? 1 : 0);
+      const float ly = fy - y0, lx = fx - x0, hy = 1.f - ly, hx = 1.f - lx;
+      const uint8_t* p = src + static_cast<int64_t>(c) * H * W;
+      const float v00 = p[y0 * W + x0], v01 = p[y0 * W + x1i], v10 = p[y1i * W + x0], v11 = p[y1i * W + x1i];
+      const float r = hy * (hx * v00 + lx * v01) + ly * (hx * v10 + lx * v11);
+      v = static_cast<uint8_t>(r);
+    }
+    dst[i] = v;
+  }
+}
+
 }  // namespace
 
 #define STREAM static_cast<cudaStream_t>(stream)
@@ -325,5 +351,11 @@ extern "C" int ptb200_add_f32_to_f16(const void* a, const float* b, float scale,
                                      void* stream) {
   add_f32_to_f16_kernel<<<grid_for(n), kThreads, 0, STREAM>>>(static_cast<const __half*>(a), b, scale,
                                                              static_cast<__half*>(out), n);
+  return LAUNCH_OK();
+}
+
+extern "C" int ptb200_resize_paste_u8(const uint8_t* src, uint8_t* dst, int h, int w, int dh, int dw, int x1,
+                                      int y1, int m0, int m1, int m2, void* stream) {
+  resize_paste_u8_kernel<<<grid_for(3LL * h * w), kThreads, 0, STREAM>>>(src, dst, h, w, dh, dw, x1, y1, m0, m1, m2);
   return LAUNCH_OK();
 }

@@ -123,14 +123,13 @@ class GuassianGeneralizedRCNN(nn.Module):
         H = max(s[0] for s in sizes)
         W = max(s[1] for s in sizes)
         same = all(s == (H, W) for s in sizes)
-        if same and all(i.is_cuda for i in imgs):
+        imgs = [i if i.is_cuda else i.to(dev, non_blocking=True) for i in imgs]
+        if same:
             batch = torch.stack(imgs) if len(imgs) > 1 else imgs[0].unsqueeze(0)
-        elif same:
-            batch = torch.stack(imgs).to(dev, non_blocking=True)
         else:
             batch = torch.zeros(len(imgs), 3 * H * W, dtype=torch.uint8, device=dev)
             for k, i in enumerate(imgs):
-                batch[k, :i.numel()] = i.reshape(-1).to(dev, non_blocking=True)
+                batch[k, :i.numel()] = i.reshape(-1)
         batch = batch.contiguous()
         hw_i = torch.tensor(sizes, dtype=torch.int32).to(dev, non_blocking=True)
         img_hw = hw_i.to(torch.float32)
