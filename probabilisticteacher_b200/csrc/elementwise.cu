@@ -21,40 +21,48 @@ inline int grid_for(int64_t n, int per_block = kThreads) {
 // preprocess: uint8 CHW images -> normalised, im2col'd fp16 rows for conv1_1 as a K=64 GEMM.
 // column (ky*3+kx)*3 + c holds ((img[c][y+ky-1][x+kx-1] - mean[c]) / std[c]) (0 outside the image,
 // matching zero padding of the normalised, zero-padded ImageList), columns 27..63 are zero.
-// One thread per (row, 8-column group).
-__global__ void preprocess_im2col_kernel(const uint8_t* __restrict__ img, const int* __restrict__ hw,
-                                         int N, int Hmax, int Wmax, int64_t img_stride, float m0,
-                                         float m1, float m2, float is0, float is1, float is2,
-                                         __half* __restrict__ out) {
+// One thread per output row (pixel): 27 byte loads (L1-resident neighbours), eight 16-byte stores.
+__global__ void __launch_bounds__(256)
+preprocess_im2col_kernel(const uint8_t* __restrict__ img, const int* __restrict__ hw, int N, int Hmax,
+                         int Wmax, int64_t img_stride, float m0, float m1, float m2, float is0, float is1,
+                         float is2, __half* __restrict__ out) {
   const int Wp = Wmax + 1;
-  const int64_t total = static_cast<int64_t>(N) * Hmax * Wp * 8;
-  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int grp = static_cast<int>(i & 7);
-    int64_t row = i >> 3;
+  const int64_t total = static_cast<int64_t>(N) * Hmax * Wp;
+  const float mean[3] = {m0, m1, m2};
+  const float istd[3] = {is0, is1, is2};
+  for (int64_t row = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; row < total;
+       row += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const int x = static_cast<int>(row % Wp);
-    row /= Wp;
-    const int y = static_cast<int>(row % Hmax);
-    const int n = static_cast<int>(row / Hmax);
+    const int64_t q = row / Wp;
+    const int y = static_cast<int>(q % Hmax);
+    const int n = static_cast<int>(q / Hmax);
     const int h = hw[2 * n], w = hw[2 * n + 1];
-    __align__(16) __half v[8];
+    __align__(16) __half v[32];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int col = grp * 8 + e;
-      float val = 0.f;
-      if (col < 27 && x < Wmax) {
-        const int t = col / 3, c = col - t * 3;
-        const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
-        if (yy >= 0 && yy < h && xx >= 0 && xx < w) {
-          const float px = static_cast<float>(img[n * img_stride + (static_cast<int64_t>(c) * h + yy) * w + xx]);
-          const float mean = c == 0 ? m0 : (c == 1 ? m1 : m2);
-          const float istd = c == 0 ? is0 : (c == 1 ? is1 : is2);
-          val = (px - mean) * istd;
-        }
+    for (int e = 27; e < 32; ++e) v[e] = __float2half_rn(0.f);
+    const uint8_t* base = img + n * img_stride;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
+      const bool in = (x < Wmax) && yy >= 0 && yy < h && xx >= 0 && xx < w;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float val = 0.f;
+        if (in) val = (static_cast<float>(base[(static_cast<int64_t>(c) * h + yy) * w + xx]) - mean[c]) * istd[c];
+        v[t * 3 + c] = __float2half_rn(val);
       }
-      v[e] = __float2half_rn(val);
     }
-    *reinterpret_cast<uint4*>(out + i * 8) = *reinterpret_cast<const uint4*>(v);
+    uint4* o = reinterpret_cast<uint4*>(out + row * 64);
+    const uint4* vv = reinterpret_cast<const uint4*>(v);
+    o[0] = vv[0];
+    o[1] = vv[1];
+    o[2] = vv[2];
+    o[3] = vv[3];
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    o[4] = z;
+    o[5] = z;
+    o[6] = z;
+    o[7] = z;
   }
 }
 
@@ -203,22 +211,46 @@ __global__ void cast_pad_rows_kernel(const float* __restrict__ src, __half* __re
   }
 }
 
-// out[c] += scale * sum_rows in[row][c]   (fp16 in, fp32 atomics). grid.x over row chunks.
-__global__ void colsum_f16_kernel(const __half* __restrict__ in, int64_t rows, int C, int64_t ld,
-                                  float scale, float* __restrict__ out) {
-  const int64_t rows_per_block = (rows + gridDim.x - 1) / gridDim.x;
-  const int64_t r0 = blockIdx.x * rows_per_block;
-  const int64_t r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
-  for (int c = threadIdx.x * 2; c < C; c += blockDim.x * 2) {
-    float a0 = 0.f, a1 = 0.f;
-    for (int64_t r = r0; r < r1; ++r) {
-      const __half2 v = *reinterpret_cast<const __half2*>(in + r * ld + c);
-      const float2 f = __half22float2(v);
-      a0 += f.x;
-      a1 += f.y;
+// out[c] += scale * sum_rows in[row][c]   (fp16 in, fp32 atomics). Each thread owns 8 consecutive
+// channels (one 16-byte load per row), thread groups stride over rows; partial sums are combined in
+// shared memory, then one atomicAdd per channel per CTA.
+__global__ void __launch_bounds__(256)
+colsum_f16_kernel(const __half* __restrict__ in, int64_t rows, int C, int64_t ld, float scale,
+                  float* __restrict__ out) {
+  __shared__ float red[256 * 8];
+  const int c8 = C >> 3;                       // 16-byte groups per row (C % 8 == 0)
+  const int tpr = c8 < 256 ? c8 : 256;         // threads cooperating on one row
+  const int rpb = 256 / tpr;                   // rows processed per block iteration
+  const int lane_c = threadIdx.x % tpr, lane_r = threadIdx.x / tpr;
+  for (int cb = lane_c; cb < c8; cb += tpr) {
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+    if (lane_r < rpb) {
+      for (int64_t r = static_cast<int64_t>(blockIdx.x) * rpb + lane_r; r < rows;
+           r += static_cast<int64_t>(gridDim.x) * rpb) {
+        const uint4 v = *reinterpret_cast<const uint4*>(in + r * ld + cb * 8);
+        const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = __half22float2(h[e]);
+          acc[2 * e] += f.x;
+          acc[2 * e + 1] += f.y;
+        }
+      }
     }
-    atomicAdd(out + c, a0 * scale);
-    if (c + 1 < C) atomicAdd(out + c + 1, a1 * scale);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) red[threadIdx.x * 8 + e] = acc[e];
+    __syncthreads();
+    if (lane_r == 0) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        float t = 0.f;
+        for (int q = 0; q < rpb; ++q) t += red[(q * tpr + lane_c) * 8 + e];
+        atomicAdd(out + cb * 8 + e, t * scale);
+      }
+    }
+    __syncthreads();
   }
 }
 
@@ -288,7 +320,7 @@ __global__ void resize_paste_u8_kernel(const uint8_t* __restrict__ src, uint8_t*
 extern "C" int ptb200_preprocess_im2col(const uint8_t* images, const int* hw_dev, int n, int hmax, int wmax,
                                         int64_t image_stride, const float* mean3, const float* std3,
                                         void* out_f16, void* stream) {
-  const int64_t total = static_cast<int64_t>(n) * hmax * (wmax + 1) * 8;
+  const int64_t total = static_cast<int64_t>(n) * hmax * (wmax + 1);
   preprocess_im2col_kernel<<<grid_for(total), kThreads, 0, STREAM>>>(
       images, hw_dev, n, hmax, wmax, image_stride, mean3[0], mean3[1], mean3[2], 1.f / std3[0],
       1.f / std3[1], 1.f / std3[2], static_cast<__half*>(out_f16));
@@ -332,8 +364,9 @@ extern "C" int ptb200_cast_pad_rows_f16(const float* src, void* dst, int rows, i
 
 extern "C" int ptb200_colsum_f16(const void* in, int64_t rows, int c, int64_t ld, float scale, float* out,
                                  void* stream) {
-  int blocks = static_cast<int>((rows + 511) / 512);
-  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (c % 8 != 0) return 1202;
+  int blocks = static_cast<int>((rows + 63) / 64);
+  if (blocks > 148 * 4) blocks = 148 * 4;
   if (blocks < 1) blocks = 1;
   colsum_f16_kernel<<<blocks, 256, 0, STREAM>>>(static_cast<const __half*>(in), rows, c, ld, scale, out);
   return LAUNCH_OK();

@@ -25,35 +25,59 @@ __device__ __forceinline__ float box_area(const float4 g) {
   return __fmul_rn(__fsub_rn(g.z, g.x), __fsub_rn(g.w, g.y));
 }
 
-// pass 1: per box max IoU / first arg-max over the image's gt boxes; per gt best IoU (atomic max).
+// pass 1: per box max IoU / first arg-max over the image's gt boxes; per gt best IoU, reduced
+// warp -> shared memory -> one global atomicMax per (CTA, gt). grid = (chunks, N).
 // boxes are shared by all images when box_img_stride == 0 (anchors).
-__global__ void match_pass1_kernel(const float4* __restrict__ gt, const int* __restrict__ gt_count, int gt_cap,
-                                   const float4* __restrict__ boxes, int64_t box_img_stride,
-                                   const int* __restrict__ box_count, int R, int N, float* __restrict__ max_iou,
-                                   int* __restrict__ matched, int* __restrict__ best_per_gt) {
-  const int64_t total = static_cast<int64_t>(N) * R;
-  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int n = static_cast<int>(i / R);
-    const int r = static_cast<int>(i - static_cast<int64_t>(n) * R);
+constexpr int kMaxGt = 128;
+__global__ void __launch_bounds__(256)
+match_pass1_kernel(const float4* __restrict__ gt, const int* __restrict__ gt_count, int gt_cap,
+                   const float4* __restrict__ boxes, int64_t box_img_stride,
+                   const int* __restrict__ box_count, int R, int N, float* __restrict__ max_iou,
+                   int* __restrict__ matched, int* __restrict__ best_per_gt) {
+  __shared__ float4 sgt[kMaxGt];
+  __shared__ float sarea[kMaxGt];
+  __shared__ int sbest[kMaxGt];
+  const int n = blockIdx.y;
+  const int M = min(gt_count[n], gt_cap);
+  for (int m = threadIdx.x; m < M; m += blockDim.x) {
+    const float4 g = gt[n * gt_cap + m];
+    sgt[m] = g;
+    sarea[m] = box_area(g);
+    sbest[m] = 0;
+  }
+  __syncthreads();
+  const int nbox = box_count == nullptr ? R : min(box_count[n], R);
+  const int per_block = (R + gridDim.x - 1) / gridDim.x;
+  const int r_begin = blockIdx.x * per_block;
+  const int r_end = min(r_begin + per_block, R);
+  const int span = (r_end - r_begin + 255) / 256 * 256;
+  for (int rr = threadIdx.x; rr < span; rr += 256) {
+    const int r = r_begin + rr;
+    const bool live = r < r_end && r < nbox;
     float best = -1.f;
     int arg = 0;
-    if (box_count == nullptr || r < box_count[n]) {
-      const float4 b = boxes[n * box_img_stride + r];
-      const int M = min(gt_count[n], gt_cap);
-      for (int m = 0; m < M; ++m) {
-        const float4 g = gt[n * gt_cap + m];
-        const float v = iou_pair(g, box_area(g), b);
-        if (v > best) {
-          best = v;
-          arg = m;
-        }
-        if (best_per_gt != nullptr) atomicMax(best_per_gt + n * gt_cap + m, __float_as_int(v));
+    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (live) b = boxes[n * box_img_stride + r];
+    for (int m = 0; m < M; ++m) {
+      const float v = live ? iou_pair(sgt[m], sarea[m], b) : 0.f;
+      if (live && v > best) {
+        best = v;
+        arg = m;
+      }
+      if (best_per_gt != nullptr) {
+        const int wmax = __reduce_max_sync(0xffffffffu, __float_as_int(v));
+        if ((threadIdx.x & 31) == 0 && wmax > 0) atomicMax(&sbest[m], wmax);
       }
     }
-    max_iou[i] = best;
-    matched[i] = arg;
+    if (r < r_end) {
+      max_iou[static_cast<int64_t>(n) * R + r] = best;
+      matched[static_cast<int64_t>(n) * R + r] = arg;
+    }
   }
+  __syncthreads();
+  if (best_per_gt != nullptr)
+    for (int m = threadIdx.x; m < M; m += blockDim.x)
+      if (sbest[m] > 0) atomicMax(best_per_gt + n * gt_cap + m, sbest[m]);
 }
 
 // pass 2 (RPN): thresholds [lo, hi] -> {0, -1, 1}, then low-quality matches -> 1.
@@ -302,8 +326,11 @@ extern "C" int ptb200_rpn_match(const float* gt_boxes, const int* gt_count, int 
                                 int num_anchors, int n, float iou_lo, float iou_hi, float* max_iou_scratch,
                                 int* best_per_gt_scratch, int* matched_idx, int* labels, void* stream) {
   cudaMemsetAsync(best_per_gt_scratch, 0, sizeof(int) * n * gt_cap, STREAM);
+  if (gt_cap > kMaxGt) return 1501;
   const int64_t total = static_cast<int64_t>(n) * num_anchors;
-  match_pass1_kernel<<<grid1d(total), 256, 0, STREAM>>>(reinterpret_cast<const float4*>(gt_boxes), gt_count, gt_cap,
+  int chunks = (num_anchors + 1023) / 1024;
+  if (chunks < 1) chunks = 1;
+  match_pass1_kernel<<<dim3(chunks, n), 256, 0, STREAM>>>(reinterpret_cast<const float4*>(gt_boxes), gt_count, gt_cap,
                                                        reinterpret_cast<const float4*>(anchors), 0, nullptr,
                                                        num_anchors, n, max_iou_scratch, matched_idx,
                                                        best_per_gt_scratch);

@@ -161,23 +161,34 @@ __global__ void nms_bitmask_kernel(const float4* __restrict__ boxes, int64_t box
     const float xx2 = fminf(bi.z, bj.z), yy2 = fminf(bi.w, bj.w);
     const float w = fmaxf(0.f, xx2 - xx1), h = fmaxf(0.f, yy2 - yy1);
     const float inter = __fmul_rn(w, h);
+    if (!(inter > 0.f) || ccls[j] != ci) continue;
     const float aj = __fmul_rn(bj.z - bj.x, bj.w - bj.y);
-    const float iou = __fdiv_rn(inter, __fsub_rn(__fadd_rn(ai, aj), inter));
-    if (iou > thr && ccls[j] == ci) bits |= 1ull << j;
+    const float uni = __fsub_rn(__fadd_rn(ai, aj), inter);
+    // decide without the division unless inter/uni is within ~1e-5 of the threshold (bit-exact result)
+    const float tu = thr * uni;
+    bool sup;
+    if (inter > tu * 1.00001f) sup = true;
+    else if (inter < tu * 0.99999f) sup = false;
+    else sup = __fdiv_rn(inter, uni) > thr;
+    if (sup) bits |= 1ull << j;
   }
   mask[(static_cast<int64_t>(n) * cap + i) * words + cb] = bits;
 }
 
-// Sequential part of NMS, one CTA per image: 64-candidate blocks are resolved by warp 0 with the
-// diagonal mask block, then all threads OR the kept rows into the running `removed` bit vector.
-// Stops after max_keep survivors. keep_idx holds positions in the sorted order.
-__global__ void __launch_bounds__(256, 1)
+// Sequential part of NMS, one CTA (1024 threads) per image: each 64-candidate block is resolved by
+// one thread against the diagonal mask block held in shared memory, then the rows that survived are
+// OR-ed into the running `removed` bit vector by all threads (4 row groups x 256 words, 4 loads in
+// flight per thread). Stops after max_keep survivors. keep_idx holds positions in the sorted order.
+__global__ void __launch_bounds__(1024, 1)
 nms_scan_kernel(const unsigned long long* __restrict__ mask, const int* __restrict__ counts, int cap, int words,
                 int max_keep, int* __restrict__ keep_idx, int* __restrict__ keep_count) {
   extern __shared__ unsigned long long removed[];  // [words]
+  __shared__ unsigned long long s_diag[64];
   __shared__ unsigned long long s_keep;
+  __shared__ int s_rows[64];
+  __shared__ int s_nk;
   __shared__ int s_total;
-  const int n = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+  const int n = blockIdx.x, tid = threadIdx.x;
   int cnt = counts[n];
   if (cnt > cap) cnt = cap;
   const unsigned long long* m = mask + static_cast<int64_t>(n) * cap * words;
@@ -187,49 +198,50 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, const int* __restri
   const int nblk = (cnt + 63) / 64;
   for (int b = 0; b < nblk; ++b) {
     if (s_total >= max_keep) break;
-    if (tid < 32) {
-      const int r0 = b * 64 + lane, r1 = r0 + 32;
-      const unsigned long long d0 = r0 < cnt ? m[static_cast<int64_t>(r0) * words + b] : 0ull;
-      const unsigned long long d1 = r1 < cnt ? m[static_cast<int64_t>(r1) * words + b] : 0ull;
+    if (tid < 64) {
+      const int r = b * 64 + tid;
+      s_diag[tid] = r < cnt ? m[static_cast<int64_t>(r) * words + b] : 0ull;
+    }
+    __syncthreads();
+    if (tid == 0) {
       unsigned long long rem = removed[b];
       const int live = min(64, cnt - b * 64);
       if (live < 64) rem |= ~0ull << live;
       unsigned long long keep = 0ull;
-#pragma unroll 4
-      for (int i = 0; i < 64; ++i) {
-        const unsigned long long di = __shfl_sync(0xffffffffu, i < 32 ? d0 : d1, i & 31);
-        if (!((rem >> i) & 1ull)) {
-          keep |= 1ull << i;
-          rem |= di;
-        }
-      }
+      int nk = 0;
       const int total = s_total;
-      // append survivors (lane handles bits lane and lane+32)
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int i = lane + 32 * h;
-        if ((keep >> i) & 1ull) {
-          const int pos = total + __popcll(keep & ((1ull << i) - 1ull));
-          if (pos < max_keep) keep_idx[n * max_keep + pos] = b * 64 + i;
+      if (rem != ~0ull) {
+#pragma unroll 8
+        for (int i = 0; i < 64; ++i) {
+          if (!((rem >> i) & 1ull)) {
+            keep |= 1ull << i;
+            rem |= s_diag[i];
+            if (total + nk < max_keep) keep_idx[n * max_keep + total + nk] = b * 64 + i;
+            s_rows[nk++] = b * 64 + i;
+          }
         }
       }
-      __syncwarp();
-      if (lane == 0) {
-        s_keep = keep;
-        s_total = total + __popcll(keep);
-      }
+      s_keep = keep;
+      s_nk = nk;
+      s_total = total + nk;
     }
     __syncthreads();
-    const unsigned long long keep = s_keep;
-    for (int w = b + 1 + tid; w < words; w += blockDim.x) {
-      unsigned long long acc = removed[w];
-      unsigned long long kb = keep;
-      while (kb) {
-        const int i = __ffsll(static_cast<long long>(kb)) - 1;
-        kb &= kb - 1ull;
-        acc |= m[static_cast<int64_t>(b * 64 + i) * words + w];
+    const int nk = s_nk;
+    if (nk > 0 && b + 1 < words) {
+      const int g = tid >> 8, w = b + 1 + (tid & 255);
+      for (int w0 = w; w0 < words; w0 += 256) {
+        unsigned long long acc = 0ull;
+        int j = g;
+        for (; j + 12 < nk; j += 16) {
+          const unsigned long long a0 = m[static_cast<int64_t>(s_rows[j]) * words + w0];
+          const unsigned long long a1 = m[static_cast<int64_t>(s_rows[j + 4]) * words + w0];
+          const unsigned long long a2 = m[static_cast<int64_t>(s_rows[j + 8]) * words + w0];
+          const unsigned long long a3 = m[static_cast<int64_t>(s_rows[j + 12]) * words + w0];
+          acc |= (a0 | a1) | (a2 | a3);
+        }
+        for (; j < nk; j += 4) acc |= m[static_cast<int64_t>(s_rows[j]) * words + w0];
+        if (acc) atomicOr(&removed[w0], acc);
       }
-      removed[w] = acc;
     }
     __syncthreads();
   }
@@ -392,7 +404,7 @@ extern "C" int ptb200_nms(const float* boxes, int64_t box_stride, const uint32_t
   dim3 grid(words, words, n);
   nms_bitmask_kernel<<<grid, 64, 0, STREAM>>>(reinterpret_cast<const float4*>(boxes), box_stride, order,
                                              order_stride, counts, cap, words, thresh, class_mod, mask_scratch);
-  nms_scan_kernel<<<n, 256, words * sizeof(unsigned long long), STREAM>>>(mask_scratch, counts, cap, words, max_keep,
+  nms_scan_kernel<<<n, 1024, words * sizeof(unsigned long long), STREAM>>>(mask_scratch, counts, cap, words, max_keep,
                                                                          keep_idx, keep_count);
   return LAUNCH_OK();
 }

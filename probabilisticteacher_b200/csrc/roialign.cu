@@ -64,6 +64,53 @@ __device__ __forceinline__ RoiGeom roi_geom(const float4 b, float scale, int P) 
   return g;
 }
 
+// Bilinear weights are separable and the sampling grid of a bin is a product grid, so the bin value
+// is sum_py sum_px Wy[py] * Wx[px] * feat[py][px] with 1-D weight vectors over the rows / columns the
+// samples touch: (gh+1)*(gw+1) pixel visits instead of 4*gh*gw taps. kMaxSpan bounds the 1-D span
+// (bins of rois up to ~kMaxSpan*7*16 px); larger bins take the generic tap loop.
+constexpr int kMaxSpan = 20;
+
+struct Axis {
+  int lo;            // first pixel index touched
+  int n;             // number of pixels touched (0 = nothing valid)
+  float w[kMaxSpan];
+};
+
+// accumulate the 1-D weights of `grid` samples of one bin along one axis (extent = H or W)
+__device__ __forceinline__ bool axis_weights(float start, float bin, int p, int grid, int extent, Axis& a) {
+  a.n = 0;
+  a.lo = 0;
+#pragma unroll
+  for (int i = 0; i < kMaxSpan; ++i) a.w[i] = 0.f;
+  bool first = true;
+  for (int i = 0; i < grid; ++i) {
+    float v = start + p * bin + (i + 0.5f) * bin / grid;
+    if (v < -1.0f || v > extent) continue;
+    if (v <= 0.f) v = 0.f;
+    int lo = static_cast<int>(v), hi;
+    if (lo >= extent - 1) {
+      hi = lo = extent - 1;
+      v = static_cast<float>(lo);
+    } else {
+      hi = lo + 1;
+    }
+    const float l = v - lo, h = 1.f - l;
+    if (first) {
+      a.lo = lo;
+      first = false;
+    }
+    const int i0 = lo - a.lo, i1 = hi - a.lo;
+    if (i1 >= kMaxSpan) return false;
+#pragma unroll
+    for (int k = 0; k < kMaxSpan; ++k) {
+      if (k == i0) a.w[k] += h;
+      if (k == i1) a.w[k] += l;
+    }
+    if (i1 + 1 > a.n) a.n = i1 + 1;
+  }
+  return true;
+}
+
 // grid: (roi, ph*P+pw) ; block: C/8 threads
 __global__ void roi_align_fwd_kernel(const __half* __restrict__ feat, int H, int W, int C,
                                      const float4* __restrict__ rois, const int* __restrict__ roi_count,
@@ -83,26 +130,47 @@ __global__ void roi_align_fwd_kernel(const __half* __restrict__ feat, int H, int
   float acc[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-  for (int iy = 0; iy < g.grid_h; ++iy) {
-    const float y = g.start_h + ph * g.bin_h + (iy + 0.5f) * g.bin_h / g.grid_h;
-    for (int ix = 0; ix < g.grid_w; ++ix) {
-      const float x = g.start_w + pw * g.bin_w + (ix + 0.5f) * g.bin_w / g.grid_w;
-      Tap t;
-      if (!bilinear_taps(y, x, H, W, Wp, t)) continue;
-      const uint4 v1 = *reinterpret_cast<const uint4*>(base + static_cast<int64_t>(t.o1) * C);
-      const uint4 v2 = *reinterpret_cast<const uint4*>(base + static_cast<int64_t>(t.o2) * C);
-      const uint4 v3 = *reinterpret_cast<const uint4*>(base + static_cast<int64_t>(t.o3) * C);
-      const uint4 v4 = *reinterpret_cast<const uint4*>(base + static_cast<int64_t>(t.o4) * C);
-      const __half2* h1 = reinterpret_cast<const __half2*>(&v1);
-      const __half2* h2 = reinterpret_cast<const __half2*>(&v2);
-      const __half2* h3 = reinterpret_cast<const __half2*>(&v3);
-      const __half2* h4 = reinterpret_cast<const __half2*>(&v4);
+  Axis ay, ax;
+  const bool sep = axis_weights(g.start_h, g.bin_h, ph, g.grid_h, H, ay) &&
+                   axis_weights(g.start_w, g.bin_w, pw, g.grid_w, W, ax);
+  if (sep) {
+    for (int iy = 0; iy < ay.n; ++iy) {
+      const float wy = ay.w[iy];
+      if (wy == 0.f) continue;
+      const __half* rowp = base + static_cast<int64_t>((ay.lo + iy) * Wp + ax.lo) * C;
+      for (int ix = 0; ix < ax.n; ++ix) {
+        const float wgt = wy * ax.w[ix];
+        if (wgt == 0.f) continue;
+        const uint4 v = *reinterpret_cast<const uint4*>(rowp + static_cast<int64_t>(ix) * C);
+        const __half2* h = reinterpret_cast<const __half2*>(&v);
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float2 a = __half22float2(h1[e]), b = __half22float2(h2[e]), c = __half22float2(h3[e]),
-                     d = __half22float2(h4[e]);
-        acc[2 * e] += t.w1 * a.x + t.w2 * b.x + t.w3 * c.x + t.w4 * d.x;
-        acc[2 * e + 1] += t.w1 * a.y + t.w2 * b.y + t.w3 * c.y + t.w4 * d.y;
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = __half22float2(h[e]);
+          acc[2 * e] += wgt * f.x;
+          acc[2 * e + 1] += wgt * f.y;
+        }
+      }
+    }
+  } else {
+    for (int iy = 0; iy < g.grid_h; ++iy) {
+      const float y = g.start_h + ph * g.bin_h + (iy + 0.5f) * g.bin_h / g.grid_h;
+      for (int ix = 0; ix < g.grid_w; ++ix) {
+        const float x = g.start_w + pw * g.bin_w + (ix + 0.5f) * g.bin_w / g.grid_w;
+        Tap t;
+        if (!bilinear_taps(y, x, H, W, Wp, t)) continue;
+        const int offs[4] = {t.o1, t.o2, t.o3, t.o4};
+        const float ws[4] = {t.w1, t.w2, t.w3, t.w4};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint4 v = *reinterpret_cast<const uint4*>(base + static_cast<int64_t>(offs[k]) * C);
+          const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 f = __half22float2(h[e]);
+            acc[2 * e] += ws[k] * f.x;
+            acc[2 * e + 1] += ws[k] * f.y;
+          }
+        }
       }
     }
   }
@@ -130,13 +198,34 @@ __global__ void roi_align_bwd_kernel(const __half* __restrict__ dout, int H, int
   const uint4 gv = *reinterpret_cast<const uint4*>(dout + (static_cast<int64_t>(roi) * P * P + bin) * C + c0);
   const __half2* gh = reinterpret_cast<const __half2*>(&gv);
   float gr[8];
+  bool any = false;
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
     const float2 f = __half22float2(gh[e]);
     gr[2 * e] = f.x / g.count;
     gr[2 * e + 1] = f.y / g.count;
+    any = any || f.x != 0.f || f.y != 0.f;
   }
+  if (!any) return;
   float* base = dfeat + static_cast<int64_t>(n) * H * Wp * C + c0;
+  Axis ay, ax;
+  const bool sep = axis_weights(g.start_h, g.bin_h, ph, g.grid_h, H, ay) &&
+                   axis_weights(g.start_w, g.bin_w, pw, g.grid_w, W, ax);
+  if (sep) {
+    for (int iy = 0; iy < ay.n; ++iy) {
+      const float wy = ay.w[iy];
+      if (wy == 0.f) continue;
+      float* rowp = base + static_cast<int64_t>((ay.lo + iy) * Wp + ax.lo) * C;
+      for (int ix = 0; ix < ax.n; ++ix) {
+        const float wgt = wy * ax.w[ix];
+        if (wgt == 0.f) continue;
+        float* p = rowp + static_cast<int64_t>(ix) * C;
+        red_add_v4(p, gr[0] * wgt, gr[1] * wgt, gr[2] * wgt, gr[3] * wgt);
+        red_add_v4(p + 4, gr[4] * wgt, gr[5] * wgt, gr[6] * wgt, gr[7] * wgt);
+      }
+    }
+    return;
+  }
   for (int iy = 0; iy < g.grid_h; ++iy) {
     const float y = g.start_h + ph * g.bin_h + (iy + 0.5f) * g.bin_h / g.grid_h;
     for (int ix = 0; ix < g.grid_w; ++ix) {
