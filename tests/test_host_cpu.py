@@ -1,0 +1,117 @@
+"""CPU: C-ABI export check, host-side containers / config / schedule, and the world_size-2 (gloo)
+data-parallel plumbing."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    import __graft_entry__ as ge
+    ge.build()
+    from probabilisticteacher_b200 import _lib
+    L = _lib.lib()
+    protos = _lib.protos()
+    assert len(protos) >= 35
+    for name in protos:
+        assert hasattr(L, name), name
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    exported = {l.split()[-1] for l in out.splitlines() if " T " in l}
+    assert set(protos) <= exported
+
+
+def test_no_cpu_fallback():
+    from probabilisticteacher_b200.config import c2f_config
+    from probabilisticteacher_b200.modeling.meta_arch.rcnn import build_model
+    with pytest.raises(RuntimeError):
+        build_model(c2f_config(), device="cpu")
+
+
+def test_config_defaults_and_overrides(tmp_path):
+    from probabilisticteacher_b200.config import c2f_config, get_cfg
+    c = get_cfg()
+    assert c.MODEL.RPN.PRE_NMS_TOPK_TRAIN == 12000 and c.UNSUPNET.TAU == [0.5, 0.5]
+    base = tmp_path / "base.yaml"
+    base.write_text("MODEL:\n  ROI_HEADS:\n    NUM_CLASSES: 3\nSOLVER:\n  STEPS: (100, 200)\n")
+    child = tmp_path / "child.yaml"
+    child.write_text('_BASE_: "base.yaml"\nUNSUPNET:\n  EMA_KEEP_RATE: 0.9996\n')
+    c.merge_from_file(str(child))
+    c.merge_from_list(["MODEL.ANCHOR_GENERATOR.NAME", "DifferentiableAnchorGenerator", "UNSUPNET.TAU", "[0.25,0.25]"])
+    assert c.MODEL.ROI_HEADS.NUM_CLASSES == 3 and c.SOLVER.STEPS == (100, 200)
+    assert c.UNSUPNET.EMA_KEEP_RATE == 0.9996 and c.UNSUPNET.TAU == [0.25, 0.25]
+    assert c2f_config().MODEL.ANCHOR_GENERATOR.NAME == "DifferentiableAnchorGenerator"
+
+
+def test_structures():
+    from probabilisticteacher_b200.structures import Boxes, FreeInstances, Instances
+    b = Boxes(torch.tensor([[0., 0., 10., 10.], [5., 5., 5., 9.]]))
+    assert b.nonempty().tolist() == [True, False] and b.area().tolist() == [100.0, 0.0]
+    b.clip((8, 8))
+    assert b.tensor[0].tolist() == [0., 0., 8., 8.]
+    i = Instances((10, 10), gt_boxes=b, gt_classes=torch.tensor([1, 2]))
+    with pytest.raises(AssertionError):
+        i.set("x", torch.zeros(3))
+    f = FreeInstances((10, 10), gt_boxes=b)
+    f.set("x", torch.zeros(3))  # no length check (pt/structures/instances.py:27-33)
+    f._count = torch.tensor(1)
+    assert len(f.trim().gt_boxes) == 1
+
+
+def test_lr_schedule():
+    from probabilisticteacher_b200.engine.trainer import warmup_multistep_lr
+    assert abs(warmup_multistep_lr(0.016, 0, (30000,), 0.1, 0.001, 400) - 0.016 * 0.001) < 1e-12
+    assert abs(warmup_multistep_lr(0.016, 400, (30000,), 0.1, 0.001, 400) - 0.016) < 1e-12
+    assert abs(warmup_multistep_lr(0.016, 30000, (30000,), 0.1, 0.001, 400) - 0.0016) < 1e-12
+
+
+def test_state_dict_layout_conversion():
+    from probabilisticteacher_b200.arena import ParamArena
+    t = torch.arange(2 * 3 * 3 * 5, dtype=torch.float32).view(2, 3, 3, 5)  # [co][ky][kx][ci]
+    ref = ParamArena._to_ref("conv", t, 512, 7)
+    assert ref.shape == (2, 5, 3, 3) and ref[1, 4, 2, 0] == t[1, 2, 0, 4]
+    f = torch.arange(2 * 49 * 4, dtype=torch.float32).view(2, 49, 4)
+    r = ParamArena._to_ref("fc1", f, 4, 7)
+    assert r.shape == (2, 196) and r[1, 3 * 49 + 10] == f[1, 10, 3]
+
+
+_WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from probabilisticteacher_b200.engine import dp
+rank = int(os.environ["RANK"])
+dist.init_process_group("gloo", rank=rank, world_size=2)
+params = torch.full((1000,), float(rank + 1))
+dp.broadcast_params(params)
+assert bool((params == 1.0).all())
+g = torch.arange(100000, dtype=torch.float32) * (rank + 1)
+works = dp.allreduce_grads(g, bucket_elems=30000, async_op=True)
+for w in works:
+    w.wait()
+assert len(works) == 4
+mean = g * dp.pre_scale()
+assert torch.allclose(mean, torch.arange(100000, dtype=torch.float32) * 1.5)
+dist.destroy_process_group()
+print("ok")
+'''
+
+
+def test_data_parallel_plumbing_gloo(tmp_path):
+    script = tmp_path / "w.py"
+    script.write_text(_WORKER)
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT="29533")
+        procs.append(subprocess.Popen([sys.executable, str(script), ROOT], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True))
+    for p in procs:
+        out = p.communicate(timeout=120)[0]
+        assert p.returncode == 0 and "ok" in out, out
+
+
+def test_bucket_bounds():
+    from probabilisticteacher_b200.engine.dp import bucket_bounds
+    assert bucket_bounds(10, 4) == [(0, 4), (4, 8), (8, 10)]
