@@ -760,23 +760,31 @@ class OracleRCNN(torch.nn.Module):
             res.append(r)
         return res, {}, aux
 
-    def forward(self, batched_inputs, branch="supervised", danchor=False, training=True, trace=None):
-        """pt/modeling/meta_arch/rcnn.py:32-92."""
+    def forward(self, batched_inputs, branch="supervised", danchor=False, training=True, trace=None,
+                proposals_override=None):
+        """pt/modeling/meta_arch/rcnn.py:32-92. `proposals_override` (tests only) replaces the RPN
+        proposals handed to the ROI heads, so that the ROI stage can be compared on identical inputs."""
         images, sizes = self.preprocess_image(batched_inputs)
         gt = [x["instances"] for x in batched_inputs] if "instances" in batched_inputs[0] else None
         feat = self.backbone(images, trace.setdefault("backbone", {}) if trace is not None else None)
         if branch == "supervised":
             props, pl, raux = self.rpn(feat, sizes, gt, training=training)
+            if proposals_override is not None:
+                props = proposals_override
             _, dl, haux = self.roi_heads(feat, props, gt, branch=branch, training=training)
             losses = dict(dl)
             losses.update(pl)
             out = (losses, [], [], None)
         elif branch == "unsup_data_weak":
             props, _, raux = self.rpn(feat, sizes, None, compute_loss=False, training=training)
+            if proposals_override is not None:
+                props = proposals_override
             roih, _, haux = self.roi_heads(feat, props, None, compute_loss=False, branch=branch, training=training)
             out = ({}, props, roih, (haux["scores"], haux["deltas"]))
         elif branch == "unsupervised":
             props, pl, raux = self.rpn(feat, sizes, gt, branch=branch, danchor=danchor, training=training)
+            if proposals_override is not None:
+                props = proposals_override
             _, dl, haux = self.roi_heads(feat, props, gt, branch=branch, training=training)
             losses = dict(dl)
             losses.update(pl)
