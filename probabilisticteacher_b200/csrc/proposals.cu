@@ -175,20 +175,19 @@ __global__ void nms_bitmask_kernel(const float4* __restrict__ boxes, int64_t box
   mask[(static_cast<int64_t>(n) * cap + i) * words + cb] = bits;
 }
 
-// Sequential part of NMS, one CTA (1024 threads) per image: each 64-candidate block is resolved by
-// one thread against the diagonal mask block held in shared memory, then the rows that survived are
-// OR-ed into the running `removed` bit vector by all threads (4 row groups x 256 words, 4 loads in
-// flight per thread). Stops after max_keep survivors. keep_idx holds positions in the sorted order.
+// Sequential part of NMS, one CTA (1024 threads) per image. Per 64-candidate block: blocks that are
+// already fully suppressed are skipped without any barrier; otherwise warp 0 loads the diagonal mask
+// block (lane l owns rows l and l+32) and resolves the 64 candidates with register shuffles, then all
+// threads OR the surviving rows into the running `removed` bit vector (4 row groups x 256 words,
+// 4 loads in flight per thread). Stops after max_keep survivors. keep_idx = positions in sorted order.
 __global__ void __launch_bounds__(1024, 1)
 nms_scan_kernel(const unsigned long long* __restrict__ mask, const int* __restrict__ counts, int cap, int words,
                 int max_keep, int* __restrict__ keep_idx, int* __restrict__ keep_count) {
   extern __shared__ unsigned long long removed[];  // [words]
-  __shared__ unsigned long long s_diag[64];
-  __shared__ unsigned long long s_keep;
   __shared__ int s_rows[64];
   __shared__ int s_nk;
   __shared__ int s_total;
-  const int n = blockIdx.x, tid = threadIdx.x;
+  const int n = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
   int cnt = counts[n];
   if (cnt > cap) cnt = cap;
   const unsigned long long* m = mask + static_cast<int64_t>(n) * cap * words;
@@ -197,37 +196,44 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, const int* __restri
   __syncthreads();
   const int nblk = (cnt + 63) / 64;
   for (int b = 0; b < nblk; ++b) {
+    // uniform decisions from state that is stable since the last barrier
     if (s_total >= max_keep) break;
-    if (tid < 64) {
-      const int r = b * 64 + tid;
-      s_diag[tid] = r < cnt ? m[static_cast<int64_t>(r) * words + b] : 0ull;
-    }
-    __syncthreads();
-    if (tid == 0) {
-      unsigned long long rem = removed[b];
-      const int live = min(64, cnt - b * 64);
-      if (live < 64) rem |= ~0ull << live;
-      unsigned long long keep = 0ull;
-      int nk = 0;
-      const int total = s_total;
-      if (rem != ~0ull) {
-#pragma unroll 8
-        for (int i = 0; i < 64; ++i) {
-          if (!((rem >> i) & 1ull)) {
-            keep |= 1ull << i;
-            rem |= s_diag[i];
-            if (total + nk < max_keep) keep_idx[n * max_keep + total + nk] = b * 64 + i;
-            s_rows[nk++] = b * 64 + i;
-          }
+    const int live = min(64, cnt - b * 64);
+    unsigned long long rem0 = removed[b];
+    if (live < 64) rem0 |= ~0ull << live;
+    if (rem0 == ~0ull) continue;
+    if (tid < 32) {
+      const int r0 = b * 64 + lane, r1 = r0 + 32;
+      const unsigned long long d0 = r0 < cnt ? m[static_cast<int64_t>(r0) * words + b] : 0ull;
+      const unsigned long long d1 = r1 < cnt ? m[static_cast<int64_t>(r1) * words + b] : 0ull;
+      unsigned long long rem = rem0, keep = 0ull;
+#pragma unroll
+      for (int i = 0; i < 64; ++i) {
+        const unsigned long long di = __shfl_sync(0xffffffffu, i < 32 ? d0 : d1, i & 31);
+        if (!((rem >> i) & 1ull)) {
+          keep |= 1ull << i;
+          rem |= di;
         }
       }
-      s_keep = keep;
-      s_nk = nk;
-      s_total = total + nk;
+      const int total = s_total;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int i = lane + 32 * h;
+        if ((keep >> i) & 1ull) {
+          const int pos = __popcll(keep & ((1ull << i) - 1ull));
+          s_rows[pos] = b * 64 + i;
+          if (total + pos < max_keep) keep_idx[n * max_keep + total + pos] = b * 64 + i;
+        }
+      }
+      __syncwarp();
+      if (lane == 0) {
+        s_nk = __popcll(keep);
+        s_total = total + __popcll(keep);
+      }
     }
     __syncthreads();
     const int nk = s_nk;
-    if (nk > 0 && b + 1 < words) {
+    if (b + 1 < words) {
       const int g = tid >> 8, w = b + 1 + (tid & 255);
       for (int w0 = w; w0 < words; w0 += 256) {
         unsigned long long acc = 0ull;

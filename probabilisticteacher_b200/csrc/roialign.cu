@@ -68,21 +68,20 @@ __device__ __forceinline__ RoiGeom roi_geom(const float4 b, float scale, int P) 
 // is sum_py sum_px Wy[py] * Wx[px] * feat[py][px] with 1-D weight vectors over the rows / columns the
 // samples touch: (gh+1)*(gw+1) pixel visits instead of 4*gh*gw taps. kMaxSpan bounds the 1-D span
 // (bins of rois up to ~kMaxSpan*7*16 px); larger bins take the generic tap loop.
-constexpr int kMaxSpan = 20;
+constexpr int kMaxSpan = 32;
 
 struct Axis {
   int lo;            // first pixel index touched
-  int n;             // number of pixels touched (0 = nothing valid)
+  int n;             // number of pixels touched (0 = nothing valid); -1 = span too large
   float w[kMaxSpan];
 };
 
-// accumulate the 1-D weights of `grid` samples of one bin along one axis (extent = H or W)
-__device__ __forceinline__ bool axis_weights(float start, float bin, int p, int grid, int extent, Axis& a) {
-  a.n = 0;
-  a.lo = 0;
-#pragma unroll
-  for (int i = 0; i < kMaxSpan; ++i) a.w[i] = 0.f;
+// 1-D weights of the `grid` samples of one bin along one axis (extent = H or W); run by ONE thread,
+// result lives in shared memory and is broadcast to the CTA.
+__device__ __forceinline__ void axis_weights(float start, float bin, int p, int grid, int extent, Axis* a) {
+  int n = 0, lo0 = 0;
   bool first = true;
+  for (int i = 0; i < kMaxSpan; ++i) a->w[i] = 0.f;
   for (int i = 0; i < grid; ++i) {
     float v = start + p * bin + (i + 0.5f) * bin / grid;
     if (v < -1.0f || v > extent) continue;
@@ -96,19 +95,20 @@ __device__ __forceinline__ bool axis_weights(float start, float bin, int p, int 
     }
     const float l = v - lo, h = 1.f - l;
     if (first) {
-      a.lo = lo;
+      lo0 = lo;
       first = false;
     }
-    const int i0 = lo - a.lo, i1 = hi - a.lo;
-    if (i1 >= kMaxSpan) return false;
-#pragma unroll
-    for (int k = 0; k < kMaxSpan; ++k) {
-      if (k == i0) a.w[k] += h;
-      if (k == i1) a.w[k] += l;
+    const int i0 = lo - lo0, i1 = hi - lo0;
+    if (i1 >= kMaxSpan) {
+      a->n = -1;
+      return;
     }
-    if (i1 + 1 > a.n) a.n = i1 + 1;
+    a->w[i0] += h;
+    a->w[i1] += l;
+    if (i1 + 1 > n) n = i1 + 1;
   }
-  return true;
+  a->lo = lo0;
+  a->n = n;
 }
 
 // grid: (roi, ph*P+pw) ; block: C/8 threads
@@ -130,9 +130,13 @@ __global__ void roi_align_fwd_kernel(const __half* __restrict__ feat, int H, int
   float acc[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-  Axis ay, ax;
-  const bool sep = axis_weights(g.start_h, g.bin_h, ph, g.grid_h, H, ay) &&
-                   axis_weights(g.start_w, g.bin_w, pw, g.grid_w, W, ax);
+  __shared__ Axis s_ay, s_ax;
+  if (threadIdx.x == 0) axis_weights(g.start_h, g.bin_h, ph, g.grid_h, H, &s_ay);
+  if (threadIdx.x == 32 % blockDim.x) axis_weights(g.start_w, g.bin_w, pw, g.grid_w, W, &s_ax);
+  __syncthreads();
+  const Axis& ay = s_ay;
+  const Axis& ax = s_ax;
+  const bool sep = ay.n >= 0 && ax.n >= 0;
   if (sep) {
     for (int iy = 0; iy < ay.n; ++iy) {
       const float wy = ay.w[iy];
@@ -206,11 +210,15 @@ __global__ void roi_align_bwd_kernel(const __half* __restrict__ dout, int H, int
     gr[2 * e + 1] = f.y / g.count;
     any = any || f.x != 0.f || f.y != 0.f;
   }
-  if (!any) return;
   float* base = dfeat + static_cast<int64_t>(n) * H * Wp * C + c0;
-  Axis ay, ax;
-  const bool sep = axis_weights(g.start_h, g.bin_h, ph, g.grid_h, H, ay) &&
-                   axis_weights(g.start_w, g.bin_w, pw, g.grid_w, W, ax);
+  __shared__ Axis s_ay, s_ax;
+  if (threadIdx.x == 0) axis_weights(g.start_h, g.bin_h, ph, g.grid_h, H, &s_ay);
+  if (threadIdx.x == 32 % blockDim.x) axis_weights(g.start_w, g.bin_w, pw, g.grid_w, W, &s_ax);
+  __syncthreads();
+  const Axis& ay = s_ay;
+  const Axis& ax = s_ax;
+  const bool sep = ay.n >= 0 && ax.n >= 0;
+  if (!any) return;
   if (sep) {
     for (int iy = 0; iy < ay.n; ++iy) {
       const float wy = ay.w[iy];
