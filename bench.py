@@ -124,12 +124,21 @@ class GemmProfiler:
 
     def __init__(self):
         self.records = []
+        self.shapes = []
+
+    def dump(self, path):
+        rows = []
+        for (name, flops, e0, e1), sh in zip(self.records, self.shapes):
+            ms = e0.elapsed_time(e1)
+            rows.append({"kind": sh[0], "shape": sh[1:], "ms": ms, "tflops": flops / ms / 1e9})
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        json.dump(rows, open(path, "w"))
 
     def begin(self, name, args):
         import torch
         if name == "ptb200_gemm_tn_f16":
             batch, rows, k, taps, n_total = args[1], args[2], args[3], args[6], args[9]
-            n_valid = args[25] if args[11] == 2 else n_total
+            n_valid = args[25] if args[11] in (2, 4) else n_total
             if k == 64 and taps == 1 and n_total == 64:
                 k = 27  # first VGG conv: 27 live im2col columns out of the K=64 operand
             flops = 2.0 * batch * rows * k * taps * n_valid
@@ -141,6 +150,10 @@ class GemmProfiler:
         e0 = torch.cuda.Event(enable_timing=True)
         e1 = torch.cuda.Event(enable_timing=True)
         e0.record()
+        if name == "ptb200_gemm_tn_f16":
+            self.shapes.append(("tn", args[1], args[2], args[3], args[6], args[9], args[10], args[11]))
+        else:
+            self.shapes.append(("wgrad", args[6], args[7], args[8], args[9], args[10], 0, 0))
         return (name, flops, e0, e1)
 
     def end(self, tok):
@@ -309,6 +322,8 @@ def main():
     torch.cuda.synchronize()
     _lib.profiler[0] = None
     tot_f, tot_t, cnt = prof.summary()
+    if os.environ.get("PTB_DUMP_GEMM") and rank == 0:
+        prof.dump(os.path.join(ROOT, "gpurun_out", "gemm_launches.json"))
     peaks = {}
     pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(pk):

@@ -22,6 +22,7 @@ extern "C" {
 #define PTB200_EPI_BIAS_F16 1
 #define PTB200_EPI_F32_SPLIT 2
 #define PTB200_EPI_MASK_F16 3
+#define PTB200_EPI_ATOMIC_F32 4 /* split-K partials: d0[row][n] += acc (fp32 atomics) */
 
 /* ---- dense contractions (tcgen05 tensor cores, TMA-staged tiles) ------------------------------ */
 
@@ -30,13 +31,14 @@ extern "C" {
  *   pt/modeling/backbone/vgg.py:45-53,65-72 (3x3 conv + bias + ReLU),
  *   pt/modeling/proposal_generator/rpn.py:96 (RPN head), pt/modeling/roi_heads/roi_heads.py:127-128
  *   (box head), pt/modeling/roi_heads/fast_rcnn.py:157-169 (predictor), and their data-gradients.
- * Rows outside [0, rows) read as zero (conv zero padding). */
+ * Rows outside [0, rows) read as zero (conv zero padding). ksplit > 1 (with PTB200_EPI_ATOMIC_F32)
+ * splits the reduction across CTAs for skinny problems (fc1 forward). */
 int ptb200_gemm_tn_f16(const void* A, int batch, int rows, int k_per_tap, int64_t lda,
                        int64_t a_batch_stride, int taps, const int* shifts_host, const void* B,
                        int n_total, int bn, int epi, const float* bias, int n_bias, void* D,
                        int64_t ldd, int64_t d_batch_stride, const void* aux, int w_valid, int wp,
                        float* d0, int ld0, float* d1, int ld1, int split, int n_valid, int max_ctas,
-                       void* stream);
+                       int ksplit, void* stream);
 
 /* Weight gradient  out[m][t*n_total + n] += scale * sum_b sum_p G[b][p][m] * X[b][p + shifts[t]][n]
  * (split-K, fp32 atomic accumulation). Replaces the wgrad kernels autograd issues at
@@ -81,6 +83,10 @@ int ptb200_colsum_f16(const void* in, int64_t rows, int c, int64_t ld, float sca
  * g0[0], g1[0] and the loss scale into the fp16 [rows][ld] operand of the backward GEMMs. */
 int ptb200_pack_grad2_f16(const float* d0, int n0, const float* d1, int n1, const float* g0,
                           const float* g1, float lscale, int64_t rows, int ld, void* out, void* stream);
+
+/* Finishes a split-K GEMM: out = half(act(in + bias)). */
+int ptb200_bias_act_cast_f16(const float* in, const float* bias, int relu, int64_t rows, int n, void* out,
+                             void* stream);
 
 int ptb200_add_f32_to_f16(const void* a, const float* b, float scale, void* out, int64_t n,
                           void* stream);

@@ -9,7 +9,7 @@ extern "C" int ptb200_gemm_tn_f16(const void* A, int batch, int rows, int k_per_
                                   int n_total, int bn, int epi, const float* bias, int n_bias, void* D,
                                   int64_t ldd, int64_t d_batch_stride, const void* aux, int w_valid,
                                   int wp, float* d0, int ld0, float* d1, int ld1, int split,
-                                  int n_valid, int max_ctas, void* stream) {
+                                  int n_valid, int max_ctas, int ksplit, void* stream) {
   GemmTnArgs a;
   a.A = A;
   a.batch = batch;
@@ -38,6 +38,7 @@ extern "C" int ptb200_gemm_tn_f16(const void* A, int batch, int rows, int k_per_
   a.split = split;
   a.n_valid = n_valid;
   a.max_ctas = max_ctas;
+  a.ksplit = ksplit;
   return gemm_tn_launch(a, static_cast<cudaStream_t>(stream));
 }
 

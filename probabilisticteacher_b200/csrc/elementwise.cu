@@ -312,6 +312,34 @@ __global__ void resize_paste_u8_kernel(const uint8_t* __restrict__ src, uint8_t*
   }
 }
 
+// out[r][c] = half(act(in[r][c] + bias[c])) : finishes a split-K GEMM whose partials were reduced in fp32
+__global__ void bias_act_cast_kernel(const float* __restrict__ in, const float* __restrict__ bias, int relu,
+                                     int64_t rows, int n, __half* __restrict__ out) {
+  const int64_t total4 = rows * n / 4;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total4;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>((i * 4) % n);
+    float4 v = reinterpret_cast<const float4*>(in)[i];
+    if (bias != nullptr) {
+      v.x += bias[c];
+      v.y += bias[c + 1];
+      v.z += bias[c + 2];
+      v.w += bias[c + 3];
+    }
+    if (relu) {
+      v.x = fmaxf(v.x, 0.f);
+      v.y = fmaxf(v.y, 0.f);
+      v.z = fmaxf(v.z, 0.f);
+      v.w = fmaxf(v.w, 0.f);
+    }
+    __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
+    uint2 o;
+    o.x = *reinterpret_cast<uint32_t*>(&a);
+    o.y = *reinterpret_cast<uint32_t*>(&b);
+    reinterpret_cast<uint2*>(out)[i] = o;
+  }
+}
+
 }  // namespace
 
 #define STREAM static_cast<cudaStream_t>(stream)
@@ -390,5 +418,13 @@ extern "C" int ptb200_add_f32_to_f16(const void* a, const float* b, float scale,
 extern "C" int ptb200_resize_paste_u8(const uint8_t* src, uint8_t* dst, int h, int w, int dh, int dw, int x1,
                                       int y1, int m0, int m1, int m2, void* stream) {
   resize_paste_u8_kernel<<<grid_for(3LL * h * w), kThreads, 0, STREAM>>>(src, dst, h, w, dh, dw, x1, y1, m0, m1, m2);
+  return LAUNCH_OK();
+}
+
+extern "C" int ptb200_bias_act_cast_f16(const float* in, const float* bias, int relu, int64_t rows, int n, void* out,
+                                        void* stream) {
+  if (n % 4 != 0) return 1203;
+  bias_act_cast_kernel<<<grid_for(rows * n / 4), kThreads, 0, STREAM>>>(in, bias, relu, rows, n,
+                                                                       static_cast<__half*>(out));
   return LAUNCH_OK();
 }

@@ -61,9 +61,10 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const int m_tiles = (p.rows + BM - 1) / BM;
   const int n_tiles = p.n_total / bn;
   const int tiles_per_batch = m_tiles * n_tiles;
-  const int num_tiles = tiles_per_batch * p.batch;
+  const int ksplit = p.ksplit;
+  const int num_tiles = tiles_per_batch * p.batch * ksplit;   // work items (tile x k-split)
   const int k_chunks = p.k_per_tap / BK;
-  const int k_iters = k_chunks * p.taps;
+  const int k_iters_total = k_chunks * p.taps;
 
   uint32_t tmem_cols = 32;
   while (tmem_cols < static_cast<uint32_t>(2 * bn)) tmem_cols <<= 1;
@@ -71,7 +72,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
-    if (p.epi != EPI_F32_SPLIT) tma_prefetch_desc(&map_d);
+    if (p.epi != EPI_F32_SPLIT && p.epi != EPI_ATOMIC_F32) tma_prefetch_desc(&map_d);
     for (int i = 0; i < stages; ++i) {
       mbar_init(&ctl->full[i], 1);
       mbar_init(&ctl->empty[i], 1);
@@ -97,26 +98,28 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int work = blockIdx.x; work < num_tiles; work += gridDim.x) {
+        const int ks = work % ksplit;
+        const int tile = work / ksplit;
         const int b = tile / tiles_per_batch;
         const int rem = tile - b * tiles_per_batch;
         const int mt = rem / n_tiles;
         const int nt = rem - mt * n_tiles;
         const int row0 = mt * BM;
         const int n0 = nt * bn;
-        for (int t = 0; t < p.taps; ++t) {
+        const int ki0 = (k_iters_total * ks) / ksplit, ki1 = (k_iters_total * (ks + 1)) / ksplit;
+        for (int ki = ki0; ki < ki1; ++ki) {
+          const int t = ki / k_chunks, kc = ki - t * k_chunks;
           const int arow = row0 + p.shifts[t];
-          for (int kc = 0; kc < k_chunks; ++kc) {
-            mbar_wait(&ctl->empty[s], ph ^ 1);
-            uint8_t* sa = smem + s * stage_bytes;
-            uint8_t* sb = sa + A_STAGE_BYTES;
-            mbar_arrive_expect_tx(&ctl->full[s], A_STAGE_BYTES + b_stage_bytes);
-            tma_load_3d(sa, &map_a, &ctl->full[s], kc * BK, arow, b);
-            tma_load_2d(sb, &map_b, &ctl->full[s], t * p.k_per_tap + kc * BK, n0);
-            if (++s == stages) {
-              s = 0;
-              ph ^= 1;
-            }
+          mbar_wait(&ctl->empty[s], ph ^ 1);
+          uint8_t* sa = smem + s * stage_bytes;
+          uint8_t* sb = sa + A_STAGE_BYTES;
+          mbar_arrive_expect_tx(&ctl->full[s], A_STAGE_BYTES + b_stage_bytes);
+          tma_load_3d(sa, &map_a, &ctl->full[s], kc * BK, arow, b);
+          tma_load_2d(sb, &map_b, &ctl->full[s], t * p.k_per_tap + kc * BK, n0);
+          if (++s == stages) {
+            s = 0;
+            ph ^= 1;
           }
         }
       }
@@ -127,9 +130,11 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     int s = 0;
     uint32_t ph = 0;
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int work = blockIdx.x; work < num_tiles; work += gridDim.x, ++it) {
       const int as = it & 1;
       const uint32_t aph = (it >> 1) & 1;
+      const int ks = work % ksplit;
+      const int k_iters = (k_iters_total * (ks + 1)) / ksplit - (k_iters_total * ks) / ksplit;
       mbar_wait(&ctl->tmem_empty[as], aph ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + as * bn;
@@ -164,7 +169,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     int it = 0;
     int st_buf = 0;
     uint32_t aux_ph[2] = {0, 0};
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int work = blockIdx.x; work < num_tiles; work += gridDim.x, ++it) {
+      const int tile = work / ksplit;
       const int b = tile / tiles_per_batch;
       const int rem = tile - b * tiles_per_batch;
       const int mt = rem / n_tiles;
@@ -188,7 +194,22 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       if (p.wp > 0) row_live = row_live && ((row % p.wp) < p.w_valid);
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * bn;
 
-      if (p.epi == EPI_F32_SPLIT) {
+      if (p.epi == EPI_ATOMIC_F32) {
+        float* orow = p.d0 + (static_cast<size_t>(b) * p.rows + row) * p.ld0 + n0;
+        for (int c0 = 0; c0 < bn; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32(t_addr + c0, v);
+          tmem_ld_wait();
+          if (row < p.rows) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(orow + c0 + 4 * j),
+                           "f"(__uint_as_float(v[4 * j])), "f"(__uint_as_float(v[4 * j + 1])),
+                           "f"(__uint_as_float(v[4 * j + 2])), "f"(__uint_as_float(v[4 * j + 3]))
+                           : "memory");
+          }
+        }
+      } else if (p.epi == EPI_F32_SPLIT) {
         for (int c0 = 0; c0 < bn; c0 += 16) {
           uint32_t v[16];
           tmem_ld_32x16(t_addr + c0, v);
@@ -334,7 +355,10 @@ static int g_num_sms = 0;
 int gemm_tn_launch(const GemmTnArgs& a, cudaStream_t stream) {
   if (a.k_per_tap % BK != 0 || a.bn % 16 != 0 || a.bn > 256 || a.bn < 16) return 1001;
   if (a.n_total % a.bn != 0) return 1002;
-  if (a.epi != EPI_F32_SPLIT && a.bn % 64 != 0) return 1003;
+  const bool f32_out = a.epi == EPI_F32_SPLIT || a.epi == EPI_ATOMIC_F32;
+  if (!f32_out && a.bn % 64 != 0) return 1003;
+  if (a.epi == EPI_ATOMIC_F32 && a.bn % 32 != 0) return 1006;
+  if (a.ksplit > 1 && a.epi != EPI_ATOMIC_F32) return 1007;
   if (a.taps < 1 || a.taps > 9) return 1004;
   if (g_num_sms == 0) {
     int dev = 0;
@@ -354,7 +378,7 @@ int gemm_tn_launch(const GemmTnArgs& a, cudaStream_t stream) {
     uint32_t box[2] = {BK, (uint32_t)a.bn};
     if (make_tmap_f16(&mb, a.B, 2, dims, str, box)) return 1011;
   }
-  if (a.epi != EPI_F32_SPLIT) {
+  if (!f32_out) {
     uint64_t dims[3] = {(uint64_t)a.n_total, (uint64_t)a.rows, (uint64_t)a.batch};
     uint64_t str[2] = {(uint64_t)a.ldd * 2, (uint64_t)a.d_batch_stride * 2};
     uint32_t box[3] = {64, BM, 1};
@@ -379,6 +403,7 @@ int gemm_tn_launch(const GemmTnArgs& a, cudaStream_t stream) {
   p.w_valid = a.w_valid;
   p.wp = a.wp;
   p.epi = a.epi;
+  p.ksplit = a.ksplit > 1 ? a.ksplit : 1;
   p.bias = a.bias;
   p.n_bias = a.n_bias;
   p.d0 = a.d0;
@@ -402,7 +427,7 @@ int gemm_tn_launch(const GemmTnArgs& a, cudaStream_t stream) {
     configured = 232448;
   }
   const int m_tiles = (a.rows + BM - 1) / BM;
-  const int num_tiles = m_tiles * (a.n_total / a.bn) * a.batch;
+  const int num_tiles = m_tiles * (a.n_total / a.bn) * a.batch * p.ksplit;
   int grid = num_tiles < g_num_sms ? num_tiles : g_num_sms;
   if (a.max_ctas > 0 && grid > a.max_ctas) grid = a.max_ctas;
   if (grid < 1) return 0;

@@ -10,6 +10,7 @@ enum GemmEpilogue {
   EPI_BIAS_F16 = 1,       // D = acc + bias -> fp16
   EPI_F32_SPLIT = 2,      // acc + bias -> fp32, columns [0,split) to d0, [split,n_valid) to d1
   EPI_MASK_F16 = 3,       // D = (aux > 0) ? acc : 0 -> fp16 (ReLU backward fused into dgrad)
+  EPI_ATOMIC_F32 = 4,     // split-K partial: d0[row][n] += acc (fp32 red.add), bias/activation applied later
 };
 
 struct GemmTnParams {
@@ -19,6 +20,7 @@ struct GemmTnParams {
   int w_valid, wp;
   int epi;
   int stages;
+  int ksplit;
   const float* bias;
   int n_bias;
   float* d0;
@@ -53,6 +55,7 @@ struct GemmTnArgs {
   int ld1;
   int split, n_valid;
   int max_ctas;  // 0 = one per SM
+  int ksplit;    // > 1 only with EPI_ATOMIC_F32
 };
 
 int gemm_tn_launch(const GemmTnArgs& a, cudaStream_t stream);

@@ -226,8 +226,8 @@ int gemm_wgrad_launch(const void* G, int64_t ldg, int64_t g_batch_stride, const 
   const int tiles = taps * (m_total / WG_BM) * (n_total / bn);
   const int total_chunks = ((rows + WG_BK - 1) / WG_BK) * batch;
   if (ksplit <= 0) {
-    ksplit = (2 * g_wg_sms + tiles - 1) / tiles;   // ~2 waves of CTAs
-    const int max_split = (total_chunks + 15) / 16;  // at least 16 k-iterations per CTA
+    ksplit = g_wg_sms / tiles;                       // aim at one full wave of CTAs
+    const int max_split = (total_chunks + 31) / 32;  // at least 32 k-iterations per CTA
     if (ksplit > max_split) ksplit = max_split;
     if (ksplit < 1) ksplit = 1;
   }

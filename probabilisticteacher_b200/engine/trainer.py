@@ -10,7 +10,7 @@ import random
 import torch
 import torch.distributed as dist
 
-from .._lib import call
+from .._lib import call, refresh_stream
 from ..modeling.meta_arch.rcnn import build_model
 from ..structures import Boxes, FreeInstances
 
@@ -108,7 +108,8 @@ class PTrainer:
             for k, v in inst.get_fields().items():
                 if k in ("gt_boxes", "pseudo_boxes"):
                     t = v.tensor * ratio
-                    t = t + t.new_tensor([x1, y1, x1, y1])
+                    t[:, 0::2] += x1
+                    t[:, 1::2] += y1
                     v = Boxes(t)
                 ni.set(k, v)
             nd["instances"] = ni
@@ -141,6 +142,7 @@ class PTrainer:
     # ------------------------------------------------------------------ the step (trainer.py:263-392)
     def run_step(self):
         assert self.model.training, "[PTrainer] model was changed to eval mode!"
+        refresh_stream()
         cfg = self.cfg
         label_data_q, label_data_k, unlabel_data_q, unlabel_data_k = next(self._data_loader_iter)
         record_dict = {}

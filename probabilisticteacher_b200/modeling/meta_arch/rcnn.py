@@ -16,7 +16,7 @@ import torch
 from torch import nn
 
 from ... import ops
-from ..._lib import call
+from ..._lib import call, refresh_stream
 from ...arena import ParamArena
 from ...structures import Boxes, FreeInstances
 from ..anchor_generator import ANCHOR_GENERATOR_REGISTRY
@@ -97,8 +97,15 @@ class GuassianGeneralizedRCNN(nn.Module):
 
     def attach_grads(self):
         """Makes every trainable parameter's .grad a view of the flat gradient arena."""
-        for (name, v, g, trainable), (_, p) in zip(self.arena.exposed_parameters(), super().named_parameters()):
-            if trainable and g is not None and (p.grad is None or p.grad.data_ptr() != g.data_ptr()):
+        pairs = getattr(self, "_grad_pairs", None)
+        if pairs is None:
+            pairs = []
+            for (name, v, g, trainable), (_, p) in zip(self.arena.exposed_parameters(), super().named_parameters()):
+                if trainable and g is not None:
+                    pairs.append((p, g))
+            self._grad_pairs = pairs
+        for p, g in pairs:
+            if p.grad is not g:
                 p.grad = g
 
     def zero_grad(self, set_to_none=False):
@@ -178,6 +185,7 @@ class GuassianGeneralizedRCNN(nn.Module):
 
     # ------------------------------------------------------------------ forward
     def forward(self, batched_inputs, branch="supervised", danchor=False, norm=False):
+        refresh_stream()
         if not self.training:
             return self.inference(batched_inputs)
         act, sizes, img_hw = self.preprocess_image(batched_inputs)
@@ -250,6 +258,7 @@ class GuassianGeneralizedRCNN(nn.Module):
     # ------------------------------------------------------------------ backward
     def _run_backward(self, fctx, g):
         """g = [g_loss_cls, g_loss_box_reg, g_loss_rpn_cls, g_loss_rpn_loc] device scalars."""
+        refresh_stream()
         self.attach_grads()
         feat = fctx["feat"]
         dfeat_roi = self.roi_heads.backward(fctx["roi"], g[0], g[1])

@@ -36,7 +36,9 @@ class GuassianROIHead(nn.Module):
         rows = x0.shape[0]
         p = "roi_heads.box_head."
         w1 = ar.hview(p + "fc1.weight").view(ar.fc_dim, -1)
-        h1 = ops.gemm_tn(x0.view(1, rows, -1), w1, epi=ops.EPI_BIAS_RELU, bias=ar.view(p + "fc1.bias"))
+        tiles = ((rows + 127) // 128) * (ar.fc_dim // 256)
+        ksplit = max(1, min(8, 148 // max(tiles, 1)))
+        h1 = ops.gemm_tn(x0.view(1, rows, -1), w1, epi=ops.EPI_BIAS_RELU, bias=ar.view(p + "fc1.bias"), ksplit=ksplit)
         h2 = ops.gemm_tn(h1, ar.hview(p + "fc2.weight"), epi=ops.EPI_BIAS_RELU, bias=ar.view(p + "fc2.bias"))
         scores, deltas = self.box_predictor(h2.view(rows, -1))
         return x0, h1.view(rows, -1), h2.view(rows, -1), scores, deltas

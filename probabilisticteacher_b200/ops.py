@@ -6,7 +6,7 @@ import torch
 
 from ._lib import call
 
-EPI_BIAS_RELU, EPI_BIAS, EPI_F32_SPLIT, EPI_MASK = 0, 1, 2, 3
+EPI_BIAS_RELU, EPI_BIAS, EPI_F32_SPLIT, EPI_MASK, EPI_ATOMIC = 0, 1, 2, 3, 4
 
 # fp16 activation in the flattened right-padded layout: t is [N, H*(W+1), C]
 FlatAct = namedtuple("FlatAct", ["t", "H", "W"])
@@ -39,7 +39,7 @@ def from_flat(a):
 
 # ------------------------------------------------------------------------------------------ GEMMs
 def gemm_tn(A, B, *, taps=1, shifts=None, bn=None, epi=EPI_BIAS, bias=None, out=None, aux=None,
-            w_valid=0, wp=0, d0=None, d1=None, split=0, n_valid=0, n_total=None):
+            w_valid=0, wp=0, d0=None, d1=None, split=0, n_valid=0, n_total=None, ksplit=1):
     """A: [batch, rows, K] fp16; B: [n_rows, taps*K] fp16. Returns out (fp16 [batch, rows, n_total]) or
     (d0, d1) for the fp32 split epilogue."""
     batch, rows, lda = A.shape
@@ -50,6 +50,16 @@ def gemm_tn(A, B, *, taps=1, shifts=None, bn=None, epi=EPI_BIAS, bias=None, out=
         bn = 256
         while n_total % bn:
             bn //= 2
+    if ksplit > 1:
+        # skinny problem: split the reduction over CTAs, reduce partials in fp32, then bias/act/cast
+        assert epi in (EPI_BIAS_RELU, EPI_BIAS) and aux is None
+        acc = torch.zeros(batch, rows, n_total, dtype=torch.float32, device=A.device)
+        call("ptb200_gemm_tn_f16", A, batch, rows, k, lda, rows * lda, taps, shifts, B, n_total, bn, EPI_ATOMIC, None,
+             0, None, 0, 0, None, 0, 0, acc, n_total, None, 0, 0, n_total, 0, ksplit)
+        if out is None:
+            out = torch.empty(batch, rows, n_total, dtype=torch.float16, device=A.device)
+        call("ptb200_bias_act_cast_f16", acc, bias, 1 if epi == EPI_BIAS_RELU else 0, batch * rows, n_total, out)
+        return out
     if epi == EPI_F32_SPLIT:
         if d0 is None:
             d0 = torch.empty(batch, rows, split, dtype=torch.float32, device=A.device)
@@ -62,7 +72,7 @@ def gemm_tn(A, B, *, taps=1, shifts=None, bn=None, epi=EPI_BIAS, bias=None, out=
         ld_d, dbs = out.shape[2], out.shape[1] * out.shape[2]
     call("ptb200_gemm_tn_f16", A, batch, rows, k, lda, rows * lda, taps, shifts, B, n_total, bn, epi, bias,
          0 if bias is None else bias.numel(), out, ld_d, dbs, aux, w_valid, wp, d0, split, d1,
-         n_valid - split, split, n_valid, 0)
+         n_valid - split, split, n_valid, 0, 1)
     return (d0, d1) if epi == EPI_F32_SPLIT else out
 
 

@@ -26,7 +26,7 @@ def _gemm(A, B, bias, epi, bn, taps=1, shifts=None, wv=0, wp=0, aux=None, n_vali
         ptr(A), batch, rows, k, ctypes.c_int64(lda), ctypes.c_int64(rows * lda), taps, sh, ptr(B),
         n_total, bn, epi, ptr(bias), 0 if bias is None else bias.numel(), ptr(D),
         ctypes.c_int64(n_total), ctypes.c_int64(rows * n_total), ptr(aux), wv, wp, ptr(d0),
-        split, ptr(d1), n_valid - split, split, n_valid, max_ctas, stream_ptr())
+        split, ptr(d1), n_valid - split, split, n_valid, max_ctas, 1, stream_ptr())
     check(rc, "gemm_tn")
     torch.cuda.synchronize()
     return (d0, d1) if epi == 2 else D
@@ -104,3 +104,15 @@ def test_mask_epilogue(cuda):
     D = _gemm(A, B, None, 3, 128, aux=aux)
     ref = (A.float() @ B.float().t()) * (aux > 0)
     assert _rel(D, ref) < 2e-3
+
+
+def test_split_k_fc(cuda):
+    from probabilisticteacher_b200 import ops
+    g = torch.Generator().manual_seed(21)
+    A = torch.randn(1, 300, 2048, generator=g).half().to(cuda)
+    B = (torch.randn(512, 2048, generator=g) / 45).half().to(cuda)
+    bias = torch.randn(512, generator=g).to(cuda)
+    D = ops.gemm_tn(A, B, epi=ops.EPI_BIAS_RELU, bias=bias, ksplit=4)
+    torch.cuda.synchronize()
+    ref = torch.relu(A[0].float() @ B.float().t() + bias)
+    assert _rel(D[0], ref) < 2e-3
