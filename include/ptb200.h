@@ -57,6 +57,12 @@ int ptb200_preprocess_im2col(const uint8_t* images, const int* hw_dev, int n, in
                              int64_t image_stride, const float* mean3_host, const float* std3_host,
                              void* out_f16, void* stream);
 
+/* Same pre-processing fused with the first VGG conv (vgg_block1.conv1, 3 -> 64, bias + ReLU): uint8 CHW
+ * images -> fp16 NHWC-flat [n][hmax*(wmax+1)][64]. wpack_f16 = weights [64][32] fp16, k = (ky*3+kx)*3+c. */
+int ptb200_conv1_u8_f16(const uint8_t* images, const int* hw_dev, int n, int hmax, int wmax,
+                        int64_t image_stride, const float* mean3_host, const float* std3_host,
+                        const void* wpack_f16, const float* bias, void* out_f16, void* stream);
+
 /* PTrainer.resize (pt/engine/trainer.py:557-590) for one CHW uint8 image: bilinear down-scale to
  * (dh, dw) pasted at (x1, y1) on a canvas filled with int(pixel_mean). */
 int ptb200_resize_paste_u8(const uint8_t* src, uint8_t* dst, int h, int w, int dh, int dw, int x1, int y1,

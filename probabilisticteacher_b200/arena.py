@@ -84,7 +84,7 @@ class ParamArena:
         self.C = C
         self.data = torch.zeros(self.total, dtype=torch.float32, device=self.device)
         self.half = torch.zeros(self.total, dtype=torch.float16, device=self.device)
-        self.conv1_half = torch.zeros(64, 64, dtype=torch.float16, device=self.device)
+        self.conv1_half = torch.zeros(64, 32, dtype=torch.float16, device=self.device)
         if with_grads:
             n = self.total - self.trainable_start
             self.grads = torch.zeros(n, dtype=torch.float32, device=self.device)
@@ -178,7 +178,7 @@ class ParamArena:
         the K-padded first conv, and (student only) the transposed operands of the data-gradient GEMMs."""
         call("ptb200_cast_f32_f16", self.data, self.half, self.total)
         w1 = self.view("backbone.vgg_block1.0.conv1.weight").view(64, 27)
-        call("ptb200_cast_pad_rows_f16", w1, self.conv1_half, 64, 27, 64)
+        call("ptb200_cast_pad_rows_f16", w1, self.conv1_half, 64, 27, 32)
         if dgrad is None:
             dgrad = self.dgrad_half is not None
         if dgrad:

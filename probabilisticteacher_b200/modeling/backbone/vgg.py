@@ -22,16 +22,12 @@ class VGG(nn.Module):
     def output_shape(self):
         return {"vgg_block5": dict(channels=self.arena.C, stride=16)}
 
-    def forward(self, im2col: ops.FlatAct, save=False):
-        """im2col: the K=64 operand of conv1_1 produced by ptb200_preprocess_im2col.
+    def forward(self, x: ops.FlatAct, save=False):
+        """x: output of vgg_block1.conv1 (+ReLU), produced from the uint8 images by the fused
+        pre-processing + first-conv kernel (see GuassianGeneralizedRCNN.preprocess_image).
         Returns ({"vgg_block5": FlatAct}, records) where records hold what backward needs."""
         ar = self.arena
         specs = ar.conv_specs
-        name0 = specs[0][0]
-        W = im2col.W
-        y = ops.gemm_tn(im2col.t, ar.conv1_half, epi=ops.EPI_BIAS_RELU, bias=ar.view(name0 + ".bias"), w_valid=W,
-                        wp=W + 1)
-        x = ops.FlatAct(y, im2col.H, im2col.W)
         records = []
         block = 1
         for name, cin, cout, trainable in specs[1:]:

@@ -123,7 +123,7 @@ class GuassianGeneralizedRCNN(nn.Module):
 
     def preprocess_image(self, batched_inputs):
         """d2 GeneralizedRCNN.preprocess_image + ImageList.from_tensors: normalise, zero-pad to the batch
-        max; emitted as the im2col operand of the first conv. Returns (FlatAct, image_sizes, img_hw)."""
+        max; fused with the first VGG conv (bias + ReLU). Returns (FlatAct C=64, image_sizes, img_hw)."""
         dev = self.device
         imgs = [x["image"] for x in batched_inputs]
         sizes = [tuple(i.shape[-2:]) for i in imgs]
@@ -140,7 +140,9 @@ class GuassianGeneralizedRCNN(nn.Module):
         batch = batch.contiguous()
         hw_i = torch.tensor(sizes, dtype=torch.int32).to(dev, non_blocking=True)
         img_hw = hw_i.to(torch.float32)
-        act = ops.preprocess_im2col(batch.view(len(imgs), -1), hw_i, H, W, self._mean, self._std)
+        name0 = self.arena.conv_specs[0][0]
+        act = ops.conv1_u8(batch.view(len(imgs), -1), hw_i, H, W, self._mean, self._std, self.arena.conv1_half,
+                           self.arena.view(name0 + ".bias"))
         return act, sizes, img_hw
 
     def _targets(self, instances):

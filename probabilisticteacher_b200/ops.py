@@ -111,6 +111,15 @@ def preprocess_im2col(images_u8, hw, hmax, wmax, mean, std):
     return FlatAct(out, hmax, wmax)
 
 
+def conv1_u8(images_u8, hw, hmax, wmax, mean, std, wpack, bias):
+    """Pre-processing + first VGG conv fused: uint8 images -> FlatAct with C = 64 (bias + ReLU applied)."""
+    N = hw.shape[0]
+    out = torch.empty(N, hmax * (wmax + 1), 64, dtype=torch.float16, device=images_u8.device)
+    call("ptb200_conv1_u8_f16", images_u8, hw, N, hmax, wmax, images_u8.stride(0), list(mean), list(std), wpack,
+         bias, out)
+    return FlatAct(out, hmax, wmax)
+
+
 def maxpool2x2(x: FlatAct):
     N, _, C = x.t.shape
     Ho, Wo = x.H // 2, x.W // 2

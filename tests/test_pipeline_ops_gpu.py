@@ -345,3 +345,26 @@ def test_ema_and_sgd(cuda):
     torch.cuda.synchronize()
     assert abs(float(ss.sqrt()) - float(norm)) < 1e-2
     assert torch.allclose(pd.cpu(), pp.detach(), atol=1e-5)
+
+
+def test_conv1_fused_preprocess(cuda):
+    from probabilisticteacher_b200 import ops
+    from probabilisticteacher_b200._lib import call
+    g = torch.Generator().manual_seed(14)
+    N, H, W = 2, 37, 53
+    img = torch.randint(0, 256, (N, 3, H, W), generator=g, dtype=torch.uint8)
+    w = torch.randn(64, 3, 3, 3, generator=g) * 0.05
+    b = torch.randn(64, generator=g)
+    mean, std = (103.53, 116.28, 123.675), (1.0, 1.0, 1.0)
+    wi = w.permute(0, 2, 3, 1).reshape(64, 27).contiguous().to(cuda)
+    wp = torch.zeros(64, 32, dtype=torch.float16, device=cuda)
+    call("ptb200_cast_pad_rows_f16", wi, wp, 64, 27, 32)
+    hw = torch.tensor([[H, W]] * N, dtype=torch.int32).to(cuda)
+    a = ops.conv1_u8(img.to(cuda).view(N, -1), hw, H, W, mean, std, wp, b.to(cuda))
+    torch.cuda.synchronize()
+    x = (img.float() - torch.tensor(mean).view(1, 3, 1, 1)).half().float()
+    ref = torch.relu(torch.nn.functional.conv2d(x, w.half().float(), b, padding=1))
+    got = a.t.reshape(N, H, W + 1, 64)
+    assert got[:, :, W].abs().max() == 0
+    r = got[:, :, :W].permute(0, 3, 1, 2).float().cpu()
+    assert (r - ref).abs().max() < 2e-3 * ref.abs().max()
