@@ -19,6 +19,7 @@
 //               or fp32 direct stores for the narrow head outputs)
 #include "ptx.cuh"
 #include "gemm_tn.h"
+#include <stdlib.h>
 
 namespace ptb {
 
@@ -35,10 +36,20 @@ struct SmemCtl {
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
   uint64_t aux_full[2];
+  uint64_t bres_full;
   uint32_t tmem_base;
   uint32_t pad;
 };
 
+// ROWWIN (3x3 convs with small Cout, where the tile is L2-bandwidth bound): a pipeline stage holds one
+// 136-row window of A (rows p0 + (ky-1)*Wp - 1 ...) shared by the three horizontal taps kx = 0..2 --
+// the taps are UMMA descriptors whose start address is offset by kx*128 B (SWIZZLE_128B is applied on
+// absolute shared-memory address bits, verified on B200 with csrc/exp_rowshift.cu) -- plus the three
+// B tiles of that filter row: 3x fewer A bytes through L2 than one box per tap.
+static constexpr int WIN_ROWS = 136;
+static constexpr int WIN_BYTES = WIN_ROWS * 128;  // 17408 = 17 * 1024
+
+template <bool ROWWIN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_d, const __grid_constant__ CUtensorMap map_aux,
@@ -47,12 +58,16 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   // carve: [stages x (A | B)] [2 x staging] [bias BN floats] [ctl]
   const int bn = p.bn;
   const int stages = p.stages;
-  const int b_stage_bytes = bn * BK * 2;
-  const int stage_bytes = A_STAGE_BYTES + b_stage_bytes;
+  const bool bres = ROWWIN && p.b_resident;
+  const int a_stage_bytes = ROWWIN ? WIN_BYTES : A_STAGE_BYTES;
+  const int b_stage_bytes = bres ? 0 : (ROWWIN ? 3 : 1) * bn * BK * 2;
+  const int stage_bytes = a_stage_bytes + b_stage_bytes;
+  constexpr int kStagingBufs = ROWWIN ? 1 : 2;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  uint8_t* staging = smem + stages * stage_bytes;
-  float* bias_s = reinterpret_cast<float*>(staging + 2 * STAGING_BYTES);
+  uint8_t* b_res = smem + stages * stage_bytes;                       // 9 * bn * 128 B when resident
+  uint8_t* staging = b_res + (bres ? 9 * bn * BK * 2 : 0);
+  float* bias_s = reinterpret_cast<float*>(staging + kStagingBufs * STAGING_BYTES);
   SmemCtl* ctl = reinterpret_cast<SmemCtl*>(bias_s + 256);
 
   const int warp = threadIdx.x >> 5;
@@ -64,7 +79,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const int ksplit = p.ksplit;
   const int num_tiles = tiles_per_batch * p.batch * ksplit;   // work items (tile x k-split)
   const int k_chunks = p.k_per_tap / BK;
-  const int k_iters_total = k_chunks * p.taps;
+  const int k_iters_total = k_chunks * (ROWWIN ? 3 : p.taps);
 
   uint32_t tmem_cols = 32;
   while (tmem_cols < static_cast<uint32_t>(2 * bn)) tmem_cols <<= 1;
@@ -82,6 +97,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       mbar_init(&ctl->tmem_empty[i], EPI_THREADS / 32);
       mbar_init(&ctl->aux_full[i], 1);
     }
+    mbar_init(&ctl->bres_full, 1);
     fence_mbar_init();
   }
   if (warp == 0) {
@@ -98,6 +114,10 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
+      if (bres) {
+        mbar_arrive_expect_tx(&ctl->bres_full, 9 * bn * BK * 2);
+        for (int ky = 0; ky < 3; ++ky) tma_load_3d(b_res + ky * 3 * bn * BK * 2, &map_b, &ctl->bres_full, 0, 0, ky * 3);
+      }
       for (int work = blockIdx.x; work < num_tiles; work += gridDim.x) {
         const int ks = work % ksplit;
         const int tile = work / ksplit;
@@ -110,13 +130,18 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int ki0 = (k_iters_total * ks) / ksplit, ki1 = (k_iters_total * (ks + 1)) / ksplit;
         for (int ki = ki0; ki < ki1; ++ki) {
           const int t = ki / k_chunks, kc = ki - t * k_chunks;
-          const int arow = row0 + p.shifts[t];
           mbar_wait(&ctl->empty[s], ph ^ 1);
           uint8_t* sa = smem + s * stage_bytes;
-          uint8_t* sb = sa + A_STAGE_BYTES;
-          mbar_arrive_expect_tx(&ctl->full[s], A_STAGE_BYTES + b_stage_bytes);
-          tma_load_3d(sa, &map_a, &ctl->full[s], kc * BK, arow, b);
-          tma_load_2d(sb, &map_b, &ctl->full[s], t * p.k_per_tap + kc * BK, n0);
+          uint8_t* sb = sa + a_stage_bytes;
+          mbar_arrive_expect_tx(&ctl->full[s], stage_bytes);
+          if (ROWWIN) {
+            // t = filter row ky: window starts one pixel left of the kx = 0 tap
+            tma_load_3d(sa, &map_a, &ctl->full[s], kc * BK, row0 + (t - 1) * p.wp - 1, b);
+            if (!bres) tma_load_3d(sb, &map_b, &ctl->full[s], kc * BK, n0, t * 3);
+          } else {
+            tma_load_3d(sa, &map_a, &ctl->full[s], kc * BK, row0 + p.shifts[t], b);
+            tma_load_2d(sb, &map_b, &ctl->full[s], t * p.k_per_tap + kc * BK, n0);
+          }
           if (++s == stages) {
             s = 0;
             ph ^= 1;
@@ -130,6 +155,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     int s = 0;
     uint32_t ph = 0;
     int it = 0;
+    if (bres) mbar_wait(&ctl->bres_full, 0);
     for (int work = blockIdx.x; work < num_tiles; work += gridDim.x, ++it) {
       const int as = it & 1;
       const uint32_t aph = (it >> 1) & 1;
@@ -143,13 +169,25 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         tc_fence_after();
         if (lane == 0) {
           const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
-          const uint32_t b_addr = a_addr + A_STAGE_BYTES;
+          // resident filter: stage index ki = filter row ky (single K chunk)
+          const uint32_t b_addr = bres ? smem_u32(b_res) + ki * 3 * bn * BK * 2 : a_addr + a_stage_bytes;
           const uint64_t da = umma_desc_sw128(a_addr, 16, 1024);
           const uint64_t db = umma_desc_sw128(b_addr, 16, 1024);
+          if (ROWWIN) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            // advancing 16 fp16 (32 B) along K inside the 128 B swizzle row = +2 in the >>4 field
-            umma_f16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (ki > 0 || k > 0) ? 1u : 0u);
+            for (int kx = 0; kx < 3; ++kx) {
+              const uint64_t dax = da + (128 >> 4) * kx;               // one pixel row further
+              const uint64_t dbx = db + ((bn * 128) >> 4) * kx;        // next tap's weight tile
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k)
+                umma_f16_ss(d_tmem, dax + 2 * k, dbx + 2 * k, idesc, (ki > 0 || kx > 0 || k > 0) ? 1u : 0u);
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) {
+              // advancing 16 fp16 (32 B) along K inside the 128 B swizzle row = +2 in the >>4 field
+              umma_f16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (ki > 0 || k > 0) ? 1u : 0u);
+            }
           }
           umma_commit(&ctl->empty[s]);
           if (ki == k_iters - 1) umma_commit(&ctl->tmem_full[as]);
@@ -234,7 +272,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           uint8_t* stg = staging + st_buf * STAGING_BYTES;
           uint8_t* auxb = stg;  // aux tile is loaded into the staging buffer itself
           // the TMA store that last read this staging buffer must have drained
-          if (et == 0) tma_store_wait_read<1>();
+          if (et == 0) {
+            if (kStagingBufs == 1) tma_store_wait_read<0>(); else tma_store_wait_read<1>();
+          }
           named_bar_sync(1, EPI_THREADS);
           if (p.epi == EPI_MASK_F16) {
             if (et == 0) {
@@ -292,7 +332,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             tma_store_3d(&map_d, stg, n0 + c0, row0, b);
             tma_store_commit();
           }
-          st_buf ^= 1;
+          if (kStagingBufs == 2) st_buf ^= 1;
         }
       }
       // this accumulator stage may now be overwritten by the MMA warp
@@ -365,14 +405,29 @@ int gemm_tn_launch(const GemmTnArgs& a, cudaStream_t stream) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
   }
+  // row-window mode: 3x3 conv tap pattern over the flattened rows and a narrow N tile (L2-bound case)
+  static int rowwin_opt = -1;
+  if (rowwin_opt < 0) {
+    const char* e = getenv("PTB200_ROWWIN");
+    rowwin_opt = (e == nullptr) ? 1 : atoi(e);
+  }
+  bool rowwin = rowwin_opt != 0 && a.taps == 9 && a.wp > 0 && a.bn <= 128 && !f32_out && a.ksplit <= 1;
+  if (rowwin)
+    for (int t = 0; t < 9; ++t) rowwin = rowwin && a.shifts[t] == (t / 3 - 1) * a.wp + (t % 3 - 1);
   CUtensorMap ma, mb, md, mx;
   {
     uint64_t dims[3] = {(uint64_t)a.k_per_tap, (uint64_t)a.rows, (uint64_t)a.batch};
     uint64_t str[2] = {(uint64_t)a.lda * 2, (uint64_t)a.a_batch_stride * 2};
-    uint32_t box[3] = {BK, BM, 1};
+    uint32_t box[3] = {BK, (uint32_t)(rowwin ? WIN_ROWS : BM), 1};
     if (make_tmap_f16(&ma, a.A, 3, dims, str, box)) return 1010;
   }
-  {
+  if (rowwin) {
+    // B viewed as [tap][n][k] so that one box brings the three taps of a filter row
+    uint64_t dims[3] = {(uint64_t)a.k_per_tap, (uint64_t)a.n_total, 9};
+    uint64_t str[2] = {(uint64_t)a.k_per_tap * 9 * 2, (uint64_t)a.k_per_tap * 2};
+    uint32_t box[3] = {BK, (uint32_t)a.bn, 3};
+    if (make_tmap_f16(&mb, a.B, 3, dims, str, box)) return 1011;
+  } else {
     uint64_t dims[2] = {(uint64_t)a.k_per_tap * a.taps, (uint64_t)a.n_total};
     uint64_t str[1] = {(uint64_t)a.k_per_tap * a.taps * 2};
     uint32_t box[2] = {BK, (uint32_t)a.bn};
@@ -412,26 +467,35 @@ int gemm_tn_launch(const GemmTnArgs& a, cudaStream_t stream) {
   p.ld1 = a.ld1;
   p.split = a.split;
   p.n_valid = a.n_valid;
-  const int stage_bytes = A_STAGE_BYTES + a.bn * BK * 2;
-  const int fixed = 2 * STAGING_BYTES + 256 * 4 + (int)sizeof(SmemCtl) + 1024;
+  // keep the whole filter resident when every CTA uses the same one (single N tile, single K chunk)
+  const bool bres = rowwin && a.n_total == a.bn && a.k_per_tap == BK;
+  p.b_resident = bres ? 1 : 0;
+  const int stage_bytes = rowwin ? WIN_BYTES + (bres ? 0 : 3 * a.bn * BK * 2) : A_STAGE_BYTES + a.bn * BK * 2;
+  const int fixed = (rowwin ? 1 : 2) * STAGING_BYTES + 256 * 4 + (int)sizeof(SmemCtl) + 1024 +
+                    (bres ? 9 * a.bn * BK * 2 : 0);
   int stages = (232448 - fixed) / stage_bytes;
   if (stages > 8) stages = 8;
   if (stages < 2) return 1005;
   p.stages = stages;
   const int smem_bytes = stages * stage_bytes + fixed;
-  static int configured = 0;
-  if (configured < smem_bytes) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          232448);
     if (e != cudaSuccess) return (int)e;
-    configured = 232448;
+    e = cudaFuncSetAttribute(gemm_tn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
   }
   const int m_tiles = (a.rows + BM - 1) / BM;
   const int num_tiles = m_tiles * (a.n_total / a.bn) * a.batch * p.ksplit;
   int grid = num_tiles < g_num_sms ? num_tiles : g_num_sms;
   if (a.max_ctas > 0 && grid > a.max_ctas) grid = a.max_ctas;
   if (grid < 1) return 0;
-  gemm_tn_kernel<<<grid, NUM_THREADS, smem_bytes, stream>>>(ma, mb, md, mx, p);
+  if (rowwin)
+    gemm_tn_kernel<true><<<grid, NUM_THREADS, smem_bytes, stream>>>(ma, mb, md, mx, p);
+  else
+    gemm_tn_kernel<false><<<grid, NUM_THREADS, smem_bytes, stream>>>(ma, mb, md, mx, p);
   return (int)cudaGetLastError();
 }
 

@@ -21,6 +21,7 @@ struct GemmTnParams {
   int epi;
   int stages;
   int ksplit;
+  int b_resident;  // ROWWIN only: whole 3x3 filter (9 x bn x 64) stays in shared memory
   const float* bias;
   int n_bias;
   float* d0;

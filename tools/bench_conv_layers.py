@@ -31,7 +31,10 @@ def main():
               ("3_2", 256, 256, 4), ("4_1", 256, 512, 8), ("4_2", 512, 512, 8), ("5_1", 512, 512, 16)]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     res = []
+    only = os.environ.get("LAYER")
     for name, cin, cout, div in layers:
+        if only and name != only:
+            continue
         H, W = H0 // div, W0 // div
         Wp = W + 1
         A = torch.randn(N, H * Wp, cin, device=dev).half()
@@ -57,6 +60,8 @@ def main():
         res.append(dict(layer=name, H=H, W=W, cin=cin, cout=cout, ms=ms, tflops=fl / ms / 1e9))
         print(res[-1], flush=True)
     # box head fc1: 4000 x 25088 x 1024
+    if only:
+        return
     for name, M, K, Nn in [("fc1_teacher", 4000, 25088, 1024), ("fc1_sup", 2048, 25088, 1024), ("fc2", 4000, 1024, 1024)]:
         A = torch.randn(1, M, K, device=dev).half()
         B = (torch.randn(Nn, K, device=dev) / K ** 0.5).half()
