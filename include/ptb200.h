@@ -131,7 +131,8 @@ int ptb200_rpn_topk_decode(const uint32_t* sorted_idx, int64_t idx_stride, const
 
 /* d2 batched_nms -> torchvision nms (proposal_utils.py:140, fast_rcnn.py:104): greedy NMS over the
  * candidates in `order` (descending score); class_mod > 0 restricts suppression to candidates with
- * equal (order value % class_mod). keep_idx holds positions in `order`. */
+ * equal (order value % class_mod). keep_idx holds positions in `order`. mask_scratch needs
+ * n * cap * roundup2(ceil(cap/64)) 64-bit words. */
 int ptb200_nms(const float* boxes, int64_t box_stride, const uint32_t* order, int64_t order_stride,
                const int* counts, int n, int cap, float thresh, int class_mod, int max_keep,
                unsigned long long* mask_scratch, int* keep_idx, int* keep_count, void* stream);

@@ -36,7 +36,7 @@ def build(force=False, verbose=False):
     for src in sources():
         obj = os.path.join(HERE, "build", os.path.basename(src)[:-3] + ".o")
         objs.append(obj)
-        cmd = [NVCC] + FLAGS + ["-c", src, "-o", obj]
+        cmd = [NVCC] + FLAGS + os.environ.get("PTB_EXTRA_FLAGS", "").split() + ["-c", src, "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
     failed = False
     for src, pr in procs:

@@ -227,8 +227,24 @@ colsum_f16_kernel(const __half* __restrict__ in, int64_t rows, int C, int64_t ld
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc[e] = 0.f;
     if (lane_r < rpb) {
-      for (int64_t r = static_cast<int64_t>(blockIdx.x) * rpb + lane_r; r < rows;
-           r += static_cast<int64_t>(gridDim.x) * rpb) {
+      const int64_t step = static_cast<int64_t>(gridDim.x) * rpb;
+      int64_t r = static_cast<int64_t>(blockIdx.x) * rpb + lane_r;
+      for (; r + 3 * step < rows; r += 4 * step) {
+        uint4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const uint4*>(in + (r + u * step) * ld + cb * 8);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const __half2* h = reinterpret_cast<const __half2*>(&v[u]);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 f = __half22float2(h[e]);
+            acc[2 * e] += f.x;
+            acc[2 * e + 1] += f.y;
+          }
+        }
+      }
+      for (; r < rows; r += step) {
         const uint4 v = *reinterpret_cast<const uint4*>(in + r * ld + cb * 8);
         const __half2* h = reinterpret_cast<const __half2*>(&v);
 #pragma unroll
@@ -393,8 +409,12 @@ extern "C" int ptb200_cast_pad_rows_f16(const float* src, void* dst, int rows, i
 extern "C" int ptb200_colsum_f16(const void* in, int64_t rows, int c, int64_t ld, float scale, float* out,
                                  void* stream) {
   if (c % 8 != 0) return 1202;
-  int blocks = static_cast<int>((rows + 63) / 64);
-  if (blocks > 148 * 4) blocks = 148 * 4;
+  // few, long-running CTAs: every CTA ends with one atomicAdd per channel, so the CTA count bounds
+  // the contention on the C output addresses
+  const int c8 = c / 8;
+  const int rpb = 256 / (c8 < 256 ? c8 : 256);  // rows per CTA iteration
+  int blocks = static_cast<int>(rows / (static_cast<int64_t>(rpb) * 4));
+  if (blocks > 148 * 2) blocks = 148 * 2;
   if (blocks < 1) blocks = 1;
   colsum_f16_kernel<<<blocks, 256, 0, STREAM>>>(static_cast<const __half*>(in), rows, c, ld, scale, out);
   return LAUNCH_OK();

@@ -10,6 +10,7 @@
 #include <math.h>
 #include <stdint.h>
 #include "../../include/ptb200.h"
+#include "ptx.cuh"
 
 namespace {
 
@@ -129,8 +130,8 @@ __global__ void rpn_topk_decode_kernel(const uint32_t* __restrict__ sorted_idx, 
 // NMS: 64x64 blocks of the (sorted) candidate list -> suppression bitmask, upper triangle only.
 __global__ void nms_bitmask_kernel(const float4* __restrict__ boxes, int64_t box_stride,
                                    const uint32_t* __restrict__ order, int64_t order_stride,
-                                   const int* __restrict__ counts, int cap, int words, float thr, int class_mod,
-                                   unsigned long long* __restrict__ mask) {
+                                   const int* __restrict__ counts, int cap, int words, int wstride, float thr,
+                                   int class_mod, unsigned long long* __restrict__ mask) {
   const int cb = blockIdx.x, rb = blockIdx.y, n = blockIdx.z;
   if (cb < rb) return;
   int cnt = counts[n];
@@ -172,85 +173,133 @@ __global__ void nms_bitmask_kernel(const float4* __restrict__ boxes, int64_t box
     else sup = __fdiv_rn(inter, uni) > thr;
     if (sup) bits |= 1ull << j;
   }
-  mask[(static_cast<int64_t>(n) * cap + i) * words + cb] = bits;
+  mask[(static_cast<int64_t>(n) * cap + i) * wstride + cb] = bits;
 }
 
-// Sequential part of NMS, one CTA (1024 threads) per image. Per 64-candidate block: blocks that are
-// already fully suppressed are skipped without any barrier; otherwise warp 0 loads the diagonal mask
-// block (lane l owns rows l and l+32) and resolves the 64 candidates with register shuffles, then all
-// threads OR the surviving rows into the running `removed` bit vector (4 row groups x 256 words,
-// 4 loads in flight per thread). Stops after max_keep survivors. keep_idx = positions in sorted order.
+// Sequential part of NMS, one CTA (1024 threads) per image. The mask rows of the NEXT 64-candidate
+// block are prefetched into shared memory (one cp.async.bulk per row, mbarrier completion) while the
+// current block is processed, so the per-block critical path only touches shared memory: one thread
+// walks the survivors of the block (ffs over the not-yet-suppressed bits, so the cost is per kept
+// box, bounded by max_keep overall), then all threads OR the surviving rows into the running
+// `removed` bit vector. Stops after max_keep survivors. keep_idx = positions in the sorted order.
+// PREFETCH = false (masks too wide for shared memory) reads the rows from global memory.
+#ifdef NMS_DEBUG
+__device__ long long g_nms_dbg[8];
+#define DBG_T(k) if (tid == 0) { const long long t_ = clock64(); g_nms_dbg[k] += t_ - t_last; t_last = t_; }
+#else
+#define DBG_T(k)
+#endif
+
+template <bool PREFETCH>
 __global__ void __launch_bounds__(1024, 1)
 nms_scan_kernel(const unsigned long long* __restrict__ mask, const int* __restrict__ counts, int cap, int words,
-                int max_keep, int* __restrict__ keep_idx, int* __restrict__ keep_count) {
-  extern __shared__ unsigned long long removed[];  // [words]
+                int wpad, int max_keep, int* __restrict__ keep_idx, int* __restrict__ keep_count) {
+  extern __shared__ __align__(16) unsigned long long sm[];
+  unsigned long long* removed = sm;                       // [wpad]
+  unsigned long long* rowbuf = sm + wpad;                 // [2][64][wpad] when PREFETCH
+  __shared__ uint64_t bar[2];
   __shared__ int s_rows[64];
   __shared__ int s_nk;
   __shared__ int s_total;
-  const int n = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+  const int n = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   int cnt = counts[n];
   if (cnt > cap) cnt = cap;
-  const unsigned long long* m = mask + static_cast<int64_t>(n) * cap * words;
-  for (int w = tid; w < words; w += blockDim.x) removed[w] = 0ull;
-  if (tid == 0) s_total = 0;
-  __syncthreads();
+  const unsigned long long* m = mask + static_cast<int64_t>(n) * cap * wpad;
+  for (int w = tid; w < wpad; w += blockDim.x) removed[w] = 0ull;
+  if (tid == 0) {
+    s_total = 0;
+    ptb::mbar_init(&bar[0], 1);
+    ptb::mbar_init(&bar[1], 1);
+    ptb::fence_mbar_init();
+  }
   const int nblk = (cnt + 63) / 64;
-  for (int b = 0; b < nblk; ++b) {
-    // uniform decisions from state that is stable since the last barrier
+  __syncthreads();
+
+  // warp 1: bulk-copies words [w0, wpad) (w0 even) of the 64 rows of block b into buffer `buf`
+  auto prefetch = [&](int b, int buf) {
+    if (b >= nblk) return;
+    const int w0 = b & ~1;
+    const uint32_t bytes = static_cast<uint32_t>(wpad - w0) * 8u;
+    const int live = min(64, cnt - b * 64);
+    if (lane == 0) ptb::mbar_arrive_expect_tx(&bar[buf], bytes * live);
+    __syncwarp();
+    for (int r = lane; r < live; r += 32)
+      ptb::bulk_load_1d(rowbuf + (static_cast<int64_t>(buf) * 64 + r) * wpad + w0,
+                        m + static_cast<int64_t>(b * 64 + r) * wpad + w0, bytes, &bar[buf]);
+  };
+  if (PREFETCH && warp == 1) prefetch(0, 0);
+#ifdef NMS_DEBUG
+  long long t_last = clock64();
+#endif
+  int b = 0;
+  for (; b < nblk; ++b) {
     if (s_total >= max_keep) break;
+    const int cur = b & 1;
+    if (PREFETCH) {
+      ptb::mbar_wait(&bar[cur], (b >> 1) & 1);
+      if (warp == 1) prefetch(b + 1, cur ^ 1);
+    }
+    DBG_T(0)
     const int live = min(64, cnt - b * 64);
     unsigned long long rem0 = removed[b];
     if (live < 64) rem0 |= ~0ull << live;
-    if (rem0 == ~0ull) continue;
-    if (tid < 32) {
-      const int r0 = b * 64 + lane, r1 = r0 + 32;
-      const unsigned long long d0 = r0 < cnt ? m[static_cast<int64_t>(r0) * words + b] : 0ull;
-      const unsigned long long d1 = r1 < cnt ? m[static_cast<int64_t>(r1) * words + b] : 0ull;
-      unsigned long long rem = rem0, keep = 0ull;
-#pragma unroll
-      for (int i = 0; i < 64; ++i) {
-        const unsigned long long di = __shfl_sync(0xffffffffu, i < 32 ? d0 : d1, i & 31);
-        if (!((rem >> i) & 1ull)) {
-          keep |= 1ull << i;
-          rem |= di;
+    if (rem0 != ~0ull) {
+      if (tid == 0) {
+        // one thread walks the survivors only: next = first zero bit of `rem` at or above i
+        unsigned long long rem = rem0;
+        const int total = s_total;
+        int k = 0;
+        unsigned long long avail = ~rem;
+        while (avail) {
+          const int i = __ffsll(static_cast<long long>(avail)) - 1;
+          unsigned long long di;
+          if (PREFETCH)
+            di = rowbuf[(static_cast<int64_t>(cur) * 64 + i) * wpad + b];
+          else
+            di = m[static_cast<int64_t>(b * 64 + i) * wpad + b];
+          s_rows[k] = i;
+          if (total + k < max_keep) keep_idx[n * max_keep + total + k] = b * 64 + i;
+          ++k;
+          rem |= di | (1ull << i);
+          avail = ~rem & ~((2ull << i) - 1ull);
+        }
+        s_nk = k;
+        s_total = total + k;
+      }
+      DBG_T(3)
+      __syncthreads();
+      DBG_T(4)
+      const int nk = s_nk;
+      if (b + 1 < words) {
+        const int g = tid >> 8;
+        for (int w0 = b + 1 + (tid & 255); w0 < words; w0 += 256) {
+          unsigned long long acc = 0ull;
+          if (PREFETCH) {
+            for (int j = g; j < nk; j += 4) acc |= rowbuf[(static_cast<int64_t>(cur) * 64 + s_rows[j]) * wpad + w0];
+          } else {
+            int j = g;
+            for (; j + 12 < nk; j += 16) {
+              const unsigned long long a0 = m[static_cast<int64_t>(b * 64 + s_rows[j]) * wpad + w0];
+              const unsigned long long a1 = m[static_cast<int64_t>(b * 64 + s_rows[j + 4]) * wpad + w0];
+              const unsigned long long a2 = m[static_cast<int64_t>(b * 64 + s_rows[j + 8]) * wpad + w0];
+              const unsigned long long a3 = m[static_cast<int64_t>(b * 64 + s_rows[j + 12]) * wpad + w0];
+              acc |= (a0 | a1) | (a2 | a3);
+            }
+            for (; j < nk; j += 4) acc |= m[static_cast<int64_t>(b * 64 + s_rows[j]) * wpad + w0];
+          }
+          if (acc) atomicOr(&removed[w0], acc);
         }
       }
-      const int total = s_total;
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int i = lane + 32 * h;
-        if ((keep >> i) & 1ull) {
-          const int pos = __popcll(keep & ((1ull << i) - 1ull));
-          s_rows[pos] = b * 64 + i;
-          if (total + pos < max_keep) keep_idx[n * max_keep + total + pos] = b * 64 + i;
-        }
-      }
-      __syncwarp();
-      if (lane == 0) {
-        s_nk = __popcll(keep);
-        s_total = total + __popcll(keep);
-      }
+      DBG_T(5)
     }
     __syncthreads();
-    const int nk = s_nk;
-    if (b + 1 < words) {
-      const int g = tid >> 8, w = b + 1 + (tid & 255);
-      for (int w0 = w; w0 < words; w0 += 256) {
-        unsigned long long acc = 0ull;
-        int j = g;
-        for (; j + 12 < nk; j += 16) {
-          const unsigned long long a0 = m[static_cast<int64_t>(s_rows[j]) * words + w0];
-          const unsigned long long a1 = m[static_cast<int64_t>(s_rows[j + 4]) * words + w0];
-          const unsigned long long a2 = m[static_cast<int64_t>(s_rows[j + 8]) * words + w0];
-          const unsigned long long a3 = m[static_cast<int64_t>(s_rows[j + 12]) * words + w0];
-          acc |= (a0 | a1) | (a2 | a3);
-        }
-        for (; j < nk; j += 4) acc |= m[static_cast<int64_t>(s_rows[j]) * words + w0];
-        if (acc) atomicOr(&removed[w0], acc);
-      }
-    }
-    __syncthreads();
+    DBG_T(6)
+#ifdef NMS_DEBUG
+    if (tid == 0) g_nms_dbg[7] += 1;
+#endif
   }
+  // the last prefetch (if any) may still be in flight: drain it before the CTA exits
+  if (PREFETCH && b < nblk) ptb::mbar_wait(&bar[b & 1], (b >> 1) & 1);
   if (tid == 0) keep_count[n] = min(s_total, max_keep);
 }
 
@@ -407,11 +456,22 @@ extern "C" int ptb200_nms(const float* boxes, int64_t box_stride, const uint32_t
                           const int* counts, int n, int cap, float thresh, int class_mod, int max_keep,
                           unsigned long long* mask_scratch, int* keep_idx, int* keep_count, void* stream) {
   const int words = (cap + 63) / 64;
+  const int wpad = (words + 1) & ~1;  // row stride of the mask in 64-bit words (16-byte aligned rows)
   dim3 grid(words, words, n);
   nms_bitmask_kernel<<<grid, 64, 0, STREAM>>>(reinterpret_cast<const float4*>(boxes), box_stride, order,
-                                             order_stride, counts, cap, words, thresh, class_mod, mask_scratch);
-  nms_scan_kernel<<<n, 1024, words * sizeof(unsigned long long), STREAM>>>(mask_scratch, counts, cap, words, max_keep,
-                                                                         keep_idx, keep_count);
+                                             order_stride, counts, cap, words, wpad, thresh, class_mod, mask_scratch);
+  const size_t smem_pf = (static_cast<size_t>(wpad) + 2ull * 64 * wpad) * sizeof(unsigned long long);
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(nms_scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    configured = true;
+  }
+  if (smem_pf <= 220 * 1024)
+    nms_scan_kernel<true><<<n, 1024, smem_pf, STREAM>>>(mask_scratch, counts, cap, words, wpad, max_keep, keep_idx,
+                                                       keep_count);
+  else
+    nms_scan_kernel<false><<<n, 1024, wpad * sizeof(unsigned long long), STREAM>>>(mask_scratch, counts, cap, words,
+                                                                                  wpad, max_keep, keep_idx, keep_count);
   return LAUNCH_OK();
 }
 
@@ -448,3 +508,12 @@ extern "C" int ptb200_roi_infer_gather(const float* cboxes, const float* cscores
       out_src_roi);
   return LAUNCH_OK();
 }
+
+#ifdef NMS_DEBUG
+extern "C" int ptb200_nms_debug_read(long long* host8) {
+  cudaMemcpyFromSymbol(host8, g_nms_dbg, sizeof(long long) * 8);
+  long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  cudaMemcpyToSymbol(g_nms_dbg, z, sizeof(z));
+  return 0;
+}
+#endif

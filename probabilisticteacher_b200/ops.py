@@ -154,7 +154,7 @@ def nms(boxes, order, counts, thresh, max_keep, class_mod=0):
     counts: int32 [N]. Returns keep_idx [N, max_keep] (positions in `order`), keep_count [N]."""
     N, cap = order.shape
     words = (cap + 63) // 64
-    mask = torch.empty(N * cap * words, dtype=torch.int64, device=boxes.device)
+    mask = torch.empty(N * cap * ((words + 1) // 2 * 2), dtype=torch.int64, device=boxes.device)
     keep_idx = torch.zeros(N, max_keep, dtype=I32, device=boxes.device)
     keep_count = torch.zeros(N, dtype=I32, device=boxes.device)
     call("ptb200_nms", boxes, boxes.shape[1], order, cap, counts, N, cap, float(thresh), class_mod, max_keep, mask,
