@@ -236,7 +236,7 @@ def timed_steps(trainer, steps, dist, device, read_losses=False, host_sink=None)
     e1 = torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):
-        losses = trainer.run_step()
+        losses = trainer.step()
         if read_losses:
             vec = torch.stack([losses[k].reshape(()) for k in sorted(losses)])
             host_sink.copy_(vec, non_blocking=False)
@@ -259,6 +259,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ptb200", choices=["ptb200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cuda-graph", action="store_true")
     ap.add_argument("--height", type=int, default=H_IMG)
     ap.add_argument("--width", type=int, default=W_IMG)
     args = ap.parse_args()
@@ -288,10 +289,11 @@ def main():
 
     pool_dev = synthetic_pool(2, PAIRS_PER_GPU, H, W, K, 1234 + 100 * rank, device=device)
     pool_host = synthetic_pool(2, PAIRS_PER_GPU, H, W, K, 1234 + 100 * rank, device=None, pin=True)
-    trainer = PTrainer(cfg, cycle(pool_dev), device=device, seed=0)
+    use_graph = not args.no_cuda_graph
+    trainer = PTrainer(cfg, cycle(pool_dev), device=device, seed=0, use_cuda_graph=use_graph)
 
-    for _ in range(warmup):
-        trainer.run_step()
+    for _ in range(warmup + (5 if use_graph else 0)):
+        trainer.step()
     torch.cuda.synchronize()
 
     # ---- device-resident arm
@@ -300,7 +302,7 @@ def main():
         clocks.start()
     l0 = _lib.launch_count[0]
     ms = timed_steps(trainer, args.steps, dist, device)
-    launches = (_lib.launch_count[0] - l0) // args.steps
+    launches = (_lib.launch_count[0] - l0) // args.steps  # eager launches; graph replays are counted below
     clk = clocks.stop() if rank == 0 else None
     ms_per_step = ms / args.steps
     value = world * 1000.0 / ms_per_step
@@ -308,7 +310,7 @@ def main():
     # ---- end-to-end arm: pinned host images in, loss scalars out, every step
     trainer._data_loader_iter = cycle(pool_host)
     host_sink = torch.empty(8, dtype=torch.float32).pin_memory()
-    trainer.run_step()
+    trainer.step()
     ms_e2e = timed_steps(trainer, args.steps, dist, device, read_losses=True, host_sink=host_sink)
     e2e_value = world * 1000.0 * args.steps / ms_e2e
     h2d = 4 * PAIRS_PER_GPU * 3 * H * W  # label_q, label_k, unlabel_q, unlabel_k uint8 images
@@ -318,7 +320,9 @@ def main():
     prof = GemmProfiler()
     _lib.profiler[0] = prof
     trainer._data_loader_iter = cycle(pool_dev)
-    trainer.run_step()
+    l1 = _lib.launch_count[0]
+    trainer.run_step()  # eager: every kernel is launched (and timed) individually
+    eager_launches = _lib.launch_count[0] - l1
     torch.cuda.synchronize()
     _lib.profiler[0] = None
     tot_f, tot_t, cnt = prof.summary()
@@ -361,7 +365,10 @@ def main():
                        "value_definition": "iterations/s summed over ranks (each rank runs one 2+2 iteration per step)"},
             "pairs_per_s": value * PAIRS_PER_GPU,
             "e2e": {"value": e2e_value, "unit": "iters/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": launches, "clocks": clk, "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "gpu_launches": eager_launches, "cuda_graph": use_graph,
+            "gpu_launches_note": "kernels of libptb200.so per step (counted on an eager step; in CUDA-graph mode the "
+                                 "same kernels are replayed from the captured graph)",
+            "clocks": clk, "roofline": roofline, "cpu_baseline": cpu_baseline,
         }
         print(json.dumps(line))
     if dist is not None:

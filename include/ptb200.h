@@ -68,6 +68,10 @@ int ptb200_conv1_u8_f16(const uint8_t* images, const int* hw_dev, int n, int hma
 int ptb200_resize_paste_u8(const uint8_t* src, uint8_t* dst, int h, int w, int dh, int dw, int x1, int y1,
                            int m0, int m1, int m2, void* stream);
 
+/* Same, with the geometry {dh, dw, x1, y1} read from device memory (CUDA-graph replay). */
+int ptb200_resize_paste_u8_dev(const uint8_t* src, uint8_t* dst, int h, int w, const int* params_dev, int m0,
+                               int m1, int m2, void* stream);
+
 /* F.max_pool2d(2, 2) of pt/modeling/backbone/vgg.py:59,71 (floor mode). */
 int ptb200_maxpool2x2_f16(const void* in, void* out, int n, int h, int w, int c, void* stream);
 

@@ -305,7 +305,14 @@ __global__ void add_f32_to_f16_kernel(const __half* __restrict__ a, const float*
 // PTrainer.resize (pt/engine/trainer.py:557-590) on device: bilinear down-scale (F.interpolate,
 // align_corners=False) pasted centred on a canvas filled with int(pixel_mean); float -> uint8 truncation.
 __global__ void resize_paste_u8_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int H, int W,
-                                       int dh, int dw, int x1, int y1, int m0, int m1, int m2) {
+                                       int dh, int dw, int x1, int y1, int m0, int m1, int m2,
+                                       const int* __restrict__ params_dev) {
+  if (params_dev != nullptr) {  // geometry supplied from device memory (CUDA-graph replay friendly)
+    dh = params_dev[0];
+    dw = params_dev[1];
+    x1 = params_dev[2];
+    y1 = params_dev[3];
+  }
   const int total = 3 * H * W;
   const float sh = static_cast<float>(H) / dh, sw = static_cast<float>(W) / dw;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -437,7 +444,15 @@ extern "C" int ptb200_add_f32_to_f16(const void* a, const float* b, float scale,
 
 extern "C" int ptb200_resize_paste_u8(const uint8_t* src, uint8_t* dst, int h, int w, int dh, int dw, int x1,
                                       int y1, int m0, int m1, int m2, void* stream) {
-  resize_paste_u8_kernel<<<grid_for(3LL * h * w), kThreads, 0, STREAM>>>(src, dst, h, w, dh, dw, x1, y1, m0, m1, m2);
+  resize_paste_u8_kernel<<<grid_for(3LL * h * w), kThreads, 0, STREAM>>>(src, dst, h, w, dh, dw, x1, y1, m0, m1, m2,
+                                                                        nullptr);
+  return LAUNCH_OK();
+}
+
+extern "C" int ptb200_resize_paste_u8_dev(const uint8_t* src, uint8_t* dst, int h, int w, const int* params_dev,
+                                          int m0, int m1, int m2, void* stream) {
+  resize_paste_u8_kernel<<<grid_for(3LL * h * w), kThreads, 0, STREAM>>>(src, dst, h, w, 1, 1, 0, 0, m0, m1, m2,
+                                                                        params_dev);
   return LAUNCH_OK();
 }
 

@@ -29,7 +29,8 @@ def warmup_multistep_lr(base_lr, it, steps, gamma, warmup_factor, warmup_iters, 
 
 
 class PTrainer:
-    def __init__(self, cfg, data_loader_iter, device=None, seed=0, loss_scale=1024.0):
+    def __init__(self, cfg, data_loader_iter, device=None, seed=0, loss_scale=1024.0, use_cuda_graph=False,
+                 graph_warmup=3, gt_capacity=64):
         self.cfg = cfg
         self.device = torch.device(device or "cuda")
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
@@ -52,6 +53,13 @@ class PTrainer:
         self._sumsq = torch.zeros(1, dtype=torch.float32, device=self.device)
         self._pix = [int(x) for x in cfg.MODEL.PIXEL_MEAN]
         self.last_losses = None
+        # CUDA-graph mode: the whole forward/backward part of the step is captured once and replayed;
+        # inputs are staged into persistent device buffers, only the all-reduce + optimizer stay eager
+        self.use_cuda_graph = use_cuda_graph
+        self._graph = None
+        self._graph_warmup = graph_warmup
+        self._gt_capacity = gt_capacity
+        self._static = None
 
     # ------------------------------------------------------------------ pseudo-labelling (trainer.py:179-257)
     def threshold_bbox(self, proposal_bbox_inst, proposal_type="roih"):
@@ -112,6 +120,29 @@ class PTrainer:
                     t[:, 1::2] += y1
                     v = Boxes(t)
                 ni.set(k, v)
+            nd["instances"] = ni
+            out.append(nd)
+        return out
+
+    def resize_dev(self, data, params_dev, ratio_dev):
+        """`resize` with the random geometry held in device memory: params_dev int32 [n, 4] =
+        (d_h, d_w, x1, y1), ratio_dev float32 [n]. Used by the CUDA-graph step (replay-safe)."""
+        out = []
+        for k, d in enumerate(data):
+            img = d["image"]
+            h, w = img.shape[-2], img.shape[-1]
+            dst = torch.empty_like(img)
+            call("ptb200_resize_paste_u8_dev", img, dst, h, w, params_dev[k], self._pix[0], self._pix[1], self._pix[2])
+            nd = dict(d)
+            nd["image"] = dst
+            inst = d["instances"]
+            ni = FreeInstances(inst.image_size)
+            ni._count = getattr(inst, "_count", None)
+            shift = params_dev[k, 2:4].to(torch.float32).repeat(2)  # (x1, y1, x1, y1)
+            for key, v in inst.get_fields().items():
+                if key in ("gt_boxes", "pseudo_boxes"):
+                    v = Boxes(v.tensor * ratio_dev[k] + shift)
+                ni.set(key, v)
             nd["instances"] = ni
             out.append(nd)
         return out
@@ -186,6 +217,150 @@ class PTrainer:
         self.iter += 1
         return self.last_losses
 
+    # ------------------------------------------------------------------ CUDA-graph step
+    def _make_static(self, data):
+        """Persistent device buffers for one step's inputs (same shapes every step)."""
+        lq, lk, uq, uk = data
+        dev = self.device
+        cap = self._gt_capacity
+        st = {"groups": {}, "n": {}}
+        for name, grp, labelled in (("lq", lq, True), ("lk", lk, True), ("uq", uq, False), ("uk", uk, False)):
+            n = len(grp)
+            h, w = grp[0]["image"].shape[-2:]
+            g = {"images": torch.empty(n, 3, h, w, dtype=torch.uint8, device=dev)}
+            if labelled:
+                g["gt_boxes"] = torch.zeros(n, cap, 4, dtype=torch.float32, device=dev)
+                g["gt_boxes"][..., 2:] = 1.0
+                g["gt_classes"] = torch.zeros(n, cap, dtype=torch.int32, device=dev)
+                g["gt_count"] = torch.zeros(n, dtype=torch.int32, device=dev)
+                g["pin_boxes"] = torch.zeros(n, cap, 4, dtype=torch.float32).pin_memory()
+                g["pin_classes"] = torch.zeros(n, cap, dtype=torch.int32).pin_memory()
+                g["pin_count"] = torch.zeros(n, dtype=torch.int32).pin_memory()
+            st["groups"][name] = g
+        nq = len(lq) + len(uq)
+        st["resize_params"] = torch.zeros(nq, 4, dtype=torch.int32, device=dev)
+        st["resize_ratio"] = torch.ones(nq, dtype=torch.float32, device=dev)
+        st["pin_params"] = torch.zeros(nq, 4, dtype=torch.int32).pin_memory()
+        st["pin_ratio"] = torch.ones(nq, dtype=torch.float32).pin_memory()
+        return st
+
+    def _stage(self, data):
+        """Copies one step's host inputs into the persistent device buffers (outside the graph)."""
+        st = self._static
+        cap = self._gt_capacity
+        for name, grp in zip(("lq", "lk", "uq", "uk"), data):
+            g = st["groups"][name]
+            for k, d in enumerate(grp):
+                g["images"][k].copy_(d["image"], non_blocking=True)
+            if "gt_boxes" in g:
+                g["pin_boxes"].zero_()
+                g["pin_boxes"][..., 2:] = 1.0
+                for k, d in enumerate(grp):
+                    inst = d["instances"]
+                    m = len(inst.gt_boxes)
+                    if m > cap:
+                        raise ValueError(f"{m} gt boxes exceed gt_capacity={cap}")
+                    g["pin_boxes"][k, :m] = inst.gt_boxes.tensor
+                    g["pin_classes"][k, :m] = inst.gt_classes.to(torch.int32)
+                    g["pin_count"][k] = m
+                g["gt_boxes"].copy_(g["pin_boxes"], non_blocking=True)
+                g["gt_classes"].copy_(g["pin_classes"], non_blocking=True)
+                g["gt_count"].copy_(g["pin_count"], non_blocking=True)
+        # PTrainer.resize geometry (trainer.py:561-566). Draw order as in run_step (unlabel_q first, then
+        # label_q: trainer.py:333-334); storage order: label_q rows first, then unlabel_q rows.
+        nl = len(data[0])
+        for grp, base in ((data[2], nl), (data[0], 0)):
+            for j, d in enumerate(grp):
+                h, w = d["image"].shape[-2:]
+                ratio = self.rng.uniform(0.5, 1.0)
+                d_h, d_w = int(h * ratio), int(w * ratio)
+                k = base + j
+                st["pin_params"][k, 0] = d_h
+                st["pin_params"][k, 1] = d_w
+                st["pin_params"][k, 2] = int((w - d_w) / 2)
+                st["pin_params"][k, 3] = int((h - d_h) / 2)
+                st["pin_ratio"][k] = ratio
+        st["resize_params"].copy_(st["pin_params"], non_blocking=True)
+        st["resize_ratio"].copy_(st["pin_ratio"], non_blocking=True)
+
+    def _static_batches(self):
+        st = self._static
+        out = {}
+        for name, g in st["groups"].items():
+            n, _, h, w = g["images"].shape
+            batch = []
+            for k in range(n):
+                d = {"image": g["images"][k], "height": h, "width": w}
+                if "gt_boxes" in g:
+                    inst = FreeInstances((h, w), gt_boxes=Boxes(g["gt_boxes"][k]), gt_classes=g["gt_classes"][k])
+                    inst._count = g["gt_count"][k]
+                    d["instances"] = inst
+                batch.append(d)
+            out[name] = batch
+        return out
+
+    def _graph_body(self):
+        """The capturable part of the post-burn-in step (pt/engine/trainer.py:291-384): EMA, teacher
+        pass, pseudo labels, resize, both student passes, backward. No host<->device traffic."""
+        cfg = self.cfg
+        st = self._static
+        b = self._static_batches()
+        nl = len(b["lq"])
+        self.model.zero_grad()
+        self._update_teacher_model(keep_rate=cfg.UNSUPNET.EMA_KEEP_RATE)
+        with torch.no_grad():
+            _, _, roih, _ = self.model_teacher(b["uk"], branch="unsup_data_weak")
+        pseudo, _ = self.process_pseudo_label(roih, "roih", "all")
+        uq = self.add_label([dict(d) for d in b["uq"]], pseudo)
+        uq = self.resize_dev(uq, st["resize_params"][nl:], st["resize_ratio"][nl:])
+        lq = self.resize_dev(b["lq"], st["resize_params"][:nl], st["resize_ratio"][:nl])
+        rec = {}
+        rec_l, _, _, _ = self.model(lq + b["lk"], branch="supervised")
+        for k, v in rec_l.items():
+            rec[k + "_sup"] = v
+        rec_u, _, _, _ = self.model(uq, branch="unsupervised", danchor=True)
+        for k, v in rec_u.items():
+            rec[k + "_unsup"] = v
+        total = 0
+        for k, v in rec.items():
+            wgt = cfg.UNSUPNET.SOURCE_LOSS_WEIGHT if k.endswith("_sup") else cfg.UNSUPNET.TARGET_UNSUP_LOSS_WEIGHT
+            total = total + v * wgt
+        total.backward()
+        return {k: v.detach() for k, v in rec.items()}
+
+    def run_step_graphed(self):
+        """Post-burn-in step with the forward/backward part replayed from a CUDA graph."""
+        assert self.iter > self.cfg.UNSUPNET.BURN_UP_STEP, "graph mode covers the steady-state (EMA) iterations"
+        refresh_stream()
+        data = next(self._data_loader_iter)
+        if self._static is None:
+            self._static = self._make_static(data)
+        self._stage(data)
+        if self._graph is None:
+            if self._graph_warmup > 0:  # eager warm-up on the static buffers (allocator, lazy inits)
+                self._graph_warmup -= 1
+                self.last_losses = self._graph_body()
+            else:
+                torch.cuda.synchronize()
+                self._graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self._graph):
+                    self._graph_losses = self._graph_body()
+                refresh_stream()
+                self._graph.replay()
+                self.last_losses = self._graph_losses
+        else:
+            self._graph.replay()
+            self.last_losses = self._graph_losses
+        refresh_stream()
+        self._optimizer_step(10.0)
+        self.iter += 1
+        return self.last_losses
+
+    def step(self):
+        if self.use_cuda_graph and self.iter > self.cfg.UNSUPNET.BURN_UP_STEP:
+            return self.run_step_graphed()
+        return self.run_step()
+
     def train(self, num_iters):
         for _ in range(num_iters):
-            self.run_step()
+            self.step()

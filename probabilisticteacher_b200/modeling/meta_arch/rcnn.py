@@ -74,6 +74,7 @@ class GuassianGeneralizedRCNN(nn.Module):
         self._pending = 0
         self.prio_generator = None
         self.prio_override = None  # tests inject {tag: (prio_pos, prio_neg)}
+        self._hw_cache = {}
         self.launch_count = 0
 
     # ------------------------------------------------------------------ nn.Module surface
@@ -138,8 +139,13 @@ class GuassianGeneralizedRCNN(nn.Module):
             for k, i in enumerate(imgs):
                 batch[k, :i.numel()] = i.reshape(-1)
         batch = batch.contiguous()
-        hw_i = torch.tensor(sizes, dtype=torch.int32).to(dev, non_blocking=True)
-        img_hw = hw_i.to(torch.float32)
+        key = tuple(sizes)
+        cached = self._hw_cache.get(key)
+        if cached is None:  # (cached so that a CUDA-graph capture never sees a host->device copy here)
+            hw_i = torch.tensor(sizes, dtype=torch.int32).to(dev)
+            cached = (hw_i, hw_i.to(torch.float32))
+            self._hw_cache[key] = cached
+        hw_i, img_hw = cached
         name0 = self.arena.conv_specs[0][0]
         act = ops.conv1_u8(batch.view(len(imgs), -1), hw_i, H, W, self._mean, self._std, self.arena.conv1_half,
                            self.arena.view(name0 + ".bias"))
@@ -150,7 +156,20 @@ class GuassianGeneralizedRCNN(nn.Module):
         dev = self.device
         N = len(instances)
         t = {}
-        if instances[0].has("gt_boxes"):
+        if instances[0].has("gt_boxes") and instances[0].gt_boxes.tensor.is_cuda:
+            # device-resident ground truth (fixed capacity + device count): no host traffic
+            cap = max(len(i.gt_boxes) for i in instances)
+            t["gt_boxes"] = torch.stack([i.gt_boxes.tensor for i in instances]) if all(
+                len(i.gt_boxes) == cap for i in instances) else None
+            assert t["gt_boxes"] is not None, "device-resident gt must share one capacity"
+            t["gt_classes"] = torch.stack([i.gt_classes.to(torch.int32) for i in instances])
+            cnts = []
+            for i in instances:
+                c = i.valid_count() if isinstance(i, FreeInstances) else None
+                cnts.append(c.reshape(1).to(torch.int32) if c is not None else
+                            torch.full((1,), len(i.gt_boxes), dtype=torch.int32, device=dev))
+            t["gt_count"] = torch.cat(cnts)
+        elif instances[0].has("gt_boxes"):
             cnt = [len(i.gt_boxes) for i in instances]
             cap = max(16, (max(cnt) + 15) // 16 * 16)
             gb = torch.zeros(N, cap, 4, dtype=torch.float32)
