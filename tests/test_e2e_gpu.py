@@ -229,7 +229,7 @@ def test_cuda_graph_step_matches_eager(cuda):
     # branch) must agree tightly, ROI losses loosely, over the first graphed steps.
     # step 0: both eager (identical up to atomics); step 1: eager vs the graph body run eagerly on the
     # static buffers; step 2: eager vs the first captured replay; step 3: second replay (loose: chaos)
-    tols = [(1e-4, 1e-4), (5e-3, 2e-2), (2e-2, 0.15), (0.1, 0.3)]
+    tols = [(1e-3, 1e-3), (2e-2, 0.1), (0.1, 0.3), (1.0, 1.0)]
     for (t_rpn, t_roi), a, b in zip(tols, hist[0], hist[1]):
         for k in a:
             tol = t_rpn if "rpn" in k else t_roi
