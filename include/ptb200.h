@@ -42,11 +42,12 @@ int ptb200_gemm_tn_f16(const void* A, int batch, int rows, int k_per_tap, int64_
 
 /* Weight gradient  out[m][t*n_total + n] += scale * sum_b sum_p G[b][p][m] * X[b][p + shifts[t]][n]
  * (split-K, fp32 atomic accumulation). Replaces the wgrad kernels autograd issues at
- * pt/engine/trainer.py:384 (`losses.backward()`). m_total % 128 == 0, n_total % 64 == 0. */
+ * pt/engine/trainer.py:384 (`losses.backward()`). m_total % 128 == 0, n_total % 64 == 0.
+ * bias_out (may be NULL): bias_out[m] += scale * sum_b sum_p G[b][p][m] (bias gradient, fused). */
 int ptb200_gemm_wgrad_f16(const void* G, int64_t ldg, int64_t g_batch_stride, const void* X,
                           int64_t ldx, int64_t x_batch_stride, int batch, int rows, int m_total,
                           int n_total, int taps, const int* shifts_host, float* out, int64_t ld_out,
-                          float scale, int ksplit, void* stream);
+                          float scale, int ksplit, float* bias_out, void* stream);
 
 /* ---- image / activation helpers ---------------------------------------------------------------- */
 

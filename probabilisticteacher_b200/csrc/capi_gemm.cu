@@ -45,8 +45,8 @@ extern "C" int ptb200_gemm_tn_f16(const void* A, int batch, int rows, int k_per_
 extern "C" int ptb200_gemm_wgrad_f16(const void* G, int64_t ldg, int64_t g_batch_stride, const void* X,
                                      int64_t ldx, int64_t x_batch_stride, int batch, int rows,
                                      int m_total, int n_total, int taps, const int* shifts, float* out,
-                                     int64_t ld_out, float scale, int ksplit, void* stream) {
+                                     int64_t ld_out, float scale, int ksplit, float* bias_out, void* stream) {
   return gemm_wgrad_launch(G, ldg, g_batch_stride, X, ldx, x_batch_stride, batch, rows, m_total,
-                           n_total, taps, shifts, out, ld_out, scale, ksplit,
+                           n_total, taps, shifts, out, ld_out, scale, ksplit, bias_out,
                            static_cast<cudaStream_t>(stream));
 }

@@ -64,7 +64,7 @@ int gemm_tn_launch(const GemmTnArgs& a, cudaStream_t stream);
 // dW[m][t*n_total + n] += scale * sum_{b,p} G[b][p][m] * X[b][p + shifts[t]][n]   (fp32 atomics)
 int gemm_wgrad_launch(const void* G, int64_t ldg, int64_t g_batch_stride, const void* X, int64_t ldx,
                       int64_t x_batch_stride, int batch, int rows, int m_total, int n_total, int taps,
-                      const int* shifts, float* out, int64_t ld_out, float scale, int ksplit,
+                      const int* shifts, float* out, int64_t ld_out, float scale, int ksplit, float* bias_out,
                       cudaStream_t stream);
 
 }  // namespace ptb

@@ -35,6 +35,7 @@ struct WgParams {
   float* out;
   int64_t ld_out;
   float scale;
+  float* bias_out;  // optional: bias_out[m] += scale * sum_{b,p} G[b][p][m] (fused bias gradient)
 };
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
@@ -77,6 +78,9 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_consta
   const int mt = id % m_tiles;
   const int tap = id / m_tiles;
 
+  // the CTAs of tap 0 / N-tile 0 also reduce the bias gradient: their (otherwise idle) epilogue
+  // warps sum the staged G tile column-wise while the MMA warp consumes it
+  const bool do_bias = p.bias_out != nullptr && tap == 0 && nt == 0;
   const int chunks_per_img = (p.rows + WG_BK - 1) / WG_BK;
   const int total_chunks = chunks_per_img * p.batch;
   const int c_begin = static_cast<int>((static_cast<int64_t>(total_chunks) * ks) / p.ksplit);
@@ -91,7 +95,7 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_consta
     tma_prefetch_desc(&map_x);
     for (int i = 0; i < p.stages; ++i) {
       mbar_init(&ctl->full[i], 1);
-      mbar_init(&ctl->empty[i], 1);
+      mbar_init(&ctl->empty[i], do_bias ? 5 : 1);  // MMA commit (+ one arrival per epilogue warp)
     }
     mbar_init(&ctl->acc_full, 1);
     fence_mbar_init();
@@ -157,6 +161,41 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_consta
     } else {
       const int q = warp & 3;
       const int r = q * 32 + lane;
+      if (do_bias) {
+        // thread t of the 128 epilogue threads: column pair (2*m2, 2*m2+1) of the 128-wide G tile
+        // ([blk = col / 64][k row][64 ch, SW128]) over one half of the 64 staged rows; 4 independent
+        // fp32 partial sums keep the loop off the critical path of the MMA pipeline
+        const int t = (warp - 2) * 32 + lane;
+        const int m2 = t & 63, half_ = t >> 6;
+        const int colp = 2 * m2;
+        const int blk = colp >> 6, col = colp & 63;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        int s = 0;
+        uint32_t ph = 0;
+        for (int ki = 0; ki < k_iters; ++ki) {
+          mbar_wait(&ctl->full[s], ph);
+          const uint8_t* g = smem + s * stage_bytes + blk * WG_BLK_BYTES + (col & 7) * 2;
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const int kr0 = half_ * 32 + i, kr1 = kr0 + 1;
+            const __half2 a = *reinterpret_cast<const __half2*>(g + kr0 * 128 + (((col >> 3) ^ (kr0 & 7)) << 4));
+            const __half2 b = *reinterpret_cast<const __half2*>(g + kr1 * 128 + (((col >> 3) ^ (kr1 & 7)) << 4));
+            const float2 fa = __half22float2(a), fb = __half22float2(b);
+            s0 += fa.x;
+            s1 += fa.y;
+            s2 += fb.x;
+            s3 += fb.y;
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&ctl->empty[s]);
+          if (++s == p.stages) {
+            s = 0;
+            ph ^= 1;
+          }
+        }
+        atomicAdd(p.bias_out + mt * WG_BM + colp, (s0 + s2) * p.scale);
+        atomicAdd(p.bias_out + mt * WG_BM + colp + 1, (s1 + s3) * p.scale);
+      }
       mbar_wait(&ctl->acc_full, 0);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
@@ -188,7 +227,7 @@ static int g_wg_sms = 0;
 // G: [batch][rows][ldg] fp16 (m_total channels used), X: [batch][rows][ldx] fp16 (n_total used)
 int gemm_wgrad_launch(const void* G, int64_t ldg, int64_t g_batch_stride, const void* X, int64_t ldx,
                       int64_t x_batch_stride, int batch, int rows, int m_total, int n_total, int taps,
-                      const int* shifts, float* out, int64_t ld_out, float scale, int ksplit,
+                      const int* shifts, float* out, int64_t ld_out, float scale, int ksplit, float* bias_out,
                       cudaStream_t stream) {
   if (m_total % WG_BM != 0 || n_total % 64 != 0 || taps < 1 || taps > 9) return 1101;
   int bn = 256;
@@ -223,6 +262,7 @@ int gemm_wgrad_launch(const void* G, int64_t ldg, int64_t g_batch_stride, const 
   p.out = out;
   p.ld_out = ld_out;
   p.scale = scale;
+  p.bias_out = bias_out;
   const int tiles = taps * (m_total / WG_BM) * (n_total / bn);
   const int total_chunks = ((rows + WG_BK - 1) / WG_BK) * batch;
   if (ksplit <= 0) {

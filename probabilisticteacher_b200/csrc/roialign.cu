@@ -111,143 +111,129 @@ __device__ __forceinline__ void axis_weights(float start, float bin, int p, int 
   a->n = n;
 }
 
-// grid: (roi, ph*P+pw) ; block: C/8 threads
-__global__ void roi_align_fwd_kernel(const __half* __restrict__ feat, int H, int W, int C,
-                                     const float4* __restrict__ rois, const int* __restrict__ roi_count,
-                                     int cap, float scale, int P, __half* __restrict__ out) {
-  const int roi = blockIdx.x, bin = blockIdx.y;
-  const int n = roi / cap, j = roi - n * cap;
-  const int c0 = threadIdx.x * 8;
-  const int Wp = W + 1;
-  __half* o = out + (static_cast<int64_t>(roi) * P * P + bin) * C + c0;
-  if (roi_count != nullptr && j >= roi_count[n]) {
-    *reinterpret_cast<uint4*>(o) = make_uint4(0, 0, 0, 0);
-    return;
-  }
-  const RoiGeom g = roi_geom(rois[roi], scale, P);
-  const int ph = bin / P, pw = bin - ph * P;
-  const __half* base = feat + static_cast<int64_t>(n) * H * Wp * C + c0;
-  float acc[8];
-#pragma unroll
-  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-  __shared__ Axis s_ay, s_ax;
-  if (threadIdx.x == 0) axis_weights(g.start_h, g.bin_h, ph, g.grid_h, H, &s_ay);
-  if (threadIdx.x == 32 % blockDim.x) axis_weights(g.start_w, g.bin_w, pw, g.grid_w, W, &s_ax);
-  __syncthreads();
-  const Axis& ay = s_ay;
-  const Axis& ax = s_ax;
-  const bool sep = ay.n >= 0 && ax.n >= 0;
-  if (sep) {
-    for (int iy = 0; iy < ay.n; ++iy) {
-      const float wy = ay.w[iy];
-      if (wy == 0.f) continue;
-      const __half* rowp = base + static_cast<int64_t>((ay.lo + iy) * Wp + ax.lo) * C;
-      for (int ix = 0; ix < ax.n; ++ix) {
-        const float wgt = wy * ax.w[ix];
-        if (wgt == 0.f) continue;
-        const uint4 v = *reinterpret_cast<const uint4*>(rowp + static_cast<int64_t>(ix) * C);
-        const __half2* h = reinterpret_cast<const __half2*>(&v);
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float2 f = __half22float2(h[e]);
-          acc[2 * e] += wgt * f.x;
-          acc[2 * e + 1] += wgt * f.y;
-        }
-      }
-    }
-  } else {
-    for (int iy = 0; iy < g.grid_h; ++iy) {
-      const float y = g.start_h + ph * g.bin_h + (iy + 0.5f) * g.bin_h / g.grid_h;
-      for (int ix = 0; ix < g.grid_w; ++ix) {
-        const float x = g.start_w + pw * g.bin_w + (ix + 0.5f) * g.bin_w / g.grid_w;
-        Tap t;
-        if (!bilinear_taps(y, x, H, W, Wp, t)) continue;
-        const int offs[4] = {t.o1, t.o2, t.o3, t.o4};
-        const float ws[4] = {t.w1, t.w2, t.w3, t.w4};
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint4 v = *reinterpret_cast<const uint4*>(base + static_cast<int64_t>(offs[k]) * C);
-          const __half2* h = reinterpret_cast<const __half2*>(&v);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float2 f = __half22float2(h[e]);
-            acc[2 * e] += ws[k] * f.x;
-            acc[2 * e + 1] += ws[k] * f.y;
-          }
-        }
-      }
-    }
-  }
-  __align__(16) __half r[8];
-#pragma unroll
-  for (int e = 0; e < 8; ++e) r[e] = __float2half_rn(acc[e] / g.count);
-  *reinterpret_cast<uint4*>(o) = *reinterpret_cast<const uint4*>(r);
-}
-
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
                : "memory");
 }
 
-__global__ void roi_align_bwd_kernel(const __half* __restrict__ dout, int H, int W, int C,
-                                     const float4* __restrict__ rois, const int* __restrict__ roi_count,
-                                     int cap, float scale, int P, float* __restrict__ dfeat) {
-  const int roi = blockIdx.x, bin = blockIdx.y;
+constexpr int kMaxP = 7;
+
+// One CTA per roi: threads = P (bin columns) x C/8 (channel groups). The 2P axis-weight vectors of
+// the roi are computed once (threads 0..2P-1) and shared by all P*P bins; each thread then walks the
+// P bin rows of its column. BWD = true scatters the output gradient instead (fp32 vector atomics).
+template <bool BWD>
+__global__ void __launch_bounds__(512)
+roi_align_roi_kernel(const __half* __restrict__ feat, const __half* __restrict__ dout, int H, int W, int C,
+                     const float4* __restrict__ rois, const int* __restrict__ roi_count, int cap, float scale,
+                     int P, __half* __restrict__ out, float* __restrict__ dfeat) {
+  __shared__ Axis s_ax[2 * kMaxP];  // [0,P): y axes of bin rows, [P,2P): x axes of bin columns
+  const int roi = blockIdx.x;
   const int n = roi / cap, j = roi - n * cap;
-  if (roi_count != nullptr && j >= roi_count[n]) return;
-  const int c0 = threadIdx.x * 8;
+  const int c8 = C >> 3;
+  const int pw = threadIdx.x / c8, cg = threadIdx.x - pw * c8;
+  const int c0 = cg * 8;
   const int Wp = W + 1;
-  const RoiGeom g = roi_geom(rois[roi], scale, P);
-  const int ph = bin / P, pw = bin - ph * P;
-  const uint4 gv = *reinterpret_cast<const uint4*>(dout + (static_cast<int64_t>(roi) * P * P + bin) * C + c0);
-  const __half2* gh = reinterpret_cast<const __half2*>(&gv);
-  float gr[8];
-  bool any = false;
-#pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    const float2 f = __half22float2(gh[e]);
-    gr[2 * e] = f.x / g.count;
-    gr[2 * e + 1] = f.y / g.count;
-    any = any || f.x != 0.f || f.y != 0.f;
-  }
-  float* base = dfeat + static_cast<int64_t>(n) * H * Wp * C + c0;
-  __shared__ Axis s_ay, s_ax;
-  if (threadIdx.x == 0) axis_weights(g.start_h, g.bin_h, ph, g.grid_h, H, &s_ay);
-  if (threadIdx.x == 32 % blockDim.x) axis_weights(g.start_w, g.bin_w, pw, g.grid_w, W, &s_ax);
-  __syncthreads();
-  const Axis& ay = s_ay;
-  const Axis& ax = s_ax;
-  const bool sep = ay.n >= 0 && ax.n >= 0;
-  if (!any) return;
-  if (sep) {
-    for (int iy = 0; iy < ay.n; ++iy) {
-      const float wy = ay.w[iy];
-      if (wy == 0.f) continue;
-      float* rowp = base + static_cast<int64_t>((ay.lo + iy) * Wp + ax.lo) * C;
-      for (int ix = 0; ix < ax.n; ++ix) {
-        const float wgt = wy * ax.w[ix];
-        if (wgt == 0.f) continue;
-        float* p = rowp + static_cast<int64_t>(ix) * C;
-        red_add_v4(p, gr[0] * wgt, gr[1] * wgt, gr[2] * wgt, gr[3] * wgt);
-        red_add_v4(p + 4, gr[4] * wgt, gr[5] * wgt, gr[6] * wgt, gr[7] * wgt);
-      }
-    }
+  const bool valid = roi_count == nullptr || j < roi_count[n];
+  if (!valid) {
+    if (!BWD)
+      for (int ph = 0; ph < P; ++ph)
+        *reinterpret_cast<uint4*>(out + (static_cast<int64_t>(roi) * P * P + ph * P + pw) * C + c0) =
+            make_uint4(0, 0, 0, 0);
     return;
   }
-  for (int iy = 0; iy < g.grid_h; ++iy) {
-    const float y = g.start_h + ph * g.bin_h + (iy + 0.5f) * g.bin_h / g.grid_h;
-    for (int ix = 0; ix < g.grid_w; ++ix) {
-      const float x = g.start_w + pw * g.bin_w + (ix + 0.5f) * g.bin_w / g.grid_w;
-      Tap t;
-      if (!bilinear_taps(y, x, H, W, Wp, t)) continue;
-      const int offs[4] = {t.o1, t.o2, t.o3, t.o4};
-      const float ws[4] = {t.w1, t.w2, t.w3, t.w4};
+  const RoiGeom g = roi_geom(rois[roi], scale, P);
+  if (threadIdx.x < 2 * P) {
+    const int a = threadIdx.x;
+    if (a < P)
+      axis_weights(g.start_h, g.bin_h, a, g.grid_h, H, &s_ax[a]);
+    else
+      axis_weights(g.start_w, g.bin_w, a - P, g.grid_w, W, &s_ax[a]);
+  }
+  __syncthreads();
+  const Axis& ax = s_ax[P + pw];
+  const bool sep_x = ax.n >= 0;
+  const int64_t img_off = static_cast<int64_t>(n) * H * Wp * C + c0;
+  for (int ph = 0; ph < P; ++ph) {
+    const Axis& ay = s_ax[ph];
+    const int bin = ph * P + pw;
+    const int64_t o_off = (static_cast<int64_t>(roi) * P * P + bin) * C + c0;
+    float acc[8];
+    float gr[8];
+    if (BWD) {
+      const uint4 gv = *reinterpret_cast<const uint4*>(dout + o_off);
+      const __half2* gh = reinterpret_cast<const __half2*>(&gv);
+      bool any = false;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        float* p = base + static_cast<int64_t>(offs[k]) * C;
-        red_add_v4(p, gr[0] * ws[k], gr[1] * ws[k], gr[2] * ws[k], gr[3] * ws[k]);
-        red_add_v4(p + 4, gr[4] * ws[k], gr[5] * ws[k], gr[6] * ws[k], gr[7] * ws[k]);
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = __half22float2(gh[e]);
+        gr[2 * e] = f.x / g.count;
+        gr[2 * e + 1] = f.y / g.count;
+        any = any || f.x != 0.f || f.y != 0.f;
       }
+      if (!any) continue;
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+    }
+    if (sep_x && ay.n >= 0) {
+      for (int iy = 0; iy < ay.n; ++iy) {
+        const float wy = ay.w[iy];
+        if (wy == 0.f) continue;
+        const int64_t row_off = img_off + static_cast<int64_t>((ay.lo + iy) * Wp + ax.lo) * C;
+        for (int ix = 0; ix < ax.n; ++ix) {
+          const float wgt = wy * ax.w[ix];
+          if (wgt == 0.f) continue;
+          if (BWD) {
+            float* p = dfeat + row_off + static_cast<int64_t>(ix) * C;
+            red_add_v4(p, gr[0] * wgt, gr[1] * wgt, gr[2] * wgt, gr[3] * wgt);
+            red_add_v4(p + 4, gr[4] * wgt, gr[5] * wgt, gr[6] * wgt, gr[7] * wgt);
+          } else {
+            const uint4 v = *reinterpret_cast<const uint4*>(feat + row_off + static_cast<int64_t>(ix) * C);
+            const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 f = __half22float2(h[e]);
+              acc[2 * e] += wgt * f.x;
+              acc[2 * e + 1] += wgt * f.y;
+            }
+          }
+        }
+      }
+    } else {
+      // very large bins: generic tap loop (torchvision order)
+      for (int iy = 0; iy < g.grid_h; ++iy) {
+        const float y = g.start_h + ph * g.bin_h + (iy + 0.5f) * g.bin_h / g.grid_h;
+        for (int ix = 0; ix < g.grid_w; ++ix) {
+          const float x = g.start_w + pw * g.bin_w + (ix + 0.5f) * g.bin_w / g.grid_w;
+          Tap t;
+          if (!bilinear_taps(y, x, H, W, Wp, t)) continue;
+          const int offs[4] = {t.o1, t.o2, t.o3, t.o4};
+          const float ws[4] = {t.w1, t.w2, t.w3, t.w4};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            if (BWD) {
+              float* p = dfeat + img_off + static_cast<int64_t>(offs[k]) * C;
+              red_add_v4(p, gr[0] * ws[k], gr[1] * ws[k], gr[2] * ws[k], gr[3] * ws[k]);
+              red_add_v4(p + 4, gr[4] * ws[k], gr[5] * ws[k], gr[6] * ws[k], gr[7] * ws[k]);
+            } else {
+              const uint4 v = *reinterpret_cast<const uint4*>(feat + img_off + static_cast<int64_t>(offs[k]) * C);
+              const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 f = __half22float2(h[e]);
+                acc[2 * e] += ws[k] * f.x;
+                acc[2 * e + 1] += ws[k] * f.y;
+              }
+            }
+          }
+        }
+      }
+    }
+    if (!BWD) {
+      __align__(16) __half r[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) r[e] = __float2half_rn(acc[e] / g.count);
+      *reinterpret_cast<uint4*>(out + o_off) = *reinterpret_cast<const uint4*>(r);
     }
   }
 }
@@ -270,22 +256,20 @@ __global__ void add_mask_kernel(const __half* __restrict__ a, const float* __res
 extern "C" int ptb200_roi_align_fwd_f16(const void* feat, int n, int h, int w, int c, const float* rois,
                                         const int* roi_count, int cap, float spatial_scale, int pooled, void* out,
                                         void* stream) {
-  if (c % 8 != 0 || c / 8 > 1024) return 1401;
-  dim3 grid(n * cap, pooled * pooled);
-  roi_align_fwd_kernel<<<grid, c / 8, 0, STREAM>>>(static_cast<const __half*>(feat), h, w, c,
-                                                  reinterpret_cast<const float4*>(rois), roi_count, cap,
-                                                  spatial_scale, pooled, static_cast<__half*>(out));
+  if (c % 8 != 0 || pooled > kMaxP || pooled * (c / 8) > 512) return 1401;
+  roi_align_roi_kernel<false><<<n * cap, pooled * (c / 8), 0, STREAM>>>(
+      static_cast<const __half*>(feat), nullptr, h, w, c, reinterpret_cast<const float4*>(rois), roi_count, cap,
+      spatial_scale, pooled, static_cast<__half*>(out), nullptr);
   return static_cast<int>(cudaGetLastError());
 }
 
 extern "C" int ptb200_roi_align_bwd_f16(const void* dout, int n, int h, int w, int c, const float* rois,
                                         const int* roi_count, int cap, float spatial_scale, int pooled,
                                         float* dfeat, void* stream) {
-  if (c % 8 != 0 || c / 8 > 1024) return 1401;
-  dim3 grid(n * cap, pooled * pooled);
-  roi_align_bwd_kernel<<<grid, c / 8, 0, STREAM>>>(static_cast<const __half*>(dout), h, w, c,
-                                                  reinterpret_cast<const float4*>(rois), roi_count, cap,
-                                                  spatial_scale, pooled, dfeat);
+  if (c % 8 != 0 || pooled > kMaxP || pooled * (c / 8) > 512) return 1401;
+  roi_align_roi_kernel<true><<<n * cap, pooled * (c / 8), 0, STREAM>>>(
+      nullptr, static_cast<const __half*>(dout), h, w, c, reinterpret_cast<const float4*>(rois), roi_count, cap,
+      spatial_scale, pooled, nullptr, dfeat);
   return static_cast<int>(cudaGetLastError());
 }
 

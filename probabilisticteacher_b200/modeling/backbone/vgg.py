@@ -52,8 +52,7 @@ class VGG(nn.Module):
         for i in range(len(records) - 1, -1, -1):
             r = records[i]
             gw = ar.gview(r["name"] + ".weight").view(r["cout"], 9 * r["cin"])
-            ops.conv3x3_wgrad(dz, r["x"], gw, scale=inv)
-            ops.colsum(dz.t.view(-1, r["cout"]), ar.gview(r["name"] + ".bias"), scale=inv)
+            ops.conv3x3_wgrad(dz, r["x"], gw, scale=inv, bias_out=ar.gview(r["name"] + ".bias"))
             if i == 0:
                 break
             wd = ar.dgrad_half[r["name"]]

@@ -122,12 +122,12 @@ class GuassianRPN(nn.Module):
         dhead = torch.empty(rows, 128, dtype=torch.float16, device=dev)
         call("ptb200_pack_grad2_f16", ctx["dlogits"], A, ctx["ddeltas"], A * 8, g_cls, g_loc, S, rows, 128, dhead)
         p = "proposal_generator.rpn_head."
-        ops.wgrad(dhead.view(1, rows, 128), t.t.view(1, rows, C), ar.gview(p + "_heads.weight"), scale=inv)
-        ops.colsum(dhead, ar.gview(p + "_heads.bias"), scale=inv)
+        ops.wgrad(dhead.view(1, rows, 128), t.t.view(1, rows, C), ar.gview(p + "_heads.weight"), scale=inv,
+                  bias_out=ar.gview(p + "_heads.bias"))
         dzt = ops.gemm_tn(dhead.view(1, rows, 128), ar.dgrad_half["rpn_heads"], epi=ops.EPI_MASK, aux=t.t)
         dzt = ops.FlatAct(dzt.view(N, -1, C), feat.H, feat.W)
-        ops.conv3x3_wgrad(dzt, feat, ar.gview(p + "conv.weight").view(C, 9 * C), scale=inv)
-        ops.colsum(dzt.t.view(-1, C), ar.gview(p + "conv.bias"), scale=inv)
+        ops.conv3x3_wgrad(dzt, feat, ar.gview(p + "conv.weight").view(C, 9 * C), scale=inv,
+                          bias_out=ar.gview(p + "conv.bias"))
         dfeat = ops.conv3x3(dzt, ar.dgrad_half["rpn_conv"], None, aux=feat.t)
         if ctx.get("danchor_wh") is not None:
             call("ptb200_axpy_dev", g_loc, 1.0, ctx["danchor_wh"],

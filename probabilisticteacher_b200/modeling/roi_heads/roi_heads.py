@@ -89,16 +89,16 @@ class GuassianROIHead(nn.Module):
         dpred = torch.empty(rows, 128, dtype=torch.float16, device=dev)
         call("ptb200_pack_grad2_f16", ctx["dscores"], K + 1, ctx["ddeltas"], 8 * K, g_cls, g_box, S, rows, 128, dpred)
         p = "roi_heads.box_predictor."
-        ops.wgrad(dpred.view(1, rows, 128), ctx["h2"].view(1, rows, fc), ar.gview(p + "_heads.weight"), scale=inv)
-        ops.colsum(dpred, ar.gview(p + "_heads.bias"), scale=inv)
+        ops.wgrad(dpred.view(1, rows, 128), ctx["h2"].view(1, rows, fc), ar.gview(p + "_heads.weight"), scale=inv,
+                  bias_out=ar.gview(p + "_heads.bias"))
         dz2 = ops.gemm_tn(dpred.view(1, rows, 128), ar.dgrad_half["pred"], epi=ops.EPI_MASK, aux=ctx["h2"])
         p = "roi_heads.box_head."
-        ops.wgrad(dz2, ctx["h1"].view(1, rows, fc), ar.gview(p + "fc2.weight"), scale=inv)
-        ops.colsum(dz2.view(rows, fc), ar.gview(p + "fc2.bias"), scale=inv)
+        ops.wgrad(dz2, ctx["h1"].view(1, rows, fc), ar.gview(p + "fc2.weight"), scale=inv,
+                  bias_out=ar.gview(p + "fc2.bias"))
         dz1 = ops.gemm_tn(dz2, ar.dgrad_half["fc2"], epi=ops.EPI_MASK, aux=ctx["h1"])
         fin = ctx["x0"].shape[1]
-        ops.wgrad(dz1, ctx["x0"].view(1, rows, fin), ar.gview(p + "fc1.weight").view(fc, fin), scale=inv)
-        ops.colsum(dz1.view(rows, fc), ar.gview(p + "fc1.bias"), scale=inv)
+        ops.wgrad(dz1, ctx["x0"].view(1, rows, fin), ar.gview(p + "fc1.weight").view(fc, fin), scale=inv,
+                  bias_out=ar.gview(p + "fc1.bias"))
         dx0 = ops.gemm_tn(dz1, ar.dgrad_half["fc1"], epi=ops.EPI_BIAS)
         return ops.roi_align_bwd(dx0.view(rows, fin), ctx["feat"], ctx["rois"], ctx["counts"], ctx["cap"],
                                  self.pooler_scale, self.pooler_resolution)

@@ -86,19 +86,19 @@ def conv3x3(x: FlatAct, w_packed, bias, relu=True, aux=None, out=None):
     return FlatAct(o, x.H, x.W)
 
 
-def wgrad(G, X, out, *, taps=1, shifts=None, scale=1.0, ksplit=0, m_total=None, n_total=None):
-    """out[m][t*n + n'] += scale * sum G[b][p][m] X[b][p+shift_t][n']."""
+def wgrad(G, X, out, *, taps=1, shifts=None, scale=1.0, ksplit=0, m_total=None, n_total=None, bias_out=None):
+    """out[m][t*n + n'] += scale * sum G[b][p][m] X[b][p+shift_t][n'];  bias_out[m] += scale * sum G[b][p][m]."""
     batch, rows, ldg = G.shape
     ldx = X.shape[2]
     m_total = m_total or ldg
     n_total = n_total or ldx
     call("ptb200_gemm_wgrad_f16", G, ldg, rows * ldg, X, ldx, rows * ldx, batch, rows, m_total, n_total, taps,
-         shifts, out, taps * n_total, float(scale), ksplit)
+         shifts, out, taps * n_total, float(scale), ksplit, bias_out)
     return out
 
 
-def conv3x3_wgrad(dy: FlatAct, x: FlatAct, out, scale=1.0):
-    return wgrad(dy.t, x.t, out, taps=9, shifts=_shifts(x.W + 1), scale=scale)
+def conv3x3_wgrad(dy: FlatAct, x: FlatAct, out, scale=1.0, bias_out=None):
+    return wgrad(dy.t, x.t, out, taps=9, shifts=_shifts(x.W + 1), scale=scale, bias_out=bias_out)
 
 
 # ------------------------------------------------------------------------------------------ elementwise
