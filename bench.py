@@ -337,8 +337,17 @@ def main():
     gt = tot_t["ptb200_gemm_tn_f16"]
     achieved = tot_f["ptb200_gemm_tn_f16"] / gt / 1e12 if gt > 0 else 0.0
     wt = tot_t["ptb200_gemm_wgrad_f16"]
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "r1_gemm_dram_traffic.json")
+    if os.path.exists(tp):  # committed summary of an ncu pass over one step (dram bytes per launch)
+        tj = json.load(open(tp)).get("void gemm_tn_kernel<0>")
+        if tj:
+            traffic = (tj["dram_read_MB_per_launch"] + tj["dram_write_MB_per_launch"]) * 1e6
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": achieved / peak_tf, "traffic": None, "kernel": "gemm_tn_kernel",
+                "frac": achieved / peak_tf, "traffic": traffic,
+                "traffic_note": "mean DRAM read+write bytes per gemm_tn_kernel launch, ncu pass over one step "
+                                "(profiles/r1_gemm_dram_traffic.json)",
+                "kernel": "gemm_tn_kernel",
                 "launches_per_step": cnt["ptb200_gemm_tn_f16"], "kernel_ms_per_step": gt * 1e3,
                 "peak_source": peak_src,
                 "wgrad_kernel": {"achieved": tot_f["ptb200_gemm_wgrad_f16"] / wt / 1e12 if wt > 0 else 0.0,
