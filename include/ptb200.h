@@ -32,13 +32,15 @@ extern "C" {
  *   pt/modeling/proposal_generator/rpn.py:96 (RPN head), pt/modeling/roi_heads/roi_heads.py:127-128
  *   (box head), pt/modeling/roi_heads/fast_rcnn.py:157-169 (predictor), and their data-gradients.
  * Rows outside [0, rows) read as zero (conv zero padding). ksplit > 1 (with PTB200_EPI_ATOMIC_F32)
- * splits the reduction across CTAs for skinny problems (fc1 forward). */
+ * splits the reduction across CTAs for skinny problems (fc1 forward). seg_counts (may be NULL, batch == 1):
+ * rows form segments of seg_cap rows of which only the first seg_counts[s] are live (fixed-capacity roi
+ * buffers); 128-row tiles without a live row are skipped and their outputs left untouched. */
 int ptb200_gemm_tn_f16(const void* A, int batch, int rows, int k_per_tap, int64_t lda,
                        int64_t a_batch_stride, int taps, const int* shifts_host, const void* B,
                        int n_total, int bn, int epi, const float* bias, int n_bias, void* D,
                        int64_t ldd, int64_t d_batch_stride, const void* aux, int w_valid, int wp,
                        float* d0, int ld0, float* d1, int ld1, int split, int n_valid, int max_ctas,
-                       int ksplit, void* stream);
+                       int ksplit, const int* seg_counts, int seg_cap, void* stream);
 
 /* Weight gradient  out[m][t*n_total + n] += scale * sum_b sum_p G[b][p][m] * X[b][p + shifts[t]][n]
  * (split-K, fp32 atomic accumulation). Replaces the wgrad kernels autograd issues at
@@ -47,7 +49,8 @@ int ptb200_gemm_tn_f16(const void* A, int batch, int rows, int k_per_tap, int64_
 int ptb200_gemm_wgrad_f16(const void* G, int64_t ldg, int64_t g_batch_stride, const void* X,
                           int64_t ldx, int64_t x_batch_stride, int batch, int rows, int m_total,
                           int n_total, int taps, const int* shifts_host, float* out, int64_t ld_out,
-                          float scale, int ksplit, float* bias_out, void* stream);
+                          float scale, int ksplit, float* bias_out, const int* seg_counts, int seg_cap,
+                          void* stream);
 
 /* ---- image / activation helpers ---------------------------------------------------------------- */
 

@@ -9,7 +9,8 @@ extern "C" int ptb200_gemm_tn_f16(const void* A, int batch, int rows, int k_per_
                                   int n_total, int bn, int epi, const float* bias, int n_bias, void* D,
                                   int64_t ldd, int64_t d_batch_stride, const void* aux, int w_valid,
                                   int wp, float* d0, int ld0, float* d1, int ld1, int split,
-                                  int n_valid, int max_ctas, int ksplit, void* stream) {
+                                  int n_valid, int max_ctas, int ksplit, const int* seg_counts, int seg_cap,
+                                  void* stream) {
   GemmTnArgs a;
   a.A = A;
   a.batch = batch;
@@ -39,14 +40,17 @@ extern "C" int ptb200_gemm_tn_f16(const void* A, int batch, int rows, int k_per_
   a.n_valid = n_valid;
   a.max_ctas = max_ctas;
   a.ksplit = ksplit;
+  a.seg_counts = seg_counts;
+  a.seg_cap = seg_cap;
   return gemm_tn_launch(a, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int ptb200_gemm_wgrad_f16(const void* G, int64_t ldg, int64_t g_batch_stride, const void* X,
                                      int64_t ldx, int64_t x_batch_stride, int batch, int rows,
                                      int m_total, int n_total, int taps, const int* shifts, float* out,
-                                     int64_t ld_out, float scale, int ksplit, float* bias_out, void* stream) {
+                                     int64_t ld_out, float scale, int ksplit, float* bias_out,
+                                     const int* seg_counts, int seg_cap, void* stream) {
   return gemm_wgrad_launch(G, ldg, g_batch_stride, X, ldx, x_batch_stride, batch, rows, m_total,
-                           n_total, taps, shifts, out, ld_out, scale, ksplit, bias_out,
+                           n_total, taps, shifts, out, ld_out, scale, ksplit, bias_out, seg_counts, seg_cap,
                            static_cast<cudaStream_t>(stream));
 }

@@ -49,6 +49,19 @@ struct SmemCtl {
 static constexpr int WIN_ROWS = 136;
 static constexpr int WIN_BYTES = WIN_ROWS * 128;  // 17408 = 17 * 1024
 
+// true when the 128-row tile starting at row0 contains at least one live row (segment mode)
+__device__ __forceinline__ bool tile_live(const int* __restrict__ seg_counts, int seg_cap, int row0, int rows) {
+  if (seg_counts == nullptr) return true;
+  int r = row0;
+  const int rend = min(row0 + BM, rows);
+  while (r < rend) {
+    const int n = r / seg_cap;
+    if (r - n * seg_cap < min(seg_counts[n], seg_cap)) return true;
+    r = (n + 1) * seg_cap;
+  }
+  return false;
+}
+
 template <bool ROWWIN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
@@ -127,6 +140,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int nt = rem - mt * n_tiles;
         const int row0 = mt * BM;
         const int n0 = nt * bn;
+        if (!tile_live(p.seg_counts, p.seg_cap, row0, p.rows)) continue;
         const int ki0 = (k_iters_total * ks) / ksplit, ki1 = (k_iters_total * (ks + 1)) / ksplit;
         for (int ki = ki0; ki < ki1; ++ki) {
           const int t = ki / k_chunks, kc = ki - t * k_chunks;
@@ -156,9 +170,15 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     uint32_t ph = 0;
     int it = 0;
     if (bres) mbar_wait(&ctl->bres_full, 0);
-    for (int work = blockIdx.x; work < num_tiles; work += gridDim.x, ++it) {
+    for (int work = blockIdx.x; work < num_tiles; work += gridDim.x) {
+      if (p.seg_counts != nullptr) {
+        const int tile_ = work / ksplit;
+        const int mt_ = (tile_ % tiles_per_batch) / n_tiles;
+        if (!tile_live(p.seg_counts, p.seg_cap, mt_ * BM, p.rows)) continue;
+      }
       const int as = it & 1;
       const uint32_t aph = (it >> 1) & 1;
+      ++it;
       const int ks = work % ksplit;
       const int k_iters = (k_iters_total * (ks + 1)) / ksplit - (k_iters_total * ks) / ksplit;
       mbar_wait(&ctl->tmem_empty[as], aph ^ 1);
@@ -207,7 +227,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     int it = 0;
     int st_buf = 0;
     uint32_t aux_ph[2] = {0, 0};
-    for (int work = blockIdx.x; work < num_tiles; work += gridDim.x, ++it) {
+    for (int work = blockIdx.x; work < num_tiles; work += gridDim.x) {
       const int tile = work / ksplit;
       const int b = tile / tiles_per_batch;
       const int rem = tile - b * tiles_per_batch;
@@ -215,8 +235,10 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const int nt = rem - mt * n_tiles;
       const int row0 = mt * BM;
       const int n0 = nt * bn;
+      if (!tile_live(p.seg_counts, p.seg_cap, row0, p.rows)) continue;
       const int as = it & 1;
       const uint32_t aph = (it >> 1) & 1;
+      ++it;
 
       // stage the bias slice (previous tile's readers are past the barrier below)
       named_bar_sync(1, EPI_THREADS);
@@ -467,6 +489,9 @@ int gemm_tn_launch(const GemmTnArgs& a, cudaStream_t stream) {
   p.ld1 = a.ld1;
   p.split = a.split;
   p.n_valid = a.n_valid;
+  p.seg_counts = a.seg_counts;
+  p.seg_cap = a.seg_cap;
+  if (a.seg_counts != nullptr && (a.batch != 1 || a.seg_cap <= 0)) return 1008;
   // keep the whole filter resident when every CTA uses the same one (single N tile, single K chunk)
   const bool bres = rowwin && a.n_total == a.bn && a.k_per_tap == BK;
   p.b_resident = bres ? 1 : 0;

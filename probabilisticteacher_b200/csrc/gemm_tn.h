@@ -30,6 +30,8 @@ struct GemmTnParams {
   int ld1;
   int split;
   int n_valid;
+  const int* seg_counts;  // optional: rows are [segments][seg_cap], only the first seg_counts[s] rows of a
+  int seg_cap;            // segment are live; 128-row tiles without any live row are skipped entirely
 };
 
 struct GemmTnArgs {
@@ -57,6 +59,8 @@ struct GemmTnArgs {
   int split, n_valid;
   int max_ctas;  // 0 = one per SM
   int ksplit;    // > 1 only with EPI_ATOMIC_F32
+  const int* seg_counts;
+  int seg_cap;
 };
 
 int gemm_tn_launch(const GemmTnArgs& a, cudaStream_t stream);
@@ -65,6 +69,6 @@ int gemm_tn_launch(const GemmTnArgs& a, cudaStream_t stream);
 int gemm_wgrad_launch(const void* G, int64_t ldg, int64_t g_batch_stride, const void* X, int64_t ldx,
                       int64_t x_batch_stride, int batch, int rows, int m_total, int n_total, int taps,
                       const int* shifts, float* out, int64_t ld_out, float scale, int ksplit, float* bias_out,
-                      cudaStream_t stream);
+                      const int* seg_counts, int seg_cap, cudaStream_t stream);
 
 }  // namespace ptb

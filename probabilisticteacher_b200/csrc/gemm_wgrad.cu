@@ -36,6 +36,8 @@ struct WgParams {
   int64_t ld_out;
   float scale;
   float* bias_out;  // optional: bias_out[m] += scale * sum_{b,p} G[b][p][m] (fused bias gradient)
+  const int* seg_counts;  // optional segment mode (batch == 1): 64-row chunks without a live row are skipped
+  int seg_cap;
 };
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
@@ -51,6 +53,18 @@ __device__ __forceinline__ void tma_load_4d(void* smem, const CUtensorMap* m, ui
       " [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_u32(smem)),
       "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
+}
+
+__device__ __forceinline__ bool chunk_live(const int* __restrict__ seg_counts, int seg_cap, int r0, int rows) {
+  if (seg_counts == nullptr) return true;
+  int r = r0;
+  const int rend = min(r0 + WG_BK, rows);
+  while (r < rend) {
+    const int n = r / seg_cap;
+    if (r - n * seg_cap < min(seg_counts[n], seg_cap)) return true;
+    r = (n + 1) * seg_cap;
+  }
+  return false;
 }
 
 __global__ void __launch_bounds__(WG_THREADS, 1)
@@ -85,7 +99,11 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_consta
   const int total_chunks = chunks_per_img * p.batch;
   const int c_begin = static_cast<int>((static_cast<int64_t>(total_chunks) * ks) / p.ksplit);
   const int c_end = static_cast<int>((static_cast<int64_t>(total_chunks) * (ks + 1)) / p.ksplit);
-  const int k_iters = c_end - c_begin;
+  int k_iters = c_end - c_begin;
+  if (p.seg_counts != nullptr) {  // count the live chunks of this CTA's range (every role does the same)
+    k_iters = 0;
+    for (int c = c_begin; c < c_end; ++c) k_iters += chunk_live(p.seg_counts, p.seg_cap, c * WG_BK, p.rows) ? 1 : 0;
+  }
 
   uint32_t tmem_cols = 32;
   while (tmem_cols < static_cast<uint32_t>(bn)) tmem_cols <<= 1;
@@ -118,6 +136,7 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_consta
         for (int c = c_begin; c < c_end; ++c) {
           const int b = c / chunks_per_img;
           const int r0 = (c - b * chunks_per_img) * WG_BK;
+          if (!chunk_live(p.seg_counts, p.seg_cap, r0, p.rows)) continue;
           mbar_wait(&ctl->empty[s], ph ^ 1);
           uint8_t* sa = smem + s * stage_bytes;
           uint8_t* sb = sa + a_bytes;
@@ -228,7 +247,8 @@ static int g_wg_sms = 0;
 int gemm_wgrad_launch(const void* G, int64_t ldg, int64_t g_batch_stride, const void* X, int64_t ldx,
                       int64_t x_batch_stride, int batch, int rows, int m_total, int n_total, int taps,
                       const int* shifts, float* out, int64_t ld_out, float scale, int ksplit, float* bias_out,
-                      cudaStream_t stream) {
+                      const int* seg_counts, int seg_cap, cudaStream_t stream) {
+  if (seg_counts != nullptr && (batch != 1 || seg_cap <= 0)) return 1103;
   if (m_total % WG_BM != 0 || n_total % 64 != 0 || taps < 1 || taps > 9) return 1101;
   int bn = 256;
   while (n_total % bn != 0) bn >>= 1;
@@ -263,6 +283,8 @@ int gemm_wgrad_launch(const void* G, int64_t ldg, int64_t g_batch_stride, const 
   p.ld_out = ld_out;
   p.scale = scale;
   p.bias_out = bias_out;
+  p.seg_counts = seg_counts;
+  p.seg_cap = seg_cap;
   const int tiles = taps * (m_total / WG_BM) * (n_total / bn);
   const int total_chunks = ((rows + WG_BK - 1) / WG_BK) * batch;
   if (ksplit <= 0) {

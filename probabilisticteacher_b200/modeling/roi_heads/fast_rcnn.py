@@ -54,7 +54,7 @@ class GuassianFastRCNNOutputLayers(nn.Module):
         if self.model_type != "GUASSIAN":
             raise ValueError("only UNSUPNET.MODEL_TYPE == 'GUASSIAN' is on the hot path")
 
-    def forward(self, h2):
+    def forward(self, h2, seg=None):
         """h2: fp16 [rows, fc_dim] -> (scores fp32 [rows, K+1], deltas fp32 [rows, 8K])."""
         ar = self.arena
         K = self.num_classes
@@ -63,7 +63,8 @@ class GuassianFastRCNNOutputLayers(nn.Module):
         rows = h2.shape[0]
         p = "roi_heads.box_predictor."
         s, d = ops.gemm_tn(h2.view(1, rows, -1), ar.hview(p + "_heads.weight"), epi=ops.EPI_F32_SPLIT,
-                           bias=ar.view(p + "_heads.bias"), split=K + 1, n_valid=n_valid, n_total=n_total, bn=n_total)
+                           bias=ar.view(p + "_heads.bias"), split=K + 1, n_valid=n_valid, n_total=n_total, bn=n_total,
+                           seg=seg)
         return s.view(rows, K + 1), d.view(rows, 8 * K)
 
     def losses(self, scores, deltas, sampled, N, cap):

@@ -38,9 +38,11 @@ class GuassianROIHead(nn.Module):
         w1 = ar.hview(p + "fc1.weight").view(ar.fc_dim, -1)
         tiles = ((rows + 127) // 128) * (ar.fc_dim // 256)
         ksplit = max(1, min(8, 148 // max(tiles, 1)))
-        h1 = ops.gemm_tn(x0.view(1, rows, -1), w1, epi=ops.EPI_BIAS_RELU, bias=ar.view(p + "fc1.bias"), ksplit=ksplit)
-        h2 = ops.gemm_tn(h1, ar.hview(p + "fc2.weight"), epi=ops.EPI_BIAS_RELU, bias=ar.view(p + "fc2.bias"))
-        scores, deltas = self.box_predictor(h2.view(rows, -1))
+        seg = (counts, cap)  # 128-row tiles without a live roi are skipped by the GEMMs
+        h1 = ops.gemm_tn(x0.view(1, rows, -1), w1, epi=ops.EPI_BIAS_RELU, bias=ar.view(p + "fc1.bias"), ksplit=ksplit,
+                         seg=seg)
+        h2 = ops.gemm_tn(h1, ar.hview(p + "fc2.weight"), epi=ops.EPI_BIAS_RELU, bias=ar.view(p + "fc2.bias"), seg=seg)
+        scores, deltas = self.box_predictor(h2.view(rows, -1), seg=seg)
         return x0, h1.view(rows, -1), h2.view(rows, -1), scores, deltas
 
     def forward(self, feat: ops.FlatAct, proposals, img_hw, targets=None, compute_loss=True, branch="",
@@ -86,19 +88,20 @@ class GuassianROIHead(nn.Module):
         rows = ctx["x0"].shape[0]
         dev = ctx["x0"].device
         fc = ar.fc_dim
+        seg = (ctx["counts"], ctx["cap"])
         dpred = torch.empty(rows, 128, dtype=torch.float16, device=dev)
         call("ptb200_pack_grad2_f16", ctx["dscores"], K + 1, ctx["ddeltas"], 8 * K, g_cls, g_box, S, rows, 128, dpred)
         p = "roi_heads.box_predictor."
         ops.wgrad(dpred.view(1, rows, 128), ctx["h2"].view(1, rows, fc), ar.gview(p + "_heads.weight"), scale=inv,
-                  bias_out=ar.gview(p + "_heads.bias"))
-        dz2 = ops.gemm_tn(dpred.view(1, rows, 128), ar.dgrad_half["pred"], epi=ops.EPI_MASK, aux=ctx["h2"])
+                  bias_out=ar.gview(p + "_heads.bias"), seg=seg)
+        dz2 = ops.gemm_tn(dpred.view(1, rows, 128), ar.dgrad_half["pred"], epi=ops.EPI_MASK, aux=ctx["h2"], seg=seg)
         p = "roi_heads.box_head."
         ops.wgrad(dz2, ctx["h1"].view(1, rows, fc), ar.gview(p + "fc2.weight"), scale=inv,
-                  bias_out=ar.gview(p + "fc2.bias"))
-        dz1 = ops.gemm_tn(dz2, ar.dgrad_half["fc2"], epi=ops.EPI_MASK, aux=ctx["h1"])
+                  bias_out=ar.gview(p + "fc2.bias"), seg=seg)
+        dz1 = ops.gemm_tn(dz2, ar.dgrad_half["fc2"], epi=ops.EPI_MASK, aux=ctx["h1"], seg=seg)
         fin = ctx["x0"].shape[1]
         ops.wgrad(dz1, ctx["x0"].view(1, rows, fin), ar.gview(p + "fc1.weight").view(fc, fin), scale=inv,
-                  bias_out=ar.gview(p + "fc1.bias"))
-        dx0 = ops.gemm_tn(dz1, ar.dgrad_half["fc1"], epi=ops.EPI_BIAS)
+                  bias_out=ar.gview(p + "fc1.bias"), seg=seg)
+        dx0 = ops.gemm_tn(dz1, ar.dgrad_half["fc1"], epi=ops.EPI_BIAS, seg=seg)
         return ops.roi_align_bwd(dx0.view(rows, fin), ctx["feat"], ctx["rois"], ctx["counts"], ctx["cap"],
                                  self.pooler_scale, self.pooler_resolution)

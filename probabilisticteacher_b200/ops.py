@@ -39,11 +39,13 @@ def from_flat(a):
 
 # ------------------------------------------------------------------------------------------ GEMMs
 def gemm_tn(A, B, *, taps=1, shifts=None, bn=None, epi=EPI_BIAS, bias=None, out=None, aux=None,
-            w_valid=0, wp=0, d0=None, d1=None, split=0, n_valid=0, n_total=None, ksplit=1):
+            w_valid=0, wp=0, d0=None, d1=None, split=0, n_valid=0, n_total=None, ksplit=1, seg=None):
     """A: [batch, rows, K] fp16; B: [n_rows, taps*K] fp16. Returns out (fp16 [batch, rows, n_total]) or
     (d0, d1) for the fp32 split epilogue."""
     batch, rows, lda = A.shape
     k = B.shape[1] // taps
+    seg_counts, seg_cap = seg if seg is not None else (None, 0)
+    alloc = torch.zeros if seg is not None else torch.empty  # skipped tiles are never written
     if n_total is None:
         n_total = B.shape[0]
     if bn is None:
@@ -55,24 +57,24 @@ def gemm_tn(A, B, *, taps=1, shifts=None, bn=None, epi=EPI_BIAS, bias=None, out=
         assert epi in (EPI_BIAS_RELU, EPI_BIAS) and aux is None
         acc = torch.zeros(batch, rows, n_total, dtype=torch.float32, device=A.device)
         call("ptb200_gemm_tn_f16", A, batch, rows, k, lda, rows * lda, taps, shifts, B, n_total, bn, EPI_ATOMIC, None,
-             0, None, 0, 0, None, 0, 0, acc, n_total, None, 0, 0, n_total, 0, ksplit)
+             0, None, 0, 0, None, 0, 0, acc, n_total, None, 0, 0, n_total, 0, ksplit, seg_counts, seg_cap)
         if out is None:
             out = torch.empty(batch, rows, n_total, dtype=torch.float16, device=A.device)
         call("ptb200_bias_act_cast_f16", acc, bias, 1 if epi == EPI_BIAS_RELU else 0, batch * rows, n_total, out)
         return out
     if epi == EPI_F32_SPLIT:
         if d0 is None:
-            d0 = torch.empty(batch, rows, split, dtype=torch.float32, device=A.device)
+            d0 = alloc(batch, rows, split, dtype=torch.float32, device=A.device)
         if d1 is None:
-            d1 = torch.empty(batch, rows, n_valid - split, dtype=torch.float32, device=A.device)
+            d1 = alloc(batch, rows, n_valid - split, dtype=torch.float32, device=A.device)
         ld_d, dbs = 0, 0
     else:
         if out is None:
-            out = torch.empty(batch, rows, n_total, dtype=torch.float16, device=A.device)
+            out = alloc(batch, rows, n_total, dtype=torch.float16, device=A.device)
         ld_d, dbs = out.shape[2], out.shape[1] * out.shape[2]
     call("ptb200_gemm_tn_f16", A, batch, rows, k, lda, rows * lda, taps, shifts, B, n_total, bn, epi, bias,
          0 if bias is None else bias.numel(), out, ld_d, dbs, aux, w_valid, wp, d0, split, d1,
-         n_valid - split, split, n_valid, 0, 1)
+         n_valid - split, split, n_valid, 0, 1, seg_counts, seg_cap)
     return (d0, d1) if epi == EPI_F32_SPLIT else out
 
 
@@ -86,14 +88,15 @@ def conv3x3(x: FlatAct, w_packed, bias, relu=True, aux=None, out=None):
     return FlatAct(o, x.H, x.W)
 
 
-def wgrad(G, X, out, *, taps=1, shifts=None, scale=1.0, ksplit=0, m_total=None, n_total=None, bias_out=None):
+def wgrad(G, X, out, *, taps=1, shifts=None, scale=1.0, ksplit=0, m_total=None, n_total=None, bias_out=None,
+          seg=None):
     """out[m][t*n + n'] += scale * sum G[b][p][m] X[b][p+shift_t][n'];  bias_out[m] += scale * sum G[b][p][m]."""
     batch, rows, ldg = G.shape
     ldx = X.shape[2]
     m_total = m_total or ldg
     n_total = n_total or ldx
     call("ptb200_gemm_wgrad_f16", G, ldg, rows * ldg, X, ldx, rows * ldx, batch, rows, m_total, n_total, taps,
-         shifts, out, taps * n_total, float(scale), ksplit, bias_out)
+         shifts, out, taps * n_total, float(scale), ksplit, bias_out, seg[0] if seg else None, seg[1] if seg else 0)
     return out
 
 

@@ -26,7 +26,7 @@ def _gemm(A, B, bias, epi, bn, taps=1, shifts=None, wv=0, wp=0, aux=None, n_vali
         ptr(A), batch, rows, k, ctypes.c_int64(lda), ctypes.c_int64(rows * lda), taps, sh, ptr(B),
         n_total, bn, epi, ptr(bias), 0 if bias is None else bias.numel(), ptr(D),
         ctypes.c_int64(n_total), ctypes.c_int64(rows * n_total), ptr(aux), wv, wp, ptr(d0),
-        split, ptr(d1), n_valid - split, split, n_valid, max_ctas, 1, stream_ptr())
+        split, ptr(d1), n_valid - split, split, n_valid, max_ctas, 1, None, 0, stream_ptr())
     check(rc, "gemm_tn")
     torch.cuda.synchronize()
     return (d0, d1) if epi == 2 else D
@@ -116,3 +116,30 @@ def test_split_k_fc(cuda):
     torch.cuda.synchronize()
     ref = torch.relu(A[0].float() @ B.float().t() + bias)
     assert _rel(D[0], ref) < 2e-3
+
+
+def test_segment_skipping(cuda):
+    """Fixed-capacity roi buffers: tiles / chunks without a live row are skipped; live rows are exact."""
+    from probabilisticteacher_b200 import ops
+    g = torch.Generator().manual_seed(31)
+    cap, nseg, K, N = 600, 3, 256, 256
+    counts = torch.tensor([130, 0, 600], dtype=torch.int32, device=cuda)
+    A = torch.randn(1, nseg * cap, K, generator=g).half().to(cuda)
+    B = (torch.randn(N, K, generator=g) / 16).half().to(cuda)
+    bias = torch.randn(N, generator=g).to(cuda)
+    D = ops.gemm_tn(A, B, epi=ops.EPI_BIAS_RELU, bias=bias, seg=(counts, cap))
+    ref = torch.relu(A[0].float() @ B.float().t() + bias)
+    live = torch.zeros(nseg * cap, dtype=torch.bool, device=cuda)
+    live[:130] = True
+    live[2 * cap:] = True
+    assert _rel(D[0][live], ref[live]) < 2e-3
+    assert D[0][cap + 128:2 * cap - 128].abs().max() == 0  # tiles entirely inside the empty segment: untouched
+    # weight gradient with the same segment structure
+    G = torch.randn(1, nseg * cap, 128, generator=g).half().to(cuda)
+    G[0][~live] = 0
+    out = torch.zeros(128, K, device=cuda)
+    bsum = torch.zeros(128, device=cuda)
+    ops.wgrad(G, A, out, bias_out=bsum, seg=(counts, cap))
+    torch.cuda.synchronize()
+    assert _rel(out, G[0].float().t() @ A[0].float()) < 1e-4
+    assert _rel(bsum, G[0].float().sum(0)) < 1e-4

@@ -15,7 +15,7 @@ def _wgrad(G, X, taps, shifts, out, scale=1.0, ksplit=0, bias_out=None):
     rc = lib().ptb200_gemm_wgrad_f16(
         ptr(G), ctypes.c_int64(m), ctypes.c_int64(rows * m), ptr(X), ctypes.c_int64(n),
         ctypes.c_int64(rows * n), batch, rows, m, n, taps, sh, ptr(out), ctypes.c_int64(taps * n),
-        ctypes.c_float(scale), ksplit, ptr(bias_out), stream_ptr())
+        ctypes.c_float(scale), ksplit, ptr(bias_out), None, 0, stream_ptr())
     check(rc, "wgrad")
     torch.cuda.synchronize()
 

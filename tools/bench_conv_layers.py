@@ -19,7 +19,7 @@ def run(A, B, bias, D, taps, shifts, bn, W, Wp, epi=0):
     rc = lib().ptb200_gemm_tn_f16(
         ptr(A), batch, rows, k, ctypes.c_int64(lda), ctypes.c_int64(rows * lda), taps, sh, ptr(B),
         n_total, bn, epi, ptr(bias), bias.numel(), ptr(D), ctypes.c_int64(n_total),
-        ctypes.c_int64(rows * n_total), None, W, Wp, None, 0, None, 0, 0, 0, 0, 1, stream_ptr())
+        ctypes.c_int64(rows * n_total), None, W, Wp, None, 0, None, 0, 0, 0, 0, 1, None, 0, stream_ptr())
     check(rc)
 
 
