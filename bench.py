@@ -260,6 +260,7 @@ def main():
     ap.add_argument("--impl", default="ptb200", choices=["ptb200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cuda-graph", action="store_true")
+    ap.add_argument("--no-concurrent", action="store_true")
     ap.add_argument("--height", type=int, default=H_IMG)
     ap.add_argument("--width", type=int, default=W_IMG)
     args = ap.parse_args()
@@ -290,7 +291,8 @@ def main():
     pool_dev = synthetic_pool(2, PAIRS_PER_GPU, H, W, K, 1234 + 100 * rank, device=device)
     pool_host = synthetic_pool(2, PAIRS_PER_GPU, H, W, K, 1234 + 100 * rank, device=None, pin=True)
     use_graph = not args.no_cuda_graph
-    trainer = PTrainer(cfg, cycle(pool_dev), device=device, seed=0, use_cuda_graph=use_graph)
+    trainer = PTrainer(cfg, cycle(pool_dev), device=device, seed=0, use_cuda_graph=use_graph,
+                       concurrent=use_graph and not args.no_concurrent)
 
     for _ in range(warmup + (5 if use_graph else 0)):
         trainer.step()
@@ -374,7 +376,7 @@ def main():
                        "value_definition": "iterations/s summed over ranks (each rank runs one 2+2 iteration per step)"},
             "pairs_per_s": value * PAIRS_PER_GPU,
             "e2e": {"value": e2e_value, "unit": "iters/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": eager_launches, "cuda_graph": use_graph,
+            "gpu_launches": eager_launches, "cuda_graph": use_graph, "concurrent_branches": use_graph and not args.no_concurrent,
             "gpu_launches_note": "kernels of libptb200.so per step (counted on an eager step; in CUDA-graph mode the "
                                  "same kernels are replayed from the captured graph)",
             "clocks": clk, "roofline": roofline, "cpu_baseline": cpu_baseline,

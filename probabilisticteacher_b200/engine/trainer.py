@@ -30,7 +30,7 @@ def warmup_multistep_lr(base_lr, it, steps, gamma, warmup_factor, warmup_iters, 
 
 class PTrainer:
     def __init__(self, cfg, data_loader_iter, device=None, seed=0, loss_scale=1024.0, use_cuda_graph=False,
-                 graph_warmup=3, gt_capacity=64):
+                 graph_warmup=3, gt_capacity=64, concurrent=False):
         self.cfg = cfg
         self.device = torch.device(device or "cuda")
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
@@ -60,6 +60,11 @@ class PTrainer:
         self._graph_warmup = graph_warmup
         self._gt_capacity = gt_capacity
         self._static = None
+        # concurrent mode (graph step only): teacher pass, supervised pass and unsupervised pass are issued
+        # on three streams (parallel branches of the captured graph), so the latency-bound proposal kernels
+        # of one pass overlap the GEMMs of the others; persistent GEMMs leave 4 SMs free for them
+        self.concurrent = concurrent
+        self._streams = None
 
     # ------------------------------------------------------------------ pseudo-labelling (trainer.py:179-257)
     def threshold_bbox(self, proposal_bbox_inst, proposal_type="roih"):
@@ -328,6 +333,93 @@ class PTrainer:
         total.backward()
         return {k: v.detach() for k, v in rec.items()}
 
+    def _resize_images_dev(self, data, params_dev):
+        out = []
+        for k, d in enumerate(data):
+            img = d["image"]
+            h, w = img.shape[-2], img.shape[-1]
+            dst = torch.empty_like(img)
+            call("ptb200_resize_paste_u8_dev", img, dst, h, w, params_dev[k], self._pix[0], self._pix[1], self._pix[2])
+            nd = dict(d)
+            nd["image"] = dst
+            out.append(nd)
+        return out
+
+    def _resize_instances_dev(self, instances, params_dev, ratio_dev):
+        out = []
+        for k, inst in enumerate(instances):
+            ni = FreeInstances(inst.image_size)
+            ni._count = getattr(inst, "_count", None)
+            shift = params_dev[k, 2:4].to(torch.float32).repeat(2)
+            for key, v in inst.get_fields().items():
+                if key in ("gt_boxes", "pseudo_boxes"):
+                    v = Boxes(v.tensor * ratio_dev[k] + shift)
+                ni.set(key, v)
+            out.append(ni)
+        return out
+
+    def _graph_body_concurrent(self):
+        """Same computation as `_graph_body`, issued as three parallel branches (teacher / supervised /
+        unsupervised forward) that join before the backward."""
+        from .. import ops
+        cfg = self.cfg
+        st = self._static
+        b = self._static_batches()
+        nl = len(b["lq"])
+        main = torch.cuda.current_stream()
+        if self._streams is None:
+            self._streams = [torch.cuda.Stream(device=self.device) for _ in range(3)]
+        s_t, s_1, s_2 = self._streams
+        ops.GEMM_MAX_CTAS[0] = 144
+        self.model.zero_grad()
+        for s in (s_t, s_1, s_2):
+            s.wait_stream(main)
+        e_pseudo = torch.cuda.Event()
+        keep = []  # tensors that cross streams stay referenced until the join
+        with torch.cuda.stream(s_t):
+            refresh_stream()
+            self._update_teacher_model(keep_rate=cfg.UNSUPNET.EMA_KEEP_RATE)
+            with torch.no_grad():
+                _, _, roih, _ = self.model_teacher(b["uk"], branch="unsup_data_weak")
+            pseudo, _ = self.process_pseudo_label(roih, "roih", "all")
+            e_pseudo.record(s_t)
+            keep.append((roih, pseudo))
+        rec = {}
+        with torch.cuda.stream(s_1):
+            refresh_stream()
+            lq = self.resize_dev(b["lq"], st["resize_params"][:nl], st["resize_ratio"][:nl])
+            rec_l, _, _, _ = self.model(lq + b["lk"], branch="supervised")
+            keep.append(lq)
+        with torch.cuda.stream(s_2):
+            refresh_stream()
+            uq_img = self._resize_images_dev(b["uq"], st["resize_params"][nl:])
+
+            def provider():
+                torch.cuda.current_stream().wait_event(e_pseudo)
+                return self._resize_instances_dev(pseudo, st["resize_params"][nl:], st["resize_ratio"][nl:])
+            rec_u, _, _, _ = self.model(uq_img, branch="unsupervised", danchor=True, targets_provider=provider)
+            keep.append(uq_img)
+        for s in (s_t, s_1, s_2):
+            main.wait_stream(s)
+        refresh_stream()
+        for k, v in rec_l.items():
+            rec[k + "_sup"] = v
+        for k, v in rec_u.items():
+            rec[k + "_unsup"] = v
+        total = 0
+        for k, v in rec.items():
+            wgt = cfg.UNSUPNET.SOURCE_LOSS_WEIGHT if k.endswith("_sup") else cfg.UNSUPNET.TARGET_UNSUP_LOSS_WEIGHT
+            total = total + v * wgt
+        ops.GEMM_MAX_CTAS[0] = 0  # the backward runs alone on the main stream: use every SM
+        self.model.backward_stream = main
+        total.backward()
+        self.model.backward_stream = None
+        for s in (s_t, s_1, s_2):  # autograd touches the forward streams again: re-join them
+            main.wait_stream(s)
+        refresh_stream()
+        self._keep = keep
+        return {k: v.detach() for k, v in rec.items()}
+
     def run_step_graphed(self):
         """Post-burn-in step with the forward/backward part replayed from a CUDA graph."""
         assert self.iter > self.cfg.UNSUPNET.BURN_UP_STEP, "graph mode covers the steady-state (EMA) iterations"
@@ -336,15 +428,16 @@ class PTrainer:
         if self._static is None:
             self._static = self._make_static(data)
         self._stage(data)
+        body = self._graph_body_concurrent if self.concurrent else self._graph_body
         if self._graph is None:
             if self._graph_warmup > 0:  # eager warm-up on the static buffers (allocator, lazy inits)
                 self._graph_warmup -= 1
-                self.last_losses = self._graph_body()
+                self.last_losses = body()
             else:
                 torch.cuda.synchronize()
                 self._graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(self._graph):
-                    self._graph_losses = self._graph_body()
+                    self._graph_losses = body()
                 refresh_stream()
                 self._graph.replay()
                 self.last_losses = self._graph_losses

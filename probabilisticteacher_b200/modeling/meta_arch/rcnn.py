@@ -75,6 +75,7 @@ class GuassianGeneralizedRCNN(nn.Module):
         self.prio_generator = None
         self.prio_override = None  # tests inject {tag: (prio_pos, prio_neg)}
         self._hw_cache = {}
+        self.backward_stream = None
         self.launch_count = 0
 
     # ------------------------------------------------------------------ nn.Module surface
@@ -205,17 +206,23 @@ class GuassianGeneralizedRCNN(nn.Module):
         return t
 
     # ------------------------------------------------------------------ forward
-    def forward(self, batched_inputs, branch="supervised", danchor=False, norm=False):
+    def forward(self, batched_inputs, branch="supervised", danchor=False, norm=False, targets_provider=None):
+        """`targets_provider` (optional, trainer-internal): callable returning the list of instances once
+        the backbone has been issued -- lets the pseudo labels of the unsupervised branch arrive from
+        another stream while this branch's backbone already runs."""
         refresh_stream()
         if not self.training:
             return self.inference(batched_inputs)
         act, sizes, img_hw = self.preprocess_image(batched_inputs)
-        targets = None
-        if "instances" in batched_inputs[0]:
-            targets = self._targets([x["instances"] for x in batched_inputs])
         need_grad = branch in ("supervised", "unsupervised") and torch.is_grad_enabled()
         feats, records = self.backbone(act, save=need_grad)
         feat = feats["vgg_block5"]
+        targets = None
+        if targets_provider is not None:
+            targets = self._targets(targets_provider())
+            refresh_stream()
+        elif "instances" in batched_inputs[0]:
+            targets = self._targets([x["instances"] for x in batched_inputs])
         if branch == "supervised":
             props, l_rpn, rctx = self.proposal_generator(feat, img_hw, targets, prio=self._prio)
             _, l_roi, hctx = self.roi_heads(feat, props, img_hw, targets, branch=branch, prio=self._prio)
@@ -279,6 +286,19 @@ class GuassianGeneralizedRCNN(nn.Module):
     # ------------------------------------------------------------------ backward
     def _run_backward(self, fctx, g):
         """g = [g_loss_cls, g_loss_box_reg, g_loss_rpn_cls, g_loss_rpn_loc] device scalars."""
+        bs = self.backward_stream
+        if bs is not None:
+            # autograd replays a node on the stream its forward ran on; the trainer's concurrent step
+            # wants the whole backward on ONE stream (after the join of the forward branches)
+            cur = torch.cuda.current_stream()
+            bs.wait_stream(cur)
+            with torch.cuda.stream(bs):
+                self._run_backward_impl(fctx, g)
+            cur.wait_stream(bs)
+            return
+        self._run_backward_impl(fctx, g)
+
+    def _run_backward_impl(self, fctx, g):
         refresh_stream()
         self.attach_grads()
         feat = fctx["feat"]

@@ -12,6 +12,9 @@ EPI_BIAS_RELU, EPI_BIAS, EPI_F32_SPLIT, EPI_MASK, EPI_ATOMIC = 0, 1, 2, 3, 4
 FlatAct = namedtuple("FlatAct", ["t", "H", "W"])
 
 I32 = torch.int32
+# upper bound on the CTAs of the persistent GEMM kernel (0 = one per SM). The concurrent step leaves a
+# few SMs free so that latency-bound kernels of another stream never wait behind persistent GEMM CTAs.
+GEMM_MAX_CTAS = [0]
 U32 = torch.int32  # uint32 payloads are carried in int32 tensors (bit patterns only)
 
 
@@ -57,7 +60,7 @@ def gemm_tn(A, B, *, taps=1, shifts=None, bn=None, epi=EPI_BIAS, bias=None, out=
         assert epi in (EPI_BIAS_RELU, EPI_BIAS) and aux is None
         acc = torch.zeros(batch, rows, n_total, dtype=torch.float32, device=A.device)
         call("ptb200_gemm_tn_f16", A, batch, rows, k, lda, rows * lda, taps, shifts, B, n_total, bn, EPI_ATOMIC, None,
-             0, None, 0, 0, None, 0, 0, acc, n_total, None, 0, 0, n_total, 0, ksplit, seg_counts, seg_cap)
+             0, None, 0, 0, None, 0, 0, acc, n_total, None, 0, 0, n_total, GEMM_MAX_CTAS[0], ksplit, seg_counts, seg_cap)
         if out is None:
             out = torch.empty(batch, rows, n_total, dtype=torch.float16, device=A.device)
         call("ptb200_bias_act_cast_f16", acc, bias, 1 if epi == EPI_BIAS_RELU else 0, batch * rows, n_total, out)
@@ -74,7 +77,7 @@ def gemm_tn(A, B, *, taps=1, shifts=None, bn=None, epi=EPI_BIAS, bias=None, out=
         ld_d, dbs = out.shape[2], out.shape[1] * out.shape[2]
     call("ptb200_gemm_tn_f16", A, batch, rows, k, lda, rows * lda, taps, shifts, B, n_total, bn, epi, bias,
          0 if bias is None else bias.numel(), out, ld_d, dbs, aux, w_valid, wp, d0, split, d1,
-         n_valid - split, split, n_valid, 0, 1, seg_counts, seg_cap)
+         n_valid - split, split, n_valid, GEMM_MAX_CTAS[0], 1, seg_counts, seg_cap)
     return (d0, d1) if epi == EPI_F32_SPLIT else out
 
 

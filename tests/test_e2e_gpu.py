@@ -191,7 +191,8 @@ def test_trainer_steps_and_ema(cuda):
     assert torch.allclose(tr.model_teacher.arena.data, expect, atol=1e-6)
 
 
-def test_cuda_graph_step_matches_eager(cuda):
+@pytest.mark.parametrize("concurrent", [False, True])
+def test_cuda_graph_step_matches_eager(cuda, concurrent):
     """The captured step (PTrainer.run_step_graphed) must reproduce the eager step: same losses (up to
     fp32 atomic-accumulation order) with identical resize geometry and sampling priorities."""
     from oracle import pt_oracle as O
@@ -209,7 +210,8 @@ def test_cuda_graph_step_matches_eager(cuda):
     R = (H // 16) * (W // 16) * 9
     trainers = []
     for use_graph in (False, True):
-        tr = PTrainer(cfg, loader(), device=cuda, seed=3, use_cuda_graph=use_graph, graph_warmup=1, gt_capacity=16)
+        tr = PTrainer(cfg, loader(), device=cuda, seed=3, use_cuda_graph=use_graph, graph_warmup=1, gt_capacity=16,
+                      concurrent=concurrent and use_graph)
         trainers.append(tr)
     L = 2000 + 16
     pr = {"rpn": (torch.rand(4, R, generator=g).to(cuda), torch.rand(4, R, generator=g).to(cuda)),
