@@ -23,6 +23,8 @@ extern "C" {
 #define PTB200_EPI_F32_SPLIT 2
 #define PTB200_EPI_MASK_F16 3
 #define PTB200_EPI_ATOMIC_F32 4 /* split-K partials: d0[row][n] += acc (fp32 atomics) */
+#define PTB200_EPI_SPLIT3_RELU_F16 5 /* f16x3 only: relu(alpha*acc + bias) -> [hi | lo | hi] triple */
+#define PTB200_EPI_SPLIT3_F16 6      /* f16x3 only: alpha*acc + bias -> [hi | lo | hi] triple */
 
 /* ---- dense contractions (tcgen05 tensor cores, TMA-staged tiles) ------------------------------ */
 
@@ -41,6 +43,37 @@ int ptb200_gemm_tn_f16(const void* A, int batch, int rows, int k_per_tap, int64_
                        int64_t ldd, int64_t d_batch_stride, const void* aux, int w_valid, int wp,
                        float* d0, int ld0, float* d1, int ld1, int split, int n_valid, int max_ctas,
                        int ksplit, const int* seg_counts, int seg_cap, void* stream);
+
+/* Split-fp16 ("f16x3") parity-precision variant of ptb200_gemm_tn_f16 (forward only): the reference
+ * computes these contractions in fp32 (AMP off, pt/engine/trainer.py:271-277 runs without autocast), so
+ * the 1e-3 parity claim of the losses is checked in this mode. Every fp32 value x travels as two fp16
+ * numbers hi = fp16(x), lo = fp16(x - hi); an activation row is the K-concatenation [hi | lo | hi]
+ * (3 * channels wide), a weight row per tap is [Wh | Wh | Wl] of W * 2^s (ptb200_split3_pack_f16), so the
+ * unchanged tensor-core main loop accumulates hi*Wh + lo*Wh + hi*Wl in fp32 (the lo*Wl term, 2^-22
+ * relative, is dropped). alpha = 2^-s is applied to the accumulator before the bias. k3_per_tap = 3 * K.
+ * Epilogues: PTB200_EPI_SPLIT3_{RELU_,}F16 (D3 is [batch][rows][3*n_total]), PTB200_EPI_F32_SPLIT, or
+ * PTB200_EPI_ATOMIC_F32 with ksplit > 1: the tensor core accumulates its fp32 sums with truncation, a bias
+ * that grows with the number of chained MMAs, so long reductions are cut into ksplit chunks whose partial
+ * sums are added in round-to-nearest fp32 (red.add into d0) and finished by ptb200_bias_act_split3_f16. */
+int ptb200_gemm_tn_f16x3(const void* A3, int batch, int rows, int k3_per_tap, int64_t lda,
+                         int64_t a_batch_stride, int taps, const int* shifts_host, const void* B3,
+                         int n_total, int bn, int epi, const float* bias, int n_bias, void* D3, int64_t ldd,
+                         int64_t d_batch_stride, int w_valid, int wp, float* d0, int ld0, float* d1, int ld1,
+                         int split, int n_valid, int max_ctas, int ksplit, const int* seg_counts, int seg_cap,
+                         float alpha, void* stream);
+
+/* out3 = triple(act(alpha * in + bias)), fp32 [rows][n] -> fp16 [rows][3n]; wp > 0: rows with
+ * (row % wp) >= w_valid are written as zero (pad column of the flat activation layout). */
+int ptb200_bias_act_split3_f16(const float* in, const float* bias, int relu, float alpha, int64_t rows, int n,
+                               int wp, int w_valid, void* out3, void* stream);
+
+/* fp32 [rows][k] -> f16x3 operand [rows][3k] of src * scale: order 0 = activation triple [hi | lo | hi],
+ * order 1 = weight triple [hi | hi | lo]. (rows counts (output channel, tap) pairs for conv weights.) */
+int ptb200_split3_pack_f16(const float* src, void* dst, int64_t rows, int k, float scale, int order,
+                           void* stream);
+
+/* f16x3 triple [rows][3k] -> fp32 [rows][k] (hi + lo); inspection / tests. */
+int ptb200_split3_unpack_f32(const void* src, float* dst, int64_t rows, int k, void* stream);
 
 /* Weight gradient  out[m][t*n_total + n] += scale * sum_b sum_p G[b][p][m] * X[b][p + shifts[t]][n]
  * (split-K, fp32 atomic accumulation). Replaces the wgrad kernels autograd issues at
@@ -67,6 +100,12 @@ int ptb200_conv1_u8_f16(const uint8_t* images, const int* hw_dev, int n, int hma
                         int64_t image_stride, const float* mean3_host, const float* std3_host,
                         const void* wpack_f16, const float* bias, void* out_f16, void* stream);
 
+/* f16x3 variant of ptb200_conv1_u8_f16: the 3 -> 64 conv is evaluated in fp32 on the CUDA cores (K = 27),
+ * output [n][hmax*(wmax+1)][192] triples. w_f32 = [64][27] (k = (ky*3+kx)*3+c). */
+int ptb200_conv1_u8_f16x3(const uint8_t* images, const int* hw_dev, int n, int hmax, int wmax,
+                          int64_t image_stride, const float* mean3_host, const float* std3_host,
+                          const float* w_f32, const float* bias, void* out_f16x3, void* stream);
+
 /* PTrainer.resize (pt/engine/trainer.py:557-590) for one CHW uint8 image: bilinear down-scale to
  * (dh, dw) pasted at (x1, y1) on a canvas filled with int(pixel_mean). */
 int ptb200_resize_paste_u8(const uint8_t* src, uint8_t* dst, int h, int w, int dh, int dw, int x1, int y1,
@@ -78,6 +117,9 @@ int ptb200_resize_paste_u8_dev(const uint8_t* src, uint8_t* dst, int h, int w, c
 
 /* F.max_pool2d(2, 2) of pt/modeling/backbone/vgg.py:59,71 (floor mode). */
 int ptb200_maxpool2x2_f16(const void* in, void* out, int n, int h, int w, int c, void* stream);
+
+/* f16x3 variant (c = channels, rows are 3*c wide): the max is taken over hi + lo. */
+int ptb200_maxpool2x2_f16x3(const void* in, void* out, int n, int h, int w, int c, void* stream);
 
 /* Backward of ReLU followed by the 2x2 max pool (autograd of vgg.py:65-72). */
 int ptb200_maxpool2x2_relu_bwd_f16(const void* x, const void* dpooled, void* dz, int n, int h, int w,
@@ -205,6 +247,10 @@ int ptb200_roi_match_unsup(const float* pseudo_boxes, const float* pseudo_logits
 int ptb200_roi_align_fwd_f16(const void* feat, int n, int h, int w, int c, const float* rois,
                              const int* roi_count, int cap, float spatial_scale, int pooled, void* out,
                              void* stream);
+/* f16x3 variant: feat rows and output bins are [hi | lo | hi] triples (3*c wide); bilinear sums in fp32. */
+int ptb200_roi_align_fwd_f16x3(const void* feat3, int n, int h, int w, int c, const float* rois,
+                               const int* roi_count, int cap, float spatial_scale, int pooled, void* out3,
+                               void* stream);
 int ptb200_roi_align_bwd_f16(const void* dout, int n, int h, int w, int c, const float* rois,
                              const int* roi_count, int cap, float spatial_scale, int pooled,
                              float* dfeat, void* stream);

@@ -85,6 +85,8 @@ class ParamArena:
         self.data = torch.zeros(self.total, dtype=torch.float32, device=self.device)
         self.half = torch.zeros(self.total, dtype=torch.float16, device=self.device)
         self.conv1_half = torch.zeros(64, 32, dtype=torch.float16, device=self.device)
+        self.precision = "f16"  # "f16x3": split-fp16 parity precision (forward only), see pack_x3
+        self.x3 = None
         if with_grads:
             n = self.total - self.trainable_start
             self.grads = torch.zeros(n, dtype=torch.float32, device=self.device)
@@ -177,12 +179,37 @@ class ParamArena:
         """fp32 masters -> fp16 GEMM operands: one cast pass for the forward operands (same offsets),
         the K-padded first conv, and (student only) the transposed operands of the data-gradient GEMMs."""
         call("ptb200_cast_f32_f16", self.data, self.half, self.total)
+        self.x3 = None  # f16x3 triples are rebuilt lazily (parity precision only)
         w1 = self.view("backbone.vgg_block1.0.conv1.weight").view(64, 27)
         call("ptb200_cast_pad_rows_f16", w1, self.conv1_half, 64, 27, 32)
         if dgrad is None:
             dgrad = self.dgrad_half is not None
         if dgrad:
             self._pack_dgrad()
+
+    def pack_x3(self):
+        """fp32 masters -> f16x3 weight triples [Wh | Wh | Wl] of W * 2^s per tensor (s chosen so that
+        max|W| * 2^s lies in [2^13, 2^14): lo parts stay in the normal fp16 range); returns and caches
+        {name: (triples [rows, taps*3k], alpha = 2^-s)}. One host sync per tensor (parity mode only)."""
+        from . import ops
+        out = {}
+        for s in self.segments.values():
+            if s.kind not in ("conv", "fc1", "mat", "rpn_heads_w", "pred_w") or s.shape[-1] % 64 != 0:
+                continue  # (the 3 -> 64 first conv runs in fp32 from the master weights; anchors are not GEMM operands)
+            v = self.view(s.name)
+            k = s.shape[-1]
+            m = float(v.abs().max())
+            e = math.floor(math.log2(16384.0 / m)) if m > 0 else 0
+            e = max(-24, min(24, e))
+            t = ops.split3_pack(v, k, 2.0 ** e, order=1).view(s.shape[0], -1)
+            out[s.name] = (t, 2.0 ** (-e))
+        self.x3 = out
+        return out
+
+    def x3view(self, name):
+        if self.x3 is None:
+            self.pack_x3()
+        return self.x3[name]
 
     def _dg(self, name, shape):
         t = self.dgrad_half.get(name)

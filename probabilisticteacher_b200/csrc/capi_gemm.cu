@@ -4,13 +4,13 @@
 
 using namespace ptb;
 
-extern "C" int ptb200_gemm_tn_f16(const void* A, int batch, int rows, int k_per_tap, int64_t lda,
-                                  int64_t a_batch_stride, int taps, const int* shifts, const void* B,
-                                  int n_total, int bn, int epi, const float* bias, int n_bias, void* D,
-                                  int64_t ldd, int64_t d_batch_stride, const void* aux, int w_valid,
-                                  int wp, float* d0, int ld0, float* d1, int ld1, int split,
-                                  int n_valid, int max_ctas, int ksplit, const int* seg_counts, int seg_cap,
-                                  void* stream) {
+static int gemm_tn_capi(const void* A, int batch, int rows, int k_per_tap, int64_t lda,
+                        int64_t a_batch_stride, int taps, const int* shifts, const void* B,
+                        int n_total, int bn, int epi, const float* bias, int n_bias, void* D,
+                        int64_t ldd, int64_t d_batch_stride, const void* aux, int w_valid,
+                        int wp, float* d0, int ld0, float* d1, int ld1, int split,
+                        int n_valid, int max_ctas, int ksplit, const int* seg_counts, int seg_cap,
+                        float alpha, void* stream) {
   GemmTnArgs a;
   a.A = A;
   a.batch = batch;
@@ -42,7 +42,35 @@ extern "C" int ptb200_gemm_tn_f16(const void* A, int batch, int rows, int k_per_
   a.ksplit = ksplit;
   a.seg_counts = seg_counts;
   a.seg_cap = seg_cap;
+  a.alpha = alpha;
   return gemm_tn_launch(a, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int ptb200_gemm_tn_f16(const void* A, int batch, int rows, int k_per_tap, int64_t lda,
+                                  int64_t a_batch_stride, int taps, const int* shifts, const void* B,
+                                  int n_total, int bn, int epi, const float* bias, int n_bias, void* D,
+                                  int64_t ldd, int64_t d_batch_stride, const void* aux, int w_valid,
+                                  int wp, float* d0, int ld0, float* d1, int ld1, int split,
+                                  int n_valid, int max_ctas, int ksplit, const int* seg_counts, int seg_cap,
+                                  void* stream) {
+  if (epi == EPI_SPLIT3_RELU_F16 || epi == EPI_SPLIT3_F16) return 1020;  // f16x3 epilogues: use ptb200_gemm_tn_f16x3
+  return gemm_tn_capi(A, batch, rows, k_per_tap, lda, a_batch_stride, taps, shifts, B, n_total, bn, epi, bias,
+                      n_bias, D, ldd, d_batch_stride, aux, w_valid, wp, d0, ld0, d1, ld1, split, n_valid, max_ctas,
+                      ksplit, seg_counts, seg_cap, 1.0f, stream);
+}
+
+extern "C" int ptb200_gemm_tn_f16x3(const void* A3, int batch, int rows, int k3_per_tap, int64_t lda,
+                                    int64_t a_batch_stride, int taps, const int* shifts, const void* B3,
+                                    int n_total, int bn, int epi, const float* bias, int n_bias, void* D3,
+                                    int64_t ldd, int64_t d_batch_stride, int w_valid, int wp, float* d0, int ld0,
+                                    float* d1, int ld1, int split, int n_valid, int max_ctas, int ksplit,
+                                    const int* seg_counts, int seg_cap, float alpha, void* stream) {
+  if (epi != EPI_SPLIT3_RELU_F16 && epi != EPI_SPLIT3_F16 && epi != EPI_F32_SPLIT && epi != EPI_ATOMIC_F32)
+    return 1021;
+  if (k3_per_tap % 3 != 0) return 1022;
+  return gemm_tn_capi(A3, batch, rows, k3_per_tap, lda, a_batch_stride, taps, shifts, B3, n_total, bn, epi, bias,
+                      n_bias, D3, ldd, d_batch_stride, nullptr, w_valid, wp, d0, ld0, d1, ld1, split, n_valid,
+                      max_ctas, ksplit, seg_counts, seg_cap, alpha, stream);
 }
 
 extern "C" int ptb200_gemm_wgrad_f16(const void* G, int64_t ldg, int64_t g_batch_stride, const void* X,

@@ -280,13 +280,57 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             for (int j = 0; j < 16; ++j) {
               const int n = n0 + c0 + j;
               if (n < p.n_valid) {
-                const float x = __uint_as_float(v[j]) + bias_s[c0 + j];
+                const float x = __uint_as_float(v[j]) * p.alpha + bias_s[c0 + j];
                 if (n < p.split)
                   p.d0[grow * p.ld0 + n] = x;
                 else
                   p.d1[grow * p.ld1 + (n - p.split)] = x;
               }
             }
+          }
+        }
+      } else if (p.epi == EPI_SPLIT3_RELU_F16 || p.epi == EPI_SPLIT3_F16) {
+        // f16x3 output: hi chunk in staging buffer 0, lo chunk in buffer 1, three TMA stores
+        // (columns [n], [n_total + n], [2 n_total + n] of the 3*n_total wide D). Never ROWWIN.
+        for (int c0 = 0; c0 < bn; c0 += 64) {
+          if (et == 0) tma_store_wait_read<0>();
+          named_bar_sync(1, EPI_THREADS);
+          uint32_t v[64];
+          tmem_ld_32x32(t_addr + c0, v);
+          tmem_ld_32x32(t_addr + c0 + 32, v + 32);
+          tmem_ld_wait();
+          uint8_t* rowh = staging + r * 128;
+          uint8_t* rowl = staging + STAGING_BYTES + r * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float f[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              f[e] = __uint_as_float(v[j * 8 + e]) * p.alpha + bias_s[c0 + j * 8 + e];
+              if (p.epi == EPI_SPLIT3_RELU_F16) f[e] = fmaxf(f[e], 0.f);
+              if (!row_live) f[e] = 0.f;
+            }
+            uint4 oh, ol;
+            uint32_t* ohp = reinterpret_cast<uint32_t*>(&oh);
+            uint32_t* olp = reinterpret_cast<uint32_t*>(&ol);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const __half2 h = __floats2half2_rn(f[2 * e], f[2 * e + 1]);
+              const float2 hf = __half22float2(h);
+              const __half2 l = __floats2half2_rn(f[2 * e] - hf.x, f[2 * e + 1] - hf.y);
+              ohp[e] = *reinterpret_cast<const uint32_t*>(&h);
+              olp[e] = *reinterpret_cast<const uint32_t*>(&l);
+            }
+            *reinterpret_cast<uint4*>(rowh + ((j ^ (r & 7)) << 4)) = oh;
+            *reinterpret_cast<uint4*>(rowl + ((j ^ (r & 7)) << 4)) = ol;
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(1, EPI_THREADS);
+          if (et == 0) {
+            tma_store_3d(&map_d, staging, n0 + c0, row0, b);
+            tma_store_3d(&map_d, staging + STAGING_BYTES, p.n_total + n0 + c0, row0, b);
+            tma_store_3d(&map_d, staging, 2 * p.n_total + n0 + c0, row0, b);
+            tma_store_commit();
           }
         }
       } else {
@@ -318,7 +362,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             uint4* dst = reinterpret_cast<uint4*>(rowp + ((j ^ (r & 7)) << 4));
             float f[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[j * 8 + e]) + bias_s[c0 + j * 8 + e];
+            for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[j * 8 + e]) * p.alpha + bias_s[c0 + j * 8 + e];
             if (p.epi == EPI_BIAS_RELU_F16) {
 #pragma unroll
               for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
@@ -433,7 +477,8 @@ int gemm_tn_launch(const GemmTnArgs& a, cudaStream_t stream) {
     const char* e = getenv("PTB200_ROWWIN");
     rowwin_opt = (e == nullptr) ? 1 : atoi(e);
   }
-  bool rowwin = rowwin_opt != 0 && a.taps == 9 && a.wp > 0 && a.bn <= 128 && !f32_out && a.ksplit <= 1;
+  const bool split3 = a.epi == EPI_SPLIT3_RELU_F16 || a.epi == EPI_SPLIT3_F16;
+  bool rowwin = rowwin_opt != 0 && a.taps == 9 && a.wp > 0 && a.bn <= 128 && !f32_out && a.ksplit <= 1 && !split3;
   if (rowwin)
     for (int t = 0; t < 9; ++t) rowwin = rowwin && a.shifts[t] == (t / 3 - 1) * a.wp + (t % 3 - 1);
   CUtensorMap ma, mb, md, mx;
@@ -456,7 +501,7 @@ int gemm_tn_launch(const GemmTnArgs& a, cudaStream_t stream) {
     if (make_tmap_f16(&mb, a.B, 2, dims, str, box)) return 1011;
   }
   if (!f32_out) {
-    uint64_t dims[3] = {(uint64_t)a.n_total, (uint64_t)a.rows, (uint64_t)a.batch};
+    uint64_t dims[3] = {(uint64_t)a.n_total * (split3 ? 3 : 1), (uint64_t)a.rows, (uint64_t)a.batch};
     uint64_t str[2] = {(uint64_t)a.ldd * 2, (uint64_t)a.d_batch_stride * 2};
     uint32_t box[3] = {64, BM, 1};
     if (make_tmap_f16(&md, a.D, 3, dims, str, box)) return 1012;
@@ -491,6 +536,7 @@ int gemm_tn_launch(const GemmTnArgs& a, cudaStream_t stream) {
   p.n_valid = a.n_valid;
   p.seg_counts = a.seg_counts;
   p.seg_cap = a.seg_cap;
+  p.alpha = a.alpha;
   if (a.seg_counts != nullptr && (a.batch != 1 || a.seg_cap <= 0)) return 1008;
   // keep the whole filter resident when every CTA uses the same one (single N tile, single K chunk)
   const bool bres = rowwin && a.n_total == a.bn && a.k_per_tap == BK;

@@ -11,6 +11,11 @@ enum GemmEpilogue {
   EPI_F32_SPLIT = 2,      // acc + bias -> fp32, columns [0,split) to d0, [split,n_valid) to d1
   EPI_MASK_F16 = 3,       // D = (aux > 0) ? acc : 0 -> fp16 (ReLU backward fused into dgrad)
   EPI_ATOMIC_F32 = 4,     // split-K partial: d0[row][n] += acc (fp32 red.add), bias/activation applied later
+  // split-fp16 ("f16x3") parity precision: x = alpha*acc + bias (ReLU for 5) is written as the K-concatenated
+  // triple [hi | lo | hi] (hi = fp16(x), lo = fp16(x - hi)) into D of width 3*n_total, so that the next
+  // GEMM against [Wh | Wh | Wl] evaluates hi*Wh + lo*Wh + hi*Wl with fp32 accumulation
+  EPI_SPLIT3_RELU_F16 = 5,
+  EPI_SPLIT3_F16 = 6,
 };
 
 struct GemmTnParams {
@@ -22,6 +27,7 @@ struct GemmTnParams {
   int stages;
   int ksplit;
   int b_resident;  // ROWWIN only: whole 3x3 filter (9 x bn x 64) stays in shared memory
+  float alpha;     // accumulator scale applied before the bias (power-of-two weight scaling of the f16x3 mode)
   const float* bias;
   int n_bias;
   float* d0;
@@ -61,6 +67,7 @@ struct GemmTnArgs {
   int ksplit;    // > 1 only with EPI_ATOMIC_F32
   const int* seg_counts;
   int seg_cap;
+  float alpha = 1.0f;
 };
 
 int gemm_tn_launch(const GemmTnArgs& a, cudaStream_t stream);

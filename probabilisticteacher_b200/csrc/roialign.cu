@@ -121,7 +121,8 @@ constexpr int kMaxP = 7;
 // One CTA per roi: threads = P (bin columns) x C/8 (channel groups). The 2P axis-weight vectors of
 // the roi are computed once (threads 0..2P-1) and shared by all P*P bins; each thread then walks the
 // P bin rows of its column. BWD = true scatters the output gradient instead (fp32 vector atomics).
-template <bool BWD>
+// X3 (forward only): feature rows and output bins are f16x3 triples [hi | lo | hi] of width 3C.
+template <bool BWD, bool X3 = false>
 __global__ void __launch_bounds__(512)
 roi_align_roi_kernel(const __half* __restrict__ feat, const __half* __restrict__ dout, int H, int W, int C,
                      const float4* __restrict__ rois, const int* __restrict__ roi_count, int cap, float scale,
@@ -133,12 +134,14 @@ roi_align_roi_kernel(const __half* __restrict__ feat, const __half* __restrict__
   const int pw = threadIdx.x / c8, cg = threadIdx.x - pw * c8;
   const int c0 = cg * 8;
   const int Wp = W + 1;
+  const int LD = X3 ? 3 * C : C;  // row pitch of feat / out in elements
   const bool valid = roi_count == nullptr || j < roi_count[n];
   if (!valid) {
     if (!BWD)
       for (int ph = 0; ph < P; ++ph)
-        *reinterpret_cast<uint4*>(out + (static_cast<int64_t>(roi) * P * P + ph * P + pw) * C + c0) =
-            make_uint4(0, 0, 0, 0);
+        for (int s3 = 0; s3 < (X3 ? 3 : 1); ++s3)
+          *reinterpret_cast<uint4*>(out + (static_cast<int64_t>(roi) * P * P + ph * P + pw) * LD + s3 * C + c0) =
+              make_uint4(0, 0, 0, 0);
     return;
   }
   const RoiGeom g = roi_geom(rois[roi], scale, P);
@@ -152,11 +155,11 @@ roi_align_roi_kernel(const __half* __restrict__ feat, const __half* __restrict__
   __syncthreads();
   const Axis& ax = s_ax[P + pw];
   const bool sep_x = ax.n >= 0;
-  const int64_t img_off = static_cast<int64_t>(n) * H * Wp * C + c0;
+  const int64_t img_off = static_cast<int64_t>(n) * H * Wp * LD + c0;
   for (int ph = 0; ph < P; ++ph) {
     const Axis& ay = s_ax[ph];
     const int bin = ph * P + pw;
-    const int64_t o_off = (static_cast<int64_t>(roi) * P * P + bin) * C + c0;
+    const int64_t o_off = (static_cast<int64_t>(roi) * P * P + bin) * LD + c0;
     float acc[8];
     float gr[8];
     if (BWD) {
@@ -179,20 +182,28 @@ roi_align_roi_kernel(const __half* __restrict__ feat, const __half* __restrict__
       for (int iy = 0; iy < ay.n; ++iy) {
         const float wy = ay.w[iy];
         if (wy == 0.f) continue;
-        const int64_t row_off = img_off + static_cast<int64_t>((ay.lo + iy) * Wp + ax.lo) * C;
+        const int64_t row_off = img_off + static_cast<int64_t>((ay.lo + iy) * Wp + ax.lo) * LD;
         for (int ix = 0; ix < ax.n; ++ix) {
           const float wgt = wy * ax.w[ix];
           if (wgt == 0.f) continue;
           if (BWD) {
-            float* p = dfeat + row_off + static_cast<int64_t>(ix) * C;
+            float* p = dfeat + row_off + static_cast<int64_t>(ix) * LD;
             red_add_v4(p, gr[0] * wgt, gr[1] * wgt, gr[2] * wgt, gr[3] * wgt);
             red_add_v4(p + 4, gr[4] * wgt, gr[5] * wgt, gr[6] * wgt, gr[7] * wgt);
           } else {
-            const uint4 v = *reinterpret_cast<const uint4*>(feat + row_off + static_cast<int64_t>(ix) * C);
+            const uint4 v = *reinterpret_cast<const uint4*>(feat + row_off + static_cast<int64_t>(ix) * LD);
             const __half2* h = reinterpret_cast<const __half2*>(&v);
+            uint4 vl = make_uint4(0, 0, 0, 0);
+            if (X3) vl = *reinterpret_cast<const uint4*>(feat + row_off + static_cast<int64_t>(ix) * LD + C);
+            const __half2* hl = reinterpret_cast<const __half2*>(&vl);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              const float2 f = __half22float2(h[e]);
+              float2 f = __half22float2(h[e]);
+              if (X3) {
+                const float2 fl = __half22float2(hl[e]);
+                f.x += fl.x;
+                f.y += fl.y;
+              }
               acc[2 * e] += wgt * f.x;
               acc[2 * e + 1] += wgt * f.y;
             }
@@ -212,15 +223,23 @@ roi_align_roi_kernel(const __half* __restrict__ feat, const __half* __restrict__
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             if (BWD) {
-              float* p = dfeat + img_off + static_cast<int64_t>(offs[k]) * C;
+              float* p = dfeat + img_off + static_cast<int64_t>(offs[k]) * LD;
               red_add_v4(p, gr[0] * ws[k], gr[1] * ws[k], gr[2] * ws[k], gr[3] * ws[k]);
               red_add_v4(p + 4, gr[4] * ws[k], gr[5] * ws[k], gr[6] * ws[k], gr[7] * ws[k]);
             } else {
-              const uint4 v = *reinterpret_cast<const uint4*>(feat + img_off + static_cast<int64_t>(offs[k]) * C);
+              const uint4 v = *reinterpret_cast<const uint4*>(feat + img_off + static_cast<int64_t>(offs[k]) * LD);
               const __half2* h = reinterpret_cast<const __half2*>(&v);
+              uint4 vl = make_uint4(0, 0, 0, 0);
+              if (X3) vl = *reinterpret_cast<const uint4*>(feat + img_off + static_cast<int64_t>(offs[k]) * LD + C);
+              const __half2* hl = reinterpret_cast<const __half2*>(&vl);
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                const float2 f = __half22float2(h[e]);
+                float2 f = __half22float2(h[e]);
+                if (X3) {
+                  const float2 fl = __half22float2(hl[e]);
+                  f.x += fl.x;
+                  f.y += fl.y;
+                }
                 acc[2 * e] += ws[k] * f.x;
                 acc[2 * e + 1] += ws[k] * f.y;
               }
@@ -231,9 +250,18 @@ roi_align_roi_kernel(const __half* __restrict__ feat, const __half* __restrict__
     }
     if (!BWD) {
       __align__(16) __half r[8];
+      __align__(16) __half rl[8];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) r[e] = __float2half_rn(acc[e] / g.count);
+      for (int e = 0; e < 8; ++e) {
+        const float x = acc[e] / g.count;
+        r[e] = __float2half_rn(x);
+        if (X3) rl[e] = __float2half_rn(x - __half2float(r[e]));
+      }
       *reinterpret_cast<uint4*>(out + o_off) = *reinterpret_cast<const uint4*>(r);
+      if (X3) {
+        *reinterpret_cast<uint4*>(out + o_off + C) = *reinterpret_cast<const uint4*>(rl);
+        *reinterpret_cast<uint4*>(out + o_off + 2 * C) = *reinterpret_cast<const uint4*>(r);
+      }
     }
   }
 }
@@ -258,6 +286,16 @@ extern "C" int ptb200_roi_align_fwd_f16(const void* feat, int n, int h, int w, i
                                         void* stream) {
   if (c % 8 != 0 || pooled > kMaxP || pooled * (c / 8) > 512) return 1401;
   roi_align_roi_kernel<false><<<n * cap, pooled * (c / 8), 0, STREAM>>>(
+      static_cast<const __half*>(feat), nullptr, h, w, c, reinterpret_cast<const float4*>(rois), roi_count, cap,
+      spatial_scale, pooled, static_cast<__half*>(out), nullptr);
+  return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int ptb200_roi_align_fwd_f16x3(const void* feat, int n, int h, int w, int c, const float* rois,
+                                          const int* roi_count, int cap, float spatial_scale, int pooled, void* out,
+                                          void* stream) {
+  if (c % 8 != 0 || pooled > kMaxP || pooled * (c / 8) > 512) return 1401;
+  roi_align_roi_kernel<false, true><<<n * cap, pooled * (c / 8), 0, STREAM>>>(
       static_cast<const __half*>(feat), nullptr, h, w, c, reinterpret_cast<const float4*>(rois), roi_count, cap,
       spatial_scale, pooled, static_cast<__half*>(out), nullptr);
   return static_cast<int>(cudaGetLastError());

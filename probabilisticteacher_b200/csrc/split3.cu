@@ -1,0 +1,233 @@
+// Helpers of the split-fp16 ("f16x3") parity-precision forward path (see ptb200_gemm_tn_f16x3 in
+// include/ptb200.h). An fp32 value x is carried as hi = fp16(x), lo = fp16(x - hi); activation rows are
+// the K-concatenation [hi | lo | hi] (3C wide), weight rows [Wh | Wh | Wl], so the tensor-core main loop
+// needs no change. Everything here is HBM-bound streaming work with 16-byte accesses, plus the first
+// VGG conv (K = 27) evaluated in fp32 on the CUDA cores.
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include "../../include/ptb200.h"
+
+namespace {
+
+constexpr int kThreads = 256;
+
+inline int grid_for(int64_t n, int per_block = kThreads) {
+  int64_t g = (n + per_block - 1) / per_block;
+  if (g < 1) g = 1;
+  if (g > 148 * 32) g = 148 * 32;
+  return static_cast<int>(g);
+}
+
+__device__ __forceinline__ void split_hl(float x, __half& h, __half& l) {
+  h = __float2half_rn(x);
+  l = __float2half_rn(x - __half2float(h));
+}
+
+// src fp32 [rows][k] -> dst fp16 [rows][3k]; order 0: [hi | lo | hi], order 1: [hi | hi | lo]
+__global__ void split3_pack_kernel(const float* __restrict__ src, __half* __restrict__ dst, int64_t rows, int k,
+                                   float scale, int order) {
+  const int64_t total = rows * k;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / k;
+    const int c = static_cast<int>(i - r * k);
+    __half h, l;
+    split_hl(src[i] * scale, h, l);
+    __half* d = dst + r * 3 * k + c;
+    d[0] = h;
+    d[k] = order == 0 ? l : h;
+    d[2 * k] = order == 0 ? h : l;
+  }
+}
+
+__global__ void split3_unpack_kernel(const __half* __restrict__ src, float* __restrict__ dst, int64_t rows, int k) {
+  const int64_t total = rows * k;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / k;
+    const int c = static_cast<int>(i - r * k);
+    const __half* s = src + r * 3 * k + c;
+    dst[i] = __half2float(s[0]) + __half2float(s[k]);
+  }
+}
+
+// 2x2 / stride 2 max pool over triples: the arg-max is taken over hi + lo (exact in fp32 for |lo| <= ulp(hi)/2),
+// its (hi, lo) pair is copied. One thread = (output pixel, 8 channels). Pad column written as zero.
+__global__ void maxpool2x2_x3_kernel(const __half* __restrict__ in, __half* __restrict__ out, int N, int H, int W,
+                                     int C) {
+  const int Wp = W + 1, Ho = H / 2, Wo = W / 2, Wop = Wo + 1, C8 = C / 8;
+  const int64_t LD = 3 * static_cast<int64_t>(C);
+  const int64_t total = static_cast<int64_t>(N) * Ho * Wop * C8;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int c8 = static_cast<int>(i % C8);
+    int64_t r = i / C8;
+    const int xo = static_cast<int>(r % Wop);
+    r /= Wop;
+    const int yo = static_cast<int>(r % Ho);
+    const int n = static_cast<int>(r / Ho);
+    __align__(16) __half oh[8], ol[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) oh[e] = ol[e] = __float2half(0.f);
+    if (xo < Wo) {
+      float best[8];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const __half* base =
+            in + ((static_cast<int64_t>(n) * H + 2 * yo + (q >> 1)) * Wp + 2 * xo + (q & 1)) * LD + c8 * 8;
+        const uint4 vh = *reinterpret_cast<const uint4*>(base);
+        const uint4 vl = *reinterpret_cast<const uint4*>(base + C);
+        const __half* hh = reinterpret_cast<const __half*>(&vh);
+        const __half* ll = reinterpret_cast<const __half*>(&vl);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float v = __half2float(hh[e]) + __half2float(ll[e]);
+          if (q == 0 || v > best[e]) {
+            best[e] = v;
+            oh[e] = hh[e];
+            ol[e] = ll[e];
+          }
+        }
+      }
+    }
+    __half* o = out + ((static_cast<int64_t>(n) * Ho + yo) * Wop + xo) * LD + c8 * 8;
+    *reinterpret_cast<uint4*>(o) = *reinterpret_cast<const uint4*>(oh);
+    *reinterpret_cast<uint4*>(o + C) = *reinterpret_cast<const uint4*>(ol);
+    *reinterpret_cast<uint4*>(o + 2 * C) = *reinterpret_cast<const uint4*>(oh);
+  }
+}
+
+// Pre-processing + first VGG conv in fp32: one thread = one pixel x 16 output channels (4 threads per pixel);
+// the 27 normalised inputs come from the L1-resident neighbourhood, the 64 x 27 filter sits in shared memory.
+__global__ void __launch_bounds__(256)
+conv1_u8_x3_kernel(const uint8_t* __restrict__ img, const int* __restrict__ hw, int N, int Hmax, int Wmax,
+                   int64_t img_stride, float m0, float m1, float m2, float is0, float is1, float is2,
+                   const float* __restrict__ w /* [64][27] */, const float* __restrict__ bias,
+                   __half* __restrict__ out /* [N][Hmax*Wp][192] */) {
+  __shared__ float ws[27][64];
+  __shared__ float bs[64];
+  for (int i = threadIdx.x; i < 27 * 64; i += blockDim.x) ws[i % 27][i / 27] = w[i];
+  if (threadIdx.x < 64) bs[threadIdx.x] = bias[threadIdx.x];
+  __syncthreads();
+  const int Wp = Wmax + 1;
+  const int64_t total = static_cast<int64_t>(N) * Hmax * Wp * 4;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int part = static_cast<int>(i & 3);
+    const int64_t pix = i >> 2;
+    const int x = static_cast<int>(pix % Wp);
+    const int64_t ny = pix / Wp;
+    const int y = static_cast<int>(ny % Hmax);
+    const int n = static_cast<int>(ny / Hmax);
+    float acc[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) acc[e] = 0.f;
+    if (x < Wmax) {
+      const int h = hw[2 * n], wd = hw[2 * n + 1];
+      const uint8_t* ib = img + n * img_stride;
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
+        const bool ok = yy >= 0 && yy < h && xx >= 0 && xx < wd;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          float v = 0.f;
+          if (ok) {
+            const float mean = c == 0 ? m0 : (c == 1 ? m1 : m2);
+            const float istd = c == 0 ? is0 : (c == 1 ? is1 : is2);
+            v = (static_cast<float>(__ldg(ib + (static_cast<int64_t>(c) * h + yy) * wd + xx)) - mean) * istd;
+          }
+          const float* wr = &ws[t * 3 + c][part * 16];
+#pragma unroll
+          for (int e = 0; e < 16; ++e) acc[e] = fmaf(v, wr[e], acc[e]);
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < 16; ++e) acc[e] = fmaxf(acc[e] + bs[part * 16 + e], 0.f);
+    }
+    __align__(16) __half oh[16], ol[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) split_hl(acc[e], oh[e], ol[e]);
+    __half* o = out + pix * 192 + part * 16;
+    const uint4* ph = reinterpret_cast<const uint4*>(oh);
+    const uint4* pl = reinterpret_cast<const uint4*>(ol);
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      *reinterpret_cast<uint4*>(o + q * 8) = ph[q];
+      *reinterpret_cast<uint4*>(o + 64 + q * 8) = pl[q];
+      *reinterpret_cast<uint4*>(o + 128 + q * 8) = ph[q];
+    }
+  }
+}
+
+// Finishes a K-chunked f16x3 GEMM (fp32 partial sums reduced with red.add): x = act(alpha * in + bias) -> triple.
+// wp > 0: rows with (row % wp) >= w_valid (the pad column of the flat activation layout) are written as zero.
+__global__ void bias_act_split3_kernel(const float* __restrict__ in, const float* __restrict__ bias, int relu,
+                                       float alpha, int64_t rows, int n, int wp, int w_valid,
+                                       __half* __restrict__ out) {
+  const int n4 = n / 4;
+  const int64_t total4 = rows * n4;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total4;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / n4;
+    const int c = static_cast<int>(i - r * n4) * 4;
+    const float4 v4 = reinterpret_cast<const float4*>(in)[i];
+    float v[4] = {v4.x, v4.y, v4.z, v4.w};
+    const bool live = wp <= 0 || static_cast<int>(r % wp) < w_valid;
+    __align__(8) __half h[4], l[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float x = v[e] * alpha + (bias != nullptr ? bias[c + e] : 0.f);
+      if (relu) x = fmaxf(x, 0.f);
+      if (!live) x = 0.f;
+      split_hl(x, h[e], l[e]);
+    }
+    __half* o = out + r * 3 * n + c;
+    *reinterpret_cast<uint2*>(o) = *reinterpret_cast<const uint2*>(h);
+    *reinterpret_cast<uint2*>(o + n) = *reinterpret_cast<const uint2*>(l);
+    *reinterpret_cast<uint2*>(o + 2 * n) = *reinterpret_cast<const uint2*>(h);
+  }
+}
+
+}  // namespace
+
+#define STREAM static_cast<cudaStream_t>(stream)
+
+extern "C" int ptb200_split3_pack_f16(const float* src, void* dst, int64_t rows, int k, float scale, int order,
+                                      void* stream) {
+  split3_pack_kernel<<<grid_for(rows * k), kThreads, 0, STREAM>>>(src, static_cast<__half*>(dst), rows, k, scale,
+                                                                  order);
+  return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int ptb200_split3_unpack_f32(const void* src, float* dst, int64_t rows, int k, void* stream) {
+  split3_unpack_kernel<<<grid_for(rows * k), kThreads, 0, STREAM>>>(static_cast<const __half*>(src), dst, rows, k);
+  return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int ptb200_maxpool2x2_f16x3(const void* in, void* out, int n, int h, int w, int c, void* stream) {
+  if (c % 8 != 0) return 1201;
+  const int64_t total = static_cast<int64_t>(n) * (h / 2) * (w / 2 + 1) * (c / 8);
+  maxpool2x2_x3_kernel<<<grid_for(total), kThreads, 0, STREAM>>>(static_cast<const __half*>(in),
+                                                                static_cast<__half*>(out), n, h, w, c);
+  return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int ptb200_conv1_u8_f16x3(const uint8_t* images, const int* hw_dev, int n, int hmax, int wmax,
+                                     int64_t image_stride, const float* mean3_host, const float* std3_host,
+                                     const float* w_f32, const float* bias, void* out_f16x3, void* stream) {
+  const int64_t total = static_cast<int64_t>(n) * hmax * (wmax + 1) * 4;
+  conv1_u8_x3_kernel<<<grid_for(total), kThreads, 0, STREAM>>>(
+      images, hw_dev, n, hmax, wmax, image_stride, mean3_host[0], mean3_host[1], mean3_host[2],
+      1.f / std3_host[0], 1.f / std3_host[1], 1.f / std3_host[2], w_f32, bias, static_cast<__half*>(out_f16x3));
+  return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int ptb200_bias_act_split3_f16(const float* in, const float* bias, int relu, float alpha, int64_t rows,
+                                          int n, int wp, int w_valid, void* out3, void* stream) {
+  if (n % 4 != 0) return 1203;
+  bias_act_split3_kernel<<<grid_for(rows * n / 4), kThreads, 0, STREAM>>>(in, bias, relu, alpha, rows, n, wp, w_valid,
+                                                                         static_cast<__half*>(out3));
+  return static_cast<int>(cudaGetLastError());
+}

@@ -30,6 +30,17 @@ class VGG(nn.Module):
         specs = ar.conv_specs
         records = []
         block = 1
+        if ar.precision == "f16x3":
+            # split-fp16 parity precision (forward only): x and every activation are [hi | lo | hi] triples
+            assert not save, "the f16x3 parity precision has no backward"
+            for name, cin, cout, _ in specs[1:]:
+                b = int(name.split("vgg_block")[1][0])
+                if b != block:
+                    x = ops.maxpool2x2_x3(x)
+                    block = b
+                w3, alpha = ar.x3view(name + ".weight")
+                x = ops.conv3x3_x3(x, w3, alpha, ar.view(name + ".bias"))
+            return {"vgg_block5": x}, records
         for name, cin, cout, trainable in specs[1:]:
             b = int(name.split("vgg_block")[1][0])
             pooled = False

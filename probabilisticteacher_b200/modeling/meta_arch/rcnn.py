@@ -42,7 +42,10 @@ class _LossBundle(torch.autograd.Function):
 
 @META_ARCH_REGISTRY.register()
 class GuassianGeneralizedRCNN(nn.Module):
-    def __init__(self, cfg, device=None, loss_scale=1024.0, with_grads=True):
+    def __init__(self, cfg, device=None, loss_scale=1024.0, with_grads=True, precision="f16"):
+        """precision: "f16" (fp16 operands / fp32 accumulation: the training and benchmark path) or "f16x3"
+        (split-fp16 operands, ~fp32 accuracy, forward only: the mode in which the 1e-3 parity of the
+        losses / logits with the reference's fp32 path is checked)."""
         super().__init__()
         self.cfg = cfg
         dev = torch.device(device or cfg.MODEL.DEVICE)
@@ -54,6 +57,9 @@ class GuassianGeneralizedRCNN(nn.Module):
                                 pooled=cfg.MODEL.ROI_BOX_HEAD.POOLER_RESOLUTION,
                                 freeze_at=cfg.MODEL.BACKBONE.FREEZE_AT, differentiable_anchors=diff, device=dev,
                                 with_grads=with_grads)
+        if precision not in ("f16", "f16x3"):
+            raise ValueError(f"unknown precision {precision!r}")
+        self.arena.precision = precision
         self.loss_scale = float(loss_scale)
         self.backbone = BACKBONE_REGISTRY.get(cfg.MODEL.BACKBONE.NAME)(cfg, self.arena, self.loss_scale)
         anchor_gen = ANCHOR_GENERATOR_REGISTRY.get(cfg.MODEL.ANCHOR_GENERATOR.NAME)(cfg, self.arena)
@@ -148,6 +154,10 @@ class GuassianGeneralizedRCNN(nn.Module):
             self._hw_cache[key] = cached
         hw_i, img_hw = cached
         name0 = self.arena.conv_specs[0][0]
+        if self.arena.precision == "f16x3":
+            act = ops.conv1_u8_x3(batch.view(len(imgs), -1), hw_i, H, W, self._mean, self._std,
+                                  self.arena.view(name0 + ".weight").view(64, 27), self.arena.view(name0 + ".bias"))
+            return act, sizes, img_hw
         act = ops.conv1_u8(batch.view(len(imgs), -1), hw_i, H, W, self._mean, self._std, self.arena.conv1_half,
                            self.arena.view(name0 + ".bias"))
         return act, sizes, img_hw
@@ -215,6 +225,8 @@ class GuassianGeneralizedRCNN(nn.Module):
             return self.inference(batched_inputs)
         act, sizes, img_hw = self.preprocess_image(batched_inputs)
         need_grad = branch in ("supervised", "unsupervised") and torch.is_grad_enabled()
+        if need_grad and self.arena.precision == "f16x3":
+            raise RuntimeError("precision='f16x3' is the forward-only parity mode: call it under torch.no_grad()")
         feats, records = self.backbone(act, save=need_grad)
         feat = feats["vgg_block5"]
         targets = None

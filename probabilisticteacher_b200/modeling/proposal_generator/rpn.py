@@ -29,9 +29,16 @@ class GuassianRPNHead(nn.Module):
         ar = self.arena
         C, A = ar.C, ar.A
         p = "proposal_generator.rpn_head."
-        t = ops.conv3x3(feat, ar.hview(p + "conv.weight").view(C, 9 * C), ar.view(p + "conv.bias"), relu=True)
         n_valid = A * 9
         n_total = (n_valid + 15) // 16 * 16
+        if ar.precision == "f16x3":
+            w3, alpha = ar.x3view(p + "conv.weight")
+            t = ops.conv3x3_x3(feat, w3, alpha, ar.view(p + "conv.bias"))
+            w3, alpha = ar.x3view(p + "_heads.weight")
+            logits, deltas = ops.gemm_tn_x3(t.t, w3, alpha, epi=ops.EPI_F32_SPLIT, bias=ar.view(p + "_heads.bias"),
+                                            split=A, n_valid=n_valid, n_total=n_total, bn=n_total)
+            return t, logits, deltas
+        t = ops.conv3x3(feat, ar.hview(p + "conv.weight").view(C, 9 * C), ar.view(p + "conv.bias"), relu=True)
         logits, deltas = ops.gemm_tn(t.t, ar.hview(p + "_heads.weight"), epi=ops.EPI_F32_SPLIT,
                                      bias=ar.view(p + "_heads.bias"), split=A, n_valid=n_valid, n_total=n_total,
                                      bn=n_total)

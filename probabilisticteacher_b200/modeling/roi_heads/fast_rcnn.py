@@ -62,6 +62,12 @@ class GuassianFastRCNNOutputLayers(nn.Module):
         n_total = (n_valid + 15) // 16 * 16
         rows = h2.shape[0]
         p = "roi_heads.box_predictor."
+        if ar.precision == "f16x3":
+            w3, alpha = ar.x3view(p + "_heads.weight")
+            s, d = ops.gemm_tn_x3(h2.view(1, rows, -1), w3, alpha, epi=ops.EPI_F32_SPLIT,
+                                  bias=ar.view(p + "_heads.bias"), split=K + 1, n_valid=n_valid, n_total=n_total,
+                                  bn=n_total, seg=seg)
+            return s.view(rows, K + 1), d.view(rows, 8 * K)
         s, d = ops.gemm_tn(h2.view(1, rows, -1), ar.hview(p + "_heads.weight"), epi=ops.EPI_F32_SPLIT,
                            bias=ar.view(p + "_heads.bias"), split=K + 1, n_valid=n_valid, n_total=n_total, bn=n_total,
                            seg=seg)

@@ -32,6 +32,8 @@ class GuassianROIHead(nn.Module):
     # ------------------------------------------------------------------ box head
     def _box_head(self, feat, rois, counts, cap):
         ar = self.arena
+        if ar.precision == "f16x3":
+            return self._box_head_x3(feat, rois, counts, cap)
         x0 = ops.roi_align_fwd(feat, rois, counts, cap, self.pooler_scale, self.pooler_resolution)
         rows = x0.shape[0]
         p = "roi_heads.box_head."
@@ -42,6 +44,20 @@ class GuassianROIHead(nn.Module):
         h1 = ops.gemm_tn(x0.view(1, rows, -1), w1, epi=ops.EPI_BIAS_RELU, bias=ar.view(p + "fc1.bias"), ksplit=ksplit,
                          seg=seg)
         h2 = ops.gemm_tn(h1, ar.hview(p + "fc2.weight"), epi=ops.EPI_BIAS_RELU, bias=ar.view(p + "fc2.bias"), seg=seg)
+        scores, deltas = self.box_predictor(h2.view(rows, -1), seg=seg)
+        return x0, h1.view(rows, -1), h2.view(rows, -1), scores, deltas
+
+    def _box_head_x3(self, feat, rois, counts, cap):
+        """Split-fp16 parity precision of the box head (forward only)."""
+        ar = self.arena
+        x0 = ops.roi_align_fwd_x3(feat, rois, counts, cap, self.pooler_scale, self.pooler_resolution)
+        rows = x0.shape[0]
+        seg = (counts, cap)
+        p = "roi_heads.box_head."
+        w3, alpha = ar.x3view(p + "fc1.weight")
+        h1 = ops.gemm_tn_x3(x0.view(1, rows, -1), w3, alpha, bias=ar.view(p + "fc1.bias"), seg=seg)
+        w3, alpha = ar.x3view(p + "fc2.weight")
+        h2 = ops.gemm_tn_x3(h1, w3, alpha, bias=ar.view(p + "fc2.bias"), seg=seg)
         scores, deltas = self.box_predictor(h2.view(rows, -1), seg=seg)
         return x0, h1.view(rows, -1), h2.view(rows, -1), scores, deltas
 

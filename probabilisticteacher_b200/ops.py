@@ -7,6 +7,7 @@ import torch
 from ._lib import call
 
 EPI_BIAS_RELU, EPI_BIAS, EPI_F32_SPLIT, EPI_MASK, EPI_ATOMIC = 0, 1, 2, 3, 4
+EPI_SPLIT3_RELU, EPI_SPLIT3 = 5, 6  # f16x3 parity precision only
 
 # fp16 activation in the flattened right-padded layout: t is [N, H*(W+1), C]
 FlatAct = namedtuple("FlatAct", ["t", "H", "W"])
@@ -89,6 +90,105 @@ def conv3x3(x: FlatAct, w_packed, bias, relu=True, aux=None, out=None):
     o = gemm_tn(x.t, w_packed, taps=9, shifts=_shifts(Wp), epi=epi, bias=bias, aux=aux, w_valid=x.W, wp=Wp,
                 out=out)
     return FlatAct(o, x.H, x.W)
+
+
+# ------------------------------------------------------------------------------------------ f16x3
+# Split-fp16 parity precision (forward only): activations are [hi | lo | hi] triples (3C wide), weights
+# [Wh | Wh | Wl] triples of W * 2^s with alpha = 2^-s (ParamArena.pack_x3). See include/ptb200.h.
+# longest chain of tensor-core accumulations (k-iterations of 64 = 4 MMAs each) before the partial sum is
+# promoted to a round-to-nearest fp32 add: the MMA accumulates with truncation. Measured on B200 with positive
+# operands (tools/x3_diag.py): mean signed error -2.4e-4 for one chain over K = 3 x 25088, -2.7e-6 / -1.2e-6 /
+# -4.8e-7 / -1.8e-7 with chunks of 8 / 4 / 2 / 1 k-iterations; the bias compounds through the 16 stacked layers.
+X3_MAX_K_ITERS = [2]
+
+
+def gemm_tn_x3(A3, B3, alpha, *, taps=1, shifts=None, bn=None, epi=EPI_SPLIT3_RELU, bias=None, w_valid=0, wp=0,
+               split=0, n_valid=0, n_total=None, seg=None, ksplit=None):
+    """A3: [batch, rows, 3K] fp16 triples; B3: [n_rows, taps*3K]. Returns the output triples
+    [batch, rows, 3*n_total] or (d0, d1) fp32 for EPI_F32_SPLIT. ksplit=None chooses the K chunking from
+    X3_MAX_K_ITERS (triple epilogues only)."""
+    batch, rows, lda = A3.shape
+    k3 = B3.shape[1] // taps
+    assert k3 == lda and k3 % 3 == 0
+    seg_counts, seg_cap = seg if seg is not None else (None, 0)
+    alloc = torch.zeros if seg is not None else torch.empty
+    if n_total is None:
+        n_total = B3.shape[0]
+    if bn is None:
+        bn = 256
+        while n_total % bn:
+            bn //= 2
+    out = d0 = d1 = None
+    ld_d = dbs = 0
+    if ksplit is None:
+        k_iters = taps * (k3 // 64)
+        ksplit = (k_iters + X3_MAX_K_ITERS[0] - 1) // X3_MAX_K_ITERS[0] if epi in (EPI_SPLIT3_RELU, EPI_SPLIT3) else 1
+    if ksplit > 1:
+        assert epi in (EPI_SPLIT3_RELU, EPI_SPLIT3)
+        acc = torch.zeros(batch, rows, n_total, dtype=torch.float32, device=A3.device)
+        call("ptb200_gemm_tn_f16x3", A3, batch, rows, k3, lda, rows * lda, taps, shifts, B3, n_total, bn, EPI_ATOMIC,
+             None, 0, None, 0, 0, 0, 0, acc, n_total, None, 0, 0, n_total, GEMM_MAX_CTAS[0], ksplit, seg_counts,
+             seg_cap, 1.0)
+        out = torch.empty(batch, rows, 3 * n_total, dtype=torch.float16, device=A3.device)
+        call("ptb200_bias_act_split3_f16", acc, bias, 1 if epi == EPI_SPLIT3_RELU else 0, float(alpha), batch * rows,
+             n_total, wp, w_valid, out)
+        return out
+    if epi == EPI_F32_SPLIT:
+        d0 = alloc(batch, rows, split, dtype=torch.float32, device=A3.device)
+        d1 = alloc(batch, rows, n_valid - split, dtype=torch.float32, device=A3.device)
+    else:
+        out = alloc(batch, rows, 3 * n_total, dtype=torch.float16, device=A3.device)
+        ld_d, dbs = 3 * n_total, rows * 3 * n_total
+    call("ptb200_gemm_tn_f16x3", A3, batch, rows, k3, lda, rows * lda, taps, shifts, B3, n_total, bn, epi, bias,
+         0 if bias is None else bias.numel(), out, ld_d, dbs, w_valid, wp, d0, split, d1, n_valid - split, split,
+         n_valid, GEMM_MAX_CTAS[0], 1, seg_counts, seg_cap, float(alpha))
+    return (d0, d1) if epi == EPI_F32_SPLIT else out
+
+
+def conv3x3_x3(x: FlatAct, w3, alpha, bias):
+    """3x3 conv + bias + ReLU over f16x3 triples. w3: [Cout, 9 * 3Cin]."""
+    Wp = x.W + 1
+    o = gemm_tn_x3(x.t, w3, alpha, taps=9, shifts=_shifts(Wp), epi=EPI_SPLIT3_RELU, bias=bias, w_valid=x.W, wp=Wp)
+    return FlatAct(o, x.H, x.W)
+
+
+def split3_pack(src_f32, k, scale=1.0, order=0):
+    """fp32 [..., k] -> fp16 [rows, 3k] triples (order 0: activation [hi|lo|hi]; 1: weight [hi|hi|lo])."""
+    rows = src_f32.numel() // k
+    dst = torch.empty(rows, 3 * k, dtype=torch.float16, device=src_f32.device)
+    call("ptb200_split3_pack_f16", src_f32.contiguous(), dst, rows, k, float(scale), order)
+    return dst
+
+
+def split3_unpack(t3, k):
+    """fp16 triples [..., 3k] -> fp32 [rows, k] (hi + lo)."""
+    rows = t3.numel() // (3 * k)
+    dst = torch.empty(rows, k, dtype=torch.float32, device=t3.device)
+    call("ptb200_split3_unpack_f32", t3.contiguous(), dst, rows, k)
+    return dst
+
+
+def conv1_u8_x3(images_u8, hw, hmax, wmax, mean, std, w_f32, bias):
+    N = hw.shape[0]
+    out = torch.empty(N, hmax * (wmax + 1), 192, dtype=torch.float16, device=images_u8.device)
+    call("ptb200_conv1_u8_f16x3", images_u8, hw, N, hmax, wmax, images_u8.stride(0), list(mean), list(std), w_f32,
+         bias, out)
+    return FlatAct(out, hmax, wmax)
+
+
+def maxpool2x2_x3(x: FlatAct):
+    N, _, C3 = x.t.shape
+    Ho, Wo = x.H // 2, x.W // 2
+    out = torch.empty(N, Ho * (Wo + 1), C3, dtype=torch.float16, device=x.t.device)
+    call("ptb200_maxpool2x2_f16x3", x.t, out, N, x.H, x.W, C3 // 3)
+    return FlatAct(out, Ho, Wo)
+
+
+def roi_align_fwd_x3(feat: FlatAct, rois, counts, cap, scale, pooled):
+    N, _, C3 = feat.t.shape
+    out = torch.empty(N * cap, pooled * pooled * C3, dtype=torch.float16, device=feat.t.device)
+    call("ptb200_roi_align_fwd_f16x3", feat.t, N, feat.H, feat.W, C3 // 3, rois, counts, cap, float(scale), pooled, out)
+    return out
 
 
 def wgrad(G, X, out, *, taps=1, shifts=None, scale=1.0, ksplit=0, m_total=None, n_total=None, bias_out=None,
