@@ -15,8 +15,8 @@
 //   warp 0    : TMA producer (A tile 128 rows x 64 k, B tile BN rows x 64 k, SWIZZLE_128B)
 //   warp 1    : tcgen05.mma issuer (M=128, N=BN, K=16 per instruction, fp32 accumulators in TMEM,
 //               two accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1)
-//   warps 2-5 : epilogue (tcgen05.ld -> bias/ReLU/pad-mask -> fp16 -> swizzled smem -> TMA store,
-//               or fp32 direct stores for the narrow head outputs)
+//   warps 2-9 : epilogue (tcgen05.ld -> bias/ReLU/pad-mask -> fp16 -> swizzled smem -> TMA store,
+//               or fp32 direct stores for the narrow head outputs); two warps per TMEM lane quarter
 #include "ptx.cuh"
 #include "gemm_tn.h"
 #include <stdlib.h>
@@ -27,8 +27,8 @@ static constexpr int BM = 128;
 static constexpr int BK = 64;
 static constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
 static constexpr int STAGING_BYTES = BM * 128;     // one 128 x 64 fp16 output chunk
-static constexpr int NUM_THREADS = 192;
-static constexpr int EPI_THREADS = 128;
+static constexpr int NUM_THREADS = 320;  // TMA warp, MMA warp, 8 epilogue warps
+static constexpr int EPI_THREADS = 256;
 
 struct SmemCtl {
   uint64_t full[8];
@@ -75,7 +75,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const int a_stage_bytes = ROWWIN ? WIN_BYTES : A_STAGE_BYTES;
   const int b_stage_bytes = bres ? 0 : (ROWWIN ? 3 : 1) * bn * BK * 2;
   const int stage_bytes = a_stage_bytes + b_stage_bytes;
-  constexpr int kStagingBufs = ROWWIN ? 1 : 2;
+  const int kStagingBufs = p.staging_bufs;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
   uint8_t* b_res = smem + stages * stage_bytes;                       // 9 * bn * 128 B when resident
@@ -169,6 +169,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     int s = 0;
     uint32_t ph = 0;
     int it = 0;
+    // warp-uniform copy of the TMEM base: a value loaded from shared memory is not provably uniform, and every
+    // tcgen05.mma then paid an ELECT / R2UR.BROADCAST waterfall (~100 cycles per MMA, the bound of the N = 64 tiles)
+    const uint32_t tmem_base_u = __shfl_sync(0xffffffffu, tmem_base, 0);
     if (bres) mbar_wait(&ctl->bres_full, 0);
     for (int work = blockIdx.x; work < num_tiles; work += gridDim.x) {
       if (p.seg_counts != nullptr) {
@@ -183,7 +186,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const int k_iters = (k_iters_total * (ks + 1)) / ksplit - (k_iters_total * ks) / ksplit;
       mbar_wait(&ctl->tmem_empty[as], aph ^ 1);
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + as * bn;
+      const uint32_t d_tmem = tmem_base_u + as * bn;
       for (int ki = 0; ki < k_iters; ++ki) {
         mbar_wait(&ctl->full[s], ph);
         tc_fence_after();
@@ -220,13 +223,19 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    // ------------------------------------------------------------------ epilogue (warps 2..9)
+    // Two warps per TMEM lane quarter, each converting one 32-column half of a 64-column chunk: with a single
+    // warp per scheduler the ~450 dependent instructions per chunk ran at ~6 cycles each and the epilogue,
+    // not the tensor pipe, bounded the small-K layers (conv1_2 .. conv3_1; ncu: tensor pipe 30 % active).
     const int q = warp & 3;            // TMEM lane quarter this warp may access
+    const int hf = (warp - 2) >> 2;    // column half handled by this warp
     const int r = q * 32 + lane;       // row of the 128-row tile owned by this thread
-    const int et = threadIdx.x - 64;   // 0..127 index among epilogue threads
+    const int et = threadIdx.x - 64;   // 0..255 index among epilogue threads
+    const int nstg = p.staging_bufs;
     int it = 0;
     int st_buf = 0;
-    uint32_t aux_ph[2] = {0, 0};
+    int staged_n0 = -1;
+    uint32_t aux_ph = 0;  // phase bit per staging buffer
     for (int work = blockIdx.x; work < num_tiles; work += gridDim.x) {
       const int tile = work / ksplit;
       const int b = tile / tiles_per_batch;
@@ -240,11 +249,14 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const uint32_t aph = (it >> 1) & 1;
       ++it;
 
-      // stage the bias slice (previous tile's readers are past the barrier below)
-      named_bar_sync(1, EPI_THREADS);
-      for (int i = et; i < bn; i += EPI_THREADS)
-        bias_s[i] = (p.bias != nullptr && n0 + i < p.n_bias) ? p.bias[n0 + i] : 0.f;
-      named_bar_sync(1, EPI_THREADS);
+      if (n0 != staged_n0) {
+        // stage the bias slice (the previous slice's readers are past the first barrier)
+        named_bar_sync(1, EPI_THREADS);
+        for (int i = et; i < bn; i += EPI_THREADS)
+          bias_s[i] = (p.bias != nullptr && n0 + i < p.n_bias) ? p.bias[n0 + i] : 0.f;
+        named_bar_sync(1, EPI_THREADS);
+        staged_n0 = n0;
+      }
 
       mbar_wait(&ctl->tmem_full[as], aph);
       tc_fence_after();
@@ -256,7 +268,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
       if (p.epi == EPI_ATOMIC_F32) {
         float* orow = p.d0 + (static_cast<size_t>(b) * p.rows + row) * p.ld0 + n0;
-        for (int c0 = 0; c0 < bn; c0 += 32) {
+        for (int c0 = 32 * hf; c0 < bn; c0 += 64) {
           uint32_t v[32];
           tmem_ld_32x32(t_addr + c0, v);
           tmem_ld_wait();
@@ -270,7 +282,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           }
         }
       } else if (p.epi == EPI_F32_SPLIT) {
-        for (int c0 = 0; c0 < bn; c0 += 16) {
+        for (int c0 = 16 * hf; c0 < bn; c0 += 32) {
           uint32_t v[16];
           tmem_ld_32x16(t_addr + c0, v);
           tmem_ld_wait();
@@ -291,22 +303,22 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
       } else if (p.epi == EPI_SPLIT3_RELU_F16 || p.epi == EPI_SPLIT3_F16) {
         // f16x3 output: hi chunk in staging buffer 0, lo chunk in buffer 1, three TMA stores
-        // (columns [n], [n_total + n], [2 n_total + n] of the 3*n_total wide D). Never ROWWIN.
+        // (columns [n], [n_total + n], [2 n_total + n] of the 3*n_total wide D). Needs both staging buffers.
         for (int c0 = 0; c0 < bn; c0 += 64) {
           if (et == 0) tma_store_wait_read<0>();
           named_bar_sync(1, EPI_THREADS);
-          uint32_t v[64];
-          tmem_ld_32x32(t_addr + c0, v);
-          tmem_ld_32x32(t_addr + c0 + 32, v + 32);
+          uint32_t v[32];
+          tmem_ld_32x32(t_addr + c0 + 32 * hf, v);
           tmem_ld_wait();
           uint8_t* rowh = staging + r * 128;
           uint8_t* rowl = staging + STAGING_BYTES + r * 128;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
+          for (int j = 0; j < 4; ++j) {
+            const int jj = 4 * hf + j;
             float f[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-              f[e] = __uint_as_float(v[j * 8 + e]) * p.alpha + bias_s[c0 + j * 8 + e];
+              f[e] = __uint_as_float(v[j * 8 + e]) * p.alpha + bias_s[c0 + jj * 8 + e];
               if (p.epi == EPI_SPLIT3_RELU_F16) f[e] = fmaxf(f[e], 0.f);
               if (!row_live) f[e] = 0.f;
             }
@@ -316,13 +328,13 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const __half2 h = __floats2half2_rn(f[2 * e], f[2 * e + 1]);
-              const float2 hf = __half22float2(h);
-              const __half2 l = __floats2half2_rn(f[2 * e] - hf.x, f[2 * e + 1] - hf.y);
+              const float2 hfl = __half22float2(h);
+              const __half2 l = __floats2half2_rn(f[2 * e] - hfl.x, f[2 * e + 1] - hfl.y);
               ohp[e] = *reinterpret_cast<const uint32_t*>(&h);
               olp[e] = *reinterpret_cast<const uint32_t*>(&l);
             }
-            *reinterpret_cast<uint4*>(rowh + ((j ^ (r & 7)) << 4)) = oh;
-            *reinterpret_cast<uint4*>(rowl + ((j ^ (r & 7)) << 4)) = ol;
+            *reinterpret_cast<uint4*>(rowh + ((jj ^ (r & 7)) << 4)) = oh;
+            *reinterpret_cast<uint4*>(rowl + ((jj ^ (r & 7)) << 4)) = ol;
           }
           fence_proxy_async_smem();
           named_bar_sync(1, EPI_THREADS);
@@ -334,39 +346,44 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           }
         }
       } else {
+        const __half2 zero2 = __float2half2_rn(0.f);
         for (int c0 = 0; c0 < bn; c0 += 64) {
           uint8_t* stg = staging + st_buf * STAGING_BYTES;
-          uint8_t* auxb = stg;  // aux tile is loaded into the staging buffer itself
           // the TMA store that last read this staging buffer must have drained
           if (et == 0) {
-            if (kStagingBufs == 1) tma_store_wait_read<0>(); else tma_store_wait_read<1>();
+            if (nstg == 1) tma_store_wait_read<0>(); else tma_store_wait_read<1>();
           }
           named_bar_sync(1, EPI_THREADS);
           if (p.epi == EPI_MASK_F16) {
-            if (et == 0) {
+            if (et == 0) {  // the aux tile is loaded into the staging buffer itself
               mbar_arrive_expect_tx(&ctl->aux_full[st_buf], STAGING_BYTES);
-              tma_load_3d(auxb, &map_aux, &ctl->aux_full[st_buf], n0 + c0, row0, b);
+              tma_load_3d(stg, &map_aux, &ctl->aux_full[st_buf], n0 + c0, row0, b);
             }
           }
-          uint32_t v[64];
-          tmem_ld_32x32(t_addr + c0, v);
-          tmem_ld_32x32(t_addr + c0 + 32, v + 32);
+          uint32_t v[32];
+          tmem_ld_32x32(t_addr + c0 + 32 * hf, v);
           tmem_ld_wait();
           if (p.epi == EPI_MASK_F16) {
-            mbar_wait(&ctl->aux_full[st_buf], aux_ph[st_buf]);
-            aux_ph[st_buf] ^= 1;
+            mbar_wait(&ctl->aux_full[st_buf], (aux_ph >> st_buf) & 1u);
+            aux_ph ^= 1u << st_buf;
           }
           uint8_t* rowp = stg + r * 128;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            uint4* dst = reinterpret_cast<uint4*>(rowp + ((j ^ (r & 7)) << 4));
+          for (int j = 0; j < 4; ++j) {
+            const int jj = 4 * hf + j;
+            uint4* dst = reinterpret_cast<uint4*>(rowp + ((jj ^ (r & 7)) << 4));
+            const float4 b0 = *reinterpret_cast<const float4*>(bias_s + c0 + jj * 8);
+            const float4 b1 = *reinterpret_cast<const float4*>(bias_s + c0 + jj * 8 + 4);
             float f[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[j * 8 + e]) * p.alpha + bias_s[c0 + j * 8 + e];
-            if (p.epi == EPI_BIAS_RELU_F16) {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
-            } else if (p.epi == EPI_MASK_F16) {
+            f[0] = __uint_as_float(v[j * 8 + 0]) * p.alpha + b0.x;
+            f[1] = __uint_as_float(v[j * 8 + 1]) * p.alpha + b0.y;
+            f[2] = __uint_as_float(v[j * 8 + 2]) * p.alpha + b0.z;
+            f[3] = __uint_as_float(v[j * 8 + 3]) * p.alpha + b0.w;
+            f[4] = __uint_as_float(v[j * 8 + 4]) * p.alpha + b1.x;
+            f[5] = __uint_as_float(v[j * 8 + 5]) * p.alpha + b1.y;
+            f[6] = __uint_as_float(v[j * 8 + 6]) * p.alpha + b1.z;
+            f[7] = __uint_as_float(v[j * 8 + 7]) * p.alpha + b1.w;
+            if (p.epi == EPI_MASK_F16) {
               // keep the gradient only where the forward activation (aux tile) was positive
               const uint4 a = *dst;
               const __half2* ah = reinterpret_cast<const __half2*>(&a);
@@ -377,19 +394,19 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 if (!(af.y > 0.f)) f[2 * e + 1] = 0.f;
               }
             }
-            if (!row_live) {
+            __half2 h[4];
 #pragma unroll
-              for (int e = 0; e < 8; ++e) f[e] = 0.f;
+            for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(f[2 * e], f[2 * e + 1]);
+            if (p.epi == EPI_BIAS_RELU_F16) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) h[e] = __hmax2(h[e], zero2);  // relu(round(x)) == round(relu(x))
             }
             uint4 o;
-            __half2 h0 = __floats2half2_rn(f[0], f[1]);
-            __half2 h1 = __floats2half2_rn(f[2], f[3]);
-            __half2 h2 = __floats2half2_rn(f[4], f[5]);
-            __half2 h3 = __floats2half2_rn(f[6], f[7]);
-            o.x = *reinterpret_cast<uint32_t*>(&h0);
-            o.y = *reinterpret_cast<uint32_t*>(&h1);
-            o.z = *reinterpret_cast<uint32_t*>(&h2);
-            o.w = *reinterpret_cast<uint32_t*>(&h3);
+            o.x = *reinterpret_cast<uint32_t*>(&h[0]);
+            o.y = *reinterpret_cast<uint32_t*>(&h[1]);
+            o.z = *reinterpret_cast<uint32_t*>(&h[2]);
+            o.w = *reinterpret_cast<uint32_t*>(&h[3]);
+            if (!row_live) o = make_uint4(0, 0, 0, 0);
             *dst = o;
           }
           fence_proxy_async_smem();
@@ -398,7 +415,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             tma_store_3d(&map_d, stg, n0 + c0, row0, b);
             tma_store_commit();
           }
-          if (kStagingBufs == 2) st_buf ^= 1;
+          if (nstg == 2) st_buf ^= 1;
         }
       }
       // this accumulator stage may now be overwritten by the MMA warp
@@ -542,7 +559,10 @@ int gemm_tn_launch(const GemmTnArgs& a, cudaStream_t stream) {
   const bool bres = rowwin && a.n_total == a.bn && a.k_per_tap == BK;
   p.b_resident = bres ? 1 : 0;
   const int stage_bytes = rowwin ? WIN_BYTES + (bres ? 0 : 3 * a.bn * BK * 2) : A_STAGE_BYTES + a.bn * BK * 2;
-  const int fixed = (rowwin ? 1 : 2) * STAGING_BYTES + 256 * 4 + (int)sizeof(SmemCtl) + 1024 +
+  // one staging buffer only where a second one would cost a pipeline stage that matters (row-window tiles
+  // with streamed filters: 65 KB per stage); the f16x3 epilogue needs both (hi and lo chunk)
+  p.staging_bufs = (rowwin && !bres) ? 1 : 2;
+  const int fixed = p.staging_bufs * STAGING_BYTES + 256 * 4 + (int)sizeof(SmemCtl) + 1024 +
                     (bres ? 9 * a.bn * BK * 2 : 0);
   int stages = (232448 - fixed) / stage_bytes;
   if (stages > 8) stages = 8;

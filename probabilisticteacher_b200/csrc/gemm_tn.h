@@ -27,6 +27,7 @@ struct GemmTnParams {
   int stages;
   int ksplit;
   int b_resident;  // ROWWIN only: whole 3x3 filter (9 x bn x 64) stays in shared memory
+  int staging_bufs;  // 1 or 2 epilogue staging buffers of 16 KB
   float alpha;     // accumulator scale applied before the bias (power-of-two weight scaling of the f16x3 mode)
   const float* bias;
   int n_bias;

@@ -129,43 +129,48 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_consta
 
   if (k_iters > 0) {
     if (warp == 0) {
-      if (lane == 0) {
-        int s = 0;
-        uint32_t ph = 0;
-        const int shift = p.shifts[tap];
-        for (int c = c_begin; c < c_end; ++c) {
-          const int b = c / chunks_per_img;
-          const int r0 = (c - b * chunks_per_img) * WG_BK;
-          if (!chunk_live(p.seg_counts, p.seg_cap, r0, p.rows)) continue;
-          mbar_wait(&ctl->empty[s], ph ^ 1);
+      // the whole warp walks the loop (converged control flow keeps the TMA operands in uniform registers:
+      // no R2UR.BROADCAST waterfall per load); lane 0 issues
+      int s = 0;
+      uint32_t ph = 0;
+      const int shift = p.shifts[tap];
+      for (int c = c_begin; c < c_end; ++c) {
+        const int b = c / chunks_per_img;
+        const int r0 = (c - b * chunks_per_img) * WG_BK;
+        if (!chunk_live(p.seg_counts, p.seg_cap, r0, p.rows)) continue;
+        mbar_wait(&ctl->empty[s], ph ^ 1);
+        if (lane == 0) {
           uint8_t* sa = smem + s * stage_bytes;
           uint8_t* sb = sa + a_bytes;
           mbar_arrive_expect_tx(&ctl->full[s], stage_bytes);
           tma_load_4d(sa, &map_g, &ctl->full[s], 0, r0, mt * (WG_BM / 64), b);
           tma_load_4d(sb, &map_x, &ctl->full[s], 0, r0 + shift, nt * (bn / 64), b);
-          if (++s == p.stages) {
-            s = 0;
-            ph ^= 1;
-          }
+        }
+        __syncwarp();
+        if (++s == p.stages) {
+          s = 0;
+          ph ^= 1;
         }
       }
     } else if (warp == 1) {
       const uint32_t idesc = umma_idesc_f16(WG_BM, bn, 1, 1);
       int s = 0;
       uint32_t ph = 0;
+      // provably warp-uniform TMEM address (see gemm_tn.cu): avoids a R2UR.BROADCAST waterfall per MMA
+      const uint32_t tmem_base_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       for (int ki = 0; ki < k_iters; ++ki) {
         mbar_wait(&ctl->full[s], ph);
         tc_fence_after();
+        const uint32_t a_addr = __shfl_sync(0xffffffffu, smem_u32(smem + s * stage_bytes), 0);
+        const uint32_t b_addr = __shfl_sync(0xffffffffu, a_addr + a_bytes, 0);
         if (lane == 0) {
-          const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
-          const uint32_t b_addr = a_addr + a_bytes;
           // MN-major SW128: LBO = stride between 64-channel blocks, SBO = stride between 8-row groups
           const uint64_t da = umma_desc_sw128(a_addr, WG_BLK_BYTES, 1024);
           const uint64_t db = umma_desc_sw128(b_addr, WG_BLK_BYTES, 1024);
 #pragma unroll
           for (int k = 0; k < WG_BK / 16; ++k) {
             // 16 reduction rows = 2048 B further into each block
-            umma_f16_ss(tmem_base, da + (2048 >> 4) * k, db + (2048 >> 4) * k, idesc,
+            umma_f16_ss(tmem_base_u, da + (2048 >> 4) * k, db + (2048 >> 4) * k, idesc,
                         (ki > 0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&ctl->empty[s]);

@@ -60,9 +60,11 @@ def main():
         res.append(dict(layer=name, H=H, W=W, cin=cin, cout=cout, ms=ms, tflops=fl / ms / 1e9))
         print(res[-1], flush=True)
     # box head fc1: 4000 x 25088 x 1024
-    if only:
+    if only and not only.startswith("fc"):
         return
     for name, M, K, Nn in [("fc1_teacher", 4000, 25088, 1024), ("fc1_sup", 2048, 25088, 1024), ("fc2", 4000, 1024, 1024)]:
+        if only and name != only:
+            continue
         A = torch.randn(1, M, K, device=dev).half()
         B = (torch.randn(Nn, K, device=dev) / K ** 0.5).half()
         bias = torch.zeros(Nn, device=dev)
