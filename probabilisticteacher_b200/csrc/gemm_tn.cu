@@ -124,7 +124,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    if (elect_one()) {
       int s = 0;
       uint32_t ph = 0;
       if (bres) {
@@ -190,7 +190,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       for (int ki = 0; ki < k_iters; ++ki) {
         mbar_wait(&ctl->full[s], ph);
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
           const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
           // resident filter: stage index ki = filter row ky (single K chunk)
           const uint32_t b_addr = bres ? smem_u32(b_res) + ki * 3 * bn * BK * 2 : a_addr + a_stage_bytes;
@@ -305,7 +305,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         // f16x3 output: hi chunk in staging buffer 0, lo chunk in buffer 1, three TMA stores
         // (columns [n], [n_total + n], [2 n_total + n] of the 3*n_total wide D). Needs both staging buffers.
         for (int c0 = 0; c0 < bn; c0 += 64) {
-          if (et == 0) tma_store_wait_read<0>();
+          if (warp == 2 && elect_one()) tma_store_wait_read<0>();
           named_bar_sync(1, EPI_THREADS);
           uint32_t v[32];
           tmem_ld_32x32(t_addr + c0 + 32 * hf, v);
@@ -338,7 +338,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           }
           fence_proxy_async_smem();
           named_bar_sync(1, EPI_THREADS);
-          if (et == 0) {
+          if (warp == 2 && elect_one()) {
             tma_store_3d(&map_d, staging, n0 + c0, row0, b);
             tma_store_3d(&map_d, staging + STAGING_BYTES, p.n_total + n0 + c0, row0, b);
             tma_store_3d(&map_d, staging, 2 * p.n_total + n0 + c0, row0, b);
@@ -350,12 +350,12 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         for (int c0 = 0; c0 < bn; c0 += 64) {
           uint8_t* stg = staging + st_buf * STAGING_BYTES;
           // the TMA store that last read this staging buffer must have drained
-          if (et == 0) {
+          if (warp == 2 && elect_one()) {
             if (nstg == 1) tma_store_wait_read<0>(); else tma_store_wait_read<1>();
           }
           named_bar_sync(1, EPI_THREADS);
           if (p.epi == EPI_MASK_F16) {
-            if (et == 0) {  // the aux tile is loaded into the staging buffer itself
+            if (warp == 2 && elect_one()) {  // the aux tile is loaded into the staging buffer itself
               mbar_arrive_expect_tx(&ctl->aux_full[st_buf], STAGING_BYTES);
               tma_load_3d(stg, &map_aux, &ctl->aux_full[st_buf], n0 + c0, row0, b);
             }
@@ -411,7 +411,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           }
           fence_proxy_async_smem();
           named_bar_sync(1, EPI_THREADS);
-          if (et == 0) {
+          if (warp == 2 && elect_one()) {
             tma_store_3d(&map_d, stg, n0 + c0, row0, b);
             tma_store_commit();
           }
@@ -423,7 +423,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       __syncwarp();
       if (lane == 0) mbar_arrive(&ctl->tmem_empty[as]);
     }
-    if (et == 0) tma_store_wait_all<0>();
+    if (warp == 2 && elect_one()) tma_store_wait_all<0>();
   }
 
   tc_fence_before();

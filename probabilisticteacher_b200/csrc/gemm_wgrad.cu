@@ -139,7 +139,7 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_consta
         const int r0 = (c - b * chunks_per_img) * WG_BK;
         if (!chunk_live(p.seg_counts, p.seg_cap, r0, p.rows)) continue;
         mbar_wait(&ctl->empty[s], ph ^ 1);
-        if (lane == 0) {
+        if (elect_one()) {
           uint8_t* sa = smem + s * stage_bytes;
           uint8_t* sb = sa + a_bytes;
           mbar_arrive_expect_tx(&ctl->full[s], stage_bytes);
@@ -163,7 +163,7 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_consta
         tc_fence_after();
         const uint32_t a_addr = __shfl_sync(0xffffffffu, smem_u32(smem + s * stage_bytes), 0);
         const uint32_t b_addr = __shfl_sync(0xffffffffu, a_addr + a_bytes, 0);
-        if (lane == 0) {
+        if (elect_one()) {
           // MN-major SW128: LBO = stride between 64-channel blocks, SBO = stride between 8-row groups
           const uint64_t da = umma_desc_sw128(a_addr, WG_BLK_BYTES, 1024);
           const uint64_t db = umma_desc_sw128(b_addr, WG_BLK_BYTES, 1024);
