@@ -11,6 +11,7 @@
 // into the fp32 gradient arena with vectorised red.global.add (gradients of the two student
 // forward passes of one step accumulate into the same arena, as autograd does for the reference).
 #include "ptx.cuh"
+#include <stdlib.h>
 #include "gemm_tn.h"
 
 namespace ptb {
@@ -67,7 +68,7 @@ __device__ __forceinline__ bool chunk_live(const int* __restrict__ seg_counts, i
   return false;
 }
 
-__global__ void __launch_bounds__(WG_THREADS, 1)
+__global__ void __launch_bounds__(WG_THREADS, 2)
 gemm_wgrad_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant__ CUtensorMap map_x,
                   const WgParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -302,6 +303,16 @@ int gemm_wgrad_launch(const void* G, int64_t ldg, int64_t g_batch_stride, const 
   const int stage_bytes = (WG_BM / 64 + bn / 64) * WG_BLK_BYTES;
   int stages = (232448 - 2048) / stage_bytes;
   if (stages > 8) stages = 8;
+  static int stage_cap = -1;  // experiment knob: PTB200_WG_STAGES=2 lets two CTAs share an SM
+  if (stage_cap < 0) {
+    const char* e = getenv("PTB200_WG_STAGES");
+    stage_cap = e ? atoi(e) : 0;
+  }
+  if (stage_cap > 0 && stages > stage_cap) stages = stage_cap;
+  // many tiles with a short reduction (fc1: 784 tiles x 63 chunks): two 2-stage CTAs per SM, so that one CTA's
+  // prologue / red.add epilogue overlaps the other's main loop (fc1 wgrad 229 -> 160 us); long reductions
+  // (conv layers) keep the deep single-CTA pipeline
+  if (stage_cap == 0 && tiles * ksplit >= 2 * g_wg_sms && total_chunks / ksplit <= 128 && stages > 2) stages = 2;
   p.stages = stages;
   const int smem_bytes = stages * stage_bytes + (int)sizeof(WgCtl) + 1024;
   static bool configured = false;
