@@ -359,8 +359,8 @@ class PTrainer:
         return out
 
     def _graph_body_concurrent(self):
-        """Same computation as `_graph_body`, issued as three parallel branches (teacher / supervised /
-        unsupervised forward) that join before the backward."""
+        """Same computation as `_graph_body`, issued as three parallel branches (teacher forward, supervised
+        forward + backward, unsupervised forward + backward) that join before the optimizer step."""
         from .. import ops
         cfg = self.cfg
         st = self._static
@@ -385,11 +385,18 @@ class PTrainer:
             e_pseudo.record(s_t)
             keep.append((roih, pseudo))
         rec = {}
+        w_sup, w_unsup = cfg.UNSUPNET.SOURCE_LOSS_WEIGHT, cfg.UNSUPNET.TARGET_UNSUP_LOSS_WEIGHT
+        # Each student pass runs its backward on its own branch as soon as its forward is done (the weighted
+        # sum of trainer.py:364-381 is linear, and both backward chains accumulate into the gradient arena
+        # with fp32 atomics): the supervised backward overlaps the latency-bound proposal / NMS kernels of the
+        # teacher and unsupervised passes instead of waiting for the join.
         with torch.cuda.stream(s_1):
             refresh_stream()
             lq = self.resize_dev(b["lq"], st["resize_params"][:nl], st["resize_ratio"][:nl])
             rec_l, _, _, _ = self.model(lq + b["lk"], branch="supervised")
             keep.append(lq)
+            sum(v * w_sup for v in rec_l.values()).backward()
+            refresh_stream()
         with torch.cuda.stream(s_2):
             refresh_stream()
             uq_img = self._resize_images_dev(b["uq"], st["resize_params"][nl:])
@@ -399,6 +406,8 @@ class PTrainer:
                 return self._resize_instances_dev(pseudo, st["resize_params"][nl:], st["resize_ratio"][nl:])
             rec_u, _, _, _ = self.model(uq_img, branch="unsupervised", danchor=True, targets_provider=provider)
             keep.append(uq_img)
+            sum(v * w_unsup for v in rec_u.values()).backward()
+            refresh_stream()
         for s in (s_t, s_1, s_2):
             main.wait_stream(s)
         refresh_stream()
@@ -406,17 +415,7 @@ class PTrainer:
             rec[k + "_sup"] = v
         for k, v in rec_u.items():
             rec[k + "_unsup"] = v
-        total = 0
-        for k, v in rec.items():
-            wgt = cfg.UNSUPNET.SOURCE_LOSS_WEIGHT if k.endswith("_sup") else cfg.UNSUPNET.TARGET_UNSUP_LOSS_WEIGHT
-            total = total + v * wgt
-        ops.GEMM_MAX_CTAS[0] = 0  # the backward runs alone on the main stream: use every SM
-        self.model.backward_stream = main
-        total.backward()
-        self.model.backward_stream = None
-        for s in (s_t, s_1, s_2):  # autograd touches the forward streams again: re-join them
-            main.wait_stream(s)
-        refresh_stream()
+        ops.GEMM_MAX_CTAS[0] = 0
         self._keep = keep
         return {k: v.detach() for k, v in rec.items()}
 
