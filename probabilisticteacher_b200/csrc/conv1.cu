@@ -6,9 +6,8 @@
 // fragment is built in registers straight from the image (L1-resident neighbourhood) and the
 // 128x64x32 product runs on the legacy mma.sync path; the kernel is bound by the 137 MB/image
 // output write, which goes out as full 128-byte rows staged through shared memory.
-#include <cuda_runtime.h>
-#include <cuda_fp16.h>
-#include <stdint.h>
+#include "ptx.cuh"
+#include <stdlib.h>
 #include "../../include/ptb200.h"
 
 namespace {
@@ -155,9 +154,287 @@ conv1_u8_kernel(const uint8_t* __restrict__ img, const int* __restrict__ hw, int
 
 }  // namespace
 
+// ------------------------------------------------------------------------------------------------
+// tcgen05 version (default). The mma.sync kernel above spends ~550 warp instructions per 32 pixels on
+// fragment assembly and runs at 4x the HBM floor of its 137 MB/image output. Here the work is
+// warp-specialised like the implicit-GEMM kernel:
+//   warp 0      : MMA issuer (two tcgen05.mma of 128 x 64 x 16 per tile, K = 27 padded to 32)
+//   warps 1-8   : im2col builders, two groups of 128 threads working on alternate tiles: one thread = one
+//                 pixel, 27 byte loads from the L1-resident neighbourhood, normalise, 4 swizzled 16-byte
+//                 stores into the K-major SWIZZLE_128B A tile of its group
+//   warps 9-16  : epilogue (tcgen05.ld -> bias + ReLU -> fp16 -> swizzled staging -> TMA store), two warps
+//                 per TMEM lane quarter
+// Tiles are 128 consecutive pixels of the flattened [H * Wp] axis (pad column written as zero).
+namespace ptb {
+int make_tmap_f16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
+                  const uint64_t* strides_bytes, const uint32_t* box);
+}
+
+namespace {
+
+using namespace ptb;
+
+constexpr int C1_THREADS = 32 + 256 + 256;
+constexpr int C1_A_BYTES = 128 * 128;       // A tile: 128 pixels x 64 k (only k < 32 is used)
+constexpr int C1_B_BYTES = 64 * 128;        // B tile: 64 channels x 64 k
+constexpr int C1_STG_BYTES = 128 * 128;     // 128 pixels x 64 channels fp16
+
+struct C1Ctl {
+  uint64_t a_full[2];
+  uint64_t a_empty[2];
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
+  uint32_t tmem_base;
+  uint32_t pad;
+};
+
+__global__ void __launch_bounds__(C1_THREADS, 1)
+conv1_u8_tc_kernel(const uint8_t* __restrict__ img, const int* __restrict__ hw, int N, int Hmax, int Wmax,
+                   int64_t img_stride, float m0, float m1, float m2, float is0, float is1, float is2,
+                   const __half* __restrict__ wpack /* [64][32] */, const float* __restrict__ bias,
+                   const __grid_constant__ CUtensorMap map_d) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* a_tiles = smem;                              // 2 x 16 KB
+  uint8_t* b_tile = a_tiles + 2 * C1_A_BYTES;           // 8 KB
+  uint8_t* staging = b_tile + C1_B_BYTES;               // 2 x 16 KB
+  float* bias_s = reinterpret_cast<float*>(staging + 2 * C1_STG_BYTES);
+  C1Ctl* ctl = reinterpret_cast<C1Ctl*>(bias_s + 64);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int Wp = Wmax + 1;
+  const int rows = Hmax * Wp;
+  const int m_tiles = (rows + 127) / 128;
+  const int num_tiles = m_tiles * N;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&map_d);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&ctl->a_full[i], 4);       // one arrival per builder warp of the group
+      mbar_init(&ctl->a_empty[i], 1);      // tcgen05.commit
+      mbar_init(&ctl->tmem_full[i], 1);
+      mbar_init(&ctl->tmem_empty[i], 8);   // one arrival per epilogue warp
+    }
+    fence_mbar_init();
+  }
+  // weights -> K-major SWIZZLE_128B B tile (row n, 16-byte chunk c at position c ^ (n & 7)); k >= 32 unused
+  for (int i = threadIdx.x; i < 64 * 4; i += blockDim.x) {
+    const int n = i >> 2, c = i & 3;
+    *reinterpret_cast<uint4*>(b_tile + n * 128 + ((c ^ (n & 7)) << 4)) =
+        *reinterpret_cast<const uint4*>(wpack + n * 32 + c * 8);
+  }
+  if (threadIdx.x < 64) bias_s[threadIdx.x] = bias[threadIdx.x];
+  fence_proxy_async_smem();
+  if (warp == 0) {
+    tmem_alloc(&ctl->tmem_base, 128);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = ctl->tmem_base;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ MMA issuer
+    const uint32_t idesc = umma_idesc_f16(128, 64, 0, 0);
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t a_base = smem_u32(a_tiles), b_addr = smem_u32(b_tile);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int s = it & 1;
+      const uint32_t ph = (it >> 1) & 1;
+      mbar_wait(&ctl->tmem_empty[s], ph ^ 1);
+      mbar_wait(&ctl->a_full[s], ph);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t da = umma_desc_sw128(a_base + s * C1_A_BYTES, 16, 1024);
+        const uint64_t db = umma_desc_sw128(b_addr, 16, 1024);
+        umma_f16_ss(tmem_u + s * 64, da, db, idesc, 0u);
+        umma_f16_ss(tmem_u + s * 64, da + 2, db + 2, idesc, 1u);
+        umma_commit(&ctl->a_empty[s]);
+        umma_commit(&ctl->tmem_full[s]);
+      }
+      __syncwarp();
+    }
+  } else if (warp <= 8) {
+    // ------------------------------------------------------------------ im2col builders
+    const int grp = (warp - 1) >> 2;                 // builds the tiles with (it & 1) == grp
+    const int r = ((warp - 1) & 3) * 32 + lane;      // pixel row of the tile owned by this thread
+    uint8_t* a_tile = a_tiles + grp * C1_A_BYTES;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      if ((it & 1) != grp) continue;
+      const uint32_t ph = (it >> 1) & 1;
+      {
+        // L2 prefetch of the image bytes of this group's NEXT tile: without it every tile exposed one DRAM
+        // latency (the row below the tile is touched for the first time). 60 threads = 4 image rows (a
+        // flattened tile may wrap into the next row) x 3 channels x 5 positions.
+        const int tile2 = tile + 2 * gridDim.x;
+        if (tile2 < num_tiles && r < 60) {
+          const int n2 = tile2 / m_tiles;
+          const int p2 = (tile2 - n2 * m_tiles) * 128;
+          const int y2 = p2 / Wp, x2 = p2 - y2 * Wp;
+          const int h2 = hw[2 * n2], w2 = hw[2 * n2 + 1];
+          const int dy = r / 15, c = (r / 5) % 3, pos = r % 5;
+          const int yy = y2 + dy - 1;
+          const int xx = pos < 3 ? x2 - 1 + 64 * pos : 64 * (pos - 3);
+          if (yy >= 0 && yy < h2 && xx < w2) {
+            const uint8_t* pa = img + n2 * img_stride + (static_cast<int64_t>(c) * h2 + yy) * w2 + (xx < 0 ? 0 : xx);
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(pa));
+          }
+        }
+      }
+      const int n = tile / m_tiles;
+      const int p = (tile - n * m_tiles) * 128 + r;
+      const int y = p / Wp, x = p - y * Wp;
+      const int h = hw[2 * n], w = hw[2 * n + 1];
+      const uint8_t* ib = img + n * img_stride;
+      float v[27];
+#pragma unroll
+      for (int k = 0; k < 27; ++k) v[k] = 0.f;
+      if (p < rows && x < Wmax) {
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy) {
+          const int yy = y + dy - 1;
+          if (yy < 0 || yy >= h) continue;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const float mean = c == 0 ? m0 : (c == 1 ? m1 : m2);
+            const float istd = c == 0 ? is0 : (c == 1 ? is1 : is2);
+            const uint8_t* rowp = ib + (static_cast<int64_t>(c) * h + yy) * w;
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx) {
+              const int xx = x + dx - 1;
+              if (xx >= 0 && xx < w) v[(dy * 3 + dx) * 3 + c] = (static_cast<float>(__ldg(rowp + xx)) - mean) * istd;
+            }
+          }
+        }
+      }
+      uint32_t pk[16];
+#pragma unroll
+      for (int k = 0; k < 13; ++k) {
+        const __half2 h2 = __floats2half2_rn(v[2 * k], v[2 * k + 1]);
+        pk[k] = *reinterpret_cast<const uint32_t*>(&h2);
+      }
+      {
+        const __half2 h2 = __floats2half2_rn(v[26], 0.f);
+        pk[13] = *reinterpret_cast<const uint32_t*>(&h2);
+        pk[14] = 0u;
+        pk[15] = 0u;
+      }
+      mbar_wait(&ctl->a_empty[grp], ph ^ 1);   // the MMAs that read this stage two tiles ago are done
+      uint8_t* rowp = a_tile + r * 128;
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        *reinterpret_cast<uint4*>(rowp + ((c ^ (r & 7)) << 4)) =
+            make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ctl->a_full[grp]);
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 9..16)
+    const int ew = warp - 9;
+    const int q = warp & 3;             // TMEM lane quarter accessible to this warp
+    const int hf = ew >> 2;             // column half
+    const int r = q * 32 + lane;
+    const __half2 zero2 = __float2half2_rn(0.f);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int s = it & 1;
+      const uint32_t ph = (it >> 1) & 1;
+      const int n = tile / m_tiles;
+      const int row0 = (tile - n * m_tiles) * 128;
+      uint8_t* stg = staging + s * C1_STG_BYTES;
+      // the TMA store that read this staging buffer two tiles ago must have drained
+      if (ew == 0 && elect_one()) tma_store_wait_read<1>();
+      named_bar_sync(1, 256);
+      mbar_wait(&ctl->tmem_full[s], ph);
+      tc_fence_after();
+      uint32_t v[32];
+      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + s * 64 + 32 * hf, v);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ctl->tmem_empty[s]);   // accumulator stage free again
+      const int row = row0 + r;
+      const bool live = row < rows && (row % Wp) < Wmax;
+      uint8_t* rowp = stg + r * 128;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int jj = 4 * hf + j;
+        const float4 b0 = *reinterpret_cast<const float4*>(bias_s + jj * 8);
+        const float4 b1 = *reinterpret_cast<const float4*>(bias_s + jj * 8 + 4);
+        __half2 h[4];
+        h[0] = __floats2half2_rn(__uint_as_float(v[j * 8 + 0]) + b0.x, __uint_as_float(v[j * 8 + 1]) + b0.y);
+        h[1] = __floats2half2_rn(__uint_as_float(v[j * 8 + 2]) + b0.z, __uint_as_float(v[j * 8 + 3]) + b0.w);
+        h[2] = __floats2half2_rn(__uint_as_float(v[j * 8 + 4]) + b1.x, __uint_as_float(v[j * 8 + 5]) + b1.y);
+        h[3] = __floats2half2_rn(__uint_as_float(v[j * 8 + 6]) + b1.z, __uint_as_float(v[j * 8 + 7]) + b1.w);
+        uint4 o;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) h[e] = __hmax2(h[e], zero2);
+        o.x = *reinterpret_cast<uint32_t*>(&h[0]);
+        o.y = *reinterpret_cast<uint32_t*>(&h[1]);
+        o.z = *reinterpret_cast<uint32_t*>(&h[2]);
+        o.w = *reinterpret_cast<uint32_t*>(&h[3]);
+        if (!live) o = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4*>(rowp + ((jj ^ (r & 7)) << 4)) = o;
+      }
+      fence_proxy_async_smem();
+      named_bar_sync(1, 256);
+      if (ew == 0 && elect_one()) {
+        tma_store_3d(&map_d, stg, 0, row0, n);
+        tma_store_commit();
+      }
+    }
+    if (ew == 0 && elect_one()) tma_store_wait_all<0>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 0) tmem_dealloc(tmem_base, 128);
+}
+
+}  // namespace
+
 extern "C" int ptb200_conv1_u8_f16(const uint8_t* images, const int* hw_dev, int n, int hmax, int wmax,
                                    int64_t image_stride, const float* mean3_host, const float* std3_host,
                                    const void* wpack_f16, const float* bias, void* out_f16, void* stream) {
+  static int use_tc = -1;
+  if (use_tc < 0) {
+    const char* e = getenv("PTB200_CONV1_TC");
+    use_tc = e ? atoi(e) : 1;
+  }
+  if (use_tc) {
+    const int64_t rows = static_cast<int64_t>(hmax) * (wmax + 1);
+    CUtensorMap md;
+    uint64_t dims[3] = {64, (uint64_t)rows, (uint64_t)n};
+    uint64_t str[2] = {128, (uint64_t)rows * 128};
+    uint32_t box[3] = {64, 128, 1};
+    if (ptb::make_tmap_f16(&md, out_f16, 3, dims, str, box)) return 1501;
+    const int smem_bytes = 2 * C1_A_BYTES + C1_B_BYTES + 2 * C1_STG_BYTES + 64 * 4 + (int)sizeof(C1Ctl) + 1024;
+    static bool configured = false;
+    if (!configured) {
+      cudaError_t e = cudaFuncSetAttribute(conv1_u8_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           smem_bytes);
+      if (e != cudaSuccess) return (int)e;
+      configured = true;
+    }
+    static int sms = 0;
+    if (sms == 0) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    const int64_t tiles = ((rows + 127) / 128) * n;
+    const int grid = tiles < sms ? (int)tiles : sms;
+    if (grid < 1) return 0;
+    conv1_u8_tc_kernel<<<grid, C1_THREADS, smem_bytes, static_cast<cudaStream_t>(stream)>>>(
+        images, hw_dev, n, hmax, wmax, image_stride, mean3_host[0], mean3_host[1], mean3_host[2],
+        1.f / std3_host[0], 1.f / std3_host[1], 1.f / std3_host[2], static_cast<const __half*>(wpack_f16), bias, md);
+    return static_cast<int>(cudaGetLastError());
+  }
   const int64_t tiles = static_cast<int64_t>(n) * hmax * ((wmax + 1 + 31) / 32);
   int64_t blocks = (tiles + 7) / 8;
   if (blocks > 148 * 16) blocks = 148 * 16;

@@ -5,6 +5,7 @@ EMA, gradient clipping and the SGD step are single fused passes over the flat ar
 runs on the device, and the data-parallel gradient all-reduce goes through torch.distributed
 (NCCL over NVLink) on the flat gradient arena. Hooks / evaluation / checkpoint writers of the
 reference trainer are out of scope."""
+import os
 import random
 
 import torch
@@ -62,9 +63,11 @@ class PTrainer:
         self._static = None
         # concurrent mode (graph step only): teacher pass, supervised pass and unsupervised pass are issued
         # on three streams (parallel branches of the captured graph), so the latency-bound proposal kernels
-        # of one pass overlap the GEMMs of the others; persistent GEMMs leave 4 SMs free for them
+        # of one pass overlap the GEMMs of the others (leaving SMs free for them did not pay: 140 / 144 / 148
+        # GEMM CTAs measured 14.55 / 14.54 / 14.42 ms per step)
         self.concurrent = concurrent
         self._streams = None
+        self.concurrent_gemm_ctas = int(os.environ.get("PTB200_GEMM_CTAS", "0"))  # 0 = one CTA per SM
 
     # ------------------------------------------------------------------ pseudo-labelling (trainer.py:179-257)
     def threshold_bbox(self, proposal_bbox_inst, proposal_type="roih"):
@@ -370,7 +373,7 @@ class PTrainer:
         if self._streams is None:
             self._streams = [torch.cuda.Stream(device=self.device) for _ in range(3)]
         s_t, s_1, s_2 = self._streams
-        ops.GEMM_MAX_CTAS[0] = 144
+        ops.GEMM_MAX_CTAS[0] = self.concurrent_gemm_ctas
         self.model.zero_grad()
         for s in (s_t, s_1, s_2):
             s.wait_stream(main)
