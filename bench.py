@@ -34,8 +34,8 @@ def synthetic_pool(n_batches, pairs, H, W, num_classes, seed, device=None, pin=T
     """SURVEY.md 8d synthetic inputs: uint8 uniform images, 12 GT boxes per source image. Returns a list
     of (label_q, label_k, unlabel_q, unlabel_k) tuples of dict lists in the reference's format."""
     import torch
-    from oracle.pt_oracle import synthetic_batch
     from probabilisticteacher_b200.structures import Boxes, FreeInstances
+    from probabilisticteacher_b200.synthetic import synthetic_batch
     pool = []
     for b in range(n_batches):
         lab = synthetic_batch(pairs, H, W, num_classes, seed + 2 * b)
@@ -125,6 +125,7 @@ class GemmProfiler:
     def __init__(self):
         self.records = []
         self.shapes = []
+        self.other = []
 
     def dump(self, path):
         rows = []
@@ -139,14 +140,21 @@ class GemmProfiler:
         if name == "ptb200_gemm_tn_f16":
             batch, rows, k, taps, n_total = args[1], args[2], args[3], args[6], args[9]
             n_valid = args[25] if args[11] in (2, 4) else n_total
-            if k == 64 and taps == 1 and n_total == 64:
-                k = 27  # first VGG conv: 27 live im2col columns out of the K=64 operand
             flops = 2.0 * batch * rows * k * taps * n_valid
         elif name == "ptb200_gemm_wgrad_f16":
             batch, rows, m, n, taps = args[6], args[7], args[8], args[9], args[10]
             flops = 2.0 * batch * rows * m * n * taps
         else:
-            return None
+            # every other entry point: time only (reported as kernels_ms_per_step); ROIAlign also books its
+            # algorithmic bytes = live rois x 7 x 7 x C x 2 B (the K-major fc1 operand written / read once)
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            extra = None
+            if name in ("ptb200_roi_align_fwd_f16", "ptb200_roi_align_bwd_f16"):
+                extra = (args[6], args[7], args[9] * args[9] * args[4] * 2)  # counts tensor, cap, bytes per roi
+            self.other.append((name, e0, e1, extra))
+            return ("other", None, e0, e1)
         e0 = torch.cuda.Event(enable_timing=True)
         e1 = torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -159,7 +167,24 @@ class GemmProfiler:
     def end(self, tok):
         if tok is not None:
             tok[3].record()
-            self.records.append(tok)
+            if tok[0] != "other":
+                self.records.append(tok)
+
+    def other_summary(self):
+        """({entry point: ms per step}, ROIAlign {name: (ms, GB/s)})."""
+        ms = {}
+        roi = {}
+        for name, e0, e1, extra in self.other:
+            t = e0.elapsed_time(e1)
+            ms[name] = ms.get(name, 0.0) + t
+            if extra is not None:
+                counts, cap, per_roi = extra
+                live = int(counts.clamp(max=cap).sum()) if counts is not None else 0
+                a = roi.setdefault(name, [0.0, 0.0])
+                a[0] += t
+                a[1] += live * per_roi
+        return ms, {k: {"ms_per_step": v[0], "algorithmic_GBps": v[1] / v[0] / 1e6 if v[0] > 0 else 0.0,
+                        "MB_per_step": v[1] / 1e6} for k, v in roi.items()}
 
     def summary(self):
         tot_f = {"ptb200_gemm_tn_f16": 0.0, "ptb200_gemm_wgrad_f16": 0.0}
@@ -261,6 +286,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cuda-graph", action="store_true")
     ap.add_argument("--no-concurrent", action="store_true")
+    ap.add_argument("--config", default="c2f", choices=["c2f", "k2c"],
+                    help="c2f: BASELINE configs 2/3 (default, the headline); k2c: config 4 (K = 1; use with "
+                         "--height 600 --width 2000)")
     ap.add_argument("--height", type=int, default=H_IMG)
     ap.add_argument("--width", type=int, default=W_IMG)
     args = ap.parse_args()
@@ -270,7 +298,7 @@ def main():
     import torch
     import torch.distributed as tdist
     from probabilisticteacher_b200 import _lib
-    from probabilisticteacher_b200.config import c2f_config
+    from probabilisticteacher_b200.config import c2f_config, k2c_config
     from probabilisticteacher_b200.engine.trainer import PTrainer
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -283,7 +311,7 @@ def main():
         tdist.init_process_group("nccl", device_id=device)
         dist = tdist
     warmup = max(args.warmup, 3)
-    cfg = c2f_config()
+    cfg = k2c_config() if args.config == "k2c" else c2f_config()
     cfg.UNSUPNET.BURN_UP_STEP = 0  # time the post-burn-in (teacher + student) iteration
     H, W = args.height, args.width
     K = cfg.MODEL.ROI_HEADS.NUM_CLASSES
@@ -328,6 +356,7 @@ def main():
     torch.cuda.synchronize()
     _lib.profiler[0] = None
     tot_f, tot_t, cnt = prof.summary()
+    other_ms, roi_stats = prof.other_summary()
     if os.environ.get("PTB_DUMP_GEMM") and rank == 0:
         prof.dump(os.path.join(ROOT, "gpurun_out", "gemm_launches.json"))
     peaks = {}
@@ -367,7 +396,8 @@ def main():
             "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f16 operands / f32 accumulate (tcgen05 kind::f16), f32 master weights",
             "data": "synthetic",
-            "config": {"workload": f"CitysScape2FoggyCityscape config (configs/pt/final_c2f.yaml + train.sh overrides), "
+            "config": {"workload": ("KITTI2CitysScape config (configs/pt/final_k2c.yaml, K = 1), " if args.config == "k2c" else
+                                    "CitysScape2FoggyCityscape config (configs/pt/final_c2f.yaml + train.sh overrides), ") +
                                    f"synthetic 3x{H}x{W}, {PAIRS_PER_GPU} source + {PAIRS_PER_GPU} target pairs per GPU, "
                                    "full post-burn-in PT iteration",
                        "global_batch": f"{PAIRS_PER_GPU * world}+{PAIRS_PER_GPU * world}",
@@ -380,6 +410,9 @@ def main():
             "gpu_launches_note": "kernels of libptb200.so per step (counted on an eager step; in CUDA-graph mode the "
                                  "same kernels are replayed from the captured graph)",
             "clocks": clk, "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "kernels_ms_per_step": {k.replace("ptb200_", ""): round(v, 4) for k, v in
+                                    sorted(other_ms.items(), key=lambda kv: -kv[1])[:12]},
+            "roialign": roi_stats,
         }
         print(json.dumps(line))
     if dist is not None:

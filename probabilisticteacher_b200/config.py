@@ -165,3 +165,11 @@ def c2f_config():
     c.MODEL.ANCHOR_GENERATOR.NAME = "DifferentiableAnchorGenerator"
     c.TEST.EVAL_PERIOD = 400
     return c
+
+
+def k2c_config():
+    """configs/pt/final_k2c.yaml (KITTI -> Cityscapes, car only): final_c2f with NUM_CLASSES = 1; the
+    train.sh overrides are kept."""
+    c = c2f_config()
+    c.MODEL.ROI_HEADS.NUM_CLASSES = 1
+    return c

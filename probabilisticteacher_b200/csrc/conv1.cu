@@ -291,22 +291,41 @@ conv1_u8_tc_kernel(const uint8_t* __restrict__ img, const int* __restrict__ hw, 
       const int h = hw[2 * n], w = hw[2 * n + 1];
       const uint8_t* ib = img + n * img_stride;
       float v[27];
+      if (p < rows && x >= 1 && x + 1 < w && y >= 1 && y + 1 < h) {
+        // interior pixel (all but the image border): 27 unpredicated byte loads off one base pointer
+        const uint8_t* b0 = ib + static_cast<int64_t>(y - 1) * w + (x - 1);
+        const int64_t plane = static_cast<int64_t>(h) * w;
 #pragma unroll
-      for (int k = 0; k < 27; ++k) v[k] = 0.f;
-      if (p < rows && x < Wmax) {
+        for (int c = 0; c < 3; ++c) {
+          const float mean = c == 0 ? m0 : (c == 1 ? m1 : m2);
+          const float istd = c == 0 ? is0 : (c == 1 ? is1 : is2);
+          const uint8_t* bc = b0 + c * plane;
 #pragma unroll
-        for (int dy = 0; dy < 3; ++dy) {
-          const int yy = y + dy - 1;
-          if (yy < 0 || yy >= h) continue;
+          for (int dy = 0; dy < 3; ++dy) {
+            const uint8_t* br = bc + dy * w;
 #pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            const float mean = c == 0 ? m0 : (c == 1 ? m1 : m2);
-            const float istd = c == 0 ? is0 : (c == 1 ? is1 : is2);
-            const uint8_t* rowp = ib + (static_cast<int64_t>(c) * h + yy) * w;
+            for (int dx = 0; dx < 3; ++dx)
+              v[(dy * 3 + dx) * 3 + c] = (static_cast<float>(__ldg(br + dx)) - mean) * istd;
+          }
+        }
+      } else {
 #pragma unroll
-            for (int dx = 0; dx < 3; ++dx) {
-              const int xx = x + dx - 1;
-              if (xx >= 0 && xx < w) v[(dy * 3 + dx) * 3 + c] = (static_cast<float>(__ldg(rowp + xx)) - mean) * istd;
+        for (int k = 0; k < 27; ++k) v[k] = 0.f;
+        if (p < rows && x < Wmax) {
+#pragma unroll
+          for (int dy = 0; dy < 3; ++dy) {
+            const int yy = y + dy - 1;
+            if (yy < 0 || yy >= h) continue;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              const float mean = c == 0 ? m0 : (c == 1 ? m1 : m2);
+              const float istd = c == 0 ? is0 : (c == 1 ? is1 : is2);
+              const uint8_t* rowp = ib + (static_cast<int64_t>(c) * h + yy) * w;
+#pragma unroll
+              for (int dx = 0; dx < 3; ++dx) {
+                const int xx = x + dx - 1;
+                if (xx >= 0 && xx < w) v[(dy * 3 + dx) * 3 + c] = (static_cast<float>(__ldg(rowp + xx)) - mean) * istd;
+              }
             }
           }
         }

@@ -115,3 +115,19 @@ def test_data_parallel_plumbing_gloo(tmp_path):
 def test_bucket_bounds():
     from probabilisticteacher_b200.engine.dp import bucket_bounds
     assert bucket_bounds(10, 4) == [(0, 4), (4, 8), (8, 10)]
+
+
+def test_synthetic_inputs_match_the_oracle_generator():
+    """bench.py's main arm draws its inputs from the package (it must not import oracle/); the generator is
+    the same stream as the oracle's, so parity runs can feed both sides identical batches."""
+    import torch
+    from oracle import pt_oracle as O
+    from probabilisticteacher_b200.synthetic import synthetic_batch
+    a = synthetic_batch(2, 64, 96, 8, 1234)
+    b = O.synthetic_batch(2, 64, 96, 8, 1234)
+    for da, db in zip(a, b):
+        assert torch.equal(da["image"], db["image"])
+        assert torch.equal(da["instances"].gt_boxes.tensor, db["instances"].gt_boxes.tensor)
+        assert torch.equal(da["instances"].gt_classes, db["instances"].gt_classes)
+    u = synthetic_batch(1, 64, 96, 8, 7, labelled=False)
+    assert "instances" not in u[0]
