@@ -28,8 +28,16 @@ __global__ void ema_kernel(float* __restrict__ teacher, const float* __restrict_
   }
 }
 
+// Deterministic squared norm: every replica must derive the SAME clip coefficient from the (bit-identical)
+// all-reduced gradients, or the data-parallel replicas drift apart in the last bits (an atomicAdd of the block
+// partials in arrival order did exactly that: tools/check_ddp.py). Block partials go to a scratch array; the
+// last block to finish adds them in index order with a fixed-shape tree.
+__device__ float g_sumsq_partial[148 * 16];
+__device__ unsigned int g_sumsq_done = 0;
+
 __global__ void sumsq_kernel(const float* __restrict__ g, int64_t n, float pre_scale, float* __restrict__ out) {
   __shared__ float sm[32];
+  __shared__ bool is_last;
   float acc = 0.f;
   const int64_t n4 = n >> 2;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n4;
@@ -50,7 +58,29 @@ __global__ void sumsq_kernel(const float* __restrict__ g, int64_t n, float pre_s
     acc = threadIdx.x < (blockDim.x >> 5) ? sm[threadIdx.x] : 0.f;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (threadIdx.x == 0) atomicAdd(out, acc);
+    if (threadIdx.x == 0) {
+      g_sumsq_partial[blockIdx.x] = acc;
+      __threadfence();
+      is_last = atomicAdd(&g_sumsq_done, 1u) == gridDim.x - 1;
+    }
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  float tot = 0.f;
+  for (unsigned int i = threadIdx.x; i < gridDim.x; i += blockDim.x) tot += __ldcg(&g_sumsq_partial[i]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = tot;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    tot = threadIdx.x < (blockDim.x >> 5) ? sm[threadIdx.x] : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+    if (threadIdx.x == 0) {
+      out[0] = tot;
+      g_sumsq_done = 0;
+    }
   }
 }
 
@@ -105,7 +135,6 @@ extern "C" int ptb200_ema_update(float* teacher, const float* student, int64_t n
 }
 
 extern "C" int ptb200_grad_sumsq(const float* grads, int64_t n, float pre_scale, float* sumsq_out, void* stream) {
-  cudaMemsetAsync(sumsq_out, 0, sizeof(float), STREAM);
   sumsq_kernel<<<grid_stream(n), 256, 0, STREAM>>>(grads, n, pre_scale, sumsq_out);
   return static_cast<int>(cudaGetLastError());
 }
