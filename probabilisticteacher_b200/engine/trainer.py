@@ -67,6 +67,13 @@ class PTrainer:
         # GEMM CTAs measured 14.55 / 14.54 / 14.42 ms per step)
         self.concurrent = concurrent
         self._streams = None
+        self._comm_stream = None
+        self._grads_reduced = False
+        # EXPERIMENTAL (off by default), world > 1 + concurrent graph step: all-reduce the head gradients inside
+        # the graph while the backbone backward runs. tools/check_ddp.py passes with it on 2 GPUs (bit-identical
+        # replicas), but bench.py at 3x800x1333 hung with it in round 1 and the cause is not yet found; the default
+        # is the single eager all-reduce after the graph (0.4 ms of 14.7 ms at 2 GPUs).
+        self.overlap_allreduce = os.environ.get("PTB200_OVERLAP_ALLREDUCE", "0") == "1"
         self.concurrent_gemm_ctas = int(os.environ.get("PTB200_GEMM_CTAS", "0"))  # 0 = one CTA per SM
 
     # ------------------------------------------------------------------ pseudo-labelling (trainer.py:179-257)
@@ -163,11 +170,11 @@ class PTrainer:
         t.pack()
 
     # ------------------------------------------------------------------ clip + SGD (trainer.py:383-386,592-603)
-    def _optimizer_step(self, clip_norm=10.0):
+    def _optimizer_step(self, clip_norm=10.0, reduced=False):
         a = self.model.arena
         n = a.grads.numel()
         pre = 1.0 / self.world
-        if self.world > 1:
+        if self.world > 1 and not reduced:
             dist.all_reduce(a.grads)
         lr = warmup_multistep_lr(self.cfg.SOLVER.BASE_LR, self.iter, self.cfg.SOLVER.STEPS, self.cfg.SOLVER.GAMMA,
                                  self.cfg.SOLVER.WARMUP_FACTOR, self.cfg.SOLVER.WARMUP_ITERS,
@@ -377,6 +384,17 @@ class PTrainer:
         self.model.zero_grad()
         for s in (s_t, s_1, s_2):
             s.wait_stream(main)
+        overlap = self.world > 1 and self.overlap_allreduce
+        head_events = []
+        if overlap:
+            if self._comm_stream is None:
+                self._comm_stream = torch.cuda.Stream(device=self.device)
+
+            def hook():
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream())
+                head_events.append(ev)
+            self.model.heads_backward_hook = hook
         e_pseudo = torch.cuda.Event()
         keep = []  # tensors that cross streams stay referenced until the join
         with torch.cuda.stream(s_t):
@@ -411,9 +429,30 @@ class PTrainer:
             keep.append(uq_img)
             sum(v * w_unsup for v in rec_u.values()).backward()
             refresh_stream()
+        if overlap:
+            # Gradient all-reduce inside the captured step, in two segments of the flat arena: everything behind
+            # the VGG backbone (29.3 M of 43.8 M floats: fc1 alone is 103 MB) is reduced on a communication
+            # stream as soon as BOTH student passes have finished their head backward, overlapping the backbone
+            # data / weight gradient GEMMs; the backbone segment follows after the join. (torch DDP's bucketed
+            # overlap at pt/engine/trainer.py:92-95, with two buckets cut at the arena's natural boundary.)
+            self.model.heads_backward_hook = None
+            g = self.model.arena.grads
+            cut = self.model.arena.segments["proposal_generator.rpn_head.conv.weight"].offset - \
+                self.model.arena.trainable_start
+            assert len(head_events) == 2
+            sc = self._comm_stream
+            sc.wait_stream(main)
+            for ev in head_events:
+                sc.wait_event(ev)
+            with torch.cuda.stream(sc):
+                dist.all_reduce(g[cut:])
         for s in (s_t, s_1, s_2):
             main.wait_stream(s)
         refresh_stream()
+        if overlap:
+            dist.all_reduce(g[:cut])
+            main.wait_stream(sc)
+            self._grads_reduced = True
         for k, v in rec_l.items():
             rec[k + "_sup"] = v
         for k, v in rec_u.items():
@@ -447,7 +486,7 @@ class PTrainer:
             self._graph.replay()
             self.last_losses = self._graph_losses
         refresh_stream()
-        self._optimizer_step(10.0)
+        self._optimizer_step(10.0, reduced=self._grads_reduced)
         self.iter += 1
         return self.last_losses
 

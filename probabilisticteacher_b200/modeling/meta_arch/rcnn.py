@@ -82,6 +82,7 @@ class GuassianGeneralizedRCNN(nn.Module):
         self.prio_override = None  # tests inject {tag: (prio_pos, prio_neg)}
         self._hw_cache = {}
         self.backward_stream = None
+        self.heads_backward_hook = None
         self.launch_count = 0
 
     # ------------------------------------------------------------------ nn.Module surface
@@ -316,6 +317,11 @@ class GuassianGeneralizedRCNN(nn.Module):
         feat = fctx["feat"]
         dfeat_roi = self.roi_heads.backward(fctx["roi"], g[0], g[1])
         dfeat_rpn = self.proposal_generator.backward(fctx["rpn"], g[2], g[3])
+        if self.heads_backward_hook is not None:
+            # every gradient outside the VGG backbone (box head, predictor, RPN head, anchors) is final for this
+            # pass: the trainer records an event here and all-reduces that arena suffix while the backbone
+            # backward still runs
+            self.heads_backward_hook()
         dz = torch.empty_like(feat.t)
         call("ptb200_add_mask_f16", dfeat_rpn.t, dfeat_roi, 1.0, feat.t, dz, dz.numel())
         self.backbone.backward(fctx["records"], ops.FlatAct(dz, feat.H, feat.W))
