@@ -69,9 +69,10 @@ class PTrainer:
         self._streams = None
         self._comm_stream = None
         self._grads_reduced = False
-        # EXPERIMENTAL (off by default), world > 1 + concurrent graph step: all-reduce the head gradients inside
-        # the graph while the backbone backward runs. tools/check_ddp.py passes with it on 2 GPUs (bit-identical
-        # replicas), but bench.py at 3x800x1333 hung with it in round 1 and the cause is not yet found; the default
+        # EXPERIMENTAL, off by default (PTB200_OVERLAP_ALLREDUCE=1): world > 1 + concurrent graph step, all-reduce
+        # the head gradients inside the graph while the backbone backward runs. tools/check_ddp.py passes with it
+        # on 2 GPUs at 320x480 (bit-identical replicas), but bench.py at 3x800x1333 hangs with it (round 1, cause
+        # not found: NCCL kernels co-scheduled with one-CTA-per-SM persistent GEMMs are the suspect). The default
         # is the single eager all-reduce after the graph (0.4 ms of 14.7 ms at 2 GPUs).
         self.overlap_allreduce = os.environ.get("PTB200_OVERLAP_ALLREDUCE", "0") == "1"
         self.concurrent_gemm_ctas = int(os.environ.get("PTB200_GEMM_CTAS", "0"))  # 0 = one CTA per SM
@@ -450,8 +451,11 @@ class PTrainer:
             main.wait_stream(s)
         refresh_stream()
         if overlap:
-            dist.all_reduce(g[:cut])
+            # the second collective must be ORDERED after the first one: synchronous collectives are issued on
+            # the caller's stream, and two collectives of one communicator running concurrently from two streams
+            # (in an order that may differ between ranks) dead-lock NCCL
             main.wait_stream(sc)
+            dist.all_reduce(g[:cut])
             self._grads_reduced = True
         for k, v in rec_l.items():
             rec[k + "_sup"] = v
