@@ -97,7 +97,7 @@ def conv3x3(x: FlatAct, w_packed, bias, relu=True, aux=None, out=None):
 # [Wh | Wh | Wl] triples of W * 2^s with alpha = 2^-s (ParamArena.pack_x3). See include/ptb200.h.
 # longest chain of tensor-core accumulations (k-iterations of 64 = 4 MMAs each) before the partial sum is
 # promoted to a round-to-nearest fp32 add: the MMA accumulates with truncation. Measured on B200 with positive
-# operands (tools/x3_diag.py): mean signed error -2.4e-4 for one chain over K = 3 x 25088, -2.7e-6 / -1.2e-6 /
+# operands (tests/dev/x3_diag.py): mean signed error -2.4e-4 for one chain over K = 3 x 25088, -2.7e-6 / -1.2e-6 /
 # -4.8e-7 / -1.8e-7 with chunks of 8 / 4 / 2 / 1 k-iterations; the bias compounds through the 16 stacked layers.
 X3_MAX_K_ITERS = [2]
 

@@ -5,7 +5,7 @@ import sys
 
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle import pt_oracle as O
 from probabilisticteacher_b200.config import c2f_config
 from probabilisticteacher_b200.modeling.meta_arch.rcnn import build_model

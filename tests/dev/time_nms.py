@@ -1,5 +1,5 @@
 import ctypes, os, sys, torch
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle import pt_oracle as O
 from probabilisticteacher_b200 import ops
 from probabilisticteacher_b200._lib import lib
