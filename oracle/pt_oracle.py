@@ -12,6 +12,10 @@ tree) is restated from those releases' published behaviour and marked "d2 v0.5".
 Pinning: `oracle/make_golden.py` imports the reference's own pt/modeling files (unmodified, from
 /root/reference, through the stub package in oracle/d2shim) and freezes their outputs under
 tests/golden/; tests/test_oracle_golden.py checks this restatement against those fixtures.
+`oracle/make_golden_model.py` additionally constructs the reference's own model classes
+(oracle/d2shim_model.py supplies working detectron2 v0.5 base classes) and runs
+GuassianGeneralizedRCNN.forward end to end; tests/test_oracle_golden_model.py checks OracleRCNN
+against that (losses bit-identical).
 The detectron2 base-class behaviour itself has no golden vectors in the reference (it ships no
 tests): that part is pinned only against torchvision ops and analytic cases ("parity unpinned" at
 the detectron2 boundary).

@@ -1,0 +1,91 @@
+"""CPU: the oracle's whole-model orchestration against the REFERENCE'S OWN MODEL CLASSES.
+
+tests/golden/pt_reference_model_golden.pt was produced by oracle/make_golden_model.py: the reference's
+`GuassianGeneralizedRCNN.forward` (pt/modeling/meta_arch/rcnn.py:30-92) with the reference's VGG, GuassianRPN,
+DifferentiableAnchorGenerator, GuassianROIHead and GuassianFastRCNNOutputLayers, imported unmodified and executed
+end to end in the three branches of a post-burn-in iteration. Here `oracle.pt_oracle.OracleRCNN` gets the same
+images, ground truth, weights (same seeded initialisers) and sampling priorities, and must reproduce the losses,
+the teacher's RPN proposals and pseudo labels, and the gradient reaching the differentiable anchors."""
+import os
+
+import torch
+
+from oracle import pt_oracle as O
+
+G = torch.load(os.path.join(os.path.dirname(__file__), "golden", "pt_reference_model_golden.pt"), weights_only=False)
+
+
+class _Sampler:
+    def __init__(self, pr):
+        self.pr = pr
+
+    def prio(self, tag, n):
+        grp, which = tag[0].split("_")
+        return self.pr[grp][0 if which == "pos" else 1][tag[1]][:n]
+
+
+def _model():
+    om = O.OracleRCNN(O.OracleCfg(num_classes=G["K"]), seed=G["seed"])
+    om.sampler = _Sampler(G["prio"])
+    return om
+
+
+def _batches():
+    H, W = G["H"], G["W"]
+    lab = [{"image": im, "height": H, "width": W,
+            "instances": O.OInst((H, W), gt_boxes=O.OBoxes(b.clone()), gt_classes=c.clone())}
+           for im, b, c in zip(G["lab_images"], G["gt_boxes"], G["gt_classes"])]
+    unl = [{"image": im, "height": H, "width": W} for im in G["unl_images"]]
+    return lab, unl
+
+
+def _close(a, b, tol=2e-5):
+    a, b = torch.as_tensor(a).double(), torch.as_tensor(b).double()
+    assert a.shape == b.shape, (a.shape, b.shape)
+    err = float((a - b).detach().abs().max()) if a.numel() else 0.0
+    assert err <= tol * max(float(b.abs().max()) if b.numel() else 1.0, 1e-6), err
+
+
+def test_supervised_branch_matches_reference_model():
+    om = _model()
+    lab, _ = _batches()
+    with torch.no_grad():
+        losses, _, _, _ = om(lab, branch="supervised")
+    assert set(losses) == set(G["sup_losses"])
+    for k, v in G["sup_losses"].items():
+        _close(losses[k], v)
+
+
+def test_teacher_branch_matches_reference_model():
+    om = _model()
+    _, unl = _batches()
+    with torch.no_grad():
+        _, props, roih, _ = om(unl, branch="unsup_data_weak")
+    for n in range(G["N"]):
+        _close(props[n].proposal_boxes.tensor, G["teacher_rpn_boxes"][n])
+        _close(props[n].objectness_logits, G["teacher_rpn_logits"][n])
+        ref = G["teacher_roih"][n]
+        assert torch.equal(roih[n].pred_classes, ref["pred_classes"])
+        for f in ("pred_boxes", "scores", "scores_logists", "boxes_sigma"):
+            v = getattr(roih[n], f)
+            _close(v.tensor if hasattr(v, "tensor") else v, ref[f])
+
+
+def test_unsupervised_branch_matches_reference_model():
+    lab, unl = _batches()
+    H, W = G["H"], G["W"]
+    unl_q = [dict(d, instances=O.OInst((H, W), pseudo_boxes=O.OBoxes(r["pred_boxes"].clone()),
+                                       scores_logists=r["scores_logists"].clone(), boxes_sigma=r["boxes_sigma"].clone()))
+             for d, r in zip(unl, G["teacher_roih"])]
+    for danchor, key in ((True, "unsup_anchor_grad"), (False, "unsup_anchor_grad_no_danchor")):
+        om = _model()
+        losses, _, _, _ = om(unl_q, branch="unsupervised", danchor=danchor)
+        if danchor:
+            assert set(losses) == set(G["unsup_losses"])
+            for k, v in G["unsup_losses"].items():
+                _close(losses[k], v)
+        sum(losses.values()).backward()
+        g = om.p("proposal_generator.anchor_generator.anchor_0").grad
+        g = torch.zeros_like(G[key]) if g is None else g
+        _close(g, G[key], 1e-3)
+    assert float(G["unsup_anchor_grad"].abs().max()) > 0 and float(G["unsup_anchor_grad_no_danchor"].abs().max()) == 0
