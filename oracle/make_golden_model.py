@@ -44,7 +44,9 @@ from pt.structures.instances import FreeInstances  # noqa: E402
 from oracle import pt_oracle as O  # noqa: E402
 from probabilisticteacher_b200.config import c2f_config  # noqa: E402
 
-H, W, N, K, SEED = 128, 160, 2, 8, 11
+# (name, image sizes, K, anchor generator, weight seed)
+CASES = [("c2f", [(128, 160), (128, 160)], 8, "DifferentiableAnchorGenerator", 11),
+         ("k1_default_anchors_mixed_sizes", [(112, 160), (128, 144)], 1, "DefaultAnchorGenerator", 12)]
 
 
 def build_reference_model(cfg, sd):
@@ -62,8 +64,12 @@ def build_reference_model(cfg, sd):
         torch.save(ck, path)
         cfg.MODEL.VGG.PRETRAIN = path
         backbone = ref_vgg.build_vgg_backbone(cfg, B["ShapeSpec"](channels=3))
-    anchor_gen = ref_ag.DifferentiableAnchorGenerator(anchor=cfg.MODEL.ANCHOR_GENERATOR.ANCHOR, strides=[16],
-                                                      offset=cfg.MODEL.ANCHOR_GENERATOR.OFFSET)
+    a = cfg.MODEL.ANCHOR_GENERATOR
+    if a.NAME == "DifferentiableAnchorGenerator":
+        anchor_gen = ref_ag.DifferentiableAnchorGenerator(anchor=a.ANCHOR, strides=[16], offset=a.OFFSET)
+    else:  # configs/Guassian-RCNN-VGG.yaml:9-12 (detectron2's own generator, restated in d2shim_model)
+        anchor_gen = B["DefaultAnchorGenerator"](sizes=a.SIZES, aspect_ratios=a.ASPECT_RATIOS, strides=[16],
+                                                 offset=a.OFFSET)
     head = ref_rpn.GuassianRPNHead(in_channels=512, num_anchors=9, box_dim=8)  # box_dim doubled, rpn.py:50-55
     r = cfg.MODEL.RPN
     rpn = ref_rpn.GuassianRPN(
@@ -108,17 +114,20 @@ def to_ref(batch):
     return out
 
 
-def main():
+def run_case(sizes, K, anchor_name, seed):
     cfg = c2f_config()
-    ocfg = O.OracleCfg(num_classes=K)
-    sd = O.OracleRCNN(ocfg, seed=SEED).ref_state_dict()  # weights are inputs: seeded initialisers, not stored
+    cfg.MODEL.ROI_HEADS.NUM_CLASSES = K
+    cfg.MODEL.ANCHOR_GENERATOR.NAME = anchor_name
+    ocfg = O.OracleCfg(num_classes=K, anchor_generator=anchor_name)
+    sd = O.OracleRCNN(ocfg, seed=seed).ref_state_dict()  # weights are inputs: seeded initialisers, not stored
     model = build_reference_model(cfg, {k: v.detach().clone() for k, v in sd.items()})
     model.train()
-
-    lab = O.synthetic_batch(N, H, W, K, 5, boxes_per_image=4)
-    unl = O.synthetic_batch(N, H, W, K, 6, labelled=False)
+    N = len(sizes)
+    lab = [O.synthetic_batch(1, h, w, K, 5 + i, boxes_per_image=4)[0] for i, (h, w) in enumerate(sizes)]
+    unl = [O.synthetic_batch(1, h, w, K, 50 + i, labelled=False)[0] for i, (h, w) in enumerate(sizes)]
     g = torch.Generator().manual_seed(99)
-    R = (H // 16) * (W // 16) * 9
+    Hm, Wm = max(s[0] for s in sizes), max(s[1] for s in sizes)
+    R = (Hm // 16) * (Wm // 16) * 9
     L = cfg.MODEL.RPN.POST_NMS_TOPK_TRAIN + 16
     prio = {"rpn": (torch.rand(N, R, generator=g), torch.rand(N, R, generator=g)),
             "roi": (torch.rand(N, L, generator=g), torch.rand(N, L, generator=g))}
@@ -128,7 +137,7 @@ def main():
         return prio[grp][0 if which == "pos" else 1][tag[1]][:n]
     d2shim_model.PRIO.provider = provider
 
-    out = dict(H=H, W=W, N=N, K=K, seed=SEED, prio=prio,
+    out = dict(sizes=sizes, N=N, K=K, seed=seed, anchor_generator=anchor_name, prio=prio,
                lab_images=[d["image"] for d in lab], unl_images=[d["image"] for d in unl],
                gt_boxes=[d["instances"].gt_boxes.tensor for d in lab],
                gt_classes=[d["instances"].gt_classes for d in lab])
@@ -150,27 +159,40 @@ def main():
         inst = FreeInstances(p.image_size, pseudo_boxes=Boxes(p.pred_boxes.tensor.clone()),
                              scores_logists=p.scores_logists.clone(), boxes_sigma=p.boxes_sigma.clone())
         unl_q.append(dict(d, instances=inst))
+    differentiable = anchor_name == "DifferentiableAnchorGenerator"
+    for danchor, key in ((True, "unsup_anchor_grad"), (False, "unsup_anchor_grad_no_danchor")):
+        model.zero_grad()
+        d2shim_model.PRIO.reset()
+        losses, _, _, _ = model(unl_q, branch="unsupervised", danchor=danchor)
+        if danchor:
+            out["unsup_losses"] = {k: v.detach().clone() for k, v in losses.items()}
+        sum(losses.values()).backward()
+        if differentiable:
+            ag = model.proposal_generator.anchor_generator.anchor_0.grad
+            out[key] = torch.zeros(9, 2) if ag is None else ag.clone()
+    # one trainable tensor's gradient of the supervised branch (autograd through the reference's own graph)
     model.zero_grad()
     d2shim_model.PRIO.reset()
-    losses, _, _, _ = model(unl_q, branch="unsupervised", danchor=True)
-    out["unsup_losses"] = {k: v.detach().clone() for k, v in losses.items()}
+    losses, _, _, _ = model(to_ref(lab), branch="supervised")
     sum(losses.values()).backward()
-    out["unsup_anchor_grad"] = model.proposal_generator.anchor_generator.anchor_0.grad.clone()
-    model.zero_grad()
-    d2shim_model.PRIO.reset()
-    losses, _, _, _ = model(unl_q, branch="unsupervised", danchor=False)
-    sum(losses.values()).backward()
-    ag = model.proposal_generator.anchor_generator.anchor_0.grad
-    out["unsup_anchor_grad_no_danchor"] = torch.zeros_like(out["unsup_anchor_grad"]) if ag is None else ag.clone()
+    out["sup_grad_rpn_objectness_w"] = model.proposal_generator.rpn_head.objectness_logits.weight.grad.clone()
+    out["sup_grad_cls_score_w"] = model.roi_heads.box_predictor.cls_score.weight.grad.clone()
+    out["sup_grad_conv5_3_b"] = model.backbone.vgg_block5[0].conv3.bias.grad.clone()
 
     for k, v in out["sup_losses"].items():
-        print("sup", k, float(v))
+        print("  sup", k, float(v))
     for k, v in out["unsup_losses"].items():
-        print("unsup", k, float(v))
-    print("teacher proposals", [len(b) for b in out["teacher_rpn_boxes"]], "detections",
+        print("  unsup", k, float(v))
+    print("  teacher proposals", [len(b) for b in out["teacher_rpn_boxes"]], "detections",
           [len(r["scores"]) for r in out["teacher_roih"]])
-    print("anchor grad |max|", float(out["unsup_anchor_grad"].abs().max()),
-          float(out["unsup_anchor_grad_no_danchor"].abs().max()))
+    return out
+
+
+def main():
+    out = {}
+    for name, sizes, K, anchor_name, seed in CASES:
+        print(name)
+        out[name] = run_case(sizes, K, anchor_name, seed)
     dst = os.path.join(ROOT, "tests", "golden", "pt_reference_model_golden.pt")
     torch.save(out, dst)
     print("wrote", dst, os.path.getsize(dst), "bytes")
