@@ -288,3 +288,65 @@ def test_x3_refuses_backward(cuda):
     lab = O.synthetic_batch(1, 96, 128, 8, 1)
     with pytest.raises(RuntimeError):
         model(_to_inst(lab), branch="supervised")
+
+
+# ------------------------------------------------------------------------------------------ vs the reference's own classes
+def _gold():
+    import os
+    return torch.load(os.path.join(os.path.dirname(__file__), "golden", "pt_reference_model_golden.pt"),
+                      weights_only=False)
+
+
+@pytest.mark.parametrize("case", ["c2f", "k1_default_anchors_mixed_sizes"])
+def test_cuda_path_vs_reference_model_golden(cuda, case):
+    """The CUDA path (f16x3 precision) against outputs of the REFERENCE'S OWN MODEL CLASSES
+    (tests/golden/pt_reference_model_golden.pt, made by oracle/make_golden_model.py from the unmodified
+    pt/modeling files): same images, ground truth, weights and sampling priorities; losses of the supervised and
+    unsupervised branches within 1e-3, teacher proposals and pseudo labels matched as in _full_iteration."""
+    from oracle import pt_oracle as O
+    from probabilisticteacher_b200.config import c2f_config
+    from probabilisticteacher_b200.modeling.meta_arch.rcnn import build_model
+    from probabilisticteacher_b200.structures import Boxes, FreeInstances
+    G = _gold()[case]
+    cfg = c2f_config()
+    cfg.MODEL.ROI_HEADS.NUM_CLASSES = G["K"]
+    cfg.MODEL.ANCHOR_GENERATOR.NAME = G["anchor_generator"]
+    model = build_model(cfg, cuda, precision="f16x3", with_grads=False)
+    sd = O.OracleRCNN(O.OracleCfg(num_classes=G["K"], anchor_generator=G["anchor_generator"]), seed=G["seed"]).ref_state_dict()
+    model.load_state_dict({k: v.detach() for k, v in sd.items()})
+    model.train()
+    model.prio_override = {k: (v[0].to(cuda), v[1].to(cuda)) for k, v in G["prio"].items()}
+    sizes = [tuple(s) for s in G["sizes"]]
+    scale = float(max(max(s) for s in sizes))
+    lab = [{"image": im, "height": s[0], "width": s[1],
+            "instances": FreeInstances(s, gt_boxes=Boxes(b.clone()), gt_classes=c.clone())}
+           for im, b, c, s in zip(G["lab_images"], G["gt_boxes"], G["gt_classes"], sizes)]
+    unl = [{"image": im, "height": s[0], "width": s[1]} for im, s in zip(G["unl_images"], sizes)]
+    with torch.no_grad():
+        lg, _, _, _ = model(lab, branch="supervised")
+        for k, v in G["sup_losses"].items():
+            a, b = float(lg[k]), float(v)
+            assert abs(a - b) <= TOL * max(abs(b), 1e-6), ("sup", k, a, b)
+        _, pg, rg, _ = model(unl, branch="unsup_data_weak")
+        for n in range(G["N"]):
+            p = pg[n].trim()
+            ref_boxes = G["teacher_rpn_boxes"][n]
+            assert len(p) == len(ref_boxes), (len(p), len(ref_boxes))
+            assert _prop_overlap(p.proposal_boxes.tensor, ref_boxes, scale) >= 0.99  # (near-tied scores may swap places)
+            assert _rel(p.objectness_logits.sort().values, G["teacher_rpn_logits"][n].sort().values) < TOL
+            ref = G["teacher_roih"][n]
+            o = O.OInst(sizes[n], pred_boxes=O.OBoxes(ref["pred_boxes"]), scores=ref["scores"],
+                        pred_classes=ref["pred_classes"], scores_logists=ref["scores_logists"],
+                        boxes_sigma=ref["boxes_sigma"])
+            g = rg[n].trim()
+            assert len(g) == len(ref["scores"])
+            frac, worst = _match_detections(g, o, scale)
+            assert frac >= 0.97 and all(x < TOL for x in worst.values()), (frac, worst)
+        unl_q = [dict(d, instances=FreeInstances(s, pseudo_boxes=Boxes(r["pred_boxes"].to(cuda)),
+                                                 scores_logists=r["scores_logists"].to(cuda),
+                                                 boxes_sigma=r["boxes_sigma"].to(cuda)))
+                 for d, r, s in zip(unl, G["teacher_roih"], sizes)]
+        lu, _, _, _ = model(unl_q, branch="unsupervised", danchor=True)
+        for k, v in G["unsup_losses"].items():
+            a, b = float(lu[k]), float(v)
+            assert abs(a - b) <= TOL * max(abs(b), 1e-6), ("unsup", k, a, b)
