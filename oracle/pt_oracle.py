@@ -15,7 +15,9 @@ tests/golden/; tests/test_oracle_golden.py checks this restatement against those
 `oracle/make_golden_model.py` additionally constructs the reference's own model classes
 (oracle/d2shim_model.py supplies working detectron2 v0.5 base classes) and runs
 GuassianGeneralizedRCNN.forward end to end; tests/test_oracle_golden_model.py checks OracleRCNN
-against that (losses bit-identical).
+against that (losses bit-identical). `oracle/make_golden_step.py` executes the reference's own
+PTrainer.run_step (pt/engine/trainer.py imported unmodified) for two iterations;
+tests/test_oracle_golden_step.py checks `run_step` below against it (losses and parameters bit-identical).
 The detectron2 base-class behaviour itself has no golden vectors in the reference (it ships no
 tests): that part is pinned only against torchvision ops and analytic cases ("parity unpinned" at
 the detectron2 boundary).
