@@ -44,9 +44,10 @@ from pt.structures.instances import FreeInstances  # noqa: E402
 from oracle import pt_oracle as O  # noqa: E402
 from probabilisticteacher_b200.config import c2f_config  # noqa: E402
 
-# (name, image sizes, K, anchor generator, weight seed)
-CASES = [("c2f", [(128, 160), (128, 160)], 8, "DifferentiableAnchorGenerator", 11),
-         ("k1_default_anchors_mixed_sizes", [(112, 160), (128, 144)], 1, "DefaultAnchorGenerator", 12)]
+# (name, image sizes, K, anchor generator, weight seed, ground-truth boxes per image)
+CASES = [("c2f", [(128, 160), (128, 160)], 8, "DifferentiableAnchorGenerator", 11, (4, 4)),
+         ("k1_default_anchors_mixed_sizes", [(112, 160), (128, 144)], 1, "DefaultAnchorGenerator", 12, (4, 4)),
+         ("c2f_image_without_gt", [(128, 160), (128, 160)], 8, "DifferentiableAnchorGenerator", 13, (3, 0))]
 
 
 def build_reference_model(cfg, sd):
@@ -114,7 +115,7 @@ def to_ref(batch):
     return out
 
 
-def run_case(sizes, K, anchor_name, seed):
+def run_case(sizes, K, anchor_name, seed, n_gt):
     cfg = c2f_config()
     cfg.MODEL.ROI_HEADS.NUM_CLASSES = K
     cfg.MODEL.ANCHOR_GENERATOR.NAME = anchor_name
@@ -123,7 +124,7 @@ def run_case(sizes, K, anchor_name, seed):
     model = build_reference_model(cfg, {k: v.detach().clone() for k, v in sd.items()})
     model.train()
     N = len(sizes)
-    lab = [O.synthetic_batch(1, h, w, K, 5 + i, boxes_per_image=4)[0] for i, (h, w) in enumerate(sizes)]
+    lab = [O.synthetic_batch(1, h, w, K, 5 + i, boxes_per_image=n_gt[i])[0] for i, (h, w) in enumerate(sizes)]
     unl = [O.synthetic_batch(1, h, w, K, 50 + i, labelled=False)[0] for i, (h, w) in enumerate(sizes)]
     g = torch.Generator().manual_seed(99)
     Hm, Wm = max(s[0] for s in sizes), max(s[1] for s in sizes)
@@ -190,9 +191,9 @@ def run_case(sizes, K, anchor_name, seed):
 
 def main():
     out = {}
-    for name, sizes, K, anchor_name, seed in CASES:
+    for name, sizes, K, anchor_name, seed, n_gt in CASES:
         print(name)
-        out[name] = run_case(sizes, K, anchor_name, seed)
+        out[name] = run_case(sizes, K, anchor_name, seed, n_gt)
     dst = os.path.join(ROOT, "tests", "golden", "pt_reference_model_golden.pt")
     torch.save(out, dst)
     print("wrote", dst, os.path.getsize(dst), "bytes")
