@@ -297,7 +297,7 @@ def _gold():
                       weights_only=False)
 
 
-@pytest.mark.parametrize("case", ["c2f", "k1_default_anchors_mixed_sizes"])
+@pytest.mark.parametrize("case", ["c2f", "k1_default_anchors_mixed_sizes", "c2f_image_without_gt"])
 def test_cuda_path_vs_reference_model_golden(cuda, case):
     """The CUDA path (f16x3 precision) against outputs of the REFERENCE'S OWN MODEL CLASSES
     (tests/golden/pt_reference_model_golden.pt, made by oracle/make_golden_model.py from the unmodified
