@@ -68,6 +68,9 @@ class PTrainer:
         self.concurrent = concurrent
         self._streams = None
         self._comm_stream = None
+        self._copy_stream = None
+        self._prefetched = None
+        self._slot = 0
         self._grads_reduced = False
         # EXPERIMENTAL, off by default (PTB200_OVERLAP_ALLREDUCE=1): world > 1 + concurrent graph step, all-reduce
         # the head gradients inside the graph while the backbone backward runs. tools/check_ddp.py passes with it
@@ -243,7 +246,9 @@ class PTrainer:
         for name, grp, labelled in (("lq", lq, True), ("lk", lk, True), ("uq", uq, False), ("uk", uk, False)):
             n = len(grp)
             h, w = grp[0]["image"].shape[-2:]
-            g = {"images": torch.empty(n, 3, h, w, dtype=torch.uint8, device=dev)}
+            g = {"images": torch.empty(n, 3, h, w, dtype=torch.uint8, device=dev),
+                 # double-buffered landing zone of the host->device image copies (see _prefetch_images)
+                 "staging": [torch.empty(n, 3, h, w, dtype=torch.uint8, device=dev) for _ in range(2)]}
             if labelled:
                 g["gt_boxes"] = torch.zeros(n, cap, 4, dtype=torch.float32, device=dev)
                 g["gt_boxes"][..., 2:] = 1.0
@@ -258,16 +263,42 @@ class PTrainer:
         st["resize_ratio"] = torch.ones(nq, dtype=torch.float32, device=dev)
         st["pin_params"] = torch.zeros(nq, 4, dtype=torch.int32).pin_memory()
         st["pin_ratio"] = torch.ones(nq, dtype=torch.float32).pin_memory()
+        st["stage_ready"] = [None, None]   # copy-stream events: images of a slot have landed
+        st["stage_free"] = [None, None]    # main-stream events: a slot's images were moved into the static buffers
         return st
 
-    def _stage(self, data):
-        """Copies one step's host inputs into the persistent device buffers (outside the graph)."""
+    def _prefetch_images(self, data, slot):
+        """Issues the host->device copies of one batch's images on a copy stream into staging slot `slot`.
+        Called right after the graph of the CURRENT step has been launched, for the NEXT step's batch, so that the
+        PCIe transfer (25.6 MB at 3x800x1333, ~1 ms) overlaps the current step's kernels."""
+        st = self._static
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        cs = self._copy_stream
+        if st["stage_free"][slot] is not None:
+            cs.wait_event(st["stage_free"][slot])
+        else:
+            cs.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(cs):
+            for name, grp in zip(("lq", "lk", "uq", "uk"), data):
+                buf = st["groups"][name]["staging"][slot]
+                for k, d in enumerate(grp):
+                    buf[k].copy_(d["image"], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(cs)
+        st["stage_ready"][slot] = ev
+
+    def _stage(self, data, slot):
+        """Moves one step's inputs into the persistent device buffers the graph reads (outside the graph): the
+        images from their staging slot (device-to-device, after the copy stream's event), ground truth and the
+        resize geometry from pinned host buffers."""
         st = self._static
         cap = self._gt_capacity
+        main = torch.cuda.current_stream()
+        main.wait_event(st["stage_ready"][slot])
         for name, grp in zip(("lq", "lk", "uq", "uk"), data):
             g = st["groups"][name]
-            for k, d in enumerate(grp):
-                g["images"][k].copy_(d["image"], non_blocking=True)
+            g["images"].copy_(g["staging"][slot], non_blocking=True)
             if "gt_boxes" in g:
                 g["pin_boxes"].zero_()
                 g["pin_boxes"][..., 2:] = 1.0
@@ -298,6 +329,9 @@ class PTrainer:
                 st["pin_ratio"][k] = ratio
         st["resize_params"].copy_(st["pin_params"], non_blocking=True)
         st["resize_ratio"].copy_(st["pin_ratio"], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(main)
+        st["stage_free"][slot] = ev
 
     def _static_batches(self):
         st = self._static
@@ -469,10 +503,16 @@ class PTrainer:
         """Post-burn-in step with the forward/backward part replayed from a CUDA graph."""
         assert self.iter > self.cfg.UNSUPNET.BURN_UP_STEP, "graph mode covers the steady-state (EMA) iterations"
         refresh_stream()
-        data = next(self._data_loader_iter)
-        if self._static is None:
-            self._static = self._make_static(data)
-        self._stage(data)
+        if self._prefetched is None:
+            data = next(self._data_loader_iter)
+            if self._static is None:
+                self._static = self._make_static(data)
+            self._slot = 0
+            self._prefetch_images(data, self._slot)
+        else:
+            data = self._prefetched
+        slot = self._slot
+        self._stage(data, slot)
         body = self._graph_body_concurrent if self.concurrent else self._graph_body
         if self._graph is None:
             if self._graph_warmup > 0:  # eager warm-up on the static buffers (allocator, lazy inits)
@@ -490,6 +530,10 @@ class PTrainer:
             self._graph.replay()
             self.last_losses = self._graph_losses
         refresh_stream()
+        # the next batch's images travel host->device while this step's kernels run
+        self._prefetched = next(self._data_loader_iter)
+        self._slot = 1 - slot
+        self._prefetch_images(self._prefetched, self._slot)
         self._optimizer_step(10.0, reduced=self._grads_reduced)
         self.iter += 1
         return self.last_losses
