@@ -108,18 +108,23 @@ class ParamArena:
         s = self.segments[name]
         return self.half[s.offset:s.offset + s.numel].view(s.shape)
 
-    def gview(self, name):
+    def gview(self, name, flat=None):
+        """View of a segment inside a flat buffer laid out like the trainable suffix (default: the gradient arena;
+        the momentum arena has the same layout)."""
         s = self.segments[name]
         o = s.offset - self.trainable_start
-        return self.grads[o:o + s.numel].view(s.shape)
+        flat = self.grads if flat is None else flat
+        return flat[o:o + s.numel].view(s.shape)
 
-    def exposed_parameters(self):
-        """(reference name, data view, grad view or None, trainable) for every reference parameter."""
+    def exposed_parameters(self, flat=None):
+        """(reference name, data view, grad view or None, trainable) for every reference parameter. `flat`
+        replaces the gradient arena as the buffer the third element views (used for the momentum arena)."""
         K, A = self.K, self.A
         out = []
+        flat = self.grads if flat is None else flat
         for s in self.segments.values():
             v = self.view(s.name)
-            g = self.gview(s.name) if (s.trainable and self.grads is not None) else None
+            g = self.gview(s.name, flat) if (s.trainable and flat is not None) else None
             if s.kind == "rpn_heads_w":
                 base = "proposal_generator.rpn_head."
                 out.append((base + "objectness_logits.weight", v[:A], None if g is None else g[:A], True))
@@ -162,20 +167,56 @@ class ParamArena:
             sd[name] = t
         return sd
 
-    def load_state_dict(self, sd):
+    def _from_ref(self, kind, src, like):
+        if kind == "conv":
+            src = src.permute(0, 2, 3, 1)
+        elif kind == "fc1":
+            src = src.reshape(src.shape[0], self.C, self.pooled * self.pooled).permute(0, 2, 1)
+        return src.reshape(like.shape)
+
+    def momentum_state_dict(self):
+        """SGD momentum buffers under the reference's parameter names / layouts (trainable parameters only)."""
+        kinds = {s.name: s.kind for s in self.segments.values()}
+        sd = OrderedDict()
+        for name, _, m, trainable in self.exposed_parameters(self.momentum):
+            if m is None or not trainable:
+                continue
+            t = self._to_ref(kinds.get(name, "mat"), m, self.C, self.pooled)
+            if name.endswith("objectness_logits.weight") or name.endswith("anchor_deltas.weight"):
+                t = t.reshape(t.shape[0], t.shape[1], 1, 1)
+            sd[name] = t
+        return sd
+
+    def load_momentum_state_dict(self, sd):
+        """Inverse of momentum_state_dict; parameters absent from `sd` keep a zero buffer (torch SGD creates the
+        buffer lazily on the first step, so a checkpoint written before step 1 has none)."""
         kinds = {s.name: s.kind for s in self.segments.values()}
         with torch.no_grad():
-            for name, v, _, _ in self.exposed_parameters():
-                if name not in sd:
-                    raise KeyError(f"{name} missing from state_dict")
+            self.momentum.zero_()
+            for name, _, m, trainable in self.exposed_parameters(self.momentum):
+                if m is None or not trainable or name not in sd:
+                    continue
                 src = sd[name].to(self.device, torch.float32)
-                kind = kinds.get(name, "mat")
-                if kind == "conv":
-                    src = src.permute(0, 2, 3, 1)
-                elif kind == "fc1":
-                    src = src.reshape(src.shape[0], self.C, self.pooled * self.pooled).permute(0, 2, 1)
-                v.copy_(src.reshape(v.shape))
+                m.copy_(self._from_ref(kinds.get(name, "mat"), src, m))
+
+    def load_state_dict(self, sd, strict=True):
+        """Copies a reference-layout state dict into the arena. strict: a missing key raises KeyError (as before);
+        otherwise missing keys are skipped. Returns (missing_keys, unexpected_keys)."""
+        kinds = {s.name: s.kind for s in self.segments.values()}
+        missing = []
+        known = set()
+        with torch.no_grad():
+            for name, v, _, _ in self.exposed_parameters():
+                known.add(name)
+                if name not in sd:
+                    if strict:
+                        raise KeyError(f"{name} missing from state_dict")
+                    missing.append(name)
+                    continue
+                src = sd[name].to(self.device, torch.float32)
+                v.copy_(self._from_ref(kinds.get(name, "mat"), src, v))
         self.pack()
+        return missing, [k for k in sd if k not in known]
 
     # ------------------------------------------------------------------ fp16 operands
     def pack(self, dgrad=None):

@@ -538,6 +538,47 @@ class PTrainer:
         self.iter += 1
         return self.last_losses
 
+    # ------------------------------------------------------------------ checkpoints (trainer.py:104-111,466-495)
+    def build_checkpointer(self, save_dir=None):
+        """`DetectionTSCheckpointer(EnsembleTSModel(teacher, student), cfg.OUTPUT_DIR, optimizer=...)`
+        (trainer.py:104-111); rank 0 writes (fvcore `save_to_disk=comm.is_main_process()`)."""
+        from ..checkpoint import ArenaSGDState, DetectionTSCheckpointer, EnsembleTSModel
+        ens = EnsembleTSModel(self.model_teacher, self.model)
+        self.checkpointer = DetectionTSCheckpointer(ens, self.cfg.OUTPUT_DIR if save_dir is None else save_dir,
+                                                    save_to_disk=self.rank == 0, optimizer=ArenaSGDState(self))
+        return self.checkpointer
+
+    def save_checkpoint(self, name=None):
+        """What `hooks.PeriodicCheckpointer` writes every SOLVER.CHECKPOINT_PERIOD iterations (trainer.py:523-527):
+        `model_{iter:07d}.pth` holding both detectors, the momentum buffers and the last finished iteration."""
+        if getattr(self, "checkpointer", None) is None:
+            self.build_checkpointer()
+        last = self.iter - 1
+        return self.checkpointer.save(name or "model_{:07d}".format(max(last, 0)), iteration=last)
+
+    def resume_or_load(self, resume=False):
+        """trainer.py:466-495: resume = everything from `<OUTPUT_DIR>/last_checkpoint` and continue at the next
+        iteration; otherwise only the weights of cfg.MODEL.WEIGHTS, starting from iteration 0. Under data
+        parallelism rank 0's arenas are broadcast afterwards (DDP `_sync_params_and_buffers`, :491-494)."""
+        if getattr(self, "checkpointer", None) is None:
+            self.build_checkpointer()
+        if resume and self.checkpointer.has_checkpoint():
+            rest = self.checkpointer.load(self.checkpointer.get_checkpoint_file())
+            self.start_iter = rest.get("iteration", -1) + 1
+            self.iter = self.start_iter
+        else:
+            self.checkpointer.load(self.cfg.MODEL.WEIGHTS, checkpointables=[])
+        if self.world > 1:
+            it = torch.tensor([self.iter], dtype=torch.int64, device=self.device)
+            dist.broadcast(it, src=0)
+            self.iter = self.start_iter = int(it.item())
+            for a in (self.model.arena, self.model_teacher.arena):
+                dist.broadcast(a.data, src=0)
+                a.pack()
+            dist.broadcast(self.model.arena.momentum, src=0)
+        # the captured graph holds no parameter values (it reads the arenas), so it stays valid
+        return self.start_iter
+
     def step(self):
         if self.use_cuda_graph and self.iter > self.cfg.UNSUPNET.BURN_UP_STEP:
             return self.run_step_graphed()

@@ -99,7 +99,11 @@ class GuassianGeneralizedRCNN(nn.Module):
         return self.arena.state_dict()
 
     def load_state_dict(self, sd, strict=True):
-        self.arena.load_state_dict(sd)
+        """strict: a missing key raises KeyError; otherwise it is skipped. Returns torch's
+        (missing_keys, unexpected_keys) named tuple (what fvcore's Checkpointer._load_model reads)."""
+        from torch.nn.modules.module import _IncompatibleKeys
+        missing, unexpected = self.arena.load_state_dict(sd, strict=strict)
+        return _IncompatibleKeys(missing, unexpected)
 
     def init_synthetic(self, seed=0):
         return self.arena.init_synthetic(seed)
