@@ -264,18 +264,21 @@ class GuassianGeneralizedRCNN(nn.Module):
         self._last_ctx = dict(rpn=rctx, roi=hctx, feat=feat, props=props)
         return losses, [], [], None
 
-    def inference(self, batched_inputs):
-        """Eval-mode path (rcnn.py:33-34): same kernels with the test-time top-k (6000 / 1000)."""
+    def inference(self, batched_inputs, do_postprocess=True):
+        """Eval-mode path (rcnn.py:33-34 -> d2 `GeneralizedRCNN.inference`): same kernels with the test-time top-k
+        (6000 / 1000), then `detector_postprocess` to the "height" / "width" of each input dict (exact-length
+        instances, one host sync per image). do_postprocess=False returns the fixed-capacity device instances."""
         with torch.no_grad():
             act, sizes, img_hw = self.preprocess_image(batched_inputs)
             feats, _ = self.backbone(act, save=False)
             feat = feats["vgg_block5"]
             props, _, _ = self.proposal_generator(feat, img_hw, None, compute_loss=False, training=False)
             res, _, _ = self.roi_heads(feat, props, img_hw, None, compute_loss=False, training=False)
-        out = []
-        for inst in self._roih_instances(res, sizes):
-            out.append({"instances": inst})
-        return out
+        instances = self._roih_instances(res, sizes)
+        if do_postprocess:
+            from ..postprocessing import postprocess_batch
+            return postprocess_batch(instances, batched_inputs, sizes)
+        return instances
 
     def _proposal_instances(self, props, sizes):
         out = []

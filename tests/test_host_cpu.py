@@ -163,3 +163,31 @@ def test_k2c_config_and_lr_schedule():
     assert abs(lr(200) - 0.016 * (0.001 * 0.5 + 0.5)) < 1e-12
     assert lr(400) == 0.016 and lr(29999) == 0.016
     assert abs(lr(30000) - 0.0016) < 1e-12
+
+
+def test_detector_postprocess():
+    """d2 v0.5 `detector_postprocess`: scale to the requested output size, clip, drop empty boxes, keep every field
+    aligned; fixed-capacity instances (device-side count) are trimmed first; the input is not modified."""
+    from probabilisticteacher_b200.modeling.postprocessing import detector_postprocess, postprocess_batch
+    from probabilisticteacher_b200.structures import Boxes, FreeInstances
+    boxes = torch.tensor([[10., 20., 110., 220.], [0., 0., 400., 300.], [390., 10., 400., 10.], [5., 5., 6., 6.]])
+    inst = FreeInstances((300, 400), pred_boxes=Boxes(boxes.clone()), scores=torch.tensor([.9, .8, .7, .6]),
+                         pred_classes=torch.tensor([1, 2, 3, 4]), scores_logists=torch.arange(36.).view(4, 9),
+                         boxes_sigma=torch.ones(4, 4))
+    inst._count = torch.tensor(3)  # the 4th row is beyond the valid count
+    out = detector_postprocess(inst, 600, 1200)
+    assert out.image_size == (600, 1200)
+    # row 2 has zero height -> dropped; row 3 was never valid
+    assert out.pred_boxes.tensor.tolist() == [[30., 40., 330., 440.], [0., 0., 1200., 600.]]
+    assert out.scores.tolist() == pytest.approx([.9, .8]) and out.pred_classes.tolist() == [1, 2]
+    assert out.scores_logists.shape == (2, 9) and out.boxes_sigma.shape == (2, 4)
+    assert torch.equal(inst.pred_boxes.tensor, boxes)
+    # clipping after a down-scale with rounding overshoot
+    big = FreeInstances((100, 100), pred_boxes=Boxes(torch.tensor([[-5., -5., 120., 90.]])), scores=torch.tensor([1.]))
+    assert detector_postprocess(big, 50, 50).pred_boxes.tensor.tolist() == [[0., 0., 50., 45.]]
+    # batch form: the output size comes from the input dict, default = network input size
+    res = postprocess_batch([inst, big], [{"height": 150, "width": 200}, {}], [(300, 400), (100, 100)])
+    assert res[0]["instances"].image_size == (150, 200) and res[1]["instances"].image_size == (100, 100)
+    assert res[0]["instances"].pred_boxes.tensor[0].tolist() == [5., 10., 55., 110.]
+    with pytest.raises(AssertionError):
+        detector_postprocess(FreeInstances((10, 10), scores=torch.ones(1)), 10, 10)
