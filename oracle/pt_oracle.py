@@ -889,6 +889,24 @@ def run_step(student: OracleRCNN, teacher: OracleRCNN, optimizer, data, cfg: Ora
     return out
 
 
+def run_step_burn_in(student: OracleRCNN, optimizer, data, cfg: OracleCfg, ratios):
+    """One source-only iteration (iter < BURN_UP_STEP), pt/engine/trainer.py:274-290,383-386: the strong and weak
+    views of the labelled batch are concatenated (q first), ALL of them go through `resize` (one ratio each, in
+    that order), one supervised forward, losses weighted 1.0, clip, SGD. The teacher is not touched. Returns the
+    4 losses (floats, the reference's un-suffixed keys) + grad_norm."""
+    label_q, label_k = data[0], data[1]
+    batch = resize_batch(list(label_q) + list(label_k), ratios, student.pixel_mean.flatten())
+    rec, _, _, _ = student(batch, branch="supervised")
+    total = sum(v * 1.0 for v in rec.values())
+    optimizer.zero_grad()
+    total.backward()
+    gn = clip_gradient(student.parameters(), cfg.clip_norm)
+    optimizer.step()
+    out = {k: float(v) for k, v in rec.items()}
+    out["grad_norm"] = gn
+    return out
+
+
 def make_optimizer(model: OracleRCNN, cfg: OracleCfg):
     """d2 v0.5 build_optimizer: SGD(momentum, weight_decay) over all requires_grad params."""
     return torch.optim.SGD([p for p in model.parameters() if p.requires_grad], lr=cfg.base_lr,

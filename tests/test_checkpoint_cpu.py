@@ -198,3 +198,10 @@ def test_key_names_are_those_of_the_reference_models_own_state_dict():
     assert set(_CpuDetector(K=G["K"], diff=True, with_grads=False).state_dict()) == ref_names
     ens = C.EnsembleTSModel(_CpuDetector(K=G["K"], with_grads=False), _CpuDetector(K=G["K"], with_grads=False))
     assert set(ens.state_dict()) == {p + k for p in ("modelTeacher.", "modelStudent.") for k in ref_names}
+
+
+def test_vgg16_caffe_key_map_against_the_reference_constructor():
+    """tests/golden/pt_reference_burnin_golden.pt records where the reference's OWN `VGG.__init__`
+    (pt/modeling/backbone/vgg.py:127-152) put each `features.N.*` tensor of a torchvision-style file."""
+    G = torch.load(os.path.join(os.path.dirname(__file__), "golden", "pt_reference_burnin_golden.pt"), weights_only=False)
+    assert dict(C.vgg16_caffe_key_map(prefix="")) == G["vgg16_caffe_mapping"]

@@ -65,3 +65,37 @@ def test_two_training_steps_match_the_reference_trainer():
     k = "roi_heads.box_predictor.cls_score.weight"
     t0, t1 = G["steps"][0]["teacher"][k], G["steps"][1]["teacher"][k]
     assert not torch.equal(t0, t1)
+
+
+GB = torch.load(os.path.join(os.path.dirname(__file__), "golden", "pt_reference_burnin_golden.pt"), weights_only=False)
+
+
+def _burnin_batch():
+    H, W = GB["H"], GB["W"]
+    out = []
+    for tag in ("q", "k"):
+        out.append([{"image": im.clone(), "height": H, "width": W,
+                     "instances": O.OInst((H, W), gt_boxes=O.OBoxes(b.clone()), gt_classes=c.clone())}
+                    for im, b, c in zip(GB[f"lab_{tag}_images"], GB[f"gt_boxes_{tag}"], GB[f"gt_classes_{tag}"])])
+    return out
+
+
+def test_two_burn_in_steps_match_the_reference_trainer():
+    """Source-only iterations (iter < BURN_UP_STEP, pt/engine/trainer.py:274-290): fixture made by
+    oracle/make_golden_burnin.py from the reference's own PTrainer.run_step."""
+    cfg = O.OracleCfg(num_classes=GB["K"], base_lr=GB["lr"])
+    student = O.OracleRCNN(cfg, seed=GB["seed"])
+    student.sampler = _Sampler(GB["prio"])
+    opt = O.make_optimizer(student, cfg)
+    for it, ref in enumerate(GB["steps"]):
+        lab_q, lab_k = _burnin_batch()
+        assert len(ref["ratios"]) == 2 * GB["N"]  # every image of q + k is resized, q first
+        out = O.run_step_burn_in(student, opt, (lab_q, lab_k), cfg, ref["ratios"])
+        assert set(ref["losses"]) == {"loss_cls", "loss_box_reg", "loss_rpn_cls", "loss_rpn_loc"}
+        for k, v in ref["losses"].items():
+            assert abs(out[k] - v) <= 2e-5 * max(abs(v), 1e-6), (it, k, out[k], v)
+        sd = student.ref_state_dict()
+        for k, v in ref["student"].items():
+            mine = sd[k].detach().reshape(-1)[_sample_idx(sd[k].numel())]
+            err = float((mine - v).abs().max())
+            assert err <= 2e-6 + 2e-5 * float(v.abs().max()), (it, k, err)

@@ -68,3 +68,78 @@ def test_trainer_checkpoint_resume(cuda, tmp_path):
     assert tr3.resume_or_load(resume=False) == 0
     assert torch.equal(tr3.model.arena.data, tr.model.arena.data)
     assert float(tr3.model.arena.momentum.abs().sum()) == 0.0
+
+
+def test_burn_in_steps_vs_reference_trainer(cuda):
+    """Source-only iterations (iter < BURN_UP_STEP, pt/engine/trainer.py:274-290) of the B200 `PTrainer.run_step`
+    against the reference's own trainer (tests/golden/pt_reference_burnin_golden.pt, oracle/make_golden_burnin.py):
+    same weights, images, `resize` ratios (q views first, then k) and sampling priorities. fp16 operands, so the
+    tolerances are those of tests/test_trainer_step_gpu.py; the teacher must stay untouched."""
+    import os
+    from oracle import pt_oracle as O
+    from probabilisticteacher_b200.config import c2f_config
+    from probabilisticteacher_b200.engine.trainer import PTrainer
+    from probabilisticteacher_b200.structures import Boxes, FreeInstances
+    G = torch.load(os.path.join(os.path.dirname(__file__), "golden", "pt_reference_burnin_golden.pt"), weights_only=False)
+    H, W, K = G["H"], G["W"], G["K"]
+    cfg = c2f_config()
+    assert cfg.UNSUPNET.BURN_UP_STEP > 2
+    cfg.SOLVER.WARMUP_ITERS = 0
+    cfg.SOLVER.BASE_LR = G["lr"]
+
+    def view(tag):
+        return [{"image": im.clone(), "height": H, "width": W,
+                 "instances": FreeInstances((H, W), gt_boxes=Boxes(b.clone()), gt_classes=c.clone())}
+                for im, b, c in zip(G[f"lab_{tag}_images"], G[f"gt_boxes_{tag}"], G[f"gt_classes_{tag}"])]
+
+    def loader():
+        while True:
+            yield view("q"), view("k"), [], []
+
+    class _Ratios:
+        def __init__(self, draws):
+            self.draws = list(draws)
+
+        def uniform(self, a, b):
+            return self.draws.pop(0)
+
+    def idx(numel, n=64):
+        g = torch.Generator().manual_seed(numel)
+        return torch.randint(0, numel, (min(n, numel),), generator=g)
+
+    def samples(model):
+        return {k: v.detach().reshape(-1).cpu()[idx(v.numel())] for k, v in model.state_dict().items()}
+
+    tr = PTrainer(cfg, loader(), device=cuda, seed=0)
+    sd = {k: v.detach() for k, v in O.OracleRCNN(O.OracleCfg(num_classes=K), seed=G["seed"]).ref_state_dict().items()}
+    tr.model.load_state_dict(sd)
+    tr.model.prio_override = {k: (v[0].to(cuda), v[1].to(cuda)) for k, v in G["prio"].items()}
+    teacher_before = tr.model_teacher.arena.data.clone()
+    init = {k: v.reshape(-1)[idx(v.numel())] for k, v in sd.items()}
+    prev, prev_ref = init, init
+    problems = []
+    for it, ref in enumerate(G["steps"]):
+        tr.rng = _Ratios(ref["ratios"])
+        losses = tr.run_step()
+        torch.cuda.synchronize()
+        assert tr.rng.draws == []  # one ratio per image of q + k
+        got = {k: float(v) for k, v in losses.items()}
+        assert set(got) == set(ref["losses"])  # un-suffixed keys during burn-in
+        print("burn-in step", it, {k: (round(got[k], 4), round(v, 4)) for k, v in ref["losses"].items()})
+        if it == 0:
+            for k, v in ref["losses"].items():
+                tol = 2e-2 if "rpn" in k else 0.1  # ROI losses depend on the fp16-sensitive proposal selection
+                if not abs(got[k] - v) <= tol * max(abs(v), 1e-3):
+                    problems.append((it, k, got[k], v))
+        st = samples(tr.model)
+        up_g = torch.cat([st[k] - prev[k] for k in sorted(st)])
+        up_r = torch.cat([ref["student"][k] - prev_ref[k] for k in sorted(st)])
+        cos = float(torch.dot(up_g, up_r) / (up_g.norm() * up_r.norm()))
+        ratio = float(up_g.norm() / up_r.norm())
+        print("   update cosine", round(cos, 4), "norm ratio", round(ratio, 4))
+        if not (cos > (0.99 if it == 0 else 0.98) and (0.95 if it == 0 else 0.9) < ratio < (1.05 if it == 0 else 1.1)):
+            problems.append(("update", it, cos, ratio))
+        prev, prev_ref = st, ref["student"]
+    assert torch.equal(tr.model_teacher.arena.data, teacher_before)
+    assert tr.iter == 2
+    assert not problems, problems
