@@ -84,6 +84,35 @@ def install():
                 batch[k, :, :i.shape[-2], :i.shape[-1]] = i
             return ImageList(batch, sizes)
 
+        def inference(self, batched_inputs, detected_instances=None, do_postprocess=True):
+            """d2 v0.5 GeneralizedRCNN.inference (what pt/modeling/meta_arch/rcnn.py:33-34 calls in eval mode)."""
+            assert not self.training and detected_instances is None
+            images = self.preprocess_image(batched_inputs)
+            features = self.backbone(images.tensor)
+            proposals, _ = self.proposal_generator(images, features, None)
+            results, _ = self.roi_heads(images, features, proposals, None)
+            if do_postprocess:
+                return GeneralizedRCNN._postprocess(results, batched_inputs, images.image_sizes)
+            return results
+
+        @staticmethod
+        def _postprocess(instances, batched_inputs, image_sizes):
+            """d2 v0.5 GeneralizedRCNN._postprocess + modeling/postprocessing.py detector_postprocess (boxes only)."""
+            processed = []
+            for res, inp, size in zip(instances, batched_inputs, image_sizes):
+                height, width = inp.get("height", size[0]), inp.get("width", size[1])
+                scale_x, scale_y = width / res.image_size[1], height / res.image_size[0]
+                out = type(res)((height, width), **res.get_fields())
+                boxes = out.pred_boxes
+                t = boxes.tensor.clone()
+                t[:, 0::2] *= scale_x   # Boxes.scale
+                t[:, 1::2] *= scale_y
+                boxes = Boxes(t)
+                boxes.clip(out.image_size)
+                out.pred_boxes = boxes
+                processed.append({"instances": out[boxes.nonempty()]})
+            return processed
+
     # ------------------------------------------------------------------ anchors
     class DefaultAnchorGenerator(nn.Module):
         """d2 v0.5 modeling/anchor_generator.py DefaultAnchorGenerator (single level)."""

@@ -1,7 +1,7 @@
 """CPU: checkpoint I/O in the reference's on-disk format (`pt/checkpoint/detection_checkpoint.py`,
 `pt/modeling/meta_arch/ts_ensemble.py`, the `vgg16_caffe.pth` key map of `pt/modeling/backbone/vgg.py:127-152`).
 The arena's device passes (`pack`) are CUDA-only, so the host logic is exercised on a CPU arena whose `pack` is a
-no-op; the same round trip runs on the real model in tests/test_zz_checkpoint_gpu.py."""
+no-op; the same round trip runs on the real model in tests/test_zz_next_rows_gpu.py."""
 import os
 
 import pytest

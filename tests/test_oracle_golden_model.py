@@ -103,3 +103,34 @@ def test_unsupervised_branch_matches_reference_model(case):
             _close(g, G[key], 1e-3)
     if differentiable:  # grad_zero (pt/modeling/utils.py:47-58): anchors learn only from the unsupervised RPN branch
         assert float(G["unsup_anchor_grad"].abs().max()) > 0 and float(G["unsup_anchor_grad_no_danchor"].abs().max()) == 0
+
+
+# ------------------------------------------------------------------------------------------ eval mode
+EVAL = torch.load(os.path.join(os.path.dirname(__file__), "golden", "pt_reference_eval_golden.pt"), weights_only=False)
+
+
+@pytest.mark.parametrize("case", sorted(EVAL))
+def test_eval_mode_inference_matches_the_reference_models(case):
+    """tests/golden/pt_reference_eval_golden.pt (oracle/make_golden_eval.py): the reference's own model classes in
+    eval mode (test-time top-k 6000 / 1000, `GuassianFastRCNNOutputLayers.inference`, then d2's
+    `detector_postprocess` to a different output size). The oracle's eval path gives the raw detections; the
+    PACKAGE's `detector_postprocess` (what `GuassianGeneralizedRCNN.inference` applies on the B200 path) must turn
+    them into the reference's final instances."""
+    from probabilisticteacher_b200.modeling.postprocessing import detector_postprocess
+    from probabilisticteacher_b200.structures import Boxes, FreeInstances
+    G = EVAL[case]
+    om = O.OracleRCNN(O.OracleCfg(num_classes=G["K"], anchor_generator=G["anchor_generator"]), seed=G["seed"])
+    batch = [{"image": im, "height": oh, "width": ow} for im, (oh, ow) in zip(G["images"], G["out_sizes"])]
+    with torch.no_grad():
+        _, _, roih, _ = om(batch, branch="unsup_data_weak", training=False)
+    for n, (r, ref) in enumerate(zip(roih, G["detections"])):
+        _close(O._bt(r.pred_boxes), ref["raw_boxes"])
+        inst = FreeInstances(tuple(G["sizes"][n]), pred_boxes=Boxes(O._bt(r.pred_boxes).clone()), scores=r.scores,
+                             pred_classes=r.pred_classes, scores_logists=r.scores_logists, boxes_sigma=r.boxes_sigma)
+        out = detector_postprocess(inst, *G["out_sizes"][n])
+        assert tuple(out.image_size) == tuple(ref["image_size"])
+        assert torch.equal(out.pred_classes, ref["pred_classes"])
+        _close(out.pred_boxes.tensor, ref["pred_boxes"])
+        _close(out.scores, ref["scores"])
+        _close(out.scores_logists, ref["scores_logists"])
+        _close(out.boxes_sigma, ref["boxes_sigma"])

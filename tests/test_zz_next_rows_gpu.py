@@ -1,8 +1,14 @@
-"""GPU: `PTrainer.save_checkpoint` / `resume_or_load` on the real arenas (`pt/engine/trainer.py:104-111,466-495`,
-`pt/checkpoint/detection_checkpoint.py`): a second trainer resumed from the file holds bit-identical student,
-teacher, momentum and fp16 operand arenas and continues at the next iteration; the file itself carries the
-reference's key names (`modelTeacher.` / `modelStudent.` + detectron2 parameter names) and layouts, checked by
-loading it into the CPU oracle's reference-named state dict. (Host logic: tests/test_checkpoint_cpu.py.)"""
+"""GPU: rows SURVEY.md 8f marks "next" (checkpoint I/O, eval path) and the burn-in branch of the trainer.
+
+* `PTrainer.save_checkpoint` / `resume_or_load` on the real arenas (`pt/engine/trainer.py:104-111,466-495`,
+  `pt/checkpoint/detection_checkpoint.py`): a second trainer resumed from the file holds bit-identical student,
+  teacher, momentum and fp16 operand arenas and continues at the next iteration; the file carries the reference's key
+  names (`modelTeacher.` / `modelStudent.` + detectron2 parameter names) and layouts. (Host logic:
+  tests/test_checkpoint_cpu.py.)
+* source-only (burn-in) steps against the reference's own trainer (tests/golden/pt_reference_burnin_golden.pt).
+* eval-mode inference + `detector_postprocess` against the reference's own model classes in eval mode
+  (tests/golden/pt_reference_eval_golden.pt).
+(The file sorts last on purpose: these tests were added after the round's last GPU session.)"""
 import pytest
 import torch
 
@@ -143,3 +149,47 @@ def test_burn_in_steps_vs_reference_trainer(cuda):
     assert torch.equal(tr.model_teacher.arena.data, teacher_before)
     assert tr.iter == 2
     assert not problems, problems
+
+
+@pytest.mark.parametrize("case", ["c2f_upscaled", "k1_default_anchors_mixed_sizes"])
+def test_eval_mode_vs_reference_model_golden(cuda, case):
+    """Eval-mode inference of the CUDA path (f16x3 precision) against the REFERENCE'S OWN MODEL CLASSES in eval mode
+    (tests/golden/pt_reference_eval_golden.pt, oracle/make_golden_eval.py): test-time top-k, pseudo-label filter,
+    `detector_postprocess` to an output size that differs from the input size. Detections are compared as sets
+    (near-tied scores at the synthetic initialisation re-order the lists, see tests/test_parity_x3_gpu.py)."""
+    import os
+    from oracle import pt_oracle as O
+    from probabilisticteacher_b200.config import c2f_config
+    from probabilisticteacher_b200.modeling.meta_arch.rcnn import build_model
+    TOL = 1e-3
+    G = torch.load(os.path.join(os.path.dirname(__file__), "golden", "pt_reference_eval_golden.pt"),
+                   weights_only=False)[case]
+    cfg = c2f_config()
+    cfg.MODEL.ROI_HEADS.NUM_CLASSES = G["K"]
+    cfg.MODEL.ANCHOR_GENERATOR.NAME = G["anchor_generator"]
+    model = build_model(cfg, cuda, precision="f16x3", with_grads=False)
+    sd = O.OracleRCNN(O.OracleCfg(num_classes=G["K"], anchor_generator=G["anchor_generator"]), seed=G["seed"]).ref_state_dict()
+    model.load_state_dict({k: v.detach() for k, v in sd.items()})
+    model.eval()
+    batch = [{"image": im, "height": oh, "width": ow} for im, (oh, ow) in zip(G["images"], G["out_sizes"])]
+    out = model(batch)
+    torch.cuda.synchronize()
+    assert len(out) == len(batch)
+    for n, (o, ref) in enumerate(zip(out, G["detections"])):
+        g = o["instances"]
+        assert tuple(g.image_size) == tuple(ref["image_size"])
+        assert abs(len(g) - len(ref["scores"])) <= 2, (len(g), len(ref["scores"]))
+        scale = float(max(ref["image_size"]))
+        gb, gc = g.pred_boxes.tensor.double().cpu(), g.pred_classes.cpu()
+        ob, oc = ref["pred_boxes"].double(), ref["pred_classes"]
+        d = (gb[:, None, :] - ob[None, :, :]).abs().amax(-1) / scale
+        d[gc[:, None] != oc[None, :]] = 1e9
+        best, idx = d.min(1)
+        ok = best < TOL
+        assert float(ok.double().mean()) >= 0.95, (n, float(ok.double().mean()))
+        for f in ("scores", "scores_logists", "boxes_sigma"):
+            a, b = getattr(g, f).double().cpu()[ok], ref[f].double()[idx[ok]]
+            err = float(((a - b).abs().reshape(len(a), -1).amax(1) / b.abs().max().clamp_min(1e-30)).max())
+            assert err < TOL, (n, f, err)
+        # boxes live in the OUTPUT resolution and inside it
+        assert float(gb[:, 2].max()) <= ref["image_size"][1] and float(gb[:, 3].max()) <= ref["image_size"][0]
