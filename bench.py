@@ -234,13 +234,13 @@ def run_reference(args):
         return 0
     steps = max(1, min(args.steps, 2))
     warm = min(args.warmup, 1)
-    v, cores, sample = cpu_oracle_iters_per_s(steps, warm)
+    v, cores, sample = cpu_oracle_iters_per_s(steps, warm, H=args.height, W=args.width)
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": "iters/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": warm, "ms_per_step": 1000.0 / v if v > 0 else None, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "CitysScape2FoggyCityscape config, synthetic 3x800x1333, 2 source + 2 target per "
-                               "iteration (CPU run on a 1+1 sample, scaled)", "l2": "inputs larger than L2"},
+        "config": {"workload": f"CitysScape2FoggyCityscape config, synthetic 3x{args.height}x{args.width}, 2 source + "
+                               "2 target per iteration (CPU run on a 1+1 sample, scaled)", "l2": "inputs larger than L2"},
         "cpu_baseline": {"value": v, "unit": "iters/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "detectron2 is not installable here (no package, no network): the reference arm is the CPU "
@@ -394,7 +394,9 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": "iters/s", "n_gpus": world, "steps": args.steps,
             "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f16 operands / f32 accumulate (tcgen05 kind::f16), f32 master weights",
+            "vs_baseline": None, "dtype": "fp16",
+            "dtype_detail": "fp16 operands / fp32 accumulate (tcgen05 kind::f16), fp32 master weights, losses and "
+                            "optimizer; the reference runs fp32 with AMP off",
             "data": "synthetic",
             "config": {"workload": ("KITTI2CitysScape config (configs/pt/final_k2c.yaml, K = 1), " if args.config == "k2c" else
                                     "CitysScape2FoggyCityscape config (configs/pt/final_c2f.yaml + train.sh overrides), ") +

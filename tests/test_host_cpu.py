@@ -191,3 +191,24 @@ def test_detector_postprocess():
     assert res[0]["instances"].pred_boxes.tensor[0].tolist() == [5., 10., 55., 110.]
     with pytest.raises(AssertionError):
         detector_postprocess(FreeInstances((10, 10), scores=torch.ones(1)), 10, 10)
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU oracle port timed on the host cores) at a reduced image size: one JSON
+    line with the keys the driver reads; under torchrun only rank 0 prints."""
+    import json
+    env = dict(os.environ, RANK="0", WORLD_SIZE="1")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "0", "--height", "96", "--width", "128"], env=env, capture_output=True,
+                         text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["unit"] == "iters/s" and line["higher_is_better"] is True
+    assert line["value"] > 0 and line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"] == {"value": line["value"], "unit": "iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert line["metric"].startswith("teacher+student training iters/sec")
+    other = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
+                           env=dict(os.environ, RANK="1", WORLD_SIZE="2"), capture_output=True, text=True, timeout=120)
+    assert other.returncode == 0 and other.stdout.strip() == ""
