@@ -18,6 +18,8 @@ GuassianGeneralizedRCNN.forward end to end; tests/test_oracle_golden_model.py ch
 against that (losses bit-identical). `oracle/make_golden_step.py` executes the reference's own
 PTrainer.run_step (pt/engine/trainer.py imported unmodified) for two iterations;
 tests/test_oracle_golden_step.py checks `run_step` below against it (losses and parameters bit-identical).
+`oracle/make_golden_burnin.py` does the same for two source-only (burn-in) iterations (`run_step_burn_in`), and
+`oracle/make_golden_eval.py` runs the reference's model classes in eval mode (`forward(..., training=False)` here).
 The detectron2 base-class behaviour itself has no golden vectors in the reference (it ships no
 tests): that part is pinned only against torchvision ops and analytic cases ("parity unpinned" at
 the detectron2 boundary).
