@@ -212,3 +212,31 @@ def test_bench_reference_arm_prints_the_contract_line():
     other = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
                            env=dict(os.environ, RANK="1", WORLD_SIZE="2"), capture_output=True, text=True, timeout=120)
     assert other.returncode == 0 and other.stdout.strip() == ""
+
+
+def test_trainer_pseudo_label_repack_host_logic():
+    """`PTrainer.threshold_bbox / process_pseudo_label / remove_label / add_label` (pt/engine/trainer.py:179-257): pure
+    container shuffling, exercised without a device (the constructor, which builds the CUDA models, is skipped)."""
+    from probabilisticteacher_b200.engine.trainer import PTrainer
+    from probabilisticteacher_b200.structures import Boxes, FreeInstances
+    tr = PTrainer.__new__(PTrainer)
+    roih = FreeInstances((60, 80), pred_boxes=Boxes(torch.tensor([[1., 2., 30., 40.], [5., 5., 9., 9.]])),
+                         scores=torch.tensor([.9, .2]), pred_classes=torch.tensor([3, 1]),
+                         scores_logists=torch.arange(18.).view(2, 9), boxes_sigma=torch.ones(2, 4))
+    roih._count = torch.tensor(2)
+    out, _ = tr.process_pseudo_label([roih], "roih", "all")
+    p = out[0]
+    # method "all": every detection becomes a pseudo label; scores / classes are NOT carried (trainer.py:203-226)
+    assert set(p.get_fields()) == {"pseudo_boxes", "scores_logists", "boxes_sigma"} and p.image_size == (60, 80)
+    assert torch.equal(p.pseudo_boxes.tensor, roih.pred_boxes.tensor) and p.valid_count() is roih.valid_count()
+    no_sigma = FreeInstances((60, 80), pred_boxes=roih.pred_boxes, scores_logists=roih.scores_logists)
+    assert set(tr.threshold_bbox(no_sigma, "roih").get_fields()) == {"pseudo_boxes", "scores_logists"}
+    rpn = FreeInstances((60, 80), proposal_boxes=Boxes(torch.tensor([[0., 0., 8., 8.]])), objectness_logits=torch.tensor([2.]))
+    q = tr.threshold_bbox(rpn, "rpn")
+    assert set(q.get_fields()) == {"gt_boxes", "objectness_logits", "pseudo_boxes"}
+    with pytest.raises(ValueError):
+        tr.process_pseudo_label([roih], "roih", "thresholding")
+    data = [{"image": 0, "instances": roih}, {"image": 1}]
+    assert all("instances" not in d for d in tr.remove_label(data))
+    labelled = tr.add_label(data, out + out)
+    assert labelled[0]["instances"] is p and labelled[1]["instances"] is p
