@@ -82,3 +82,25 @@ def test_oracle_step_runs_and_decreases_nothing_weird():
     out = O.run_step(s, t, opt, (lq, [dict(d) for d in lq], uq, [dict(d) for d in uq]), cfg, [0.8], [0.9])
     assert len([k for k in out if k.startswith("loss")]) == 8
     assert all(math.isfinite(v) for v in out.values())
+
+
+def test_pairwise_iou_matches_torchvision_and_zero_overlap_rule():
+    """d2 v0.5 `pairwise_iou` = torchvision `box_iou` wherever boxes overlap and exactly 0 elsewhere (also for
+    degenerate boxes, where inter / union would be 0 / 0)."""
+    from torchvision.ops import box_iou
+    g = torch.Generator().manual_seed(4)
+    xy = torch.rand(40, 2, generator=g) * 200
+    a = torch.cat([xy, xy + torch.rand(40, 2, generator=g) * 150 + 1], 1)
+    xy = torch.rand(300, 2, generator=g) * 200
+    b = torch.cat([xy, xy + torch.rand(300, 2, generator=g) * 150 + 1], 1)
+    assert torch.allclose(O.pairwise_iou(a, b), box_iou(a, b), atol=1e-7)
+    deg = torch.tensor([[5., 5., 5., 5.]])
+    assert O.pairwise_iou(deg, deg).tolist() == [[0.0]]
+
+
+def test_clip_and_nonempty():
+    b = torch.tensor([[-3., -2., 50., 70.], [10., 10., 10., 30.], [20., 5., 25., 9.]])
+    c = O.clip_boxes(b, (40, 30))  # (h, w): x in [0, 30], y in [0, 40]
+    assert c.tolist() == [[0., 0., 30., 40.], [10., 10., 10., 30.], [20., 5., 25., 9.]]
+    assert O.nonempty(c).tolist() == [True, False, True]
+    assert O.nonempty(c, threshold=4.5).tolist() == [True, False, False]
