@@ -13,6 +13,7 @@ import torch.distributed as dist
 
 from .._lib import call, refresh_stream
 from ..modeling.meta_arch.rcnn import build_model
+from ..solver import lr_at_iter
 from ..structures import Boxes, FreeInstances
 
 
@@ -180,9 +181,7 @@ class PTrainer:
         pre = 1.0 / self.world
         if self.world > 1 and not reduced:
             dist.all_reduce(a.grads)
-        lr = warmup_multistep_lr(self.cfg.SOLVER.BASE_LR, self.iter, self.cfg.SOLVER.STEPS, self.cfg.SOLVER.GAMMA,
-                                 self.cfg.SOLVER.WARMUP_FACTOR, self.cfg.SOLVER.WARMUP_ITERS,
-                                 self.cfg.SOLVER.WARMUP_METHOD)
+        lr = lr_at_iter(self.cfg, self.iter)  # pt/solver/build.py: WarmupMultiStepLR unless the config says otherwise
         call("ptb200_grad_sumsq", a.grads, n, pre, self._sumsq)
         call("ptb200_clip_sgd_step", a.data[a.trainable_start:], a.grads, a.momentum, n, float(lr),
              float(self.cfg.SOLVER.MOMENTUM), float(self.cfg.SOLVER.WEIGHT_DECAY), float(clip_norm), pre,

@@ -240,3 +240,33 @@ def test_trainer_pseudo_label_repack_host_logic():
     assert all("instances" not in d for d in tr.remove_label(data))
     labelled = tr.add_label(data, out + out)
     assert labelled[0]["instances"] is p and labelled[1]["instances"] is p
+
+
+def test_lr_schedules_closed_form():
+    """`solver.lr_at_iter` against the reference's own WarmupTwoStageMultiStepLR stepping a torch optimizer
+    (tests/golden/pt_reference_lr_golden.json, oracle/make_golden_lr.py), the d2 formulas of the other two
+    schedulers, and the dispatch errors of pt/solver/build.py."""
+    import json
+    import math
+    from probabilisticteacher_b200.config import c2f_config
+    from probabilisticteacher_b200.solver import lr_at_iter
+    cases = json.load(open(os.path.join(ROOT, "tests", "golden", "pt_reference_lr_golden.json")))
+    for c in cases:
+        cfg = c2f_config()
+        cfg.SOLVER.LR_SCHEDULER_NAME = "WarmupTwoStageMultiStepLR"
+        cfg.SOLVER.BASE_LR, cfg.SOLVER.STEPS, cfg.SOLVER.FACTOR_LIST = c["base_lr"], tuple(c["steps"]), tuple(c["factor_list"])
+        cfg.SOLVER.WARMUP_FACTOR, cfg.SOLVER.WARMUP_ITERS, cfg.SOLVER.WARMUP_METHOD = \
+            c["warmup_factor"], c["warmup_iters"], c["warmup_method"]
+        for it, want in enumerate(c["lrs"]):
+            assert lr_at_iter(cfg, it) == pytest.approx(want, rel=1e-12, abs=0), (c["steps"], it)
+    cfg = c2f_config()
+    cfg.SOLVER.LR_SCHEDULER_NAME = "WarmupCosineLR"
+    assert lr_at_iter(cfg, 15000) == pytest.approx(0.016 * 0.5 * (1 + math.cos(math.pi * 0.5)), abs=1e-12)
+    assert lr_at_iter(cfg, 0) == pytest.approx(0.016 * 0.001)
+    cfg.SOLVER.LR_SCHEDULER_NAME = "WarmupTwoStageMultiStepLR"
+    cfg.SOLVER.FACTOR_LIST = (1,)  # one milestone needs two factors
+    with pytest.raises(ValueError):
+        lr_at_iter(cfg, 0)
+    cfg.SOLVER.LR_SCHEDULER_NAME = "Poly"
+    with pytest.raises(ValueError):
+        lr_at_iter(cfg, 0)
