@@ -583,6 +583,19 @@ class PTrainer:
             return self.run_step_graphed()
         return self.run_step()
 
-    def train(self, num_iters):
-        for _ in range(num_iters):
+    def train(self, num_iters=None):
+        """`train_loop(start_iter, max_iter)` (trainer.py:154-176) without the d2 hook machinery: runs to
+        cfg.SOLVER.MAX_ITER (or for `num_iters` iterations); when a checkpointer has been built
+        (`build_checkpointer` / `resume_or_load`) a checkpoint is written every SOLVER.CHECKPOINT_PERIOD iterations
+        and `model_final` at MAX_ITER, as `hooks.PeriodicCheckpointer` does (trainer.py:523-527)."""
+        end = self.max_iter if num_iters is None else min(self.iter + num_iters, self.max_iter)
+        period = int(self.cfg.SOLVER.CHECKPOINT_PERIOD)
+        ck = getattr(self, "checkpointer", None)
+        while self.iter < end:
             self.step()
+            if ck is not None:
+                if period > 0 and self.iter % period == 0:  # fvcore PeriodicCheckpointer.step: (iteration + 1) % period
+                    self.save_checkpoint()
+                if self.iter >= self.max_iter:
+                    self.save_checkpoint("model_final")
+        return self.last_losses

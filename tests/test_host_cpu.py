@@ -270,3 +270,30 @@ def test_lr_schedules_closed_form():
     cfg.SOLVER.LR_SCHEDULER_NAME = "Poly"
     with pytest.raises(ValueError):
         lr_at_iter(cfg, 0)
+
+
+def test_train_loop_checkpoint_cadence():
+    """`PTrainer.train`: fvcore PeriodicCheckpointer cadence (every CHECKPOINT_PERIOD finished iterations, named after
+    the 0-based iteration that just finished, plus `model_final` at MAX_ITER) -- host logic on a stub (no device)."""
+    from probabilisticteacher_b200.config import c2f_config
+    from probabilisticteacher_b200.engine.trainer import PTrainer
+    tr = PTrainer.__new__(PTrainer)
+    cfg = c2f_config()
+    cfg.SOLVER.CHECKPOINT_PERIOD, cfg.SOLVER.MAX_ITER = 4, 12
+    tr.cfg, tr.iter, tr.max_iter, tr.last_losses, tr.rank = cfg, 0, 12, None, 0
+    saved = []
+
+    class _Ck:
+        def save(self, name, **kw):
+            saved.append((name, kw))
+    tr.checkpointer = _Ck()
+
+    def step():
+        tr.iter += 1
+    tr.step = step
+    tr.train(3)
+    assert tr.iter == 3 and saved == []
+    tr.train()
+    assert tr.iter == 12
+    assert saved == [("model_0000003", {"iteration": 3}), ("model_0000007", {"iteration": 7}),
+                     ("model_0000011", {"iteration": 11}), ("model_final", {"iteration": 11})]
