@@ -260,3 +260,37 @@ def test_resize_kernel_vs_reference_resize(cuda):
                 assert torch.equal(got["instances"].gt_classes.cpu(), ref[k]["instances"].gt_classes)
         # inputs are not modified (the reference deep-copies first, trainer.py:558)
         assert torch.equal(batch[0]["image"], O.synthetic_batch(n, H, W, 8, 5)[0]["image"])
+
+
+def test_anchor_generators_bit_exact(cuda):
+    """SURVEY 8a-4 on its own: `ptb200_cell_anchors_from_wh` + `ptb200_anchor_grid` against the oracle's restatement of
+    `pt/modeling/anchor_generator.py:108-164` / detectron2's DefaultAnchorGenerator (pinned by the function-level
+    fixture and detectron2's known-answer table): every anchor coordinate is one fp32 addition of an exactly
+    representable grid shift and a cell coordinate, so the comparison is BIT-EXACT, at the four feature-map sizes of
+    BASELINE.json's configs and with a half-stride offset."""
+    from oracle import pt_oracle as O
+    from probabilisticteacher_b200.arena import ParamArena
+    from probabilisticteacher_b200.config import c2f_config
+    from probabilisticteacher_b200.modeling.anchor_generator import DefaultAnchorGenerator, DifferentiableAnchorGenerator
+    cfg = c2f_config()
+    arena = ParamArena(num_classes=8, differentiable_anchors=True, device=cuda, with_grads=False)
+    wh = torch.tensor(cfg.MODEL.ANCHOR_GENERATOR.ANCHOR[0]) * torch.linspace(0.9, 1.13, 18).view(9, 2)  # "learned" values
+    arena.view("proposal_generator.anchor_generator.anchor_0").copy_(wh)
+    for offset in (0.0, 0.5):
+        cfg.MODEL.ANCHOR_GENERATOR.OFFSET = offset
+        gens = ((DifferentiableAnchorGenerator(cfg, arena), O.differentiable_cell_anchors(wh)),
+                (DefaultAnchorGenerator(cfg, arena), O.default_cell_anchors(cfg.MODEL.ANCHOR_GENERATOR.SIZES[0],
+                                                                            cfg.MODEL.ANCHOR_GENERATOR.ASPECT_RATIOS[0])))
+        for gen, cell in gens:
+            for H, W in ((50, 83), (37, 75), (37, 125), (64, 128), (1, 1)):
+                got = gen(H, W)
+                torch.cuda.synchronize()
+                want = O.grid_anchors(cell, H, W, 16, offset)
+                assert got.shape == (H * W * 9, 4)
+                assert torch.equal(got.cpu(), want), (type(gen).__name__, H, W, offset)
+    # the layout contract of SURVEY 8a-4: anchors[(y*W + x)*9 + a] = (x*16, y*16, x*16, y*16) + cell[a]
+    cfg.MODEL.ANCHOR_GENERATOR.OFFSET = 0.0
+    a = DefaultAnchorGenerator(cfg, arena)(50, 83).cpu()
+    cell = O.default_cell_anchors((128, 256, 512), (0.5, 1.0, 2.0))
+    y, x, k = 17, 44, 5
+    assert torch.equal(a[(y * 83 + x) * 9 + k], torch.tensor([x * 16., y * 16., x * 16., y * 16.]) + cell[k])
