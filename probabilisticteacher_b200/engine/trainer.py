@@ -11,6 +11,7 @@ import random
 import torch
 import torch.distributed as dist
 
+from . import dp
 from .._lib import call, refresh_stream
 from ..modeling.meta_arch.rcnn import build_model
 from ..solver import lr_at_iter
@@ -178,9 +179,9 @@ class PTrainer:
     def _optimizer_step(self, clip_norm=10.0, reduced=False):
         a = self.model.arena
         n = a.grads.numel()
-        pre = 1.0 / self.world
-        if self.world > 1 and not reduced:
-            dist.all_reduce(a.grads)
+        pre = dp.pre_scale()  # SUM all-reduce, 1/world folded into the clip / SGD kernels: DDP's gradient averaging
+        if not reduced:
+            dp.allreduce_grads(a.grads, bucket_elems=n)  # one collective over the whole arena (no-op at world 1)
         lr = lr_at_iter(self.cfg, self.iter)  # pt/solver/build.py: WarmupMultiStepLR unless the config says otherwise
         call("ptb200_grad_sumsq", a.grads, n, pre, self._sumsq)
         call("ptb200_clip_sgd_step", a.data[a.trainable_start:], a.grads, a.momentum, n, float(lr),
