@@ -42,7 +42,7 @@ class PTrainer:
         self.model_teacher = build_model(cfg, self.device, loss_scale=loss_scale, with_grads=False)
         self.model.init_synthetic(seed)
         if self.world > 1:  # DDP _sync_params_and_buffers (trainer.py:491-496)
-            dist.broadcast(self.model.arena.data, src=0)
+            dp.broadcast_params(self.model.arena.data, src=0)
             self.model.arena.pack()
         self.model_teacher.arena.data.copy_(self.model.arena.data)
         self.model_teacher.arena.pack()
