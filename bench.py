@@ -86,7 +86,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -333,7 +333,6 @@ def main():
     l0 = _lib.launch_count[0]
     ms = timed_steps(trainer, args.steps, dist, device)
     launches = (_lib.launch_count[0] - l0) // args.steps  # eager launches; graph replays are counted below
-    clk = clocks.stop() if rank == 0 else None
     ms_per_step = ms / args.steps
     value = world * 1000.0 / ms_per_step
 
@@ -343,6 +342,7 @@ def main():
     trainer.step()
     ms_e2e = timed_steps(trainer, args.steps, dist, device, read_losses=True, host_sink=host_sink)
     e2e_value = world * 1000.0 * args.steps / ms_e2e
+    clk = clocks.stop() if rank == 0 else None  # sampled over BOTH timed regions (device-resident and end-to-end)
     h2d = 4 * PAIRS_PER_GPU * 3 * H * W  # label_q, label_k, unlabel_q, unlabel_k uint8 images
     d2h = 8 * 4
 
