@@ -104,3 +104,29 @@ def test_clip_and_nonempty():
     assert c.tolist() == [[0., 0., 30., 40.], [10., 10., 10., 30.], [20., 5., 25., 9.]]
     assert O.nonempty(c).tolist() == [True, False, True]
     assert O.nonempty(c, threshold=4.5).tolist() == [True, False, False]
+
+
+def test_nms_ties_duplicates_and_exact_threshold():
+    """Integer-grid boxes (IoUs exactly equal to the threshold), exact duplicates, zero-area boxes, five distinct
+    scores: the oracle's NMS keeps exactly what torchvision keeps, in the same order; batched NMS keeps the same set."""
+    from torchvision.ops import nms as tv_nms
+    from torchvision.ops import boxes as tvb
+    g = torch.Generator().manual_seed(0)
+    exact = 0
+    for trial in range(60):
+        n = int(torch.randint(1, 400, (1,), generator=g))
+        xy = torch.randint(0, 40, (n, 2), generator=g).float() * 4
+        wh = torch.randint(0, 12, (n, 2), generator=g).float() * 8
+        b = torch.cat([xy, xy + wh], 1)
+        if trial % 3 == 0:
+            b[::7] = b[0].clone()
+        s = torch.randint(0, 5, (n,), generator=g).float() / 4
+        for thr in (0.5, 0.7):
+            assert torch.equal(O.nms(b, s, thr), tv_nms(b, s, thr))
+            exact += int((O.pairwise_iou(b, b) == thr).sum())
+        idx = torch.randint(0, 8, (n,), generator=g)
+        # batched NMS: same kept SET and same score sequence; the order among EQUAL scores is implementation-defined
+        # (torchvision's final sort is not stable, the oracle's and the CUDA path's is: ascending index)
+        mine, tv = O.batched_nms(b, s, idx, 0.5), tvb._batched_nms_vanilla(b, s, idx, 0.5)
+        assert torch.equal(mine.sort().values, tv.sort().values) and torch.equal(s[mine], s[tv])
+    assert exact > 100  # the family really contains IoU == threshold pairs

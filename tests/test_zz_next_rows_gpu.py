@@ -294,3 +294,36 @@ def test_anchor_generators_bit_exact(cuda):
     cell = O.default_cell_anchors((128, 256, 512), (0.5, 1.0, 2.0))
     y, x, k = 17, 44, 5
     assert torch.equal(a[(y * 83 + x) * 9 + k], torch.tensor([x * 16., y * 16., x * 16., y * 16.]) + cell[k])
+
+
+@pytest.mark.parametrize("thr,classes", [(0.5, 0), (0.7, 0), (0.5, 8)])
+def test_nms_collisions_bit_exact(cuda, thr, classes):
+    """NMS keep indices on the inputs where implementations usually part ways: boxes on an integer grid (many IoUs
+    EXACTLY equal to the threshold: `>` must stay strict), exact duplicates, zero-area boxes and heavily tied scores
+    (order = stable sort, as torchvision / the oracle). The oracle agrees with torchvision on this family
+    (tests/test_oracle_cpu.py::test_nms_ties_duplicates_and_exact_threshold)."""
+    from oracle import pt_oracle as O
+    from probabilisticteacher_b200 import ops
+    g = torch.Generator().manual_seed(int(thr * 10) + classes)
+    n = 3000
+    xy = torch.randint(0, 40, (n, 2), generator=g).float() * 4
+    wh = torch.randint(0, 12, (n, 2), generator=g).float() * 8   # includes zero-width / zero-height boxes
+    b = torch.cat([xy, xy + wh], 1)
+    b[::7] = b[0].clone()                                         # exact duplicates
+    s = torch.randint(0, 5, (n,), generator=g).float() / 4       # five distinct scores
+    order = torch.argsort(-s, stable=True).to(torch.int32)
+    if classes:
+        ref = O.batched_nms(b, s, torch.arange(n) % classes, thr)
+    else:
+        ref = O.nms(b, s, thr)
+    max_keep = 2000
+    cap = ((n + 63) // 64) * 64
+    order_p = torch.zeros(1, cap, dtype=torch.int32)
+    order_p[0, :n] = order
+    keep_idx, keep_count = ops.nms(b[None].to(cuda), order_p.to(cuda), torch.tensor([n], dtype=torch.int32).to(cuda),
+                                   thr, max_keep, class_mod=classes)
+    torch.cuda.synchronize()
+    kc = int(keep_count[0])
+    got = order[keep_idx[0, :kc].cpu().long()].long()
+    assert kc == min(len(ref), max_keep)
+    assert torch.equal(got, ref[:max_keep])
