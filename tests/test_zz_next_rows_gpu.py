@@ -327,3 +327,41 @@ def test_nms_collisions_bit_exact(cuda, thr, classes):
     got = order[keep_idx[0, :kc].cpu().long()].long()
     assert kc == min(len(ref), max_keep)
     assert torch.equal(got, ref[:max_keep])
+
+
+def test_rpn_match_collisions(cuda):
+    """Anchor labelling on the inputs where the Matcher's tie rules decide (detectron2 `Matcher`): a
+    DUPLICATED ground-truth box (arg-max tie -> the first index), a ZERO-AREA ground-truth box (its best IoU is 0, so
+    the low-quality rule promotes every anchor whose IoU with it is 0 -- detectron2's quirk, kept), a box that
+    coincides exactly with an anchor (IoU 1) and an image with a single far-off-grid box. Indices and labels must equal
+    the oracle's bit for bit."""
+    from oracle import pt_oracle as O
+    from probabilisticteacher_b200.modeling import sampling
+    H, W = 25, 38
+    cell = O.default_cell_anchors((64, 128, 256), (0.5, 1.0, 2.0))
+    anchors = O.grid_anchors(cell, H, W, 16, 0.0)
+    R = anchors.shape[0]
+    N, cap = 3, 64
+    gt = torch.zeros(N, cap, 4)
+    a_mid = anchors[(12 * W + 20) * 9 + 4].clone()          # exactly an anchor
+    normal = torch.tensor([[40., 60., 200., 180.], [300., 100., 420., 330.], [100., 200., 180., 390.]])
+    rows = [torch.cat([normal, normal[:1], a_mid[None]]),                        # duplicate of box 0 + exact anchor
+            torch.cat([normal[:2], torch.tensor([[250., 250., 250., 300.]])]),   # zero-area box
+            torch.tensor([[3., 5., 9., 11.]])]                                   # one tiny box near the corner
+    cnt = torch.tensor([len(r) for r in rows], dtype=torch.int32)
+    for n, r in enumerate(rows):
+        gt[n, :len(r)] = r
+    matched, labels = sampling.rpn_match(gt.to(cuda), cnt.to(cuda), anchors.to(cuda), N, 0.3, 0.7)
+    torch.cuda.synchronize()
+    for n in range(N):
+        iou = O.pairwise_iou(gt[n, :cnt[n]], anchors)
+        rm, rl = O.matcher(iou, (0.3, 0.7), (0, -1, 1), True)
+        assert torch.equal(labels[n].cpu().to(torch.int8), rl), n
+        assert torch.equal(matched[n].cpu().long(), rm), n
+    # what the cases are meant to exercise really happens
+    iou0 = O.pairwise_iou(gt[0, :cnt[0]], anchors)
+    assert torch.equal(iou0[0], iou0[3]) and int((matched[0].cpu() == 3).sum()) == 0      # tie -> first index
+    assert float(iou0[4].max()) == 1.0
+    lab1 = labels[1].cpu()
+    iou1 = O.pairwise_iou(gt[1, :cnt[1]], anchors)
+    assert float(iou1[2].max()) == 0.0 and int((lab1 == 1).sum()) >= int((iou1.max(0).values == 0).sum()) > 0
