@@ -584,9 +584,22 @@ class PTrainer:
             return self.run_step_graphed()
         return self.run_step()
 
-    def train(self, num_iters=None):
+    def check_finite(self):
+        """Lazy divergence check (one host sync; NOT part of the step): the non-finite-proposal flags of both detectors
+        (`proposal_utils.py:117-122` raises per image, on the host, in training) and the last step's losses. Raises
+        FloatingPointError."""
+        self.model.proposal_generator.raise_if_nonfinite()
+        self.model_teacher.proposal_generator.raise_if_nonfinite()
+        if self.last_losses:
+            total = torch.stack([v.reshape(()).float() for v in self.last_losses.values()]).sum()
+            if not bool(torch.isfinite(total)):
+                raise FloatingPointError(f"Loss became infinite or NaN at iteration={self.iter - 1}!\n"
+                                         f"loss_dict = { {k: float(v) for k, v in self.last_losses.items()} }")
+
+    def train(self, num_iters=None, check_period=20):
         """`train_loop(start_iter, max_iter)` (trainer.py:154-176) without the d2 hook machinery: runs to
-        cfg.SOLVER.MAX_ITER (or for `num_iters` iterations); when a checkpointer has been built
+        cfg.SOLVER.MAX_ITER (or for `num_iters` iterations), checking for divergence every `check_period` iterations
+        (the reference does it every iteration at the price of a host sync per image); when a checkpointer has been built
         (`build_checkpointer` / `resume_or_load`) a checkpoint is written every SOLVER.CHECKPOINT_PERIOD iterations
         and `model_final` at MAX_ITER, as `hooks.PeriodicCheckpointer` does (trainer.py:523-527)."""
         end = self.max_iter if num_iters is None else min(self.iter + num_iters, self.max_iter)
@@ -594,6 +607,8 @@ class PTrainer:
         ck = getattr(self, "checkpointer", None)
         while self.iter < end:
             self.step()
+            if check_period > 0 and (self.iter % check_period == 0 or self.iter >= end):
+                self.check_finite()
             if ck is not None:
                 if period > 0 and self.iter % period == 0:  # fvcore PeriodicCheckpointer.step: (iteration + 1) % period
                     self.save_checkpoint()

@@ -113,6 +113,15 @@ class GuassianRPN(nn.Module):
         ctx.update(logits=logits, deltas=deltas, anchors=anchors)
         return dict(boxes=boxes, scores=scores, count=count), loss2, ctx
 
+    def raise_if_nonfinite(self):
+        """The reference checks every image's decoded proposals on the host and raises in training
+        (`proposal_utils.py:117-122`). Here the decode kernel drops non-finite candidates and sets a device flag
+        instead (no per-image synchronisation); this reads the flag (ONE host sync), clears it and raises the
+        reference's error. Called by `PTrainer.check_finite` every few iterations, not inside the step."""
+        if int(self.nonfinite_flag.item()) != 0:
+            self.nonfinite_flag.zero_()
+            raise FloatingPointError("Predicted boxes or scores contain Inf/NaN. Training has diverged.")
+
     # ------------------------------------------------------------------ backward
     def backward(self, ctx, g_cls, g_loc):
         """g_cls / g_loc: device scalars (upstream gradients of loss_rpn_cls / loss_rpn_loc).

@@ -287,13 +287,28 @@ def test_train_loop_checkpoint_cadence():
         def save(self, name, **kw):
             saved.append((name, kw))
     tr.checkpointer = _Ck()
+    checks = []
+
+    class _Gen:
+        def raise_if_nonfinite(self):
+            checks.append(tr.iter)
+
+    class _Model:
+        proposal_generator = _Gen()
+    tr.model, tr.model_teacher = _Model(), _Model()
 
     def step():
         tr.iter += 1
     tr.step = step
-    tr.train(3)
+    tr.train(3, check_period=2)
     assert tr.iter == 3 and saved == []
+    assert checks == [2, 2, 3, 3]  # both detectors, every 2nd iteration and at the end of the call
     tr.train()
     assert tr.iter == 12
+    tr.last_losses = {"loss_cls": torch.tensor(float("inf"))}
+    tr.iter, tr.max_iter = 0, 1
+    with pytest.raises(FloatingPointError):
+        tr.train(check_period=1)
+    tr.max_iter = 12
     assert saved == [("model_0000003", {"iteration": 3}), ("model_0000007", {"iteration": 7}),
                      ("model_0000011", {"iteration": 11}), ("model_final", {"iteration": 11})]

@@ -365,3 +365,53 @@ def test_rpn_match_collisions(cuda):
     lab1 = labels[1].cpu()
     iou1 = O.pairwise_iou(gt[1, :cnt[1]], anchors)
     assert float(iou1[2].max()) == 0.0 and int((lab1 == 1).sum()) >= int((iou1.max(0).values == 0).sum()) > 0
+
+
+def test_nonfinite_proposals_are_dropped_and_flagged(cuda):
+    """Error convention of SURVEY 8b: the reference raises FloatingPointError when a decoded proposal or its score is
+    Inf/NaN in training and silently filters such rows in eval (`proposal_utils.py:117-127`). Here the decode kernel
+    always filters them and sets a device flag that `GuassianRPN.raise_if_nonfinite` turns into the reference's
+    error lazily. With one NaN logit and one Inf delta injected, the selected proposals must equal the oracle's
+    eval-mode result on the same inputs (the two bad anchors gone, everything else bit-identical in order)."""
+    import types
+    from oracle import pt_oracle as O
+    from probabilisticteacher_b200.modeling.proposal_generator.proposal_utils import find_top_rpn_proposals
+    from probabilisticteacher_b200.modeling.proposal_generator.rpn import GuassianRPN
+    g = torch.Generator().manual_seed(12)
+    N, H, W, A = 2, 12, 17, 9
+    R = H * W * A
+    anchors = O.grid_anchors(O.differentiable_cell_anchors(torch.tensor(O.OracleCfg().anchor_wh)), H, W, 16, 0.0)
+    lg = torch.zeros(N, H, W + 1, A)
+    lg[:, :, :W] = torch.randn(N, H, W, A, generator=g)
+    dl = torch.zeros(N, H, W + 1, A * 8)
+    dl[:, :, :W] = torch.randn(N, H, W, A * 8, generator=g) * 0.2
+    flag = torch.zeros(1, dtype=torch.int32, device=cuda)
+    hw = torch.tensor([[H * 16.0, W * 16.0]] * N, device=cuda)
+
+    def run():
+        out = find_top_rpn_proposals(lg.reshape(N, -1, A).to(cuda), dl.reshape(N, -1, A * 8).to(cuda), anchors.to(cuda),
+                                     N, H, W, A, hw, 0.7, 12000, 2000, 0.0, flag)
+        torch.cuda.synchronize()
+        return out
+
+    run()
+    rpn = types.SimpleNamespace(nonfinite_flag=flag)
+    GuassianRPN.raise_if_nonfinite(rpn)  # clean inputs: no error
+    lg[0, 3, 5, 2] = float("nan")
+    dl[1, 7, 9, 4 * 8 + 0] = float("inf")  # dx of anchor 4 at (7, 9): the decoded box is non-finite (dw / dh are clamped)
+    boxes, scores, count = run()
+    assert int(flag) != 0
+    with pytest.raises(FloatingPointError):
+        GuassianRPN.raise_if_nonfinite(rpn)
+    assert int(flag) == 0  # cleared by the check
+    # oracle, eval-mode filtering (training=False keeps the reference from raising); same top-k sizes as the call above
+    lo = lg[:, :, :W].reshape(N, R)
+    do = dl[:, :, :W].reshape(N, R, 8)
+    pr = O.apply_deltas(do[..., :4].reshape(-1, 4), anchors.expand(N, R, 4).reshape(-1, 4), (1., 1., 1., 1.)).view(N, R, 4)
+    ref = O.find_top_rpn_proposals(pr, lo.clone(), [(H * 16, W * 16)] * N, 0.7, 12000, 2000, 0, False, do[..., 4:])
+    for n in range(N):
+        c = int(count[n])
+        rb, rs = O._bt(ref[n].proposal_boxes), ref[n].objectness_logits
+        assert c == len(rs), (n, c, len(rs))
+        assert (boxes[n, :c].cpu() - rb).abs().max() < 1e-2 and (scores[n, :c].cpu() - rs).abs().max() < 1e-5
+        assert bool(torch.isfinite(boxes[n, :c]).all()) and bool(torch.isfinite(scores[n, :c]).all())
