@@ -62,17 +62,22 @@ int ptb200_gemm_tn_f16x3(const void* A3, int batch, int rows, int k3_per_tap, in
                          int split, int n_valid, int max_ctas, int ksplit, const int* seg_counts, int seg_cap,
                          float alpha, void* stream);
 
-/* out3 = triple(act(alpha * in + bias)), fp32 [rows][n] -> fp16 [rows][3n]; wp > 0: rows with
+/* Bias + ReLU of the same layers (pt/modeling/backbone/vgg.py:65-72, the box head of roi_heads.py:127-128) applied to
+ * the fp32 partial sums of a K-chunked f16x3 GEMM:
+ * out3 = triple(act(alpha * in + bias)), fp32 [rows][n] -> fp16 [rows][3n]; wp > 0: rows with
  * (row % wp) >= w_valid are written as zero (pad column of the flat activation layout). */
 int ptb200_bias_act_split3_f16(const float* in, const float* bias, int relu, float alpha, int64_t rows, int n,
                                int wp, int w_valid, void* out3, void* stream);
 
-/* fp32 [rows][k] -> f16x3 operand [rows][3k] of src * scale: order 0 = activation triple [hi | lo | hi],
+/* Operand preparation that has no counterpart in the reference (it feeds fp32 tensors to cuDNN / cuBLAS at
+ * vgg.py:45-53, rpn.py:96, fast_rcnn.py:157-169 directly):
+ * fp32 [rows][k] -> f16x3 operand [rows][3k] of src * scale: order 0 = activation triple [hi | lo | hi],
  * order 1 = weight triple [hi | hi | lo]. (rows counts (output channel, tap) pairs for conv weights.) */
 int ptb200_split3_pack_f16(const float* src, void* dst, int64_t rows, int k, float scale, int order,
                            void* stream);
 
-/* f16x3 triple [rows][3k] -> fp32 [rows][k] (hi + lo); inspection / tests. */
+/* f16x3 triple [rows][3k] -> fp32 [rows][k] (hi + lo); inspection / tests (gives back the fp32 tensor the
+ * reference's layer would have produced, e.g. `features["vgg_block5"]` of pt/modeling/meta_arch/rcnn.py:45). */
 int ptb200_split3_unpack_f32(const void* src, float* dst, int64_t rows, int k, void* stream);
 
 /* Weight gradient  out[m][t*n_total + n] += scale * sum_b sum_p G[b][p][m] * X[b][p + shifts[t]][n]
@@ -94,13 +99,15 @@ int ptb200_preprocess_im2col(const uint8_t* images, const int* hw_dev, int n, in
                              int64_t image_stride, const float* mean3_host, const float* std3_host,
                              void* out_f16, void* stream);
 
-/* Same pre-processing fused with the first VGG conv (vgg_block1.conv1, 3 -> 64, bias + ReLU): uint8 CHW
+/* Same pre-processing (d2 preprocess_image, rcnn.py:38-43) fused with the first VGG conv (vgg_block1.conv1 of
+ * pt/modeling/backbone/vgg.py:45-53,65-72, 3 -> 64, bias + ReLU): uint8 CHW
  * images -> fp16 NHWC-flat [n][hmax*(wmax+1)][64]. wpack_f16 = weights [64][32] fp16, k = (ky*3+kx)*3+c. */
 int ptb200_conv1_u8_f16(const uint8_t* images, const int* hw_dev, int n, int hmax, int wmax,
                         int64_t image_stride, const float* mean3_host, const float* std3_host,
                         const void* wpack_f16, const float* bias, void* out_f16, void* stream);
 
-/* f16x3 variant of ptb200_conv1_u8_f16: the 3 -> 64 conv is evaluated in fp32 on the CUDA cores (K = 27),
+/* f16x3 variant of ptb200_conv1_u8_f16 (rcnn.py:38-43 + vgg.py:45-53,65-72): the 3 -> 64 conv is evaluated in fp32
+ * on the CUDA cores (K = 27),
  * output [n][hmax*(wmax+1)][192] triples. w_f32 = [64][27] (k = (ky*3+kx)*3+c). */
 int ptb200_conv1_u8_f16x3(const uint8_t* images, const int* hw_dev, int n, int hmax, int wmax,
                           int64_t image_stride, const float* mean3_host, const float* std3_host,
@@ -111,43 +118,54 @@ int ptb200_conv1_u8_f16x3(const uint8_t* images, const int* hw_dev, int n, int h
 int ptb200_resize_paste_u8(const uint8_t* src, uint8_t* dst, int h, int w, int dh, int dw, int x1, int y1,
                            int m0, int m1, int m2, void* stream);
 
-/* Same, with the geometry {dh, dw, x1, y1} read from device memory (CUDA-graph replay). */
+/* Same (pt/engine/trainer.py:557-590), with the geometry {dh, dw, x1, y1} read from device memory (CUDA-graph
+ * replay: the random ratio of :561 is drawn on the host and copied into a persistent device buffer). */
 int ptb200_resize_paste_u8_dev(const uint8_t* src, uint8_t* dst, int h, int w, const int* params_dev, int m0,
                                int m1, int m2, void* stream);
 
 /* F.max_pool2d(2, 2) of pt/modeling/backbone/vgg.py:59,71 (floor mode). */
 int ptb200_maxpool2x2_f16(const void* in, void* out, int n, int h, int w, int c, void* stream);
 
-/* f16x3 variant (c = channels, rows are 3*c wide): the max is taken over hi + lo. */
+/* f16x3 variant of F.max_pool2d(2, 2) (vgg.py:59,71; c = channels, rows are 3*c wide): the max is taken over
+ * hi + lo. */
 int ptb200_maxpool2x2_f16x3(const void* in, void* out, int n, int h, int w, int c, void* stream);
 
 /* Backward of ReLU followed by the 2x2 max pool (autograd of vgg.py:65-72). */
 int ptb200_maxpool2x2_relu_bwd_f16(const void* x, const void* dpooled, void* dz, int n, int h, int w,
                                    int c, void* stream);
 
-/* fp32 master weights -> fp16 GEMM operands. */
+/* fp32 master weights -> fp16 GEMM operands: the cast the reference never needs (fp32 nn.Parameter tensors go to
+ * cuDNN / cuBLAS as they are; vgg.py:45-53, rpn.py:44-55, fast_rcnn.py:157-169). transpose_pack builds the
+ * [Cin][tap][Cout] operand of the data-gradient GEMM that autograd derives from the same weights
+ * (pt/engine/trainer.py:384); cast_pad_rows pads the K = 27 first-conv filter to 32. */
 int ptb200_cast_f32_f16(const float* src, void* dst, int64_t n, void* stream);
 int ptb200_transpose_pack_f16(const float* src, void* dst, int rows, int cols, int taps, int flip,
                               int64_t ld_dst, void* stream);
 int ptb200_cast_pad_rows_f16(const float* src, void* dst, int rows, int cols, int ld_dst, void* stream);
 
-/* Bias gradient: out[c] += scale * sum_rows in[row][c]. */
+/* Bias gradient (autograd of the `+ bias` in d2 Conv2d / nn.Linear, run by `losses.backward()` at
+ * pt/engine/trainer.py:384): out[c] += scale * sum_rows in[row][c]. */
 int ptb200_colsum_f16(const void* in, int64_t rows, int c, int64_t ld, float scale, float* out,
                       void* stream);
 
-/* Packs the unit gradients of two loss terms (n0 and n1 columns) scaled by the upstream gradients
+/* Head of the backward chain (autograd of the loss sums at pt/engine/trainer.py:364-384 w.r.t. the two head
+ * outputs: objectness + anchor deltas of rpn.py:96, cls_score + bbox_pred of fast_rcnn.py:157-169):
+ * packs the unit gradients of two loss terms (n0 and n1 columns) scaled by the upstream gradients
  * g0[0], g1[0] and the loss scale into the fp16 [rows][ld] operand of the backward GEMMs. */
 int ptb200_pack_grad2_f16(const float* d0, int n0, const float* d1, int n1, const float* g0,
                           const float* g1, float lscale, int64_t rows, int ld, void* out, void* stream);
 
-/* Finishes a split-K GEMM: out = half(act(in + bias)). */
+/* Finishes a split-K GEMM (fc1 of the box head, roi_heads.py:127-128): out = half(act(in + bias)). */
 int ptb200_bias_act_cast_f16(const float* in, const float* bias, int relu, int64_t rows, int n, void* out,
                              void* stream);
 
+/* out = half(a + scale * b): autograd's accumulation of two gradient paths into one tensor (the RPN and ROI
+ * branches both consume `features["vgg_block5"]`, pt/modeling/meta_arch/rcnn.py:45-61). */
 int ptb200_add_f32_to_f16(const void* a, const float* b, float scale, void* out, int64_t n,
                           void* stream);
 
-/* out = (aux > 0) ? a + scale * b : 0  (sums the two gradient paths into the backbone output). */
+/* out = (aux > 0) ? a + scale * b : 0: the same accumulation fused with the backward of the last backbone ReLU
+ * (vgg.py:65-72; sums the RPN and ROI gradient paths into the backbone output, rcnn.py:45-61). */
 int ptb200_add_mask_f16(const void* a, const float* b, float scale, const void* aux, void* out,
                         int64_t n, void* stream);
 
@@ -247,10 +265,14 @@ int ptb200_roi_match_unsup(const float* pseudo_boxes, const float* pseudo_logits
 int ptb200_roi_align_fwd_f16(const void* feat, int n, int h, int w, int c, const float* rois,
                              const int* roi_count, int cap, float spatial_scale, int pooled, void* out,
                              void* stream);
-/* f16x3 variant: feat rows and output bins are [hi | lo | hi] triples (3*c wide); bilinear sums in fp32. */
+/* f16x3 variant of the same call (roi_heads.py:68-73,126): feat rows and output bins are [hi | lo | hi] triples
+ * (3*c wide); bilinear sums in fp32. */
 int ptb200_roi_align_fwd_f16x3(const void* feat3, int n, int h, int w, int c, const float* rois,
                                const int* roi_count, int cap, float spatial_scale, int pooled, void* out3,
                                void* stream);
+/* Backward of the same call (torchvision roi_align's autograd, run by `losses.backward()` at
+ * pt/engine/trainer.py:384): scatters dout [n*cap][pooled*pooled][c] into the fp32 feature gradient dfeat
+ * [n][h*(w+1)][c] with vector atomics. */
 int ptb200_roi_align_bwd_f16(const void* dout, int n, int h, int w, int c, const float* rois,
                              const int* roi_count, int cap, float spatial_scale, int pooled,
                              float* dfeat, void* stream);

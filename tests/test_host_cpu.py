@@ -312,3 +312,23 @@ def test_train_loop_checkpoint_cadence():
     tr.max_iter = 12
     assert saved == [("model_0000003", {"iteration": 3}), ("model_0000007", {"iteration": 7}),
                      ("model_0000011", {"iteration": 11}), ("model_final", {"iteration": 11})]
+
+
+def test_every_entry_point_cites_the_reference_and_is_documented():
+    """include/ptb200.h is the boundary contract: every prototype sits under a comment that names the reference
+    interface it replaces (a reference file with line numbers, detectron2 / torchvision behaviour, or autograd of a
+    cited call), and every entry point appears in INTEGRATION.md's replacement table."""
+    import re
+    text = open(os.path.join(ROOT, "include", "ptb200.h")).read()
+    pairs = re.findall(r"/\*((?:(?!\*/).)*)\*/\s*((?:int\s+ptb200_\w+\s*\([^;]*\)\s*;\s*)+)", text, flags=re.S)
+    covered = {}
+    for comment, protos in pairs:
+        for name in re.findall(r"int\s+(ptb200_\w+)", protos):
+            covered[name] = comment
+    declared = set(re.findall(r"\bint\s+(ptb200_\w+)\s*\(", re.sub(r"/\*.*?\*/", "", text, flags=re.S)))
+    assert declared == set(covered), sorted(declared - set(covered))
+    cite = re.compile(r"\.py(:\d+)?|d2 |detectron2|torchvision|torch\.sort")
+    uncited = sorted(n for n, c in covered.items() if not cite.search(c))
+    assert not uncited, uncited
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    assert not [n for n in declared if n not in doc]
