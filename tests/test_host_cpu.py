@@ -332,3 +332,21 @@ def test_every_entry_point_cites_the_reference_and_is_documented():
     assert not uncited, uncited
     doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
     assert not [n for n in declared if n not in doc]
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    """No silent fallback: without libptb200.so (or with a symbol missing) the loader raises."""
+    from probabilisticteacher_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "libptb200.so"))
+    with pytest.raises(_lib.PTB200Error, match="no CPU fallback"):
+        _lib.lib()
+    # a library that lacks a declared symbol is refused as well
+    src = tmp_path / "stub.c"
+    src.write_text("int ptb200_ema_update(void) { return 0; }\n")
+    subprocess.check_call(["gcc", "-shared", "-fPIC", "-o", str(tmp_path / "libptb200.so"), str(src)])
+    with pytest.raises(_lib.PTB200Error, match="does not export"):
+        _lib.lib()
+    with pytest.raises(TypeError):
+        monkeypatch.undo()
+        _lib.call("ptb200_ema_update", 1, 2)  # wrong arity is caught before the call
