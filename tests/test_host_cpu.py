@@ -350,3 +350,34 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     with pytest.raises(TypeError):
         monkeypatch.undo()
         _lib.call("ptb200_ema_update", 1, 2)  # wrong arity is caught before the call
+
+
+def test_product_code_never_imports_the_oracle():
+    """oracle/ is the checker: only tests/, __graft_entry__.smoke() and bench.py's CPU legs may import it. Static scan
+    of every module of the package, of tools/ and of bench.py (where the import must live inside the CPU-baseline
+    function, never at module level or in the main arm)."""
+    import ast
+    import glob
+
+    def oracle_imports(path):
+        tree = ast.parse(open(path).read())
+        hits = []
+        for node in ast.walk(tree):
+            mods = []
+            if isinstance(node, ast.Import):
+                mods = [a.name for a in node.names]
+            elif isinstance(node, ast.ImportFrom):
+                mods = [node.module or ""]
+            hits += [(m, node.lineno) for m in mods if m == "oracle" or m.startswith("oracle.")]
+        return tree, hits
+
+    files = glob.glob(os.path.join(ROOT, "probabilisticteacher_b200", "**", "*.py"), recursive=True)
+    files += glob.glob(os.path.join(ROOT, "tools", "*.py"))
+    assert len(files) > 20
+    for f in files:
+        assert oracle_imports(f)[1] == [], f
+    tree, hits = oracle_imports(os.path.join(ROOT, "bench.py"))
+    assert hits, "bench.py's cpu_baseline leg times the oracle"
+    allowed = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "cpu_oracle_iters_per_s"]
+    lo, hi = allowed[0].lineno, allowed[0].end_lineno
+    assert all(lo <= line <= hi for _, line in hits), hits
