@@ -203,7 +203,7 @@ def main():
     r = ref_pu.add_ground_truth_to_proposals([Boxes(gtb[0])], [p])[0]
     out["append_gt"] = dict(gt=gtb[0], props=props[0], boxes=r.proposal_boxes.tensor, logits=r.objectness_logits)
 
-    dst = os.path.join(ROOT, "tests", "golden", "pt_reference_golden.pt")
+    dst = os.path.join(os.environ.get("PT_GOLDEN_DIR", os.path.join(ROOT, "tests", "golden")), "pt_reference_golden.pt")
     torch.save(out, dst)
     print("wrote", dst, os.path.getsize(dst), "bytes")
 

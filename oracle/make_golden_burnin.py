@@ -120,7 +120,7 @@ def main():
     teacher_after = S.sample_params(teacher)
     assert all(torch.equal(teacher_before[k], teacher_after[k]) for k in teacher_before)  # burn-in never touches it
     assert sorted(captured[-1]) == ["loss_box_reg", "loss_cls", "loss_rpn_cls", "loss_rpn_loc"]
-    dst = os.path.join(ROOT, "tests", "golden", "pt_reference_burnin_golden.pt")
+    dst = os.path.join(os.environ.get("PT_GOLDEN_DIR", os.path.join(ROOT, "tests", "golden")), "pt_reference_burnin_golden.pt")
     torch.save(out, dst)
     print("wrote", dst, os.path.getsize(dst), "bytes")
 

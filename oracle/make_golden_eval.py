@@ -58,7 +58,7 @@ def main():
     for name, sizes, out_sizes, K, ag, seed in CASES:
         print(name)
         out[name] = run_case(sizes, out_sizes, K, ag, seed)
-    dst = os.path.join(ROOT, "tests", "golden", "pt_reference_eval_golden.pt")
+    dst = os.path.join(os.environ.get("PT_GOLDEN_DIR", os.path.join(ROOT, "tests", "golden")), "pt_reference_eval_golden.pt")
     torch.save(out, dst)
     print("wrote", dst, os.path.getsize(dst), "bytes")
 

@@ -43,7 +43,7 @@ def main():
         batches = [[[d["id"] for d in part] for part in b] for b in ds]
         print(f"seed {seed}: {n} pairs, batch ({bl}, {bu}) -> {len(batches)} batches")
         cases.append(dict(label=lab, unlabel=unl, batch=[bl, bu], batches=batches))
-    dst = os.path.join(ROOT, "tests", "golden", "pt_reference_loader_golden.json")
+    dst = os.path.join(os.environ.get("PT_GOLDEN_DIR", os.path.join(ROOT, "tests", "golden")), "pt_reference_loader_golden.json")
     json.dump(cases, open(dst, "w"))
     print("wrote", dst, os.path.getsize(dst), "bytes")
 

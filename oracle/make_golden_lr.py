@@ -64,7 +64,7 @@ def main():
             sch.step()
         out.append(dict(c, lrs=lrs))
         print(c["steps"], c["factor_list"], [round(x, 6) for x in lrs[:3]], "...", round(lrs[-1], 6))
-    dst = os.path.join(ROOT, "tests", "golden", "pt_reference_lr_golden.json")
+    dst = os.path.join(os.environ.get("PT_GOLDEN_DIR", os.path.join(ROOT, "tests", "golden")), "pt_reference_lr_golden.json")
     json.dump(out, open(dst, "w"))
     print("wrote", dst)
 

@@ -194,7 +194,7 @@ def main():
     for name, sizes, K, anchor_name, seed, n_gt in CASES:
         print(name)
         out[name] = run_case(sizes, K, anchor_name, seed, n_gt)
-    dst = os.path.join(ROOT, "tests", "golden", "pt_reference_model_golden.pt")
+    dst = os.path.join(os.environ.get("PT_GOLDEN_DIR", os.path.join(ROOT, "tests", "golden")), "pt_reference_model_golden.pt")
     torch.save(out, dst)
     print("wrote", dst, os.path.getsize(dst), "bytes")
 

@@ -105,7 +105,7 @@ def main():
                                  teacher=sample_params(teacher)))
         print("step", it, {k: round(v, 5) for k, v in captured[-1].items()}, "ratios", [round(r, 4) for r in draws[n0:]])
     random.uniform = real_uniform
-    dst = os.path.join(ROOT, "tests", "golden", "pt_reference_step_golden.pt")
+    dst = os.path.join(os.environ.get("PT_GOLDEN_DIR", os.path.join(ROOT, "tests", "golden")), "pt_reference_step_golden.pt")
     torch.save(out, dst)
     print("wrote", dst, os.path.getsize(dst), "bytes")
 
