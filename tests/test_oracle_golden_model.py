@@ -134,3 +134,47 @@ def test_eval_mode_inference_matches_the_reference_models(case):
         _close(out.scores, ref["scores"])
         _close(out.scores_logists, ref["scores_logists"])
         _close(out.boxes_sigma, ref["boxes_sigma"])
+
+
+# ------------------------------------------------------------------------------------------ BASELINE config 1, full size
+def _config1_inputs(G):
+    g = torch.Generator().manual_seed(G["prio_seed"])
+    R = (G["H"] // 16) * (G["W"] // 16) * 9
+    L = 2000 + 16
+    N = G["N"]
+    prio = {"rpn": (torch.rand(N, R, generator=g), torch.rand(N, R, generator=g)),
+            "roi": (torch.rand(N, L, generator=g), torch.rand(N, L, generator=g))}
+    lab = O.synthetic_batch(N, G["H"], G["W"], G["K"], G["lab_seed"])
+    unl = O.synthetic_batch(N, G["H"], G["W"], G["K"], G["unl_seed"], labelled=False)
+    return prio, lab, unl
+
+
+def test_config1_full_size_matches_the_reference_models():
+    """BASELINE.json config 1 (Guassian-RCNN-VGG.yaml, 1 source + 1 target synthetic 3x800x1333 image, one iteration's
+    losses): tests/golden/pt_reference_config1_golden.pt holds what the reference's own model classes compute at FULL
+    size (oracle/make_golden_config1.py); the oracle must reproduce the 8 losses, the teacher's proposals and its 100
+    pseudo labels. (The CUDA path is compared with the same fixture in tests/test_zz_next_rows_gpu.py.)"""
+    G = torch.load(os.path.join(os.path.dirname(__file__), "golden", "pt_reference_config1_golden.pt"), weights_only=False)
+    prio, lab, unl = _config1_inputs(G)
+    om = O.OracleRCNN(O.OracleCfg(num_classes=G["K"], anchor_generator=G["anchor_generator"]), seed=G["weight_seed"])
+    om.sampler = _Sampler(prio)
+    with torch.no_grad():
+        ls, _, _, _ = om(lab, branch="supervised")
+        for k, v in G["sup_losses"].items():
+            _close(ls[k], v)
+        _, props, roih, _ = om(unl, branch="unsup_data_weak")
+        for n in range(G["N"]):
+            _close(O._bt(props[n].proposal_boxes), G["teacher_rpn_boxes"][n])
+            _close(props[n].objectness_logits, G["teacher_rpn_logits"][n])
+            ref = G["teacher_roih"][n]
+            assert torch.equal(roih[n].pred_classes, ref["pred_classes"])
+            _close(O._bt(roih[n].pred_boxes), ref["pred_boxes"])
+            _close(roih[n].scores, ref["scores"])
+            _close(roih[n].scores_logists, ref["scores_logists"])
+            _close(roih[n].boxes_sigma, ref["boxes_sigma"])
+        unl_q = [dict(d, instances=O.OInst(r.image_size, pseudo_boxes=O.OBoxes(O._bt(r.pred_boxes)),
+                                           scores_logists=r.scores_logists, boxes_sigma=r.boxes_sigma))
+                 for d, r in zip(unl, roih)]
+        lu, _, _, _ = om(unl_q, branch="unsupervised", danchor=True)
+        for k, v in G["unsup_losses"].items():
+            _close(lu[k], v)
