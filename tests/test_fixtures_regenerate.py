@@ -43,7 +43,8 @@ _CASES = [("make_golden_loader.py", "pt_reference_loader_golden.json"), ("make_g
           ("make_golden.py", "pt_reference_golden.pt")]
 if os.environ.get("PT_REGEN_ALL") == "1":
     _CASES += [("make_golden_eval.py", "pt_reference_eval_golden.pt"), ("make_golden_burnin.py", "pt_reference_burnin_golden.pt"),
-               ("make_golden_model.py", "pt_reference_model_golden.pt"), ("make_golden_step.py", "pt_reference_step_golden.pt")]
+               ("make_golden_model.py", "pt_reference_model_golden.pt"), ("make_golden_step.py", "pt_reference_step_golden.pt"),
+               ("make_golden_config1.py", "pt_reference_config1_golden.pt")]
 
 
 @pytest.mark.parametrize("script,fixture", _CASES)
