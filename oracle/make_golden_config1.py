@@ -21,9 +21,19 @@ from oracle import make_golden_model as M  # noqa: E402
 O, d2shim_model = M.O, M.d2shim_model
 from probabilisticteacher_b200.config import c2f_config  # noqa: E402
 
-H, W, K, N = 800, 1333, 8, 1
-WEIGHT_SEED, LAB_SEED, UNL_SEED, PRIO_SEED = 23, 1, 2, 7
-ANCHORS = "DefaultAnchorGenerator"
+# python oracle/make_golden_config1.py config4  -> tests/golden/pt_reference_config4_golden.pt: BASELINE config 4's
+# model and size (configs/pt/final_k2c.yaml: K = 1, train.sh's DifferentiableAnchorGenerator, one 3x600x2000 pair)
+CASE = sys.argv[1] if len(sys.argv) > 1 else "config1"
+if CASE == "config1":
+    H, W, K, N = 800, 1333, 8, 1
+    WEIGHT_SEED, LAB_SEED, UNL_SEED, PRIO_SEED = 23, 1, 2, 7
+    ANCHORS = "DefaultAnchorGenerator"
+elif CASE == "config4":
+    H, W, K, N = 600, 2000, 1, 1
+    WEIGHT_SEED, LAB_SEED, UNL_SEED, PRIO_SEED = 29, 3, 4, 9
+    ANCHORS = "DifferentiableAnchorGenerator"
+else:
+    raise SystemExit(f"unknown case {CASE!r}")
 
 
 def prios():
@@ -76,7 +86,7 @@ def main():
         losses, _, _, _ = model(unl_q, branch="unsupervised", danchor=True)
         out["unsup_losses"] = {k: float(v) for k, v in losses.items()}
         print("unsup", out["unsup_losses"])
-    dst = os.path.join(os.environ.get("PT_GOLDEN_DIR", os.path.join(ROOT, "tests", "golden")), "pt_reference_config1_golden.pt")
+    dst = os.path.join(os.environ.get("PT_GOLDEN_DIR", os.path.join(ROOT, "tests", "golden")), f"pt_reference_{CASE}_golden.pt")
     torch.save(out, dst)
     print("wrote", dst, os.path.getsize(dst), "bytes")
 

@@ -328,7 +328,12 @@ def find_top_rpn_proposals(proposals, logits, image_sizes, nms_thresh, pre_nms_t
                            min_box_size, training, sigma):
     """pt/modeling/proposal_generator/proposal_utils.py:27-154, single feature level.
     proposals (N,R,4), logits (N,R), sigma (N,R,4) raw sigma logits. Keeps the reference quirk at
-    :94 -- sigma is taken from the FIRST k rows, not gathered by topk_idx."""
+    :94 -- sigma is taken from the FIRST k rows, not gathered by topk_idx.
+    Tie order: the reference calls `logits.sort(descending=True)` (:87) without `stable`, so the order among EQUAL
+    logits -- and through the :94 quirk the sigma row they are re-scored with -- is whatever the torch build does.
+    Here (and in the CUDA path) ties are broken by ascending anchor index. fp32 ties do occur at full size
+    (12 among the best 12 000 of 41 625 logits in tests/golden/pt_reference_config4_golden.pt, where they move 2 of
+    the 2 000 proposals); none occur in the other fixtures, which this function reproduces exactly."""
     N, R = logits.shape
     k = min(R, pre_nms_topk)
     sl, idx = logits.sort(descending=True, dim=1, stable=True)

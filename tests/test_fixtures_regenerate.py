@@ -44,14 +44,16 @@ _CASES = [("make_golden_loader.py", "pt_reference_loader_golden.json"), ("make_g
 if os.environ.get("PT_REGEN_ALL") == "1":
     _CASES += [("make_golden_eval.py", "pt_reference_eval_golden.pt"), ("make_golden_burnin.py", "pt_reference_burnin_golden.pt"),
                ("make_golden_model.py", "pt_reference_model_golden.pt"), ("make_golden_step.py", "pt_reference_step_golden.pt"),
-               ("make_golden_config1.py", "pt_reference_config1_golden.pt")]
+               ("make_golden_config1.py", "pt_reference_config1_golden.pt"),
+               ("make_golden_config1.py config4", "pt_reference_config4_golden.pt")]
 
 
 @pytest.mark.parametrize("script,fixture", _CASES)
 def test_fixture_is_reproduced_by_its_script(tmp_path, script, fixture):
     env = dict(os.environ, PT_GOLDEN_DIR=str(tmp_path), PT_REFERENCE=REF)
-    out = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", script)], env=env, capture_output=True, text=True,
-                         timeout=900)
+    name, *args = script.split()
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", name)] + args, env=env, capture_output=True,
+                         text=True, timeout=900)
     assert out.returncode == 0, out.stderr[-3000:]
     new, old = os.path.join(str(tmp_path), fixture), os.path.join(ROOT, "tests", "golden", fixture)
     if fixture.endswith(".json"):

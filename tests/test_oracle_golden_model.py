@@ -149,23 +149,49 @@ def _config1_inputs(G):
     return prio, lab, unl
 
 
-def test_config1_full_size_matches_the_reference_models():
+def _overlap(a, b, scale, tol=1e-5):
+    """Fraction of the rows of a that also appear in b (same box to tol * scale)."""
+    d = (a.double()[:, None, :] - b.double()[None, :, :]).abs().amax(-1) / scale
+    return float((d.min(1).values < tol).double().mean())
+
+
+@pytest.mark.parametrize("case", ["config1", "config4"])
+def test_full_size_configs_match_the_reference_models(case):
     """BASELINE.json config 1 (Guassian-RCNN-VGG.yaml, 1 source + 1 target synthetic 3x800x1333 image, one iteration's
-    losses): tests/golden/pt_reference_config1_golden.pt holds what the reference's own model classes compute at FULL
-    size (oracle/make_golden_config1.py); the oracle must reproduce the 8 losses, the teacher's proposals and its 100
-    pseudo labels. (The CUDA path is compared with the same fixture in tests/test_zz_next_rows_gpu.py.)"""
-    G = torch.load(os.path.join(os.path.dirname(__file__), "golden", "pt_reference_config1_golden.pt"), weights_only=False)
+    losses) and config 4's model and size (final_k2c.yaml: K = 1, differentiable anchors, 3x600x2000):
+    tests/golden/pt_reference_{case}_golden.pt hold what the reference's own model classes compute at FULL size
+    (oracle/make_golden_config1.py). (The CUDA path is compared with the same fixtures in tests/test_zz_next_rows_gpu.py.)
+
+    config1: the oracle reproduces the 8 losses, the teacher's proposals and its 100 pseudo labels exactly.
+    config4: 12 of the 12 000 best RPN logits of this input are EQUAL in fp32. The reference sorts them with
+    `logits.sort(descending=True)` (proposal_utils.py:87), whose order among equal keys is unspecified; the position in
+    that order picks the sigma row used for re-scoring (the :94 quirk), so the reference's own proposal list depends on
+    torch's tie order. The oracle and the CUDA path break ties by ascending anchor index. Hence here: RPN losses and
+    pseudo labels exact, proposal lists equal as sets up to the tied candidates (measured: 1998 of 2000), ROI losses
+    (which see the sampled subset of those lists) to 1e-2."""
+    strict = case == "config1"
+    G = torch.load(os.path.join(os.path.dirname(__file__), "golden", f"pt_reference_{case}_golden.pt"), weights_only=False)
     prio, lab, unl = _config1_inputs(G)
     om = O.OracleRCNN(O.OracleCfg(num_classes=G["K"], anchor_generator=G["anchor_generator"]), seed=G["weight_seed"])
     om.sampler = _Sampler(prio)
+    scale = float(max(G["H"], G["W"]))
+
+    def loss_close(mine, ref, k):
+        tol = 2e-5 if (strict or "rpn" in k) else 1e-2
+        assert abs(float(mine) - ref) <= tol * max(abs(ref), 1e-6), (k, float(mine), ref)
+
     with torch.no_grad():
         ls, _, _, _ = om(lab, branch="supervised")
         for k, v in G["sup_losses"].items():
-            _close(ls[k], v)
+            loss_close(ls[k], v, k)
         _, props, roih, _ = om(unl, branch="unsup_data_weak")
         for n in range(G["N"]):
-            _close(O._bt(props[n].proposal_boxes), G["teacher_rpn_boxes"][n])
-            _close(props[n].objectness_logits, G["teacher_rpn_logits"][n])
+            if strict:
+                _close(O._bt(props[n].proposal_boxes), G["teacher_rpn_boxes"][n])
+                _close(props[n].objectness_logits, G["teacher_rpn_logits"][n])
+            else:
+                assert len(props[n].objectness_logits) == len(G["teacher_rpn_logits"][n])
+                assert _overlap(O._bt(props[n].proposal_boxes), G["teacher_rpn_boxes"][n], scale) >= 0.995
             ref = G["teacher_roih"][n]
             assert torch.equal(roih[n].pred_classes, ref["pred_classes"])
             _close(O._bt(roih[n].pred_boxes), ref["pred_boxes"])
@@ -177,4 +203,4 @@ def test_config1_full_size_matches_the_reference_models():
                  for d, r in zip(unl, roih)]
         lu, _, _, _ = om(unl_q, branch="unsupervised", danchor=True)
         for k, v in G["unsup_losses"].items():
-            _close(lu[k], v)
+            loss_close(lu[k], v, k)

@@ -417,10 +417,12 @@ def test_nonfinite_proposals_are_dropped_and_flagged(cuda):
         assert bool(torch.isfinite(boxes[n, :c]).all()) and bool(torch.isfinite(scores[n, :c]).all())
 
 
-def test_config1_full_size_vs_reference_model_golden(cuda):
-    """BASELINE.json config 1 at FULL SIZE against the REFERENCE'S OWN MODEL CLASSES
-    (tests/golden/pt_reference_config1_golden.pt, oracle/make_golden_config1.py: Guassian-RCNN-VGG.yaml's model, 1 source
-    + 1 target synthetic 3x800x1333 image, the forward passes of one post-burn-in iteration). CUDA path in the f16x3
+@pytest.mark.parametrize("case", ["config1", "config4"])
+def test_full_size_configs_vs_reference_model_golden(cuda, case):
+    """BASELINE.json config 1 and config 4's model / size at FULL SIZE against the REFERENCE'S OWN MODEL CLASSES
+    (tests/golden/pt_reference_{case}_golden.pt, oracle/make_golden_config1.py: Guassian-RCNN-VGG.yaml's model, 1 source
+    + 1 target synthetic 3x800x1333 image; final_k2c.yaml's K = 1 model with differentiable anchors at 3x600x2000; the
+    forward passes of one post-burn-in iteration). CUDA path in the f16x3
     parity precision, every stage selecting its OWN proposals. Asserted at 1e-3: the RPN losses of both student
     branches (they do not depend on proposal selection); asserted as sets: the teacher's proposals and pseudo labels.
     The ROI-stage losses are printed only: at full size a near-threshold NMS flip changes which rois get sampled
@@ -432,7 +434,7 @@ def test_config1_full_size_vs_reference_model_golden(cuda):
     from probabilisticteacher_b200.modeling.meta_arch.rcnn import build_model
     from probabilisticteacher_b200.structures import Boxes, FreeInstances
     TOL = 1e-3
-    G = torch.load(os.path.join(os.path.dirname(__file__), "golden", "pt_reference_config1_golden.pt"), weights_only=False)
+    G = torch.load(os.path.join(os.path.dirname(__file__), "golden", f"pt_reference_{case}_golden.pt"), weights_only=False)
     H, W, K, N = G["H"], G["W"], G["K"], G["N"]
     cfg = c2f_config()
     cfg.MODEL.ROI_HEADS.NUM_CLASSES = K
