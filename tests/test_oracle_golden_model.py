@@ -204,3 +204,35 @@ def test_full_size_configs_match_the_reference_models(case):
         lu, _, _, _ = om(unl_q, branch="unsupervised", danchor=True)
         for k, v in G["unsup_losses"].items():
             loss_close(lu[k], v, k)
+
+
+@pytest.mark.parametrize("case", ["second_image_empty", "all_empty"])
+def test_unsupervised_branch_without_pseudo_labels(case):
+    """The "empty input" edge of the unsupervised branch: tests/golden/pt_reference_empty_pseudo_golden.pt
+    (oracle/make_golden_empty_pseudo.py) holds the reference's own losses when the teacher produced no pseudo label for
+    one image / for no image at all (then loss_cls = loss_box_reg = NaN, a mean over zero rois, and both RPN losses
+    are 0). The oracle must agree, NaN included."""
+    import math
+    G = torch.load(os.path.join(os.path.dirname(__file__), "golden", "pt_reference_empty_pseudo_golden.pt"), weights_only=False)
+    g = torch.Generator().manual_seed(G["prio_seed"])
+    N, R, L = G["N"], (G["H"] // 16) * (G["W"] // 16) * 9, 2000 + 16
+    prio = {"rpn": (torch.rand(N, R, generator=g), torch.rand(N, R, generator=g)),
+            "roi": (torch.rand(N, L, generator=g), torch.rand(N, L, generator=g))}
+    om = O.OracleRCNN(O.OracleCfg(num_classes=G["K"]), seed=G["weight_seed"])
+    om.sampler = _Sampler(prio)
+    unl = O.synthetic_batch(N, G["H"], G["W"], G["K"], G["unl_seed"], labelled=False)
+    c = G["cases"][case]
+    q = []
+    for d, r, n in zip(unl, G["teacher_roih"], c["keep"]):
+        n = len(r["pred_boxes"]) if n is None else n
+        q.append(dict(d, instances=O.OInst((G["H"], G["W"]), pseudo_boxes=O.OBoxes(r["pred_boxes"][:n]),
+                                           scores_logists=r["scores_logists"][:n], boxes_sigma=r["boxes_sigma"][:n])))
+    with torch.no_grad():
+        lo, _, _, _ = om(q, branch="unsupervised", danchor=True)
+    for k, v in c["losses"].items():
+        if math.isnan(v):
+            assert math.isnan(float(lo[k])), (k, float(lo[k]))
+        else:
+            assert abs(float(lo[k]) - v) <= 2e-5 * max(abs(v), 1e-6), (k, float(lo[k]), v)
+    if case == "all_empty":
+        assert math.isnan(c["losses"]["loss_cls"]) and c["losses"]["loss_rpn_loc"] == 0.0

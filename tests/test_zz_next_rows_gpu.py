@@ -485,3 +485,49 @@ def test_full_size_configs_vs_reference_model_golden(cuda, case):
         for k in ("loss_rpn_cls", "loss_rpn_loc"):
             a, b = float(lu[k]), G["unsup_losses"][k]
             assert abs(a - b) <= TOL * max(abs(b), 1e-6), ("unsup", k, a, b)
+
+
+@pytest.mark.parametrize("case", ["second_image_empty", "all_empty"])
+def test_unsupervised_branch_without_pseudo_labels(cuda, case):
+    """The "empty input" edge of the unsupervised branch against the reference's own model classes
+    (tests/golden/pt_reference_empty_pseudo_golden.pt, oracle/make_golden_empty_pseudo.py): no pseudo label for one
+    image -> all four losses at 1e-3 (f16x3); none at all -> both RPN losses exactly 0, and the ROI losses, which the
+    reference returns as NaN (a mean over zero rois), are NaN or 0 here (a guarded division is acceptable: training has
+    nothing to learn from such a batch either way)."""
+    import math
+    import os
+    from oracle import pt_oracle as O
+    from probabilisticteacher_b200.config import c2f_config
+    from probabilisticteacher_b200.modeling.meta_arch.rcnn import build_model
+    from probabilisticteacher_b200.structures import Boxes, FreeInstances
+    G = torch.load(os.path.join(os.path.dirname(__file__), "golden", "pt_reference_empty_pseudo_golden.pt"), weights_only=False)
+    H, W, K, N = G["H"], G["W"], G["K"], G["N"]
+    model = build_model(c2f_config(), cuda, precision="f16x3", with_grads=False)
+    sd = O.OracleRCNN(O.OracleCfg(num_classes=K), seed=G["weight_seed"]).ref_state_dict()
+    model.load_state_dict({k: v.detach() for k, v in sd.items()})
+    model.train()
+    g = torch.Generator().manual_seed(G["prio_seed"])
+    R, L = (H // 16) * (W // 16) * 9, 2000 + 16
+    model.prio_override = {"rpn": (torch.rand(N, R, generator=g).to(cuda), torch.rand(N, R, generator=g).to(cuda)),
+                           "roi": (torch.rand(N, L, generator=g).to(cuda), torch.rand(N, L, generator=g).to(cuda))}
+    unl = O.synthetic_batch(N, H, W, K, G["unl_seed"], labelled=False)
+    c = G["cases"][case]
+    q = []
+    for d, r, n in zip(unl, G["teacher_roih"], c["keep"]):
+        n = len(r["pred_boxes"]) if n is None else n
+        q.append({"image": d["image"], "height": H, "width": W,
+                  "instances": FreeInstances((H, W), pseudo_boxes=Boxes(r["pred_boxes"][:n].to(cuda)),
+                                             scores_logists=r["scores_logists"][:n].to(cuda),
+                                             boxes_sigma=r["boxes_sigma"][:n].to(cuda))})
+    with torch.no_grad():
+        lu, _, _, _ = model(q, branch="unsupervised", danchor=True)
+    torch.cuda.synchronize()
+    got = {k: float(v) for k, v in lu.items()}
+    print(case, got, c["losses"])
+    for k, v in c["losses"].items():
+        if math.isnan(v):
+            assert math.isnan(got[k]) or got[k] == 0.0, (k, got[k])
+        elif v == 0.0:
+            assert got[k] == 0.0, (k, got[k])
+        else:
+            assert abs(got[k] - v) <= 1e-3 * abs(v), (k, got[k], v)
