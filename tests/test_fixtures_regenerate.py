@@ -32,7 +32,7 @@ def _same(a, b, path="root"):
         for i, (x, y) in enumerate(zip(a, b)):
             _same(x, y, f"{path}[{i}]")
     elif isinstance(a, float):
-        assert a == pytest.approx(b, rel=1e-5, abs=1e-7), path
+        assert a == pytest.approx(b, rel=1e-5, abs=1e-7, nan_ok=True), path
     else:
         assert a == b, path
 
@@ -45,7 +45,8 @@ if os.environ.get("PT_REGEN_ALL") == "1":
     _CASES += [("make_golden_eval.py", "pt_reference_eval_golden.pt"), ("make_golden_burnin.py", "pt_reference_burnin_golden.pt"),
                ("make_golden_model.py", "pt_reference_model_golden.pt"), ("make_golden_step.py", "pt_reference_step_golden.pt"),
                ("make_golden_config1.py", "pt_reference_config1_golden.pt"),
-               ("make_golden_config1.py config4", "pt_reference_config4_golden.pt")]
+               ("make_golden_config1.py config4", "pt_reference_config4_golden.pt"),
+               ("make_golden_empty_pseudo.py", "pt_reference_empty_pseudo_golden.pt")]
 
 
 @pytest.mark.parametrize("script,fixture", _CASES)
