@@ -1,6 +1,7 @@
 """Generates tests/golden/pt_reference_empty_pseudo_golden.pt: the unsupervised branch of the REFERENCE'S OWN MODEL
 CLASSES (`GuassianGeneralizedRCNN.forward(branch="unsupervised", danchor=True)`) when the teacher delivered NO pseudo
-label for one image of the batch, and for none at all -- the "empty input" edge of rows a-6 / a-8 / a-11 / a-15.
+label for one image of the batch, and for none at all -- the "empty input" edge of rows a-6 / a-8 / a-11 / a-15 --
+plus the supervised branch on a batch in which no image has any ground-truth box.
 The reference returns finite losses in the first case and (loss_cls, loss_box_reg) = NaN (a mean over zero rois),
 (loss_rpn_cls, loss_rpn_loc) = 0 in the second.
 
@@ -52,6 +53,14 @@ def main():
             losses, _, _, _ = model(q, branch="unsupervised", danchor=True)
         out["cases"][case] = dict(keep=keep, losses={k: float(v) for k, v in losses.items()})
         print(case, out["cases"][case]["losses"])
+    # supervised branch when NO image of the batch has ground truth (rows a-6 / a-7 / a-11 / a-14): every anchor and
+    # every proposal is background, both regression losses are (minus) zero
+    lab = O.synthetic_batch(N, H, W, K, UNL_SEED + 10, boxes_per_image=0)
+    with torch.no_grad():
+        d2shim_model.PRIO.reset()
+        losses, _, _, _ = model(M.to_ref(lab), branch="supervised")
+    out["supervised_no_gt"] = dict(lab_seed=UNL_SEED + 10, losses={k: float(v) for k, v in losses.items()})
+    print("supervised_no_gt", out["supervised_no_gt"]["losses"])
     dst = os.path.join(os.environ.get("PT_GOLDEN_DIR", os.path.join(ROOT, "tests", "golden")), "pt_reference_empty_pseudo_golden.pt")
     torch.save(out, dst)
     print("wrote", dst, os.path.getsize(dst), "bytes")

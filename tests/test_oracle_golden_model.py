@@ -236,3 +236,22 @@ def test_unsupervised_branch_without_pseudo_labels(case):
             assert abs(float(lo[k]) - v) <= 2e-5 * max(abs(v), 1e-6), (k, float(lo[k]), v)
     if case == "all_empty":
         assert math.isnan(c["losses"]["loss_cls"]) and c["losses"]["loss_rpn_loc"] == 0.0
+
+
+def test_supervised_branch_without_any_ground_truth():
+    """Same fixture: a supervised batch in which NO image has a ground-truth box (every anchor / proposal is
+    background; the reference returns -0.0 for both regression losses)."""
+    G = torch.load(os.path.join(os.path.dirname(__file__), "golden", "pt_reference_empty_pseudo_golden.pt"), weights_only=False)
+    g = torch.Generator().manual_seed(G["prio_seed"])
+    N, R, L = G["N"], (G["H"] // 16) * (G["W"] // 16) * 9, 2000 + 16
+    prio = {"rpn": (torch.rand(N, R, generator=g), torch.rand(N, R, generator=g)),
+            "roi": (torch.rand(N, L, generator=g), torch.rand(N, L, generator=g))}
+    om = O.OracleRCNN(O.OracleCfg(num_classes=G["K"]), seed=G["weight_seed"])
+    om.sampler = _Sampler(prio)
+    c = G["supervised_no_gt"]
+    lab = O.synthetic_batch(N, G["H"], G["W"], G["K"], c["lab_seed"], boxes_per_image=0)
+    with torch.no_grad():
+        lo, _, _, _ = om(lab, branch="supervised")
+    for k, v in c["losses"].items():
+        assert abs(float(lo[k]) - v) <= 2e-5 * max(abs(v), 1e-6), (k, float(lo[k]), v)
+    assert c["losses"]["loss_box_reg"] == 0.0 and c["losses"]["loss_rpn_loc"] == 0.0 and c["losses"]["loss_cls"] > 1.0

@@ -531,3 +531,38 @@ def test_unsupervised_branch_without_pseudo_labels(cuda, case):
             assert got[k] == 0.0, (k, got[k])
         else:
             assert abs(got[k] - v) <= 1e-3 * abs(v), (k, got[k], v)
+
+
+def test_supervised_branch_without_any_ground_truth(cuda):
+    """A supervised batch in which NO image has a ground-truth box, against the reference's own model classes
+    (tests/golden/pt_reference_empty_pseudo_golden.pt): classification losses at 1e-3 (f16x3), both regression losses
+    zero."""
+    import os
+    from oracle import pt_oracle as O
+    from probabilisticteacher_b200.config import c2f_config
+    from probabilisticteacher_b200.modeling.meta_arch.rcnn import build_model
+    from probabilisticteacher_b200.structures import Boxes, FreeInstances
+    G = torch.load(os.path.join(os.path.dirname(__file__), "golden", "pt_reference_empty_pseudo_golden.pt"), weights_only=False)
+    H, W, K, N = G["H"], G["W"], G["K"], G["N"]
+    model = build_model(c2f_config(), cuda, precision="f16x3", with_grads=False)
+    sd = O.OracleRCNN(O.OracleCfg(num_classes=K), seed=G["weight_seed"]).ref_state_dict()
+    model.load_state_dict({k: v.detach() for k, v in sd.items()})
+    model.train()
+    g = torch.Generator().manual_seed(G["prio_seed"])
+    R, L = (H // 16) * (W // 16) * 9, 2000 + 16
+    model.prio_override = {"rpn": (torch.rand(N, R, generator=g).to(cuda), torch.rand(N, R, generator=g).to(cuda)),
+                           "roi": (torch.rand(N, L, generator=g).to(cuda), torch.rand(N, L, generator=g).to(cuda))}
+    c = G["supervised_no_gt"]
+    lab = [{"image": d["image"], "height": H, "width": W,
+            "instances": FreeInstances((H, W), gt_boxes=Boxes(torch.zeros(0, 4)), gt_classes=torch.zeros(0, dtype=torch.int64))}
+           for d in O.synthetic_batch(N, H, W, K, c["lab_seed"], boxes_per_image=0)]
+    with torch.no_grad():
+        ls, _, _, _ = model(lab, branch="supervised")
+    torch.cuda.synchronize()
+    got = {k: float(v) for k, v in ls.items()}
+    print(got, c["losses"])
+    for k, v in c["losses"].items():
+        if v == 0.0:
+            assert abs(got[k]) <= 1e-12, (k, got[k])
+        else:
+            assert abs(got[k] - v) <= 1e-3 * abs(v), (k, got[k], v)
