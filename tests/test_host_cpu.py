@@ -191,6 +191,12 @@ def test_detector_postprocess():
     assert res[0]["instances"].pred_boxes.tensor[0].tolist() == [5., 10., 55., 110.]
     with pytest.raises(AssertionError):
         detector_postprocess(FreeInstances((10, 10), scores=torch.ones(1)), 10, 10)
+    # no detection at all (device count 0 over a fixed-capacity buffer): an empty instance at the requested size
+    none = FreeInstances((300, 400), pred_boxes=Boxes(torch.zeros(100, 4)), scores=torch.zeros(100),
+                         pred_classes=torch.zeros(100, dtype=torch.int64))
+    none._count = torch.tensor(0)
+    e = detector_postprocess(none, 600, 800)
+    assert len(e) == 0 and e.image_size == (600, 800) and e.pred_boxes.tensor.shape == (0, 4) and e.scores.shape == (0,)
 
 
 def test_bench_reference_arm_prints_the_contract_line():
