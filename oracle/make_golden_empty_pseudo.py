@@ -53,6 +53,23 @@ def main():
             losses, _, _, _ = model(q, branch="unsupervised", danchor=True)
         out["cases"][case] = dict(keep=keep, losses={k: float(v) for k, v in losses.items()})
         print(case, out["cases"][case]["losses"])
+    # the unsupervised branch under other UNSUPNET settings than train.sh's (configs/pt/final_c2f.yaml itself says
+    # TAU [0.25, 0.25]; EFL off; other EFL_LAMBDA exponents), full pseudo labels: exercises the `efl` / `tau` /
+    # `lambda` arguments of the loss kernels
+    out["unsupnet_variants"] = []
+    for efl, tau, lam in ((False, [0.25, 0.25], [0.5, 0.5]), (True, [0.5, 0.25], [1.0, 2.0])):
+        vcfg = c2f_config()
+        vcfg.UNSUPNET.EFL, vcfg.UNSUPNET.TAU, vcfg.UNSUPNET.EFL_LAMBDA = efl, tau, lam
+        vmodel = M.build_reference_model(vcfg, {k: v.detach().clone() for k, v in sd.items()})
+        vmodel.train()
+        q = [dict(d, instances=M.FreeInstances(p.image_size, pseudo_boxes=M.Boxes(p.pred_boxes.tensor.clone()),
+                                               scores_logists=p.scores_logists.clone(), boxes_sigma=p.boxes_sigma.clone()))
+             for d, p in zip(M.to_ref(unl), roih)]
+        with torch.no_grad():
+            d2shim_model.PRIO.reset()
+            losses, _, _, _ = vmodel(q, branch="unsupervised", danchor=True)
+        out["unsupnet_variants"].append(dict(efl=efl, tau=tau, efl_lambda=lam, losses={k: float(v) for k, v in losses.items()}))
+        print("variant", efl, tau, lam, out["unsupnet_variants"][-1]["losses"])
     # supervised branch when NO image of the batch has ground truth (rows a-6 / a-7 / a-11 / a-14): every anchor and
     # every proposal is background, both regression losses are (minus) zero
     lab = O.synthetic_batch(N, H, W, K, UNL_SEED + 10, boxes_per_image=0)

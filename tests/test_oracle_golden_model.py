@@ -255,3 +255,25 @@ def test_supervised_branch_without_any_ground_truth():
     for k, v in c["losses"].items():
         assert abs(float(lo[k]) - v) <= 2e-5 * max(abs(v), 1e-6), (k, float(lo[k]), v)
     assert c["losses"]["loss_box_reg"] == 0.0 and c["losses"]["loss_rpn_loc"] == 0.0 and c["losses"]["loss_cls"] > 1.0
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+def test_unsupervised_branch_other_unsupnet_settings(variant):
+    """Same fixture: the unsupervised branch of the reference's own classes with EFL off / TAU [0.25, 0.25] (the value
+    configs/pt/final_c2f.yaml itself carries) and with EFL_LAMBDA [1, 2] / TAU [0.5, 0.25]."""
+    G = torch.load(os.path.join(os.path.dirname(__file__), "golden", "pt_reference_empty_pseudo_golden.pt"), weights_only=False)
+    v = G["unsupnet_variants"][variant]
+    g = torch.Generator().manual_seed(G["prio_seed"])
+    N, R, L = G["N"], (G["H"] // 16) * (G["W"] // 16) * 9, 2000 + 16
+    prio = {"rpn": (torch.rand(N, R, generator=g), torch.rand(N, R, generator=g)),
+            "roi": (torch.rand(N, L, generator=g), torch.rand(N, L, generator=g))}
+    om = O.OracleRCNN(O.OracleCfg(num_classes=G["K"], efl=v["efl"], tau=tuple(v["tau"]), efl_lambda=tuple(v["efl_lambda"])),
+                      seed=G["weight_seed"])
+    om.sampler = _Sampler(prio)
+    unl = O.synthetic_batch(N, G["H"], G["W"], G["K"], G["unl_seed"], labelled=False)
+    q = [dict(d, instances=O.OInst((G["H"], G["W"]), pseudo_boxes=O.OBoxes(r["pred_boxes"]), scores_logists=r["scores_logists"],
+                                   boxes_sigma=r["boxes_sigma"])) for d, r in zip(unl, G["teacher_roih"])]
+    with torch.no_grad():
+        lo, _, _, _ = om(q, branch="unsupervised", danchor=True)
+    for k, ref in v["losses"].items():
+        assert abs(float(lo[k]) - ref) <= 2e-5 * max(abs(ref), 1e-6), (k, float(lo[k]), ref)

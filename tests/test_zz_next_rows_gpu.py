@@ -566,3 +566,41 @@ def test_supervised_branch_without_any_ground_truth(cuda):
             assert abs(got[k]) <= 1e-12, (k, got[k])
         else:
             assert abs(got[k] - v) <= 1e-3 * abs(v), (k, got[k], v)
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+def test_unsupervised_branch_other_unsupnet_settings(cuda, variant):
+    """The `efl` / `tau` / `lambda` arguments of the unsupervised loss kernels away from train.sh's values (EFL off with
+    TAU [0.25, 0.25], the value configs/pt/final_c2f.yaml itself carries; EFL_LAMBDA [1, 2] with TAU [0.5, 0.25]) against
+    the reference's own model classes (tests/golden/pt_reference_empty_pseudo_golden.pt): all four losses of the
+    unsupervised branch at 1e-3 in the f16x3 precision."""
+    import os
+    from oracle import pt_oracle as O
+    from probabilisticteacher_b200.config import c2f_config
+    from probabilisticteacher_b200.modeling.meta_arch.rcnn import build_model
+    from probabilisticteacher_b200.structures import Boxes, FreeInstances
+    G = torch.load(os.path.join(os.path.dirname(__file__), "golden", "pt_reference_empty_pseudo_golden.pt"), weights_only=False)
+    v = G["unsupnet_variants"][variant]
+    H, W, K, N = G["H"], G["W"], G["K"], G["N"]
+    cfg = c2f_config()
+    cfg.UNSUPNET.EFL, cfg.UNSUPNET.TAU, cfg.UNSUPNET.EFL_LAMBDA = v["efl"], list(v["tau"]), list(v["efl_lambda"])
+    model = build_model(cfg, cuda, precision="f16x3", with_grads=False)
+    sd = O.OracleRCNN(O.OracleCfg(num_classes=K), seed=G["weight_seed"]).ref_state_dict()
+    model.load_state_dict({k: t.detach() for k, t in sd.items()})
+    model.train()
+    g = torch.Generator().manual_seed(G["prio_seed"])
+    R, L = (H // 16) * (W // 16) * 9, 2000 + 16
+    model.prio_override = {"rpn": (torch.rand(N, R, generator=g).to(cuda), torch.rand(N, R, generator=g).to(cuda)),
+                           "roi": (torch.rand(N, L, generator=g).to(cuda), torch.rand(N, L, generator=g).to(cuda))}
+    unl = O.synthetic_batch(N, H, W, K, G["unl_seed"], labelled=False)
+    q = [{"image": d["image"], "height": H, "width": W,
+          "instances": FreeInstances((H, W), pseudo_boxes=Boxes(r["pred_boxes"].to(cuda)),
+                                     scores_logists=r["scores_logists"].to(cuda), boxes_sigma=r["boxes_sigma"].to(cuda))}
+         for d, r in zip(unl, G["teacher_roih"])]
+    with torch.no_grad():
+        lu, _, _, _ = model(q, branch="unsupervised", danchor=True)
+    torch.cuda.synchronize()
+    got = {k: float(t) for k, t in lu.items()}
+    print(v["efl"], v["tau"], v["efl_lambda"], got, v["losses"])
+    for k, ref in v["losses"].items():
+        assert abs(got[k] - ref) <= 1e-3 * abs(ref), (k, got[k], ref)
