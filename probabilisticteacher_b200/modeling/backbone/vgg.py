@@ -77,4 +77,9 @@ class VGG(nn.Module):
 @BACKBONE_REGISTRY.register()
 def build_vgg_backbone(cfg, arena, loss_scale):
     assert cfg.MODEL.VGG.DEPTH == 16, "only VGG16 is on the hot path (configs/Guassian-RCNN-VGG.yaml:8)"
+    if cfg.MODEL.BACKBONE.FREEZE_AT < 1:
+        # vgg.py:175-180 freezes blocks 1..FREEZE_AT (detectron2 default 2, which every reference config keeps). The
+        # first conv is fused with the uint8 pre-processing and has no weight-gradient kernel: refusing is better
+        # than training with a conv1_1 that silently never receives a gradient.
+        raise ValueError("MODEL.BACKBONE.FREEZE_AT must be >= 1 on this path (vgg_block1.conv1 is forward-only)")
     return VGG(arena, loss_scale)

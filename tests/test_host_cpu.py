@@ -387,3 +387,15 @@ def test_product_code_never_imports_the_oracle():
     allowed = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "cpu_oracle_iters_per_s"]
     lo, hi = allowed[0].lineno, allowed[0].end_lineno
     assert all(lo <= line <= hi for _, line in hits), hits
+
+
+def test_unsupported_freeze_at_is_refused():
+    """FREEZE_AT = 0 would leave the fused, forward-only first conv in the trainable set without a gradient kernel:
+    the builder refuses it instead of training silently wrong (every reference config keeps detectron2's default 2)."""
+    from probabilisticteacher_b200.config import c2f_config
+    from probabilisticteacher_b200.modeling.backbone.vgg import build_vgg_backbone
+    cfg = c2f_config()
+    assert cfg.MODEL.BACKBONE.FREEZE_AT == 2
+    cfg.MODEL.BACKBONE.FREEZE_AT = 0
+    with pytest.raises(ValueError, match="FREEZE_AT"):
+        build_vgg_backbone(cfg, None, 1024.0)
