@@ -173,3 +173,50 @@ def k2c_config():
     c = c2f_config()
     c.MODEL.ROI_HEADS.NUM_CLASSES = 1
     return c
+
+
+def validate_cfg(cfg):
+    """Refuses configurations whose value the reference honours but this path would silently ignore (the kernels are
+    specialised to the structure every reference config uses: configs/Guassian-RCNN-VGG.yaml + configs/pt/*.yaml on
+    detectron2 v0.5 defaults). Raises ValueError naming the key. Values that ARE honoured (thresholds, batch sizes,
+    top-k sizes, loss weights, UNSUPNET.*, NUM_CLASSES, anchor shapes, pixel statistics ...) are not restricted."""
+    m = cfg.MODEL
+
+    def need(key, ok, why):
+        if not ok:
+            raise ValueError(f"{key}: unsupported value on the B200 path ({why})")
+
+    need("MODEL.MASK_ON", not m.MASK_ON, "box heads only")
+    need("MODEL.VGG.DEPTH", m.VGG.DEPTH == 16, "VGG16 backbone")
+    need("MODEL.VGG.OUT_FEATURES", list(m.VGG.OUT_FEATURES) == ["vgg_block5"], "single stride-16 feature map")
+    need("MODEL.VGG.NORM", str(m.VGG.NORM) in ("None", ""), "no normalisation layers (pt/config.py:74)")
+    need("MODEL.BACKBONE.FREEZE_AT", m.BACKBONE.FREEZE_AT >= 1, "the fused first conv is forward-only")
+    n_cell = len(m.ANCHOR_GENERATOR.SIZES[0]) * len(m.ANCHOR_GENERATOR.ASPECT_RATIOS[0])
+    if m.ANCHOR_GENERATOR.NAME == "DefaultAnchorGenerator":
+        need("MODEL.ANCHOR_GENERATOR.SIZES x ASPECT_RATIOS", len(m.ANCHOR_GENERATOR.SIZES) == 1 and n_cell == 9,
+             "9 cell anchors on one level")
+    else:
+        need("MODEL.ANCHOR_GENERATOR.ANCHOR", len(m.ANCHOR_GENERATOR.ANCHOR) == 1 and len(m.ANCHOR_GENERATOR.ANCHOR[0]) == 9,
+             "9 learnable (w, h) pairs on one level (pt/config.py:84-92)")
+    r = m.RPN
+    need("MODEL.RPN.IN_FEATURES", list(r.IN_FEATURES) == ["vgg_block5"], "single level")
+    need("MODEL.RPN.IOU_LABELS", list(r.IOU_LABELS) == [0, -1, 1] and len(r.IOU_THRESHOLDS) == 2, "bg / ignore / fg matcher")
+    need("MODEL.RPN.BOUNDARY_THRESH", r.BOUNDARY_THRESH == -1, "no anchor boundary filter")
+    need("MODEL.RPN.BBOX_REG_WEIGHTS", tuple(float(x) for x in r.BBOX_REG_WEIGHTS) == (1.0, 1.0, 1.0, 1.0), "unit weights")
+    need("MODEL.RPN.BBOX_REG_LOSS_WEIGHT", float(r.BBOX_REG_LOSS_WEIGHT) == 1.0, "LOSS_WEIGHT scales both RPN losses")
+    h = m.ROI_HEADS
+    need("MODEL.ROI_HEADS.IN_FEATURES", list(h.IN_FEATURES) == ["vgg_block5"], "single level")
+    need("MODEL.ROI_HEADS.IOU_LABELS", list(h.IOU_LABELS) == [0, 1] and len(h.IOU_THRESHOLDS) == 1, "bg / fg matcher")
+    need("MODEL.ROI_HEADS.PROPOSAL_APPEND_GT", bool(h.PROPOSAL_APPEND_GT), "ground truth is always appended")
+    need("MODEL.ROI_HEADS.NUM_CLASSES", 1 <= h.NUM_CLASSES <= 14, "cls_score + bbox_pred share one 128-row block: K + 1 + 8K <= 128")
+    b = m.ROI_BOX_HEAD
+    need("MODEL.ROI_BOX_HEAD.NAME", b.NAME == "FastRCNNConvFCHead" and b.NUM_FC == 2 and b.NUM_CONV == 0, "two FC layers")
+    need("MODEL.ROI_BOX_HEAD.FC_DIM", b.FC_DIM % 256 == 0, "GEMM tile width")
+    need("MODEL.ROI_BOX_HEAD.POOLER_RESOLUTION", b.POOLER_RESOLUTION == 7, "ROIAlign kernel geometry")
+    need("MODEL.ROI_BOX_HEAD.POOLER_TYPE", b.POOLER_TYPE == "ROIAlignV2" and b.POOLER_SAMPLING_RATIO == 0,
+         "aligned ROIAlign with the adaptive sampling grid")
+    need("MODEL.ROI_BOX_HEAD.CLS_AGNOSTIC_BBOX_REG", not b.CLS_AGNOSTIC_BBOX_REG, "class-specific Gaussian box head")
+    need("MODEL.ROI_BOX_HEAD.TRAIN_ON_PRED_BOXES", not b.TRAIN_ON_PRED_BOXES, "")
+    need("MODEL.ROI_BOX_HEAD.BBOX_REG_LOSS_WEIGHT", float(b.BBOX_REG_LOSS_WEIGHT) == 1.0, "")
+    need("UNSUPNET.MODEL_TYPE", cfg.UNSUPNET.MODEL_TYPE == "GUASSIAN", "Gaussian heads only")
+    return cfg

@@ -18,6 +18,7 @@ from torch import nn
 from ... import ops
 from ..._lib import call, refresh_stream
 from ...arena import ParamArena
+from ...config import validate_cfg
 from ...structures import Boxes, FreeInstances
 from ..anchor_generator import ANCHOR_GENERATOR_REGISTRY
 from ..backbone.vgg import build_vgg_backbone  # noqa: F401  (registers)
@@ -51,6 +52,7 @@ class GuassianGeneralizedRCNN(nn.Module):
         dev = torch.device(device or cfg.MODEL.DEVICE)
         if dev.type != "cuda":
             raise RuntimeError("probabilisticteacher_b200 has no CPU path: a CUDA device is required")
+        validate_cfg(cfg)  # refuse settings the reference honours but these kernels would silently ignore
         diff = cfg.MODEL.ANCHOR_GENERATOR.NAME == "DifferentiableAnchorGenerator"
         self.arena = ParamArena(num_classes=cfg.MODEL.ROI_HEADS.NUM_CLASSES, num_cell=9,
                                 fc_dim=cfg.MODEL.ROI_BOX_HEAD.FC_DIM,

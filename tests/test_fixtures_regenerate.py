@@ -40,6 +40,7 @@ def _same(a, b, path="root"):
 # The whole-model fixtures (convolutions -> discrete proposal selection) take ~25 s each to regenerate and were checked
 # byte-identical when committed; they are re-run only on request (PT_REGEN_ALL=1) to keep the CPU suite short.
 _CASES = [("make_golden_loader.py", "pt_reference_loader_golden.json"), ("make_golden_lr.py", "pt_reference_lr_golden.json"),
+          ("make_golden_cfg.py", "pt_reference_cfg_golden.json"),
           ("make_golden.py", "pt_reference_golden.pt")]
 if os.environ.get("PT_REGEN_ALL") == "1":
     _CASES += [("make_golden_eval.py", "pt_reference_eval_golden.pt"), ("make_golden_burnin.py", "pt_reference_burnin_golden.pt"),

@@ -399,3 +399,89 @@ def test_unsupported_freeze_at_is_refused():
     cfg.MODEL.BACKBONE.FREEZE_AT = 0
     with pytest.raises(ValueError, match="FREEZE_AT"):
         build_vgg_backbone(cfg, None, 1024.0)
+
+
+def _leaves(d, prefix=""):
+    for k, v in d.items():
+        if isinstance(v, dict):
+            yield from _leaves(v, prefix + k + ".")
+        else:
+            yield prefix + k, v
+
+
+def _norm(v):
+    import ast
+    if isinstance(v, str):
+        try:
+            v = ast.literal_eval(v)
+        except (ValueError, SyntaxError):
+            pass
+    if isinstance(v, (list, tuple)):
+        return [_norm(x) for x in v]
+    return v
+
+
+def test_config_helpers_restate_the_reference_yaml_files():
+    """tests/golden/pt_reference_cfg_golden.json = the reference's own yaml files (base + child, parsed independently of
+    the package's loader by oracle/make_golden_cfg.py) and train.sh's overrides. Every value they set on the hot path
+    must be what `c2f_config()` / `k2c_config()` -- the configurations bench.py and the tests run -- carry."""
+    import json
+    from probabilisticteacher_b200.config import c2f_config, k2c_config, validate_cfg
+    G = json.load(open(os.path.join(ROOT, "tests", "golden", "pt_reference_cfg_golden.json")))
+    off_path = ("DATASETS.", "DATALOADER.", "OUTPUT_DIR", "TEST.EVALUATOR", "INPUT.")  # data pipeline / bookkeeping
+    for name, helper in (("final_c2f", c2f_config), ("final_k2c", k2c_config)):
+        want = dict(_leaves(G[name]))
+        want.update(G["train_sh"])
+        cfg = validate_cfg(helper())
+        have = dict(_leaves(cfg))
+        checked = 0
+        for k, v in want.items():
+            if k.startswith(off_path):
+                continue
+            assert k in have, (name, k)
+            assert _norm(have[k]) == _norm(v), (name, k, have[k], v)
+            checked += 1
+        assert checked >= 40
+    # the other three reference configs differ from these two only off the hot path
+    for other, same_as in (("final_c2b", "final_c2f"), ("final_c2f_0.02", "final_c2f"), ("final_s2c", "final_k2c")):
+        a = {k: v for k, v in _leaves(G[other]) if not k.startswith(off_path)}
+        b = {k: v for k, v in _leaves(G[same_as]) if not k.startswith(off_path)}
+        assert a == b, other
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/configs"), reason="reference tree not mounted")
+def test_reference_yaml_files_load_through_the_package_config():
+    """`get_cfg().merge_from_file(<the reference's own yaml>)` (with its `_BASE_` chain) + train.sh's overrides gives
+    a configuration the B200 path accepts and that equals the helper on every hot-path key."""
+    from probabilisticteacher_b200.config import c2f_config, get_cfg, validate_cfg
+    c = get_cfg()
+    c.merge_from_file("/root/reference/configs/pt/final_c2f.yaml")
+    c.merge_from_list(["MODEL.ANCHOR_GENERATOR.NAME", "DifferentiableAnchorGenerator", "UNSUPNET.EFL", "True",
+                       "UNSUPNET.EFL_LAMBDA", "[0.5,0.5]", "UNSUPNET.TAU", "[0.5,0.5]"])
+    validate_cfg(c)
+    a, b = dict(_leaves(c)), dict(_leaves(c2f_config()))
+    off_path = ("DATASETS.", "DATALOADER.", "OUTPUT_DIR", "TEST.EVALUATOR")
+    diff = {k for k in set(a) | set(b) if not k.startswith(off_path) and _norm(a.get(k)) != _norm(b.get(k))}
+    assert not diff, diff
+
+
+def test_validate_cfg_names_the_unsupported_key():
+    from probabilisticteacher_b200.config import c2f_config, validate_cfg
+    cases = [("MODEL.ROI_HEADS.NUM_CLASSES", 20), ("MODEL.ROI_BOX_HEAD.NUM_FC", 3), ("MODEL.ROI_BOX_HEAD.POOLER_RESOLUTION", 14),
+             ("MODEL.RPN.BBOX_REG_WEIGHTS", (1.0, 1.0, 2.0, 2.0)), ("MODEL.ROI_BOX_HEAD.CLS_AGNOSTIC_BBOX_REG", True),
+             ("MODEL.BACKBONE.FREEZE_AT", 0), ("MODEL.MASK_ON", True), ("UNSUPNET.MODEL_TYPE", "LAPLACE"),
+             ("MODEL.ANCHOR_GENERATOR.ANCHOR", [[[10.0, 10.0]] * 5])]
+    for key, bad in cases:
+        cfg = c2f_config()
+        node = cfg
+        *parents, leaf = key.split(".")
+        for p in parents:
+            node = node[p]
+        node[leaf] = bad
+        with pytest.raises(ValueError, match=key.split(".")[-2]):
+            validate_cfg(cfg)
+    cfg = c2f_config()
+    cfg.MODEL.ANCHOR_GENERATOR.NAME = "DefaultAnchorGenerator"
+    cfg.MODEL.ANCHOR_GENERATOR.SIZES = [[32, 64, 128, 256, 512]]
+    with pytest.raises(ValueError, match="ANCHOR_GENERATOR"):
+        validate_cfg(cfg)
