@@ -277,3 +277,34 @@ def test_unsupervised_branch_other_unsupnet_settings(variant):
         lo, _, _, _ = om(q, branch="unsupervised", danchor=True)
     for k, ref in v["losses"].items():
         assert abs(float(lo[k]) - ref) <= 2e-5 * max(abs(ref), 1e-6), (k, float(lo[k]), ref)
+
+
+def test_every_hyper_parameter_away_from_its_default():
+    """tests/golden/pt_reference_oddcfg_golden.pt (oracle/make_golden_oddcfg.py): the reference's own model classes
+    under a configuration where every honoured hyper-parameter differs from the defaults. The oracle, configured
+    likewise, reproduces all 8 losses, the teacher's proposals and its (here 20) pseudo labels."""
+    G = torch.load(os.path.join(os.path.dirname(__file__), "golden", "pt_reference_oddcfg_golden.pt"), weights_only=False)
+    g = torch.Generator().manual_seed(G["prio_seed"])
+    N, R, L = G["N"], (G["H"] // 16) * (G["W"] // 16) * 9, G["roi_prio_len"]
+    prio = {"rpn": (torch.rand(N, R, generator=g), torch.rand(N, R, generator=g)),
+            "roi": (torch.rand(N, L, generator=g), torch.rand(N, L, generator=g))}
+    om = O.OracleRCNN(O.OracleCfg(num_classes=G["K"], **G["oracle_kw"]), seed=G["weight_seed"])
+    om.sampler = _Sampler(prio)
+    lab = O.synthetic_batch(N, G["H"], G["W"], G["K"], G["lab_seed"], boxes_per_image=4)
+    unl = O.synthetic_batch(N, G["H"], G["W"], G["K"], G["unl_seed"], labelled=False)
+    with torch.no_grad():
+        ls, _, _, _ = om(lab, branch="supervised")
+        for k, v in G["sup_losses"].items():
+            _close(ls[k], v)
+        _, props, roih, _ = om(unl, branch="unsup_data_weak")
+        for n in range(N):
+            _close(O._bt(props[n].proposal_boxes), G["teacher_rpn_boxes"][n])
+            ref = G["teacher_roih"][n]
+            assert len(ref["scores"]) == 20 and torch.equal(roih[n].pred_classes, ref["pred_classes"])
+            _close(O._bt(roih[n].pred_boxes), ref["pred_boxes"])
+            _close(roih[n].scores, ref["scores"])
+        q = [dict(d, instances=O.OInst(r.image_size, pseudo_boxes=O.OBoxes(O._bt(r.pred_boxes)), scores_logists=r.scores_logists,
+                                       boxes_sigma=r.boxes_sigma)) for d, r in zip(unl, roih)]
+        lu, _, _, _ = om(q, branch="unsupervised", danchor=True)
+        for k, v in G["unsup_losses"].items():
+            _close(lu[k], v)

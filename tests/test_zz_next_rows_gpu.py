@@ -604,3 +604,63 @@ def test_unsupervised_branch_other_unsupnet_settings(cuda, variant):
     print(v["efl"], v["tau"], v["efl_lambda"], got, v["losses"])
     for k, ref in v["losses"].items():
         assert abs(got[k] - ref) <= 1e-3 * abs(ref), (k, got[k], ref)
+
+
+def test_every_hyper_parameter_away_from_its_default(cuda):
+    """The CUDA path (f16x3) under a configuration in which EVERY honoured hyper-parameter differs from the defaults
+    (pixel std, anchor offset, RPN / ROI IoU thresholds, batch sizes, fractions, top-k sizes 300 / 50, pseudo-label filter
+    thresholds, 20 detections per image, box-regression weights), against the reference's own model classes
+    (tests/golden/pt_reference_oddcfg_golden.pt, oracle/make_golden_oddcfg.py): a kernel or wrapper that ignored one of
+    them cannot reproduce these losses."""
+    import os
+    from oracle import pt_oracle as O
+    from probabilisticteacher_b200.config import c2f_config
+    from probabilisticteacher_b200.modeling.meta_arch.rcnn import build_model
+    from probabilisticteacher_b200.structures import Boxes, FreeInstances
+    TOL = 1e-3
+    G = torch.load(os.path.join(os.path.dirname(__file__), "golden", "pt_reference_oddcfg_golden.pt"), weights_only=False)
+    H, W, K, N = G["H"], G["W"], G["K"], G["N"]
+    cfg = c2f_config()
+    for key, value in G["overrides"]:
+        node = cfg
+        *parents, leaf = key.split(".")
+        for p in parents:
+            node = node[p]
+        node[leaf] = value
+    model = build_model(cfg, cuda, precision="f16x3", with_grads=False)
+    sd = O.OracleRCNN(O.OracleCfg(num_classes=K, **G["oracle_kw"]), seed=G["weight_seed"]).ref_state_dict()
+    model.load_state_dict({k: t.detach() for k, t in sd.items()})
+    model.train()
+    g = torch.Generator().manual_seed(G["prio_seed"])
+    R, L = (H // 16) * (W // 16) * 9, G["roi_prio_len"]
+    model.prio_override = {"rpn": (torch.rand(N, R, generator=g).to(cuda), torch.rand(N, R, generator=g).to(cuda)),
+                           "roi": (torch.rand(N, L, generator=g).to(cuda), torch.rand(N, L, generator=g).to(cuda))}
+    lab = [{"image": d["image"], "height": H, "width": W,
+            "instances": FreeInstances((H, W), gt_boxes=Boxes(d["instances"].gt_boxes.tensor.clone()),
+                                       gt_classes=d["instances"].gt_classes.clone())}
+           for d in O.synthetic_batch(N, H, W, K, G["lab_seed"], boxes_per_image=4)]
+    unl = [{"image": d["image"], "height": H, "width": W} for d in O.synthetic_batch(N, H, W, K, G["unl_seed"], labelled=False)]
+    scale = float(max(H, W))
+    with torch.no_grad():
+        ls, _, _, _ = model(lab, branch="supervised")
+        print("sup", {k: (round(float(ls[k]), 5), round(v, 5)) for k, v in G["sup_losses"].items()})
+        for k, v in G["sup_losses"].items():
+            assert abs(float(ls[k]) - v) <= TOL * abs(v), ("sup", k, float(ls[k]), v)
+        _, pg, rg, _ = model(unl, branch="unsup_data_weak")
+        for n in range(N):
+            p, ref_boxes = pg[n].trim(), G["teacher_rpn_boxes"][n]
+            assert len(p) == len(ref_boxes), (len(p), len(ref_boxes))
+            d = (p.proposal_boxes.tensor.double().cpu()[:, None, :] - ref_boxes.double()[None, :, :]).abs().amax(-1) / scale
+            assert float((d.min(1).values < TOL).double().mean()) >= 0.9
+            det, ref = rg[n].trim(), G["teacher_roih"][n]
+            assert len(det) == len(ref["scores"]) == 20
+            dd = (det.pred_boxes.tensor.double().cpu()[:, None, :] - ref["pred_boxes"].double()[None, :, :]).abs().amax(-1) / scale
+            dd[det.pred_classes.cpu()[:, None] != ref["pred_classes"][None, :]] = 1e9
+            assert float((dd.min(1).values < TOL).double().mean()) >= 0.9
+        q = [dict(d, instances=FreeInstances((H, W), pseudo_boxes=Boxes(r["pred_boxes"].to(cuda)),
+                                             scores_logists=r["scores_logists"].to(cuda), boxes_sigma=r["boxes_sigma"].to(cuda)))
+             for d, r in zip(unl, G["teacher_roih"])]
+        lu, _, _, _ = model(q, branch="unsupervised", danchor=True)
+        print("unsup", {k: (round(float(lu[k]), 5), round(v, 5)) for k, v in G["unsup_losses"].items()})
+        for k, v in G["unsup_losses"].items():
+            assert abs(float(lu[k]) - v) <= TOL * abs(v), ("unsup", k, float(lu[k]), v)
