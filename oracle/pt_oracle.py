@@ -867,11 +867,14 @@ def clip_gradient(params, clip_norm):
 
 
 def run_step(student: OracleRCNN, teacher: OracleRCNN, optimizer, data, cfg: OracleCfg, ratios_unlabel,
-             ratios_label, keep_rate=None):
+             ratios_label, keep_rate=None, update_teacher=True):
     """One post-burn-in iteration, pt/engine/trainer.py:291-392. data = (label_q, label_k, unlabel_q,
-    unlabel_k) lists of dicts. Returns the dict of the 8 weighted losses (floats)."""
+    unlabel_k) lists of dicts. Returns the 8 losses as the reference logs them (floats, UNWEIGHTED: `metrics_dict =
+    record_dict`, :379-381; SOURCE_LOSS_WEIGHT / TARGET_UNSUP_LOSS_WEIGHT only enter the sum that is back-propagated,
+    :364-377). update_teacher=False: an iteration at which (iter - BURN_UP_STEP) % TEACHER_UPDATE_ITER != 0 (:296-301)."""
     label_q, label_k, unlabel_q, unlabel_k = data
-    ema_update(teacher, student, cfg.ema_keep_rate if keep_rate is None else keep_rate)
+    if update_teacher:
+        ema_update(teacher, student, cfg.ema_keep_rate if keep_rate is None else keep_rate)
     with torch.no_grad():
         _, _, roih, _ = teacher(unlabel_k, branch="unsup_data_weak")
     pseudo = [OInst(r.image_size, pseudo_boxes=OBoxes(_bt(r.pred_boxes)), scores_logists=r.scores_logists,
@@ -882,11 +885,12 @@ def run_step(student: OracleRCNN, teacher: OracleRCNN, optimizer, data, cfg: Ora
     rec = {}
     l_sup, _, _, _ = student(label_q + label_k, branch="supervised")
     for k, v in l_sup.items():
-        rec[k + "_sup"] = v * cfg.source_loss_weight
+        rec[k + "_sup"] = v
     l_un, _, _, _ = student(unlabel_q, branch="unsupervised", danchor=True)
     for k, v in l_un.items():
-        rec[k + "_unsup"] = v * cfg.target_unsup_loss_weight
-    total = sum(rec.values())
+        rec[k + "_unsup"] = v
+    total = sum(v * (cfg.source_loss_weight if k.endswith("_sup") else cfg.target_unsup_loss_weight)
+                for k, v in rec.items())
     optimizer.zero_grad()
     total.backward()
     gn = clip_gradient(student.parameters(), cfg.clip_norm)

@@ -48,7 +48,8 @@ if os.environ.get("PT_REGEN_ALL") == "1":
                ("make_golden_config1.py", "pt_reference_config1_golden.pt"),
                ("make_golden_config1.py config4", "pt_reference_config4_golden.pt"),
                ("make_golden_empty_pseudo.py", "pt_reference_empty_pseudo_golden.pt"),
-               ("make_golden_oddcfg.py", "pt_reference_oddcfg_golden.pt")]
+               ("make_golden_oddcfg.py", "pt_reference_oddcfg_golden.pt"),
+               ("make_golden_step_oddcfg.py", "pt_reference_step_oddcfg_golden.pt")]
 
 
 @pytest.mark.parametrize("script,fixture", _CASES)

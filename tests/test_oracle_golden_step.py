@@ -99,3 +99,42 @@ def test_two_burn_in_steps_match_the_reference_trainer():
             mine = sd[k].detach().reshape(-1)[_sample_idx(sd[k].numel())]
             err = float((mine - v).abs().max())
             assert err <= 2e-6 + 2e-5 * float(v.abs().max()), (it, k, err)
+
+
+def test_three_steps_with_trainer_hyper_parameters_off_their_defaults():
+    """tests/golden/pt_reference_step_oddcfg_golden.pt (oracle/make_golden_step_oddcfg.py): the reference's own
+    PTrainer.run_step for three iterations with loss weights 0.5 / 2.0, EMA keep rate 0.99, TEACHER_UPDATE_ITER 2
+    (copy, skip, EMA), momentum 0.8, weight decay 5e-4, lr 0.004."""
+    G3 = torch.load(os.path.join(os.path.dirname(__file__), "golden", "pt_reference_step_oddcfg_golden.pt"), weights_only=False)
+    t = G3["trainer_cfg"]
+    cfg = O.OracleCfg(num_classes=G3["K"], base_lr=t["base_lr"], momentum=t["momentum"], weight_decay=t["weight_decay"],
+                      ema_keep_rate=t["ema_keep_rate"], source_loss_weight=t["source_loss_weight"],
+                      target_unsup_loss_weight=t["target_unsup_loss_weight"])
+    student = O.OracleRCNN(cfg, seed=G3["seed"])
+    teacher = O.OracleRCNN(cfg, seed=G3["teacher_seed"])
+    student.sampler = _Sampler(G3["prio"])
+    opt = O.make_optimizer(student, cfg)
+    N, H, W = G3["N"], G3["H"], G3["W"]
+
+    def batch():
+        lab = [{"image": im.clone(), "height": H, "width": W,
+                "instances": O.OInst((H, W), gt_boxes=O.OBoxes(b.clone()), gt_classes=c.clone())}
+               for im, b, c in zip(G3["lab_images"], G3["gt_boxes"], G3["gt_classes"])]
+        unl = [{"image": im.clone(), "height": H, "width": W} for im in G3["unl_images"]]
+        return lab, unl
+
+    for it, ref in enumerate(G3["steps"]):
+        lab, unl = batch()
+        lab_k, _ = batch()
+        _, unl_k = batch()
+        ratios = ref["ratios"]
+        out = O.run_step(student, teacher, opt, (lab, lab_k, unl, unl_k), cfg, ratios[:N], ratios[N:],
+                         keep_rate=0.0 if it == 0 else None, update_teacher=it % t["teacher_update_iter"] == 0)
+        for k, v in ref["losses"].items():
+            assert abs(out[k] - v) <= 2e-5 * max(abs(v), 1e-6), (it, k, out[k], v)
+        for name, model in (("student", student), ("teacher", teacher)):
+            sd = model.ref_state_dict()
+            for k, v in ref[name].items():
+                mine = sd[k].detach().reshape(-1)[_sample_idx(sd[k].numel())]
+                err = float((mine - v).abs().max())
+                assert err <= 2e-6 + 2e-5 * float(v.abs().max()), (it, name, k, err)

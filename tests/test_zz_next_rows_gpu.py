@@ -664,3 +664,98 @@ def test_every_hyper_parameter_away_from_its_default(cuda):
         print("unsup", {k: (round(float(lu[k]), 5), round(v, 5)) for k, v in G["unsup_losses"].items()})
         for k, v in G["unsup_losses"].items():
             assert abs(float(lu[k]) - v) <= TOL * abs(v), ("unsup", k, float(lu[k]), v)
+
+
+def test_trainer_hyper_parameters_off_their_defaults(cuda):
+    """Three post-burn-in steps of the B200 `PTrainer` with the trainer-level hyper-parameters away from their defaults
+    (loss weights 0.5 / 2.0, EMA keep rate 0.99, TEACHER_UPDATE_ITER 2, momentum 0.8, weight decay 5e-4, lr 0.004)
+    against the reference's own trainer (tests/golden/pt_reference_step_oddcfg_golden.pt,
+    oracle/make_golden_step_oddcfg.py). Exact: the teacher is the initial student after step 0 and UNCHANGED after
+    step 1 (TEACHER_UPDATE_ITER); tight: the EMA at step 2 (keep rate); fp16-path tolerances (as in
+    tests/test_trainer_step_gpu.py): the losses of step 0 and direction / size of the student's updates (lr, momentum,
+    weight decay, clip, loss weights)."""
+    import os
+    from oracle import pt_oracle as O
+    from probabilisticteacher_b200.config import c2f_config
+    from probabilisticteacher_b200.engine.trainer import PTrainer
+    from probabilisticteacher_b200.structures import Boxes, FreeInstances
+    G = torch.load(os.path.join(os.path.dirname(__file__), "golden", "pt_reference_step_oddcfg_golden.pt"), weights_only=False)
+    H, W, K, t = G["H"], G["W"], G["K"], G["trainer_cfg"]
+    cfg = c2f_config()
+    cfg.UNSUPNET.BURN_UP_STEP = 0
+    cfg.UNSUPNET.SOURCE_LOSS_WEIGHT, cfg.UNSUPNET.TARGET_UNSUP_LOSS_WEIGHT = t["source_loss_weight"], t["target_unsup_loss_weight"]
+    cfg.UNSUPNET.EMA_KEEP_RATE, cfg.UNSUPNET.TEACHER_UPDATE_ITER = t["ema_keep_rate"], t["teacher_update_iter"]
+    cfg.SOLVER.MOMENTUM, cfg.SOLVER.WEIGHT_DECAY, cfg.SOLVER.BASE_LR, cfg.SOLVER.WARMUP_ITERS = \
+        t["momentum"], t["weight_decay"], t["base_lr"], 0
+
+    def batch():
+        lab = [{"image": im.clone(), "height": H, "width": W,
+                "instances": FreeInstances((H, W), gt_boxes=Boxes(b.clone()), gt_classes=c.clone())}
+               for im, b, c in zip(G["lab_images"], G["gt_boxes"], G["gt_classes"])]
+        unl = [{"image": im.clone(), "height": H, "width": W} for im in G["unl_images"]]
+        return lab, unl
+
+    def loader():
+        while True:
+            lab, unl = batch()
+            lab_k, _ = batch()
+            _, unl_k = batch()
+            yield lab, lab_k, unl, unl_k
+
+    class _Ratios:
+        def __init__(self, draws):
+            self.draws = list(draws)
+
+        def uniform(self, a, b):
+            return self.draws.pop(0)
+
+    def idx(numel, n=64):
+        g = torch.Generator().manual_seed(numel)
+        return torch.randint(0, numel, (min(n, numel),), generator=g)
+
+    def samples(model):
+        return {k: v.detach().reshape(-1).cpu()[idx(v.numel())] for k, v in model.state_dict().items()}
+
+    tr = PTrainer(cfg, loader(), device=cuda, seed=0)
+    ocfg = O.OracleCfg(num_classes=K)
+    sd = {k: v.detach() for k, v in O.OracleRCNN(ocfg, seed=G["seed"]).ref_state_dict().items()}
+    sd_t = {k: v.detach() for k, v in O.OracleRCNN(ocfg, seed=G["teacher_seed"]).ref_state_dict().items()}
+    tr.model.load_state_dict(sd)
+    tr.model_teacher.load_state_dict(sd_t)
+    tr.model.prio_override = {k: (v[0].to(cuda), v[1].to(cuda)) for k, v in G["prio"].items()}
+    init = {k: v.reshape(-1)[idx(v.numel())] for k, v in sd.items()}
+    prev, prev_ref, teacher_prev = init, init, None
+    problems = []
+    for it, ref in enumerate(G["steps"]):
+        tr.rng = _Ratios(ref["ratios"])
+        losses = tr.run_step()
+        torch.cuda.synchronize()
+        got = {k: float(v) for k, v in losses.items()}
+        print("step", it, {k: (round(got[k], 4), round(v, 4)) for k, v in ref["losses"].items()})
+        if it == 0:  # the trainer reports UNWEIGHTED losses (metrics_dict = record_dict, trainer.py:379-381)
+            for k, v in ref["losses"].items():
+                tol = (2e-2 if "rpn" in k else 0.1) if k.endswith("_sup") else 0.3
+                if not abs(got[k] - v) <= tol * max(abs(v), 1e-3):
+                    problems.append((it, k, got[k], v))
+        st, te = samples(tr.model), samples(tr.model_teacher)
+        if it == 0:
+            for k, v in init.items():
+                assert torch.equal(te[k], v), k                       # copy of the initial student
+        elif it == 1:
+            for k in te:
+                assert torch.equal(te[k], teacher_prev[k]), k          # TEACHER_UPDATE_ITER = 2: untouched
+        else:
+            for k, v in ref["teacher"].items():                        # EMA with keep rate 0.99
+                err = float((te[k] - v).abs().max())
+                assert err <= 1e-6 + 2e-4 * float(v.abs().max()), (k, err)
+            assert any(not torch.equal(te[k], teacher_prev[k]) for k in te)
+        teacher_prev = te
+        up_g = torch.cat([st[k] - prev[k] for k in sorted(st)])
+        up_r = torch.cat([ref["student"][k] - prev_ref[k] for k in sorted(st)])
+        cos = float(torch.dot(up_g, up_r) / (up_g.norm() * up_r.norm()))
+        ratio = float(up_g.norm() / up_r.norm())
+        print("   update cosine", round(cos, 4), "norm ratio", round(ratio, 4))
+        if not (cos > (0.99 if it == 0 else 0.97) and (0.95 if it == 0 else 0.9) < ratio < (1.05 if it == 0 else 1.1)):
+            problems.append(("update", it, cos, ratio))
+        prev, prev_ref = st, ref["student"]
+    assert not problems, problems
