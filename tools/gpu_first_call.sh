@@ -10,7 +10,7 @@ tag=${1:-rN}
 out=gpurun_out
 mkdir -p $out
 py=python
-echo "== new tests"; timeout 900 $py -m pytest tests/test_zz_next_rows_gpu.py -q -s > $out/${tag}_new_tests.log 2>&1; echo "rc=$?"; tail -5 $out/${tag}_new_tests.log
+echo "== new tests"; timeout 900 $py -m pytest tests/test_zz_next_rows_gpu.py -q -rxX --runxfail > $out/${tag}_new_tests.log 2>&1; echo "rc=$?"; tail -5 $out/${tag}_new_tests.log
 echo "== gpu suite"; timeout 1500 $py -m pytest tests -m gpu -x -q > $out/${tag}_gpu_tests.log 2>&1; echo "rc=$?"; tail -3 $out/${tag}_gpu_tests.log
 echo "== bench"; timeout 600 $py bench.py --steps 20 --warmup 3 > $out/${tag}_bench_1gpu.json 2> $out/${tag}_bench.err; echo "rc=$?"; cut -c1-400 $out/${tag}_bench_1gpu.json
 echo "== launch list"
