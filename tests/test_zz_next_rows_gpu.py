@@ -764,3 +764,28 @@ def test_trainer_hyper_parameters_off_their_defaults(cuda):
             problems.append(("update", it, cos, ratio))
         prev, prev_ref = st, ref["student"]
     assert not problems, problems
+
+
+def test_eval_mode_postprocess_scaling(cuda):
+    """`detector_postprocess` on the device-resident detections of an eval-mode forward: asking for twice the
+    resolution doubles every box (exact in fp32) and changes nothing else. Applied twice to the SAME raw detections (a
+    second forward may differ in the last bit: the split-K fc1 accumulates with atomics)."""
+    from oracle import pt_oracle as O
+    from probabilisticteacher_b200.config import c2f_config
+    from probabilisticteacher_b200.modeling.meta_arch.rcnn import build_model
+    from probabilisticteacher_b200.modeling.postprocessing import postprocess_batch
+    model = build_model(c2f_config(), cuda)
+    model.init_synthetic(seed=7)
+    model.eval()
+    batch = O.synthetic_batch(2, 160, 224, 8, 5, labelled=False)
+    out = model(batch)  # post-processed to the "height" / "width" of the inputs (= the network input size here)
+    assert len(out) == 2 and out[0]["instances"].image_size == (160, 224)
+    raw = model.inference(batch, do_postprocess=False)
+    sizes = [(160, 224)] * 2
+    p1 = postprocess_batch(raw, batch, sizes)
+    p2 = postprocess_batch(raw, [dict(d, height=320, width=448) for d in batch], sizes)
+    for a, b2 in zip(p1, p2):
+        ia, ib = a["instances"], b2["instances"]
+        assert ib.image_size == (320, 448) and ia.image_size == (160, 224)
+        assert torch.equal(ib.pred_boxes.tensor, ia.pred_boxes.tensor * 2) and torch.equal(ib.scores, ia.scores)
+        assert torch.equal(ib.pred_classes, ia.pred_classes) and 0 < len(ia) <= 100
