@@ -230,6 +230,9 @@ class GuassianGeneralizedRCNN(nn.Module):
         refresh_stream()
         if not self.training:
             return self.inference(batched_inputs)
+        if norm and "instances" in batched_inputs[0]:
+            # rcnn.py:37-38 calls `self.preprocess_image_norm`, which the reference defines nowhere: same failure here
+            raise AttributeError("'GuassianGeneralizedRCNN' object has no attribute 'preprocess_image_norm'")
         act, sizes, img_hw = self.preprocess_image(batched_inputs)
         need_grad = branch in ("supervised", "unsupervised") and torch.is_grad_enabled()
         if need_grad and self.arena.precision == "f16x3":
