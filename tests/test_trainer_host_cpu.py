@@ -202,3 +202,48 @@ def test_run_step_host_logic_burn_in():
     cfg.SOLVER.WARMUP_ITERS = 0
     assert cfg.UNSUPNET.BURN_UP_STEP > 2
     _run("pt_reference_burnin_golden.pt", cfg, O.OracleCfg(num_classes=8), batches)
+
+
+def test_resize_host_bookkeeping(monkeypatch):
+    """`PTrainer.resize` / `resize_dev` with the kernel behind them emulated in torch (F.interpolate + truncation, what
+    the oracle's restatement of pt/engine/trainer.py:557-590 does): the geometry handed to the kernel, the box
+    scaling / shifting, the untouched inputs and the carried fields are the product's host code."""
+    import torch.nn.functional as F
+
+    def fake_call(name, src, dst, h, w, *rest):
+        if name == "ptb200_resize_paste_u8_dev":
+            params, m = rest[0], rest[1:4]
+            d_h, d_w, x1, y1 = (int(v) for v in params)
+        else:
+            assert name == "ptb200_resize_paste_u8"
+            d_h, d_w, x1, y1 = rest[:4]
+            m = rest[4:7]
+        dst.copy_(torch.tensor(m, dtype=torch.uint8).view(3, 1, 1).expand_as(dst))
+        dst[:, y1:y1 + d_h, x1:x1 + d_w] = F.interpolate(src.unsqueeze(0).float(), size=(d_h, d_w), align_corners=False,
+                                                         mode="bilinear").squeeze(0).to(torch.uint8)
+    monkeypatch.setattr(trainer_mod, "call", fake_call)
+    mean = torch.tensor([103.53, 116.28, 123.675])
+    tr = PTrainer.__new__(PTrainer)
+    tr.device, tr._pix = torch.device("cpu"), [int(x) for x in mean]
+    H, W, ratios = 96, 131, [0.5, 0.8125, 1.0]
+    batch = O.synthetic_batch(3, H, W, 8, 5)
+    ref = O.resize_batch(batch, ratios, mean)
+
+    def mine():
+        return [{"image": d["image"].clone(), "height": H, "width": W, "file_name": f"img{k}",
+                 "instances": FreeInstances((H, W), gt_boxes=Boxes(d["instances"].gt_boxes.tensor.clone()),
+                                            gt_classes=d["instances"].gt_classes.clone())} for k, d in enumerate(batch)]
+    tr.rng = _Ratios(ratios)
+    data = mine()
+    host = tr.resize(data)
+    params = torch.tensor([[int(H * r), int(W * r), int((W - int(W * r)) / 2), int((H - int(H * r)) / 2)] for r in ratios],
+                          dtype=torch.int32)
+    dev = tr.resize_dev(mine(), params, torch.tensor(ratios))
+    for k in range(3):
+        for got in (host[k], dev[k]):
+            assert torch.equal(got["image"], ref[k]["image"])
+            assert torch.allclose(got["instances"].gt_boxes.tensor, O._bt(ref[k]["instances"].gt_boxes), atol=1e-4)
+            assert torch.equal(got["instances"].gt_classes, ref[k]["instances"].gt_classes)
+            assert got["instances"].image_size == (H, W) and got["file_name"] == f"img{k}"
+        assert torch.equal(data[k]["image"], batch[k]["image"])  # inputs untouched (the reference deep-copies, :558)
+        assert torch.equal(data[k]["instances"].gt_boxes.tensor, batch[k]["instances"].gt_boxes.tensor)
