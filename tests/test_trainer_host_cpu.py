@@ -247,3 +247,41 @@ def test_resize_host_bookkeeping(monkeypatch):
             assert got["instances"].image_size == (H, W) and got["file_name"] == f"img{k}"
         assert torch.equal(data[k]["image"], batch[k]["image"])  # inputs untouched (the reference deep-copies, :558)
         assert torch.equal(data[k]["instances"].gt_boxes.tensor, batch[k]["instances"].gt_boxes.tensor)
+
+
+def test_model_targets_padding_host_logic():
+    """`GuassianGeneralizedRCNN._targets`: ground truth / pseudo labels of a batch -> fixed-capacity tensors + counts
+    (capacity = next multiple of 16 >= the largest count, >= 16; images without boxes give count 0; device-resident
+    pseudo labels keep their device-side count)."""
+    import types
+    from probabilisticteacher_b200.modeling.meta_arch.rcnn import GuassianGeneralizedRCNN
+    me = types.SimpleNamespace(device=torch.device("cpu"))
+    g = torch.Generator().manual_seed(0)
+
+    def inst(m):
+        xy = torch.rand(m, 2, generator=g) * 50
+        return FreeInstances((100, 120), gt_boxes=Boxes(torch.cat([xy, xy + 10], 1)), gt_classes=torch.arange(m) % 8)
+    batch = [inst(3), inst(0), inst(17)]
+    t = GuassianGeneralizedRCNN._targets(me, batch)
+    assert t["gt_boxes"].shape == (3, 32, 4) and t["gt_classes"].shape == (3, 32) and t["gt_classes"].dtype == torch.int32
+    assert t["gt_count"].tolist() == [3, 0, 17]
+    for k, i in enumerate(batch):
+        m = len(i.gt_boxes)
+        assert torch.equal(t["gt_boxes"][k, :m], i.gt_boxes.tensor) and float(t["gt_boxes"][k, m:].abs().sum()) == 0
+        assert torch.equal(t["gt_classes"][k, :m].long(), i.gt_classes)
+    # pseudo labels: capacity 100 buffers with a device-side count (the teacher's output fed back unchanged)
+    def pseudo(n_valid):
+        p = FreeInstances((100, 120), pseudo_boxes=Boxes(torch.rand(100, 4, generator=g)),
+                          scores_logists=torch.rand(100, 9, generator=g), boxes_sigma=torch.rand(100, 4, generator=g))
+        p._count = torch.tensor(n_valid)
+        return p
+    t = GuassianGeneralizedRCNN._targets(me, [pseudo(100), pseudo(37)])
+    assert t["pseudo_boxes"].shape == (2, 100, 4) and t["scores_logists"].shape == (2, 100, 9)
+    assert t["pseudo_count"].tolist() == [100, 37] and t["pseudo_count"].dtype == torch.int32
+    # exact-length pseudo labels of different lengths (e.g. loaded from the reference): padded to the longest
+    a = FreeInstances((100, 120), pseudo_boxes=Boxes(torch.rand(5, 4, generator=g)), scores_logists=torch.rand(5, 9, generator=g),
+                      boxes_sigma=torch.rand(5, 4, generator=g))
+    b = FreeInstances((100, 120), pseudo_boxes=Boxes(torch.zeros(0, 4)), scores_logists=torch.zeros(0, 9), boxes_sigma=torch.zeros(0, 4))
+    t = GuassianGeneralizedRCNN._targets(me, [a, b])
+    assert t["pseudo_boxes"].shape == (2, 16, 4) and t["pseudo_count"].tolist() == [5, 0]
+    assert torch.equal(t["pseudo_boxes"][0, :5], a.pseudo_boxes.tensor) and float(t["pseudo_boxes"][1].abs().sum()) == 0
