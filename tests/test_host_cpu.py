@@ -485,3 +485,31 @@ def test_validate_cfg_names_the_unsupported_key():
     cfg.MODEL.ANCHOR_GENERATOR.SIZES = [[32, 64, 128, 256, 512]]
     with pytest.raises(ValueError, match="ANCHOR_GENERATOR"):
         validate_cfg(cfg)
+
+
+def test_every_call_site_matches_the_header_arity():
+    """Static check of the Python -> C-ABI call sites: every `call("ptb200_...", ...)` in the package passes exactly the
+    parameters the header declares (the trailing `stream` may be omitted: `_lib.call` fills it in), and names an entry
+    point that exists. Catches signature drift without a GPU (at run time `_lib.call` raises TypeError)."""
+    import ast
+    import glob
+    from probabilisticteacher_b200 import _lib
+    protos = _lib.protos()
+    seen = set()
+    for path in glob.glob(os.path.join(ROOT, "probabilisticteacher_b200", "**", "*.py"), recursive=True):
+        tree = ast.parse(open(path).read())
+        for node in ast.walk(tree):
+            if not (isinstance(node, ast.Call) and isinstance(node.func, ast.Name) and node.func.id == "call" and node.args):
+                continue
+            first = node.args[0]
+            if not (isinstance(first, ast.Constant) and isinstance(first.value, str) and first.value.startswith("ptb200_")):
+                continue
+            name = first.value
+            assert name in protos, (path, node.lineno, name)
+            if any(isinstance(a, ast.Starred) for a in node.args) or node.keywords:
+                continue  # (none today) variadic sites cannot be counted statically
+            n_args, n_decl = len(node.args) - 1, len(protos[name])
+            assert n_args in (n_decl, n_decl - 1), (os.path.relpath(path, ROOT), node.lineno, name, n_args, n_decl)
+            seen.add(name)
+    # the tools / tests bind a few entry points through ctypes directly; most must be reachable from the package
+    assert len(seen) >= 40, sorted(set(protos) - seen)
