@@ -171,14 +171,23 @@ class DetectionTSCheckpointer:
         return os.path.join(self.save_dir, last)
 
     # ------------------------------------------------------------------ load
-    def load(self, path, checkpointables=None):
+    def load(self, path, checkpointables=None, trusted=False):
         """Returns what the file held besides the objects that consumed their entry (e.g. `iteration`). An empty
-        path means "no checkpoint": the model keeps its initialisation (fvcore behaviour)."""
+        path means "no checkpoint": the model keeps its initialisation (fvcore behaviour).
+        Files are read with `torch.load(weights_only=True)` (tensors and plain containers only: everything this class
+        and the reference's checkpointer write). trusted=True falls back to full unpickling for files that carry
+        other objects (numpy arrays of model-zoo pickles) -- only for files whose origin you trust."""
         if not path:
             return {}
         if not os.path.isfile(path):
             raise AssertionError(f"Checkpoint {path} not found!")
-        checkpoint = torch.load(path, map_location="cpu", weights_only=False)
+        try:
+            checkpoint = torch.load(path, map_location="cpu", weights_only=True)
+        except Exception as e:  # noqa: BLE001  (pickle.UnpicklingError and friends)
+            if not trusted:
+                raise RuntimeError(f"{path} holds objects beyond tensors / plain containers ({type(e).__name__}); "
+                                   "pass trusted=True to unpickle it if you trust its origin") from e
+            checkpoint = torch.load(path, map_location="cpu", weights_only=False)
         if "model" not in checkpoint:  # a bare state dict (e.g. vgg16_caffe.pth-style files)
             checkpoint = {"model": checkpoint}
         self.last_incompatible = self._load_model(checkpoint)
@@ -215,7 +224,7 @@ def load_vgg16_caffe(model, path_or_state_dict):
     everything else keeps its initialisation. Returns IncompatibleKeys of the partial load."""
     sd = path_or_state_dict
     if isinstance(sd, (str, os.PathLike)):
-        sd = torch.load(sd, map_location="cpu", weights_only=False)
+        sd = torch.load(sd, map_location="cpu", weights_only=True)  # a state dict: tensors only
     mapped = OrderedDict()
     for src, dst in vgg16_caffe_key_map().items():
         mapped[dst] = sd[src]  # KeyError on a file that is not a VGG16, as `state_dict[...]` at vgg.py:149

@@ -205,3 +205,18 @@ def test_vgg16_caffe_key_map_against_the_reference_constructor():
     (pt/modeling/backbone/vgg.py:127-152) put each `features.N.*` tensor of a torchvision-style file."""
     G = torch.load(os.path.join(os.path.dirname(__file__), "golden", "pt_reference_burnin_golden.pt"), weights_only=False)
     assert dict(C.vgg16_caffe_key_map(prefix="")) == G["vgg16_caffe_mapping"]
+
+
+def test_untrusted_pickles_are_refused(tmp_path):
+    """Checkpoints are read with weights_only=True; a file that needs full unpickling is refused unless the caller
+    says it trusts it."""
+    import numpy as np
+    m = _CpuDetector(seed=1)
+    sd = {k: (v.numpy() if k.endswith("fc2.bias") else v) for k, v in m.state_dict().items()}  # a numpy entry
+    torch.save({"model": sd}, tmp_path / "zoo.pth")
+    ck = C.DetectionTSCheckpointer(_CpuDetector(seed=2), str(tmp_path))
+    with pytest.raises(RuntimeError, match="trusted=True"):
+        ck.load(str(tmp_path / "zoo.pth"))
+    ck.load(str(tmp_path / "zoo.pth"), trusted=True)  # numpy arrays become tensors (_convert_ndarray_to_tensor)
+    assert torch.equal(ck.model.state_dict()["roi_heads.box_head.fc2.bias"], m.state_dict()["roi_heads.box_head.fc2.bias"])
+    assert isinstance(np.zeros(1), np.ndarray)
