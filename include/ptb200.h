@@ -25,6 +25,8 @@ extern "C" {
 #define PTB200_EPI_ATOMIC_F32 4 /* split-K partials: d0[row][n] += acc (fp32 atomics) */
 #define PTB200_EPI_SPLIT3_RELU_F16 5 /* f16x3 only: relu(alpha*acc + bias) -> [hi | lo | hi] triple */
 #define PTB200_EPI_SPLIT3_F16 6      /* f16x3 only: alpha*acc + bias -> [hi | lo | hi] triple */
+#define PTB200_EPI_SPLIT3_MASK_F16 7 /* f16x3 only: (aux > 0 ? alpha*acc : 0) -> triple (ReLU backward) */
+#define PTB200_EPI_F32_STORE 8       /* f16x3 only: alpha*acc + bias -> fp32 d0[row][n] */
 
 /* ---- dense contractions (tcgen05 tensor cores, TMA-staged tiles) ------------------------------ */
 
@@ -44,23 +46,29 @@ int ptb200_gemm_tn_f16(const void* A, int batch, int rows, int k_per_tap, int64_
                        float* d0, int ld0, float* d1, int ld1, int split, int n_valid, int max_ctas,
                        int ksplit, const int* seg_counts, int seg_cap, void* stream);
 
-/* Split-fp16 ("f16x3") parity-precision variant of ptb200_gemm_tn_f16 (forward only): the reference
- * computes these contractions in fp32 (AMP off, pt/engine/trainer.py:271-277 runs without autocast), so
- * the 1e-3 parity claim of the losses is checked in this mode. Every fp32 value x travels as two fp16
- * numbers hi = fp16(x), lo = fp16(x - hi); an activation row is the K-concatenation [hi | lo | hi]
- * (3 * channels wide), a weight row per tap is [Wh | Wh | Wl] of W * 2^s (ptb200_split3_pack_f16), so the
- * unchanged tensor-core main loop accumulates hi*Wh + lo*Wh + hi*Wl in fp32 (the lo*Wl term, 2^-22
- * relative, is dropped). alpha = 2^-s is applied to the accumulator before the bias. k3_per_tap = 3 * K.
- * Epilogues: PTB200_EPI_SPLIT3_{RELU_,}F16 (D3 is [batch][rows][3*n_total]), PTB200_EPI_F32_SPLIT, or
- * PTB200_EPI_ATOMIC_F32 with ksplit > 1: the tensor core accumulates its fp32 sums with truncation, a bias
- * that grows with the number of chained MMAs, so long reductions are cut into ksplit chunks whose partial
- * sums are added in round-to-nearest fp32 (red.add into d0) and finished by ptb200_bias_act_split3_f16. */
+/* Split-fp16 ("f16x3") fp32-equivalent variant of ptb200_gemm_tn_f16, forward AND backward: the reference
+ * computes these contractions and their autograd in fp32 (AMP off, pt/engine/trainer.py:271-277,383-386 run
+ * without autocast), so the 1e-3 parity claim of losses AND parameter gradients is checked -- and a training
+ * step is timed -- in this mode. Every fp32 value x travels as two fp16 numbers hi = fp16(x), lo = fp16(x - hi);
+ * an activation (or output-gradient) row is the K-concatenation [hi | lo | hi] (3 * channels wide), a weight
+ * row per tap is [Wh | Wh | Wl] of W * 2^s (ptb200_split3_pack_f16 / ptb200_transpose_pack_f16x3), so the
+ * tensor-core main loop accumulates hi*Wh + lo*Wh + hi*Wl in fp32 (the lo*Wl term, 2^-22 relative, is
+ * dropped). alpha = 2^-s is applied to the accumulator before the bias. k3_per_tap = 3 * K.
+ * The tensor core adds into its fp32 accumulator with truncation, a bias that grows with the number of chained
+ * MMAs; the kernel therefore runs the reduction in chunks of `chunk` k-iterations of 64 (0 = default 4) on
+ * alternating TMEM accumulator stages and its epilogue warps promote every finished chunk into fp32 register
+ * accumulators (round to nearest) while the next chunk runs.
+ * Epilogues: PTB200_EPI_SPLIT3_{RELU_,}F16 (D3 is [batch][rows][3*n_total]); PTB200_EPI_SPLIT3_MASK_F16 (ReLU
+ * backward fused into a data-gradient GEMM: aux3 = the forward activation triples, same geometry as D3);
+ * PTB200_EPI_F32_STORE (fp32 d0[row][n], ld0 = row pitch); PTB200_EPI_ATOMIC_F32 with ksplit > 1 (skinny
+ * problems, finished by ptb200_bias_act_split3_f16); PTB200_EPI_F32_SPLIT (narrow fp32 heads, single chain).
+ * bn must be 64, 128 or 256 except for PTB200_EPI_F32_SPLIT. */
 int ptb200_gemm_tn_f16x3(const void* A3, int batch, int rows, int k3_per_tap, int64_t lda,
                          int64_t a_batch_stride, int taps, const int* shifts_host, const void* B3,
                          int n_total, int bn, int epi, const float* bias, int n_bias, void* D3, int64_t ldd,
                          int64_t d_batch_stride, int w_valid, int wp, float* d0, int ld0, float* d1, int ld1,
                          int split, int n_valid, int max_ctas, int ksplit, const int* seg_counts, int seg_cap,
-                         float alpha, void* stream);
+                         float alpha, const void* aux3, int chunk, void* stream);
 
 /* Bias + ReLU of the same layers (pt/modeling/backbone/vgg.py:65-72, the box head of roi_heads.py:127-128) applied to
  * the fp32 partial sums of a K-chunked f16x3 GEMM:
@@ -134,6 +142,11 @@ int ptb200_maxpool2x2_f16x3(const void* in, void* out, int n, int h, int w, int 
 int ptb200_maxpool2x2_relu_bwd_f16(const void* x, const void* dpooled, void* dz, int n, int h, int w,
                                    int c, void* stream);
 
+/* f16x3 counterpart (autograd of vgg.py:59,65-72 in the reference's fp32): x3 = pre-pool activation triples
+ * [n][h*(w+1)][3c], dpooled = fp32 gradient of the pooled map [n][(h/2)*(w/2+1)][c], dz3 = gradient triples. */
+int ptb200_maxpool2x2_relu_bwd_f16x3(const void* x3, const float* dpooled, void* dz3, int n, int h, int w, int c,
+                                     void* stream);
+
 /* fp32 master weights -> fp16 GEMM operands: the cast the reference never needs (fp32 nn.Parameter tensors go to
  * cuDNN / cuBLAS as they are; vgg.py:45-53, rpn.py:44-55, fast_rcnn.py:157-169). transpose_pack builds the
  * [Cin][tap][Cout] operand of the data-gradient GEMM that autograd derives from the same weights
@@ -142,6 +155,11 @@ int ptb200_cast_f32_f16(const float* src, void* dst, int64_t n, void* stream);
 int ptb200_transpose_pack_f16(const float* src, void* dst, int rows, int cols, int taps, int flip,
                               int64_t ld_dst, void* stream);
 int ptb200_cast_pad_rows_f16(const float* src, void* dst, int rows, int cols, int ld_dst, void* stream);
+/* f16x3 data-gradient operand of the same weights (autograd of vgg.py:45-53, rpn.py:44-55, roi_heads.py:127-128,
+ * fast_rcnn.py:157-169 in fp32): src fp32 [rows][taps][cols] -> dst3[col][tap (flipped when flip)][Wh | Wh | Wl]
+ * (3*rows wide) of src * scale. */
+int ptb200_transpose_pack_f16x3(const float* src, void* dst3, int rows, int cols, int taps, int flip, float scale,
+                                void* stream);
 
 /* Bias gradient (autograd of the `+ bias` in d2 Conv2d / nn.Linear, run by `losses.backward()` at
  * pt/engine/trainer.py:384): out[c] += scale * sum_rows in[row][c]. */
@@ -154,6 +172,11 @@ int ptb200_colsum_f16(const void* in, int64_t rows, int c, int64_t ld, float sca
  * g0[0], g1[0] and the loss scale into the fp16 [rows][ld] operand of the backward GEMMs. */
 int ptb200_pack_grad2_f16(const float* d0, int n0, const float* d1, int n1, const float* g0,
                           const float* g1, float lscale, int64_t rows, int ld, void* out, void* stream);
+
+/* f16x3 counterpart of ptb200_pack_grad2_f16 (same autograd entry, pt/engine/trainer.py:364-384, in the
+ * reference's fp32): out3 = gradient triples [rows][3*ld]. */
+int ptb200_pack_grad2_f16x3(const float* d0, int n0, const float* d1, int n1, const float* g0, const float* g1,
+                            float lscale, int64_t rows, int ld, void* out3, void* stream);
 
 /* Finishes a split-K GEMM (fc1 of the box head, roi_heads.py:127-128): out = half(act(in + bias)). */
 int ptb200_bias_act_cast_f16(const float* in, const float* bias, int relu, int64_t rows, int n, void* out,
@@ -168,6 +191,11 @@ int ptb200_add_f32_to_f16(const void* a, const float* b, float scale, void* out,
  * (vgg.py:65-72; sums the RPN and ROI gradient paths into the backbone output, rcnn.py:45-61). */
 int ptb200_add_mask_f16(const void* a, const float* b, float scale, const void* aux, void* out,
                         int64_t n, void* stream);
+
+/* f16x3 counterpart (rcnn.py:45-61 + the last ReLU of vgg.py:65-72, fp32 autograd): out3 = triple of
+ * ((aux_hi + aux_lo) > 0 ? a + b : 0); a (may be NULL), b fp32 [rows][c]; aux3, out3 triples [rows][3c]. */
+int ptb200_add_mask_f16x3(const float* a, const float* b, const void* aux3, void* out3, int64_t rows, int c,
+                          void* stream);
 
 /* ---- sorting ----------------------------------------------------------------------------------- */
 
@@ -277,6 +305,12 @@ int ptb200_roi_align_bwd_f16(const void* dout, int n, int h, int w, int c, const
                              const int* roi_count, int cap, float spatial_scale, int pooled,
                              float* dfeat, void* stream);
 
+/* Same backward (torchvision roi_align's autograd behind roi_heads.py:68-73,126) with an fp32 output gradient
+ * (f16x3 training path: the fc1 data-gradient GEMM stores fp32). */
+int ptb200_roi_align_bwd_f32(const float* dout, int n, int h, int w, int c, const float* rois,
+                             const int* roi_count, int cap, float spatial_scale, int pooled,
+                             float* dfeat, void* stream);
+
 /* ---- losses (fused forward + unit-gradient backward) --------------------------------------------- */
 
 /* pt/modeling/proposal_generator/rpn.py:191-255 (+ box_regression.py:33-35,142-176). loss2 = {cls, loc}. */
@@ -312,6 +346,11 @@ int ptb200_axpy_dev(const float* alpha_dev, float scale, const float* x, float* 
 
 /* pt/engine/trainer.py:431-449: teacher = keep * teacher + (1 - keep) * student over the flat arena. */
 int ptb200_ema_update(float* teacher, const float* student, int64_t n, float keep_rate, void* stream);
+/* Same update with the keep rate read from device memory (CUDA-graph replays of the step): the host stages
+ * EMA_KEEP_RATE on the iterations where (iter - BURN_UP_STEP) % TEACHER_UPDATE_ITER == 0 and 1.0 on the others
+ * (pt/engine/trainer.py:296-298); keep == 1 leaves the teacher untouched bit for bit. */
+int ptb200_ema_update_dev(float* teacher, const float* student, int64_t n, const float* keep_rate_dev,
+                          void* stream);
 
 /* pt/engine/trainer.py:592-603 (global L2 norm) and torch.optim.SGD(momentum, weight_decay) step
  * (trainer.py:386) fused; the clip coefficient clip/max(norm, clip) is evaluated on device. */

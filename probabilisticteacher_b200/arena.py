@@ -88,8 +88,10 @@ class ParamArena:
         self.data = torch.zeros(self.total, dtype=torch.float32, device=self.device)
         self.half = torch.zeros(self.total, dtype=torch.float16, device=self.device)
         self.conv1_half = torch.zeros(64, 32, dtype=torch.float16, device=self.device)
-        self.precision = "f16"  # "f16x3": split-fp16 parity precision (forward only), see pack_x3
+        self.precision = "f16"  # "f16x3": split-fp16 fp32-equivalent precision, see pack_x3
         self.x3 = None
+        self._x3_exp = None
+        self.dgrad_x3 = None
         if with_grads:
             n = self.total - self.trainable_start
             self.grads = torch.zeros(n, dtype=torch.float32, device=self.device)
@@ -215,44 +217,99 @@ class ParamArena:
                     continue
                 src = sd[name].to(self.device, torch.float32)
                 v.copy_(self._from_ref(kinds.get(name, "mat"), src, v))
+        self._x3_exp = None  # new weights: new f16x3 scales
         self.pack()
         return missing, [k for k in sd if k not in known]
 
     # ------------------------------------------------------------------ fp16 operands
     def pack(self, dgrad=None):
         """fp32 masters -> fp16 GEMM operands: one cast pass for the forward operands (same offsets),
-        the K-padded first conv, and (student only) the transposed operands of the data-gradient GEMMs."""
-        call("ptb200_cast_f32_f16", self.data, self.half, self.total)
-        self.x3 = None  # f16x3 triples are rebuilt lazily (parity precision only)
-        w1 = self.view("backbone.vgg_block1.0.conv1.weight").view(64, 27)
-        call("ptb200_cast_pad_rows_f16", w1, self.conv1_half, 64, 27, 32)
+        the K-padded first conv, and (student only) the transposed operands of the data-gradient GEMMs. In the
+        f16x3 precision the weight triples (forward, and data-gradient for the student) are refreshed as well, into
+        persistent buffers and with the power-of-two scales fixed at the last `refresh_x3_scales()` (no host sync:
+        the call is CUDA-graph capturable once the scales exist)."""
         if dgrad is None:
             dgrad = self.dgrad_half is not None
+        if self.precision == "f16x3":
+            self.pack_x3(dgrad=dgrad)
+            return
+        call("ptb200_cast_f32_f16", self.data, self.half, self.total)
+        w1 = self.view("backbone.vgg_block1.0.conv1.weight").view(64, 27)
+        call("ptb200_cast_pad_rows_f16", w1, self.conv1_half, 64, 27, 32)
         if dgrad:
             self._pack_dgrad()
 
-    def pack_x3(self):
-        """fp32 masters -> f16x3 weight triples [Wh | Wh | Wl] of W * 2^s per tensor (s chosen so that
-        max|W| * 2^s lies in [2^13, 2^14): lo parts stay in the normal fp16 range); returns and caches
-        {name: (triples [rows, taps*3k], alpha = 2^-s)}. One host sync per tensor (parity mode only)."""
-        from . import ops
-        out = {}
-        for s in self.segments.values():
-            if s.kind not in ("conv", "fc1", "mat", "rpn_heads_w", "pred_w") or s.shape[-1] % 64 != 0:
-                continue  # (the 3 -> 64 first conv runs in fp32 from the master weights; anchors are not GEMM operands)
-            v = self.view(s.name)
+    # ------------------------------------------------------------------ f16x3 operands
+    _X3_KINDS = ("conv", "fc1", "mat", "rpn_heads_w", "pred_w")
+
+    def _x3_segments(self):
+        # (the 3 -> 64 first conv runs in fp32 from the master weights; anchors are not GEMM operands)
+        return [s for s in self.segments.values() if s.kind in self._X3_KINDS and s.shape[-1] % 64 == 0]
+
+    def refresh_x3_scales(self):
+        """Per-tensor power-of-two scale 2^e with max|W| * 2^e in [2^12, 2^13): the lo halves stay normal fp16
+        numbers and the hi halves keep an 8x margin to the fp16 maximum while training moves the weights. ONE host
+        sync (all maxima are reduced on the device first); called on the first pack and after load_state_dict."""
+        segs = self._x3_segments()
+        m = torch.stack([self.view(s.name).abs().max() for s in segs]).tolist()
+        self._x3_exp = {}
+        for s, mx in zip(segs, m):
+            e = math.floor(math.log2(8192.0 / mx)) if mx > 0 and math.isfinite(mx) else 0
+            self._x3_exp[s.name] = max(-24, min(24, e))
+
+    # data-gradient operands: arena segment -> (key, rows = Cout, cols = Cin, taps, flip)
+    def _x3_dgrad_specs(self):
+        specs = []
+        first_trainable = True
+        for name, cin, cout, trainable in self.conv_specs:
+            if not trainable:
+                continue
+            if first_trainable:  # its input is the frozen part: no data-gradient needed
+                first_trainable = False
+                continue
+            specs.append((name + ".weight", name, cout, cin, 9, 1))
+        C, fc = self.C, self.fc_dim
+        fin = self.pooled * self.pooled * C
+        specs.append(("proposal_generator.rpn_head.conv.weight", "rpn_conv", C, C, 9, 1))
+        specs.append(("proposal_generator.rpn_head._heads.weight", "rpn_heads", 128, C, 1, 0))
+        specs.append(("roi_heads.box_head.fc1.weight", "fc1", fc, fin, 1, 0))
+        specs.append(("roi_heads.box_head.fc2.weight", "fc2", fc, fc, 1, 0))
+        specs.append(("roi_heads.box_predictor._heads.weight", "pred", 128, fc, 1, 0))
+        return specs
+
+    def pack_x3(self, dgrad=False):
+        """fp32 masters -> f16x3 weight triples [Wh | Wh | Wl] of W * 2^s per tensor; caches
+        {name: (triples [rows, taps*3k], alpha = 2^-s)} in `self.x3` and, with dgrad, the transposed
+        data-gradient operands {key: (triples [Cin, taps*3*Cout], alpha)} in `self.dgrad_x3`."""
+        if getattr(self, "_x3_exp", None) is None:
+            self.refresh_x3_scales()
+        if self.x3 is None:
+            self.x3 = {}
+        for s in self._x3_segments():
             k = s.shape[-1]
-            m = float(v.abs().max())
-            e = math.floor(math.log2(16384.0 / m)) if m > 0 else 0
-            e = max(-24, min(24, e))
-            t = ops.split3_pack(v, k, 2.0 ** e, order=1).view(s.shape[0], -1)
-            out[s.name] = (t, 2.0 ** (-e))
-        self.x3 = out
-        return out
+            e = self._x3_exp[s.name]
+            rows = s.numel // k
+            ent = self.x3.get(s.name)
+            if ent is None:
+                ent = (torch.empty(s.shape[0], (rows // s.shape[0]) * 3 * k, dtype=torch.float16, device=self.device),
+                       2.0 ** (-e))
+            self.x3[s.name] = (ent[0], 2.0 ** (-e))
+            call("ptb200_split3_pack_f16", self.view(s.name), ent[0], rows, k, 2.0 ** e, 1)
+        if dgrad:
+            if getattr(self, "dgrad_x3", None) is None:
+                self.dgrad_x3 = {}
+            for seg_name, key, rows, cols, taps, flip in self._x3_dgrad_specs():
+                e = self._x3_exp[seg_name]
+                ent = self.dgrad_x3.get(key)
+                if ent is None:
+                    ent = (torch.empty(cols, taps * 3 * rows, dtype=torch.float16, device=self.device), 0.0)
+                self.dgrad_x3[key] = (ent[0], 2.0 ** (-e))
+                call("ptb200_transpose_pack_f16x3", self.view(seg_name), ent[0], rows, cols, taps, flip, 2.0 ** e)
+        return self.x3
 
     def x3view(self, name):
         if self.x3 is None:
-            self.pack_x3()
+            self.pack_x3(dgrad=self.dgrad_half is not None)
         return self.x3[name]
 
     def _dg(self, name, shape):
@@ -304,8 +361,12 @@ class ParamArena:
         sd[p + "anchor_deltas.weight"] = torch.randn(A * 8, C, 1, 1, generator=g) * 0.01
         sd[p + "anchor_deltas.bias"] = torch.zeros(A * 8)
         if "proposal_generator.anchor_generator.anchor_0" in self.segments:
-            from .config import get_cfg
-            sd["proposal_generator.anchor_generator.anchor_0"] = torch.tensor(get_cfg().MODEL.ANCHOR_GENERATOR.ANCHOR[0])
+            # keep what DifferentiableAnchorGenerator.__init__ wrote from the model's own cfg
+            cur = self.view("proposal_generator.anchor_generator.anchor_0").detach().cpu().clone()
+            if not bool(cur.any()):  # a bare arena (no generator constructed on it): the default config's anchors
+                from .config import get_cfg
+                cur = torch.tensor(get_cfg().MODEL.ANCHOR_GENERATOR.ANCHOR[0])
+            sd["proposal_generator.anchor_generator.anchor_0"] = cur
         fin = C * self.pooled ** 2
         for name, fi, fo in (("roi_heads.box_head.fc1", fin, self.fc_dim), ("roi_heads.box_head.fc2", self.fc_dim, self.fc_dim)):
             bound = math.sqrt(3.0 / fi)

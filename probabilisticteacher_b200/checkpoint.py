@@ -110,19 +110,96 @@ class EnsembleTSModel:
         return IncompatibleKeys(missing, unexpected, incorrect)
 
 
+def reference_trainable_order(arena):
+    """Trainable parameter names in the order of the reference model's `named_parameters()` -- the order detectron2's
+    `build_optimizer` hands the parameters to torch SGD (one param group each), hence the integer keys of a
+    reference optimizer `state_dict()`. Recorded from the reference's own classes (oracle/make_golden_model.py):
+    backbone blocks, RPN head (conv, objectness_logits, anchor_deltas: weight then bias each), anchor_0, box head,
+    cls_score, bbox_pred. (Differs from the arena order, which keeps the fused head blocks together.)"""
+    have = {name for name, _, _, trainable in arena.exposed_parameters(arena.momentum) if trainable}
+    order = [f"{name}.{kind}" for name, _, _, trainable in arena.conv_specs if trainable for kind in ("weight", "bias")]
+    for mod in ("proposal_generator.rpn_head.conv", "proposal_generator.rpn_head.objectness_logits",
+                "proposal_generator.rpn_head.anchor_deltas"):
+        order += [mod + ".weight", mod + ".bias"]
+    order.append("proposal_generator.anchor_generator.anchor_0")
+    for mod in ("roi_heads.box_head.fc1", "roi_heads.box_head.fc2", "roi_heads.box_predictor.cls_score",
+                "roi_heads.box_predictor.bbox_pred"):
+        order += [mod + ".weight", mod + ".bias"]
+    return [n for n in order if n in have]
+
+
 class ArenaSGDState:
-    """Checkpointable standing in for the reference's `optimizer=` / `scheduler=` entries: the momentum arena
-    under the reference's parameter names and layouts plus the iteration the LR schedule is a pure function of
-    (`PTrainer._optimizer_step` evaluates WarmupMultiStepLR from `trainer.iter`; there is no scheduler object)."""
+    """Checkpointable standing in for the reference's `optimizer=` entry (`trainer.py:104-111`). Written in torch
+    SGD's own `state_dict()` format -- `state[i]["momentum_buffer"]` in the reference layouts, one param group per
+    parameter in the reference's parameter order, as detectron2 v0.5 `build_optimizer` creates them -- so the file
+    loads into the reference's optimizer; the same buffers are stored by NAME under the extra key
+    `momentum_buffers` (ignored by torch). Loading accepts both: by name when present, else by position with every
+    shape checked (a reference-written file). The LR schedule is a pure function of `trainer.iter` here."""
 
     def __init__(self, trainer):
         self.trainer = trainer
 
     def state_dict(self):
-        return {"momentum_buffers": self.trainer.model.arena.momentum_state_dict(), "iter": int(self.trainer.iter)}
+        tr = self.trainer
+        arena = tr.model.arena
+        by_name = arena.momentum_state_dict()
+        order = reference_trainable_order(arena)
+        cfg = getattr(tr, "cfg", None)
+        if cfg is not None:
+            from .solver import lr_at_iter
+            sol = cfg.SOLVER
+            lr, mom, wd, base = (float(lr_at_iter(cfg, max(int(tr.iter) - 1, 0))), float(sol.MOMENTUM),
+                                 float(sol.WEIGHT_DECAY), float(sol.BASE_LR))
+        else:  # detectron2 defaults
+            lr, mom, wd, base = 0.001, 0.9, 1e-4, 0.001
+        state = {i: {"momentum_buffer": by_name[n]} for i, n in enumerate(order)} if int(tr.iter) > 0 else {}
+        groups = [{"lr": lr, "momentum": mom, "dampening": 0, "nesterov": False, "weight_decay": wd,
+                   "initial_lr": base, "params": [i]} for i in range(len(order))]
+        return {"state": state, "param_groups": groups, "momentum_buffers": by_name, "param_names": order,
+                "iter": int(tr.iter)}
 
     def load_state_dict(self, sd):
-        self.trainer.model.arena.load_momentum_state_dict(sd.get("momentum_buffers", {}))
+        arena = self.trainer.model.arena
+        if "momentum_buffers" in sd:
+            arena.load_momentum_state_dict(sd["momentum_buffers"])
+            return
+        if "state" not in sd or "param_groups" not in sd:
+            raise ValueError("optimizer entry is neither torch SGD's state_dict nor this trainer's: keys "
+                             f"{sorted(sd)}")
+        # a file written by the reference trainer: integer keys = position in the reference's parameter order
+        order = reference_trainable_order(arena)
+        n_params = sum(len(g["params"]) for g in sd["param_groups"])
+        if n_params != len(order):
+            raise ValueError(f"optimizer state holds {n_params} parameters, this model trains {len(order)}: "
+                             "refusing to guess the mapping (load the weights only, checkpointables=[])")
+        ref_shapes = {k: tuple(v.shape) for k, v in arena.momentum_state_dict().items()}
+        flat = [i for g in sd["param_groups"] for i in g["params"]]
+        by_name = {}
+        for pos, key in enumerate(flat):
+            ent = sd["state"].get(key)
+            if ent is None or ent.get("momentum_buffer") is None:
+                continue  # torch creates the buffer lazily: zero here
+            buf = ent["momentum_buffer"]
+            if tuple(buf.shape) != ref_shapes[order[pos]]:
+                raise ValueError(f"optimizer state {key}: shape {tuple(buf.shape)} does not match "
+                                 f"{order[pos]} {ref_shapes[order[pos]]}")
+            by_name[order[pos]] = buf
+        arena.load_momentum_state_dict(by_name)
+
+
+class SchedulerState:
+    """`scheduler=` entry of the reference's checkpoints (`trainer.py:104-111`): torch LR schedulers store
+    `last_epoch`; here the schedule is a pure function of the iteration, so loading only cross-checks it."""
+
+    def __init__(self, trainer):
+        self.trainer = trainer
+
+    def state_dict(self):
+        it = int(self.trainer.iter)
+        return {"last_epoch": it, "_step_count": it + 1, "base_lrs": [float(self.trainer.cfg.SOLVER.BASE_LR)]}
+
+    def load_state_dict(self, sd):
+        self.last_epoch = int(sd.get("last_epoch", -1))
 
 
 class DetectionTSCheckpointer:

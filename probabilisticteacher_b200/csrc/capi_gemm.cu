@@ -64,13 +64,51 @@ extern "C" int ptb200_gemm_tn_f16x3(const void* A3, int batch, int rows, int k3_
                                     int n_total, int bn, int epi, const float* bias, int n_bias, void* D3,
                                     int64_t ldd, int64_t d_batch_stride, int w_valid, int wp, float* d0, int ld0,
                                     float* d1, int ld1, int split, int n_valid, int max_ctas, int ksplit,
-                                    const int* seg_counts, int seg_cap, float alpha, void* stream) {
-  if (epi != EPI_SPLIT3_RELU_F16 && epi != EPI_SPLIT3_F16 && epi != EPI_F32_SPLIT && epi != EPI_ATOMIC_F32)
-    return 1021;
+                                    const int* seg_counts, int seg_cap, float alpha, const void* aux3, int chunk,
+                                    void* stream) {
   if (k3_per_tap % 3 != 0) return 1022;
-  return gemm_tn_capi(A3, batch, rows, k3_per_tap, lda, a_batch_stride, taps, shifts, B3, n_total, bn, epi, bias,
-                      n_bias, D3, ldd, d_batch_stride, nullptr, w_valid, wp, d0, ld0, d1, ld1, split, n_valid,
-                      max_ctas, ksplit, seg_counts, seg_cap, alpha, stream);
+  if (epi == EPI_F32_SPLIT) {
+    // narrow fp32 heads (N = 96 / 128, K <= 3 * 1024: at most 192 chained MMAs): one accumulation chain
+    return gemm_tn_capi(A3, batch, rows, k3_per_tap, lda, a_batch_stride, taps, shifts, B3, n_total, bn, epi, bias,
+                        n_bias, D3, ldd, d_batch_stride, nullptr, w_valid, wp, d0, ld0, d1, ld1, split, n_valid,
+                        max_ctas, ksplit, seg_counts, seg_cap, alpha, stream);
+  }
+  if (epi != EPI_SPLIT3_RELU_F16 && epi != EPI_SPLIT3_F16 && epi != EPI_SPLIT3_MASK_F16 && epi != EPI_F32_STORE &&
+      epi != EPI_ATOMIC_F32)
+    return 1021;
+  GemmTnArgs a;
+  a.A = A3;
+  a.batch = batch;
+  a.rows = rows;
+  a.k_per_tap = k3_per_tap;
+  a.lda = lda;
+  a.a_batch_stride = a_batch_stride;
+  a.taps = taps;
+  for (int i = 0; i < 9; ++i) a.shifts[i] = (shifts != nullptr && i < taps) ? shifts[i] : 0;
+  a.B = B3;
+  a.n_total = n_total;
+  a.bn = bn;
+  a.epi = epi;
+  a.bias = bias;
+  a.n_bias = n_bias;
+  a.D = D3;
+  a.ldd = ldd;
+  a.d_batch_stride = d_batch_stride;
+  a.aux = aux3;
+  a.w_valid = w_valid;
+  a.wp = wp;
+  a.d0 = d0;
+  a.ld0 = ld0;
+  a.d1 = nullptr;
+  a.ld1 = 0;
+  a.split = 0;
+  a.n_valid = n_total;
+  a.max_ctas = max_ctas;
+  a.ksplit = ksplit;
+  a.seg_counts = seg_counts;
+  a.seg_cap = seg_cap;
+  a.alpha = alpha;
+  return gemm_tn_promote_launch(a, chunk, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int ptb200_gemm_wgrad_f16(const void* G, int64_t ldg, int64_t g_batch_stride, const void* X,

@@ -44,7 +44,7 @@ struct SmemCtl {
 // ROWWIN (3x3 convs with small Cout, where the tile is L2-bandwidth bound): a pipeline stage holds one
 // 136-row window of A (rows p0 + (ky-1)*Wp - 1 ...) shared by the three horizontal taps kx = 0..2 --
 // the taps are UMMA descriptors whose start address is offset by kx*128 B (SWIZZLE_128B is applied on
-// absolute shared-memory address bits, verified on B200 with csrc/exp_rowshift.cu) -- plus the three
+// absolute shared-memory address bits, verified on B200 with tools/exp_rowshift.cu) -- plus the three
 // B tiles of that filter row: 3x fewer A bytes through L2 than one box per tap.
 static constexpr int WIN_ROWS = 136;
 static constexpr int WIN_BYTES = WIN_ROWS * 128;  // 17408 = 17 * 1024

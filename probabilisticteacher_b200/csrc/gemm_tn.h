@@ -16,6 +16,9 @@ enum GemmEpilogue {
   // GEMM against [Wh | Wh | Wl] evaluates hi*Wh + lo*Wh + hi*Wl with fp32 accumulation
   EPI_SPLIT3_RELU_F16 = 5,
   EPI_SPLIT3_F16 = 6,
+  // gemm_tn_x3.cu (in-kernel fp32 promotion) only:
+  EPI_SPLIT3_MASK_F16 = 7,  // (aux > 0 ? alpha*acc : 0) -> triple; aux = forward activation triple (hi + lo)
+  EPI_F32_STORE = 8,        // alpha*acc + bias -> fp32 d0[row][n] (pad-column rows written as zero)
 };
 
 struct GemmTnParams {
@@ -39,6 +42,7 @@ struct GemmTnParams {
   int n_valid;
   const int* seg_counts;  // optional: rows are [segments][seg_cap], only the first seg_counts[s] rows of a
   int seg_cap;            // segment are live; 128-row tiles without any live row are skipped entirely
+  int chunk = 0;          // gemm_tn_x3.cu: k-iterations (of 64) per fp32 promotion of the TMEM partial sums
 };
 
 struct GemmTnArgs {
@@ -72,6 +76,8 @@ struct GemmTnArgs {
 };
 
 int gemm_tn_launch(const GemmTnArgs& a, cudaStream_t stream);
+// f16x3 GEMM with in-kernel fp32 promotion (gemm_tn_x3.cu); a.D / a.aux are [batch][rows][3*n_total] triples
+int gemm_tn_promote_launch(const GemmTnArgs& a, int chunk, cudaStream_t stream);
 
 // dW[m][t*n_total + n] += scale * sum_{b,p} G[b][p][m] * X[b][p + shifts[t]][n]   (fp32 atomics)
 int gemm_wgrad_launch(const void* G, int64_t ldg, int64_t g_batch_stride, const void* X, int64_t ldx,

@@ -1,0 +1,472 @@
+// f16x3 ("split-fp16", fp32-equivalent) implicit GEMM for sm_100a with IN-KERNEL fp32 PROMOTION.
+//
+// Same contraction as gemm_tn.cu (D[b][p][n] = sum_t sum_k A[b][p + shift_t][k] * B[n][t*K + k], K-major fp16
+// operands staged by TMA, tcgen05.mma kind::f16 into TMEM), used where the reference computes in fp32
+// (pt/engine/trainer.py:271-277 runs without autocast): activations are [hi | lo | hi] triples, weights
+// [Wh | Wh | Wl] triples, so the main loop evaluates hi*Wh + lo*Wh + hi*Wl.
+//
+// What is different from gemm_tn.cu: the tensor core adds into its fp32 accumulator with TRUNCATION (measured on
+// B200: one chain over K = 3 x 25088 is biased by -2.4e-4 relative, ~0.5 ulp per MMA), which compounds through 16
+// stacked layers. Round 1 cut the reduction into split-K chunks that were summed with red.global.add (round to
+// nearest) -- 50-100 fp32 atomic passes over every output tensor. Here the MMA warp still works in chunks of
+// `chunk` k-iterations (4 MMAs each) alternating between the two TMEM accumulator stages, but the epilogue warps
+// PROMOTE each finished chunk into fp32 REGISTER accumulators (tcgen05.ld + FADD, round to nearest) while the
+// tensor core runs the next chunk; the output tile is written once. The tensor pipe stays the bound: a chunk of 4
+// k-iterations at N = 256 is 2048 tensor cycles against ~128 FADD + 4 tcgen05.ld per epilogue thread.
+//
+// Epilogues (all from the register accumulators):
+//   EPI_SPLIT3_RELU_F16 / EPI_SPLIT3_F16 : act(alpha*acc + bias) -> [hi | lo | hi] triple (forward)
+//   EPI_SPLIT3_MASK_F16                  : (aux > 0 ? alpha*acc : 0) -> triple; aux = forward activation triple
+//                                          (ReLU backward fused into the data-gradient GEMM)
+//   EPI_F32_STORE                        : alpha*acc (+ bias) -> fp32 d0[row][n] (data gradients consumed by the
+//                                          max-pool / ROIAlign backward kernels)
+//   EPI_ATOMIC_F32                       : split-K partial (skinny problems): d0[row][n] += acc
+#include "ptx.cuh"
+#include "gemm_tn.h"
+#include <stdlib.h>
+
+namespace ptb {
+
+int make_tmap_f16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
+                  const uint64_t* strides_bytes, const uint32_t* box);
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int A_STAGE_BYTES = BM * BK * 2;
+constexpr int STAGING_BYTES = BM * 128;
+constexpr int NUM_THREADS = 320;  // TMA warp, MMA warp, 8 epilogue warps
+constexpr int EPI_THREADS = 256;
+
+struct Ctl {
+  uint64_t full[8];
+  uint64_t empty[8];
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
+  uint64_t aux_full;
+  uint32_t tmem_base;
+  uint32_t pad;
+};
+
+__device__ __forceinline__ bool tile_live(const int* __restrict__ seg_counts, int seg_cap, int row0, int rows) {
+  if (seg_counts == nullptr) return true;
+  int r = row0;
+  const int rend = min(row0 + BM, rows);
+  while (r < rend) {
+    const int n = r / seg_cap;
+    if (r - n * seg_cap < min(seg_counts[n], seg_cap)) return true;
+    r = (n + 1) * seg_cap;
+  }
+  return false;
+}
+
+__device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(a, b);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+template <int NCH>  // N tile = 64 * NCH columns
+__global__ void __maxnreg__(200)  // 320 threads x 200 registers = one CTA per SM
+gemm_tn_promote_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                       const __grid_constant__ CUtensorMap map_d, const __grid_constant__ CUtensorMap map_aux,
+                       const GemmTnParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  constexpr int bn = 64 * NCH;
+  constexpr int stage_bytes = A_STAGE_BYTES + bn * BK * 2;
+  const int stages = p.stages;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* staging = smem + stages * stage_bytes;  // two 16 KB buffers: hi chunk, lo chunk
+  float* bias_s = reinterpret_cast<float*>(staging + 2 * STAGING_BYTES);
+  Ctl* ctl = reinterpret_cast<Ctl*>(bias_s + 256);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int m_tiles = (p.rows + BM - 1) / BM;
+  const int n_tiles = p.n_total / bn;
+  const int tiles_per_batch = m_tiles * n_tiles;
+  const int ksplit = p.ksplit;
+  const int num_tiles = tiles_per_batch * p.batch * ksplit;
+  const int k_chunks = p.k_per_tap / BK;
+  const int k_iters_total = k_chunks * p.taps;
+  const int chunk = p.chunk;
+
+  constexpr uint32_t tmem_cols = 2 * bn < 32 ? 32 : 2 * bn;  // 128 / 256 / 512: powers of two
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+    if (p.epi != EPI_F32_STORE && p.epi != EPI_ATOMIC_F32) tma_prefetch_desc(&map_d);
+    for (int i = 0; i < stages; ++i) {
+      mbar_init(&ctl->full[i], 1);
+      mbar_init(&ctl->empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&ctl->tmem_full[i], 1);
+      mbar_init(&ctl->tmem_empty[i], EPI_THREADS / 32);
+    }
+    mbar_init(&ctl->aux_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(&ctl->tmem_base, tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = ctl->tmem_base;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (elect_one()) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int work = blockIdx.x; work < num_tiles; work += gridDim.x) {
+        const int ks = work % ksplit;
+        const int tile = work / ksplit;
+        const int b = tile / tiles_per_batch;
+        const int rem = tile - b * tiles_per_batch;
+        const int mt = rem / n_tiles;
+        const int nt = rem - mt * n_tiles;
+        const int row0 = mt * BM;
+        const int n0 = nt * bn;
+        if (!tile_live(p.seg_counts, p.seg_cap, row0, p.rows)) continue;
+        const int ki0 = (k_iters_total * ks) / ksplit, ki1 = (k_iters_total * (ks + 1)) / ksplit;
+        for (int ki = ki0; ki < ki1; ++ki) {
+          const int t = ki / k_chunks, kc = ki - t * k_chunks;
+          mbar_wait(&ctl->empty[s], ph ^ 1);
+          uint8_t* sa = smem + s * stage_bytes;
+          uint8_t* sb = sa + A_STAGE_BYTES;
+          mbar_arrive_expect_tx(&ctl->full[s], stage_bytes);
+          tma_load_3d(sa, &map_a, &ctl->full[s], kc * BK, row0 + p.shifts[t], b);
+          tma_load_2d(sb, &map_b, &ctl->full[s], t * p.k_per_tap + kc * BK, n0);
+          if (++s == stages) {
+            s = 0;
+            ph ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (chunked)
+    const uint32_t idesc = umma_idesc_f16(BM, bn, 0, 0);
+    int s = 0;
+    uint32_t ph = 0;
+    int it = 0;  // accumulator-stage use counter: one per CHUNK
+    const uint32_t tmem_base_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    for (int work = blockIdx.x; work < num_tiles; work += gridDim.x) {
+      if (p.seg_counts != nullptr) {
+        const int tile_ = work / ksplit;
+        const int mt_ = (tile_ % tiles_per_batch) / n_tiles;
+        if (!tile_live(p.seg_counts, p.seg_cap, mt_ * BM, p.rows)) continue;
+      }
+      const int ks = work % ksplit;
+      const int k_iters = (k_iters_total * (ks + 1)) / ksplit - (k_iters_total * ks) / ksplit;
+      for (int kb = 0; kb < k_iters; kb += chunk) {
+        const int kn = min(chunk, k_iters - kb);
+        const int as = it & 1;
+        const uint32_t aph = (it >> 1) & 1;
+        ++it;
+        mbar_wait(&ctl->tmem_empty[as], aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base_u + as * bn;
+        for (int ki = 0; ki < kn; ++ki) {
+          mbar_wait(&ctl->full[s], ph);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
+            const uint64_t da = umma_desc_sw128(a_addr, 16, 1024);
+            const uint64_t db = umma_desc_sw128(a_addr + A_STAGE_BYTES, 16, 1024);
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)
+              umma_f16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (ki > 0 || k > 0) ? 1u : 0u);
+            umma_commit(&ctl->empty[s]);
+            if (ki == kn - 1) umma_commit(&ctl->tmem_full[as]);
+          }
+          __syncwarp();
+          if (++s == stages) {
+            s = 0;
+            ph ^= 1;
+          }
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ promotion + epilogue (warps 2..9)
+    const int q = warp & 3;            // TMEM lane quarter this warp may access
+    const int hf = (warp - 2) >> 2;    // which 32-column half of every 64-column group this warp owns
+    const int r = q * 32 + lane;       // row of the 128-row tile owned by this thread
+    const int et = threadIdx.x - 64;
+    int it = 0;
+    int staged_n0 = -1;
+    uint32_t aux_ph = 0;
+    for (int work = blockIdx.x; work < num_tiles; work += gridDim.x) {
+      const int tile = work / ksplit;
+      const int ks = work % ksplit;
+      const int b = tile / tiles_per_batch;
+      const int rem = tile - b * tiles_per_batch;
+      const int mt = rem / n_tiles;
+      const int nt = rem - mt * n_tiles;
+      const int row0 = mt * BM;
+      const int n0 = nt * bn;
+      if (!tile_live(p.seg_counts, p.seg_cap, row0, p.rows)) continue;
+      const int k_iters = (k_iters_total * (ks + 1)) / ksplit - (k_iters_total * ks) / ksplit;
+
+      if (n0 != staged_n0) {
+        named_bar_sync(1, EPI_THREADS);
+        for (int i = et; i < bn; i += EPI_THREADS)
+          bias_s[i] = (p.bias != nullptr && n0 + i < p.n_bias) ? p.bias[n0 + i] : 0.f;
+        named_bar_sync(1, EPI_THREADS);
+        staged_n0 = n0;
+      }
+
+      float acc[NCH][32];
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch)
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[ch][j] = 0.f;
+
+      for (int kb = 0; kb < k_iters; kb += chunk) {
+        const int as = it & 1;
+        const uint32_t aph = (it >> 1) & 1;
+        ++it;
+        mbar_wait(&ctl->tmem_full[as], aph);
+        tc_fence_after();
+        const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * bn + 32 * hf;
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) {
+          uint32_t v[32];
+          tmem_ld_32x32(t_addr + ch * 64, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[ch][j] += __uint_as_float(v[j]);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ctl->tmem_empty[as]);
+      }
+
+      const int row = row0 + r;
+      bool row_live = row < p.rows;
+      if (p.wp > 0) row_live = row_live && ((row % p.wp) < p.w_valid);
+
+      if (p.epi == EPI_ATOMIC_F32) {
+        if (row < p.rows) {
+          float* orow = p.d0 + (static_cast<size_t>(b) * p.rows + row) * p.ld0 + n0 + 32 * hf;
+#pragma unroll
+          for (int ch = 0; ch < NCH; ++ch)
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(orow + ch * 64 + 4 * j),
+                           "f"(acc[ch][4 * j]), "f"(acc[ch][4 * j + 1]), "f"(acc[ch][4 * j + 2]),
+                           "f"(acc[ch][4 * j + 3])
+                           : "memory");
+        }
+      } else if (p.epi == EPI_F32_STORE) {
+        if (row < p.rows) {
+          float* orow = p.d0 + (static_cast<size_t>(b) * p.rows + row) * p.ld0 + n0 + 32 * hf;
+#pragma unroll
+          for (int ch = 0; ch < NCH; ++ch)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float4 o;
+              const float* bs = bias_s + ch * 64 + 32 * hf + 4 * j;
+              o.x = row_live ? acc[ch][4 * j] * p.alpha + bs[0] : 0.f;
+              o.y = row_live ? acc[ch][4 * j + 1] * p.alpha + bs[1] : 0.f;
+              o.z = row_live ? acc[ch][4 * j + 2] * p.alpha + bs[2] : 0.f;
+              o.w = row_live ? acc[ch][4 * j + 3] * p.alpha + bs[3] : 0.f;
+              *reinterpret_cast<float4*>(orow + ch * 64 + 4 * j) = o;
+            }
+        }
+      } else {
+        // triple output: hi chunk in staging buffer 0, lo chunk in buffer 1, three TMA stores per 64 columns
+        uint8_t* rowh = staging + r * 128;
+        uint8_t* rowl = staging + STAGING_BYTES + r * 128;
+        const bool masked = p.epi == EPI_SPLIT3_MASK_F16;
+        const bool relu = p.epi == EPI_SPLIT3_RELU_F16;
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) {
+          const int c0 = ch * 64;
+          if (warp == 2 && elect_one()) tma_store_wait_read<0>();
+          named_bar_sync(1, EPI_THREADS);
+          if (masked) {
+            if (warp == 2 && elect_one()) {  // forward activation (hi, lo) tiles land in the staging buffers
+              mbar_arrive_expect_tx(&ctl->aux_full, 2 * STAGING_BYTES);
+              tma_load_3d(staging, &map_aux, &ctl->aux_full, n0 + c0, row0, b);
+              tma_load_3d(staging + STAGING_BYTES, &map_aux, &ctl->aux_full, p.n_total + n0 + c0, row0, b);
+            }
+            mbar_wait(&ctl->aux_full, aux_ph);
+            aux_ph ^= 1u;
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int jj = 4 * hf + j;
+            uint4* dh = reinterpret_cast<uint4*>(rowh + ((jj ^ (r & 7)) << 4));
+            uint4* dl = reinterpret_cast<uint4*>(rowl + ((jj ^ (r & 7)) << 4));
+            float f[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              f[e] = acc[ch][j * 8 + e] * p.alpha + bias_s[c0 + jj * 8 + e];
+              if (relu) f[e] = fmaxf(f[e], 0.f);
+              if (!row_live) f[e] = 0.f;
+            }
+            if (masked) {
+              const uint4 ah = *dh, al = *dl;
+              const __half2* ahp = reinterpret_cast<const __half2*>(&ah);
+              const __half2* alp = reinterpret_cast<const __half2*>(&al);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 xh = __half22float2(ahp[e]), xl = __half22float2(alp[e]);
+                if (!(xh.x + xl.x > 0.f)) f[2 * e] = 0.f;
+                if (!(xh.y + xl.y > 0.f)) f[2 * e + 1] = 0.f;
+              }
+            }
+            uint4 oh, ol;
+            split_pair(f[0], f[1], oh.x, ol.x);
+            split_pair(f[2], f[3], oh.y, ol.y);
+            split_pair(f[4], f[5], oh.z, ol.z);
+            split_pair(f[6], f[7], oh.w, ol.w);
+            *dh = oh;
+            *dl = ol;
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(1, EPI_THREADS);
+          if (warp == 2 && elect_one()) {
+            tma_store_3d(&map_d, staging, n0 + c0, row0, b);
+            tma_store_3d(&map_d, staging + STAGING_BYTES, p.n_total + n0 + c0, row0, b);
+            tma_store_3d(&map_d, staging, 2 * p.n_total + n0 + c0, row0, b);
+            tma_store_commit();
+          }
+        }
+      }
+    }
+    if (warp == 2 && elect_one()) tma_store_wait_all<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 0) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+int g_num_sms = 0;
+
+template <int NCH>
+int launch_nch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& md, const CUtensorMap& mx,
+               GemmTnParams& p, int max_ctas, cudaStream_t stream) {
+  constexpr int bn = 64 * NCH;
+  constexpr int stage_bytes = A_STAGE_BYTES + bn * BK * 2;
+  const int fixed = 2 * STAGING_BYTES + 256 * 4 + (int)sizeof(Ctl) + 1024;
+  int stages = (232448 - fixed) / stage_bytes;
+  if (stages > 8) stages = 8;
+  if (stages < 2) return 1005;
+  p.stages = stages;
+  const int smem_bytes = stages * stage_bytes + fixed;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tn_promote_kernel<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         232448);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  const int m_tiles = (p.rows + BM - 1) / BM;
+  const int num_tiles = m_tiles * (p.n_total / bn) * p.batch * p.ksplit;
+  int grid = num_tiles < g_num_sms ? num_tiles : g_num_sms;
+  if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
+  if (grid < 1) return 0;
+  gemm_tn_promote_kernel<NCH><<<grid, NUM_THREADS, smem_bytes, stream>>>(ma, mb, md, mx, p);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace
+
+// a.D / a.aux: triples [batch][rows][3*n_total] (ldd = their row pitch); chunk = k-iterations of 64 per promotion
+int gemm_tn_promote_launch(const GemmTnArgs& a, int chunk, cudaStream_t stream) {
+  if (a.k_per_tap % BK != 0) return 1001;
+  if (a.bn != 64 && a.bn != 128 && a.bn != 256) return 1003;
+  if (a.n_total % a.bn != 0) return 1002;
+  if (a.taps < 1 || a.taps > 9) return 1004;
+  const bool f32_out = a.epi == EPI_F32_STORE || a.epi == EPI_ATOMIC_F32;
+  const bool triple = a.epi == EPI_SPLIT3_RELU_F16 || a.epi == EPI_SPLIT3_F16 || a.epi == EPI_SPLIT3_MASK_F16;
+  if (!f32_out && !triple) return 1021;
+  if (a.ksplit > 1 && a.epi != EPI_ATOMIC_F32) return 1007;
+  if (a.seg_counts != nullptr && (a.batch != 1 || a.seg_cap <= 0)) return 1008;
+  if (a.epi == EPI_SPLIT3_MASK_F16 && a.aux == nullptr) return 1009;
+  if (f32_out && a.d0 == nullptr) return 1009;
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  CUtensorMap ma, mb, md, mx;
+  {
+    uint64_t dims[3] = {(uint64_t)a.k_per_tap, (uint64_t)a.rows, (uint64_t)a.batch};
+    uint64_t str[2] = {(uint64_t)a.lda * 2, (uint64_t)a.a_batch_stride * 2};
+    uint32_t box[3] = {BK, BM, 1};
+    if (make_tmap_f16(&ma, a.A, 3, dims, str, box)) return 1010;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)a.k_per_tap * a.taps, (uint64_t)a.n_total};
+    uint64_t str[1] = {(uint64_t)a.k_per_tap * a.taps * 2};
+    uint32_t box[2] = {BK, (uint32_t)a.bn};
+    if (make_tmap_f16(&mb, a.B, 2, dims, str, box)) return 1011;
+  }
+  if (triple) {
+    uint64_t dims[3] = {(uint64_t)a.n_total * 3, (uint64_t)a.rows, (uint64_t)a.batch};
+    uint64_t str[2] = {(uint64_t)a.ldd * 2, (uint64_t)a.d_batch_stride * 2};
+    uint32_t box[3] = {64, BM, 1};
+    if (make_tmap_f16(&md, a.D, 3, dims, str, box)) return 1012;
+    if (a.epi == EPI_SPLIT3_MASK_F16) {
+      if (make_tmap_f16(&mx, a.aux, 3, dims, str, box)) return 1013;
+    } else {
+      mx = md;
+    }
+  } else {
+    md = ma;
+    mx = ma;
+  }
+  GemmTnParams p;
+  p.batch = a.batch;
+  p.rows = a.rows;
+  p.k_per_tap = a.k_per_tap;
+  p.taps = a.taps;
+  for (int i = 0; i < 9; ++i) p.shifts[i] = i < a.taps ? a.shifts[i] : 0;
+  p.n_total = a.n_total;
+  p.bn = a.bn;
+  p.w_valid = a.w_valid;
+  p.wp = a.wp;
+  p.epi = a.epi;
+  p.ksplit = a.ksplit > 1 ? a.ksplit : 1;
+  p.b_resident = 0;
+  p.staging_bufs = 2;
+  p.bias = a.bias;
+  p.n_bias = a.n_bias;
+  p.d0 = a.d0;
+  p.ld0 = a.ld0;
+  p.d1 = nullptr;
+  p.ld1 = 0;
+  p.split = 0;
+  p.n_valid = a.n_total;
+  p.seg_counts = a.seg_counts;
+  p.seg_cap = a.seg_cap;
+  p.alpha = a.alpha;
+  static int chunk_env = -1;
+  if (chunk_env < 0) {
+    const char* e = getenv("PTB200_X3_CHUNK");
+    chunk_env = e ? atoi(e) : 0;
+  }
+  p.chunk = chunk_env > 0 ? chunk_env : (chunk > 0 ? chunk : 4);
+  switch (a.bn) {
+    case 64: return launch_nch<1>(ma, mb, md, mx, p, a.max_ctas, stream);
+    case 128: return launch_nch<2>(ma, mb, md, mx, p, a.max_ctas, stream);
+    default: return launch_nch<4>(ma, mb, md, mx, p, a.max_ctas, stream);
+  }
+}
+
+}  // namespace ptb

@@ -9,7 +9,15 @@
 
 namespace {
 
-__global__ void ema_kernel(float* __restrict__ teacher, const float* __restrict__ student, int64_t n, float keep) {
+// keep_dev != nullptr: the keep rate is read from device memory (CUDA-graph replays of the step: the host writes
+// the EMA keep rate on update iterations and 1.0 on the others, pt/engine/trainer.py:296-298; keep == 1 leaves the
+// teacher untouched, bit for bit)
+__global__ void ema_kernel(float* __restrict__ teacher, const float* __restrict__ student, int64_t n, float keep,
+                           const float* __restrict__ keep_dev) {
+  if (keep_dev != nullptr) {
+    keep = keep_dev[0];
+    if (keep == 1.f) return;
+  }
   const float ks = 1.f - keep;
   const int64_t n4 = n >> 2;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n4;
@@ -130,7 +138,13 @@ inline int grid_stream(int64_t n) {
 #define STREAM static_cast<cudaStream_t>(stream)
 
 extern "C" int ptb200_ema_update(float* teacher, const float* student, int64_t n, float keep_rate, void* stream) {
-  ema_kernel<<<grid_stream(n), 256, 0, STREAM>>>(teacher, student, n, keep_rate);
+  ema_kernel<<<grid_stream(n), 256, 0, STREAM>>>(teacher, student, n, keep_rate, nullptr);
+  return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int ptb200_ema_update_dev(float* teacher, const float* student, int64_t n, const float* keep_rate_dev,
+                                     void* stream) {
+  ema_kernel<<<grid_stream(n), 256, 0, STREAM>>>(teacher, student, n, 1.f, keep_rate_dev);
   return static_cast<int>(cudaGetLastError());
 }
 

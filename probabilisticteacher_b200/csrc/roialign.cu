@@ -122,9 +122,10 @@ constexpr int kMaxP = 7;
 // the roi are computed once (threads 0..2P-1) and shared by all P*P bins; each thread then walks the
 // P bin rows of its column. BWD = true scatters the output gradient instead (fp32 vector atomics).
 // X3 (forward only): feature rows and output bins are f16x3 triples [hi | lo | hi] of width 3C.
-template <bool BWD, bool X3 = false>
+// GF32 (backward only): the output gradient is fp32 (f16x3 training path) instead of fp16.
+template <bool BWD, bool X3 = false, bool GF32 = false>
 __global__ void __launch_bounds__(512)
-roi_align_roi_kernel(const __half* __restrict__ feat, const __half* __restrict__ dout, int H, int W, int C,
+roi_align_roi_kernel(const __half* __restrict__ feat, const void* __restrict__ dout_v, int H, int W, int C,
                      const float4* __restrict__ rois, const int* __restrict__ roi_count, int cap, float scale,
                      int P, __half* __restrict__ out, float* __restrict__ dfeat) {
   __shared__ Axis s_ax[2 * kMaxP];  // [0,P): y axes of bin rows, [P,2P): x axes of bin columns
@@ -163,15 +164,26 @@ roi_align_roi_kernel(const __half* __restrict__ feat, const __half* __restrict__
     float acc[8];
     float gr[8];
     if (BWD) {
-      const uint4 gv = *reinterpret_cast<const uint4*>(dout + o_off);
-      const __half2* gh = reinterpret_cast<const __half2*>(&gv);
       bool any = false;
+      if (GF32) {
+        const float* gp = static_cast<const float*>(dout_v) + o_off;
+        const float4 g0 = *reinterpret_cast<const float4*>(gp), g1 = *reinterpret_cast<const float4*>(gp + 4);
+        const float gf[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float2 f = __half22float2(gh[e]);
-        gr[2 * e] = f.x / g.count;
-        gr[2 * e + 1] = f.y / g.count;
-        any = any || f.x != 0.f || f.y != 0.f;
+        for (int e = 0; e < 8; ++e) {
+          gr[e] = gf[e] / g.count;
+          any = any || gf[e] != 0.f;
+        }
+      } else {
+        const uint4 gv = *reinterpret_cast<const uint4*>(static_cast<const __half*>(dout_v) + o_off);
+        const __half2* gh = reinterpret_cast<const __half2*>(&gv);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = __half22float2(gh[e]);
+          gr[2 * e] = f.x / g.count;
+          gr[2 * e + 1] = f.y / g.count;
+          any = any || f.x != 0.f || f.y != 0.f;
+        }
       }
       if (!any) continue;
     } else {
@@ -308,6 +320,16 @@ extern "C" int ptb200_roi_align_bwd_f16(const void* dout, int n, int h, int w, i
   roi_align_roi_kernel<true><<<n * cap, pooled * (c / 8), 0, STREAM>>>(
       nullptr, static_cast<const __half*>(dout), h, w, c, reinterpret_cast<const float4*>(rois), roi_count, cap,
       spatial_scale, pooled, nullptr, dfeat);
+  return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int ptb200_roi_align_bwd_f32(const float* dout, int n, int h, int w, int c, const float* rois,
+                                        const int* roi_count, int cap, float spatial_scale, int pooled,
+                                        float* dfeat, void* stream) {
+  if (c % 8 != 0 || pooled > kMaxP || pooled * (c / 8) > 512) return 1401;
+  roi_align_roi_kernel<true, false, true><<<n * cap, pooled * (c / 8), 0, STREAM>>>(
+      nullptr, dout, h, w, c, reinterpret_cast<const float4*>(rois), roi_count, cap, spatial_scale, pooled, nullptr,
+      dfeat);
   return static_cast<int>(cudaGetLastError());
 }
 

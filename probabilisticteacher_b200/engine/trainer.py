@@ -18,28 +18,19 @@ from ..solver import lr_at_iter
 from ..structures import Boxes, FreeInstances
 
 
-def warmup_multistep_lr(base_lr, it, steps, gamma, warmup_factor, warmup_iters, warmup_method="linear"):
-    """detectron2 WarmupMultiStepLR (configs/pt/final_c2f.yaml:6)."""
-    f = 1.0
-    if it < warmup_iters:
-        if warmup_method == "constant":
-            f = warmup_factor
-        else:
-            alpha = it / warmup_iters
-            f = warmup_factor * (1 - alpha) + alpha
-    k = sum(1 for s in steps if it >= s)
-    return base_lr * f * (gamma ** k)
-
-
 class PTrainer:
     def __init__(self, cfg, data_loader_iter, device=None, seed=0, loss_scale=1024.0, use_cuda_graph=False,
-                 graph_warmup=3, gt_capacity=64, concurrent=False):
+                 graph_warmup=3, gt_capacity=64, concurrent=False, precision="f16"):
+        """precision: "f16x3" = fp32-equivalent forward + backward (meets the 1e-3 parity with the reference's fp32
+        step), "f16" = fp16 operands with fp32 accumulation / master weights (throughput mode)."""
         self.cfg = cfg
+        self.precision = precision
         self.device = torch.device(device or "cuda")
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self.rank = dist.get_rank() if self.world > 1 else 0
-        self.model = build_model(cfg, self.device, loss_scale=loss_scale)
-        self.model_teacher = build_model(cfg, self.device, loss_scale=loss_scale, with_grads=False)
+        self.model = build_model(cfg, self.device, loss_scale=loss_scale, precision=precision)
+        self.model_teacher = build_model(cfg, self.device, loss_scale=loss_scale, with_grads=False,
+                                         precision=precision)
         self.model.init_synthetic(seed)
         if self.world > 1:  # DDP _sync_params_and_buffers (trainer.py:491-496)
             dp.broadcast_params(self.model.arena.data, src=0)
@@ -170,9 +161,13 @@ class PTrainer:
 
     # ------------------------------------------------------------------ EMA (trainer.py:431-449)
     @torch.no_grad()
-    def _update_teacher_model(self, keep_rate=0.996):
+    def _update_teacher_model(self, keep_rate=0.996, keep_dev=None):
+        """keep_dev (device fp32 scalar) replaces keep_rate in the captured step: see `_stage`."""
         s, t = self.model.arena, self.model_teacher.arena
-        call("ptb200_ema_update", t.data, s.data, t.total, float(keep_rate))
+        if keep_dev is not None:
+            call("ptb200_ema_update_dev", t.data, s.data, t.total, keep_dev)
+        else:
+            call("ptb200_ema_update", t.data, s.data, t.total, float(keep_rate))
         t.pack()
 
     # ------------------------------------------------------------------ clip + SGD (trainer.py:383-386,592-603)
@@ -254,15 +249,20 @@ class PTrainer:
                 g["gt_boxes"][..., 2:] = 1.0
                 g["gt_classes"] = torch.zeros(n, cap, dtype=torch.int32, device=dev)
                 g["gt_count"] = torch.zeros(n, dtype=torch.int32, device=dev)
-                g["pin_boxes"] = torch.zeros(n, cap, 4, dtype=torch.float32).pin_memory()
-                g["pin_classes"] = torch.zeros(n, cap, dtype=torch.int32).pin_memory()
-                g["pin_count"] = torch.zeros(n, dtype=torch.int32).pin_memory()
+                # pinned host staging, one set per slot: the host runs ahead of the device (a graph replay is launched
+                # in microseconds), so a buffer is rewritten only after the copies that read it have completed
+                g["pin_boxes"] = [torch.zeros(n, cap, 4, dtype=torch.float32).pin_memory() for _ in range(2)]
+                g["pin_classes"] = [torch.zeros(n, cap, dtype=torch.int32).pin_memory() for _ in range(2)]
+                g["pin_count"] = [torch.zeros(n, dtype=torch.int32).pin_memory() for _ in range(2)]
             st["groups"][name] = g
         nq = len(lq) + len(uq)
         st["resize_params"] = torch.zeros(nq, 4, dtype=torch.int32, device=dev)
         st["resize_ratio"] = torch.ones(nq, dtype=torch.float32, device=dev)
-        st["pin_params"] = torch.zeros(nq, 4, dtype=torch.int32).pin_memory()
-        st["pin_ratio"] = torch.ones(nq, dtype=torch.float32).pin_memory()
+        st["pin_params"] = [torch.zeros(nq, 4, dtype=torch.int32).pin_memory() for _ in range(2)]
+        st["pin_ratio"] = [torch.ones(nq, dtype=torch.float32).pin_memory() for _ in range(2)]
+        st["ema_keep"] = torch.ones(1, dtype=torch.float32, device=dev)
+        st["pin_keep"] = [torch.ones(1, dtype=torch.float32).pin_memory() for _ in range(2)]
+        st["pin_done"] = [None, None]      # main-stream events: the host->device copies out of a slot's pinned buffers ran
         st["stage_ready"] = [None, None]   # copy-stream events: images of a slot have landed
         st["stage_free"] = [None, None]    # main-stream events: a slot's images were moved into the static buffers
         return st
@@ -296,23 +296,29 @@ class PTrainer:
         cap = self._gt_capacity
         main = torch.cuda.current_stream()
         main.wait_event(st["stage_ready"][slot])
+        if st["pin_done"][slot] is not None:
+            # the copies issued two steps ago from this slot's pinned buffers must have run before the host
+            # rewrites them (they have, unless the host is more than a full step ahead of the device)
+            st["pin_done"][slot].synchronize()
         for name, grp in zip(("lq", "lk", "uq", "uk"), data):
             g = st["groups"][name]
             g["images"].copy_(g["staging"][slot], non_blocking=True)
             if "gt_boxes" in g:
-                g["pin_boxes"].zero_()
-                g["pin_boxes"][..., 2:] = 1.0
+                pb, pc, pn = g["pin_boxes"][slot], g["pin_classes"][slot], g["pin_count"][slot]
+                pb.zero_()
+                pb[..., 2:] = 1.0
+                pc.zero_()
                 for k, d in enumerate(grp):
                     inst = d["instances"]
                     m = len(inst.gt_boxes)
                     if m > cap:
                         raise ValueError(f"{m} gt boxes exceed gt_capacity={cap}")
-                    g["pin_boxes"][k, :m] = inst.gt_boxes.tensor
-                    g["pin_classes"][k, :m] = inst.gt_classes.to(torch.int32)
-                    g["pin_count"][k] = m
-                g["gt_boxes"].copy_(g["pin_boxes"], non_blocking=True)
-                g["gt_classes"].copy_(g["pin_classes"], non_blocking=True)
-                g["gt_count"].copy_(g["pin_count"], non_blocking=True)
+                    pb[k, :m] = inst.gt_boxes.tensor
+                    pc[k, :m] = inst.gt_classes.to(torch.int32)
+                    pn[k] = m
+                g["gt_boxes"].copy_(pb, non_blocking=True)
+                g["gt_classes"].copy_(pc, non_blocking=True)
+                g["gt_count"].copy_(pn, non_blocking=True)
         # PTrainer.resize geometry (trainer.py:561-566). Draw order as in run_step (unlabel_q first, then
         # label_q: trainer.py:333-334); storage order: label_q rows first, then unlabel_q rows.
         nl = len(data[0])
@@ -322,16 +328,23 @@ class PTrainer:
                 ratio = self.rng.uniform(0.5, 1.0)
                 d_h, d_w = int(h * ratio), int(w * ratio)
                 k = base + j
-                st["pin_params"][k, 0] = d_h
-                st["pin_params"][k, 1] = d_w
-                st["pin_params"][k, 2] = int((w - d_w) / 2)
-                st["pin_params"][k, 3] = int((h - d_h) / 2)
-                st["pin_ratio"][k] = ratio
-        st["resize_params"].copy_(st["pin_params"], non_blocking=True)
-        st["resize_ratio"].copy_(st["pin_ratio"], non_blocking=True)
+                pp, pr = st["pin_params"][slot], st["pin_ratio"][slot]
+                pp[k, 0] = d_h
+                pp[k, 1] = d_w
+                pp[k, 2] = int((w - d_w) / 2)
+                pp[k, 3] = int((h - d_h) / 2)
+                pr[k] = ratio
+        st["resize_params"].copy_(st["pin_params"][slot], non_blocking=True)
+        st["resize_ratio"].copy_(st["pin_ratio"][slot], non_blocking=True)
+        # teacher update cadence (trainer.py:296-298): the captured EMA reads its keep rate from device memory
+        cfg = self.cfg
+        update = (self.iter - cfg.UNSUPNET.BURN_UP_STEP) % cfg.UNSUPNET.TEACHER_UPDATE_ITER == 0
+        st["pin_keep"][slot][0] = float(cfg.UNSUPNET.EMA_KEEP_RATE) if update else 1.0
+        st["ema_keep"].copy_(st["pin_keep"][slot], non_blocking=True)
         ev = torch.cuda.Event()
         ev.record(main)
         st["stage_free"][slot] = ev
+        st["pin_done"][slot] = ev
 
     def _static_batches(self):
         st = self._static
@@ -357,7 +370,7 @@ class PTrainer:
         b = self._static_batches()
         nl = len(b["lq"])
         self.model.zero_grad()
-        self._update_teacher_model(keep_rate=cfg.UNSUPNET.EMA_KEEP_RATE)
+        self._update_teacher_model(keep_dev=st["ema_keep"])
         with torch.no_grad():
             _, _, roih, _ = self.model_teacher(b["uk"], branch="unsup_data_weak")
         pseudo, _ = self.process_pseudo_label(roih, "roih", "all")
@@ -434,7 +447,7 @@ class PTrainer:
         keep = []  # tensors that cross streams stay referenced until the join
         with torch.cuda.stream(s_t):
             refresh_stream()
-            self._update_teacher_model(keep_rate=cfg.UNSUPNET.EMA_KEEP_RATE)
+            self._update_teacher_model(keep_dev=st["ema_keep"])
             with torch.no_grad():
                 _, _, roih, _ = self.model_teacher(b["uk"], branch="unsup_data_weak")
             pseudo, _ = self.process_pseudo_label(roih, "roih", "all")
@@ -542,10 +555,11 @@ class PTrainer:
     def build_checkpointer(self, save_dir=None):
         """`DetectionTSCheckpointer(EnsembleTSModel(teacher, student), cfg.OUTPUT_DIR, optimizer=...)`
         (trainer.py:104-111); rank 0 writes (fvcore `save_to_disk=comm.is_main_process()`)."""
-        from ..checkpoint import ArenaSGDState, DetectionTSCheckpointer, EnsembleTSModel
+        from ..checkpoint import ArenaSGDState, DetectionTSCheckpointer, EnsembleTSModel, SchedulerState
         ens = EnsembleTSModel(self.model_teacher, self.model)
         self.checkpointer = DetectionTSCheckpointer(ens, self.cfg.OUTPUT_DIR if save_dir is None else save_dir,
-                                                    save_to_disk=self.rank == 0, optimizer=ArenaSGDState(self))
+                                                    save_to_disk=self.rank == 0, optimizer=ArenaSGDState(self),
+                                                    scheduler=SchedulerState(self))
         return self.checkpointer
 
     def save_checkpoint(self, name=None):
@@ -557,13 +571,18 @@ class PTrainer:
         return self.checkpointer.save(name or "model_{:07d}".format(max(last, 0)), iteration=last)
 
     def resume_or_load(self, resume=False):
-        """trainer.py:466-495: resume = everything from `<OUTPUT_DIR>/last_checkpoint` and continue at the next
-        iteration; otherwise only the weights of cfg.MODEL.WEIGHTS, starting from iteration 0. Under data
-        parallelism rank 0's arenas are broadcast afterwards (DDP `_sync_params_and_buffers`, :491-494)."""
+        """trainer.py:466-495. resume=True loads model + optimizer + scheduler from `cfg.MODEL.WEIGHTS` (the reference
+        passes that path, not `last_checkpoint`: trainer.py:478-481) and continues at the stored iteration + 1; when
+        MODEL.WEIGHTS is empty, `<OUTPUT_DIR>/last_checkpoint` is used (what the reference's docstring describes).
+        resume=False loads only the weights of cfg.MODEL.WEIGHTS and starts from iteration 0. Under data parallelism
+        rank 0's arenas are broadcast afterwards (DDP `_sync_params_and_buffers`, :491-494)."""
         if getattr(self, "checkpointer", None) is None:
             self.build_checkpointer()
-        if resume and self.checkpointer.has_checkpoint():
-            rest = self.checkpointer.load(self.checkpointer.get_checkpoint_file())
+        if resume:
+            path = self.cfg.MODEL.WEIGHTS
+            if not path and self.checkpointer.has_checkpoint():
+                path = self.checkpointer.get_checkpoint_file()
+            rest = self.checkpointer.load(path, checkpointables=["optimizer", "scheduler"])
             self.start_iter = rest.get("iteration", -1) + 1
             self.iter = self.start_iter
         else:

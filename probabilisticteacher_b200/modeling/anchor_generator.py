@@ -28,6 +28,11 @@ class DifferentiableAnchorGenerator(nn.Module, _GridMixin):
         self.offset = cfg.MODEL.ANCHOR_GENERATOR.OFFSET
         self.num_cell = arena.A
         self.differentiable = True
+        # the learnable (w, h) pairs start from cfg.MODEL.ANCHOR_GENERATOR.ANCHOR (anchor_generator.py:66-72), so a
+        # model built from cfg alone (e.g. followed by a backbone-only weight file) has usable anchors
+        anchor = torch.tensor(cfg.MODEL.ANCHOR_GENERATOR.ANCHOR[0], dtype=torch.float32)
+        with torch.no_grad():
+            arena.view("proposal_generator.anchor_generator.anchor_0").copy_(anchor.to(arena.device))
 
     def forward(self, H, W):
         wh = self.arena.view("proposal_generator.anchor_generator.anchor_0")

@@ -31,15 +31,19 @@ class VGG(nn.Module):
         records = []
         block = 1
         if ar.precision == "f16x3":
-            # split-fp16 parity precision (forward only): x and every activation are [hi | lo | hi] triples
-            assert not save, "the f16x3 parity precision has no backward"
-            for name, cin, cout, _ in specs[1:]:
+            # split-fp16 fp32-equivalent precision: x and every activation are [hi | lo | hi] triples
+            for name, cin, cout, trainable in specs[1:]:
                 b = int(name.split("vgg_block")[1][0])
+                pooled = False
                 if b != block:
                     x = ops.maxpool2x2_x3(x)
                     block = b
+                    pooled = True
                 w3, alpha = ar.x3view(name + ".weight")
-                x = ops.conv3x3_x3(x, w3, alpha, ar.view(name + ".bias"))
+                y = ops.conv3x3_x3(x, w3, alpha, ar.view(name + ".bias"))
+                if save and trainable:
+                    records.append(dict(name=name, x=x, y=y, pooled=pooled, cin=cin, cout=cout))
+                x = y
             return {"vgg_block5": x}, records
         for name, cin, cout, trainable in specs[1:]:
             b = int(name.split("vgg_block")[1][0])
@@ -60,6 +64,8 @@ class VGG(nn.Module):
         the loss scale. Accumulates weight / bias gradients into the arena."""
         ar = self.arena
         inv = 1.0 / self.loss_scale
+        if ar.precision == "f16x3":
+            return self._backward_x3(records, dz)
         for i in range(len(records) - 1, -1, -1):
             r = records[i]
             gw = ar.gview(r["name"] + ".weight").view(r["cout"], 9 * r["cin"])
@@ -72,6 +78,26 @@ class VGG(nn.Module):
                 dz = ops.maxpool2x2_relu_bwd(records[i - 1]["y"], dp)
             else:
                 dz = ops.conv3x3(dz, wd, None, aux=r["x"].t)
+
+
+    def _backward_x3(self, records, dz: ops.FlatAct):
+        """Same chain in the f16x3 precision (the reference's fp32 autograd, pt/engine/trainer.py:383-386): dz and
+        every saved activation are triples; data gradients that feed a max-pool backward are stored in fp32."""
+        ar = self.arena
+        inv = 1.0 / self.loss_scale
+        for i in range(len(records) - 1, -1, -1):
+            r = records[i]
+            gw = ar.gview(r["name"] + ".weight").view(r["cout"], 9 * r["cin"])
+            ops.conv3x3_wgrad_x3(dz, r["x"], gw, r["cout"], r["cin"], scale=inv,
+                                 bias_out=ar.gview(r["name"] + ".bias"))
+            if i == 0:
+                break
+            wd3, alpha = ar.dgrad_x3[r["name"]]
+            if r["pooled"]:
+                dp = ops.conv3x3_dgrad_x3(dz, wd3, alpha)
+                dz = ops.maxpool2x2_relu_bwd_x3(records[i - 1]["y"], dp)
+            else:
+                dz = ops.conv3x3_dgrad_x3(dz, wd3, alpha, aux=r["x"].t)
 
 
 @BACKBONE_REGISTRY.register()

@@ -82,6 +82,8 @@ class GuassianRPN(nn.Module):
         dev = feat.t.device
         rows = N * H * (W + 1)
         norm = self.loss_weight / (self.batch_size_per_image * N)
+        # MODEL.RPN.LOSS_WEIGHT multiplies the supervised losses only (rpn.py:136-141); loss_rpn_unsupervised is unweighted
+        norm_unsup = 1.0 / (self.batch_size_per_image * N)
         if branch == "unsupervised":
             matched, labels = sampling.rpn_match(targets["pseudo_boxes"], targets["pseudo_count"], anchors, N,
                                                  self.iou_thresholds[0], self.iou_thresholds[1])
@@ -93,7 +95,7 @@ class GuassianRPN(nn.Module):
             call("ptb200_rpn_loss_unsup", logits, A, deltas, A * 8, labels, matched, targets["pseudo_boxes"],
                  targets["scores_logists"], targets["boxes_sigma"], targets["pseudo_boxes"].shape[1], anchors, N, H, W,
                  A, targets["scores_logists"].shape[2], int(bool(u.EFL)), float(u.EFL_LAMBDA[0]),
-                 float(u.EFL_LAMBDA[1]), float(u.TAU[0]), float(u.TAU[1]), norm, loss2, dl, dd, da)
+                 float(u.EFL_LAMBDA[1]), float(u.TAU[0]), float(u.TAU[1]), norm_unsup, loss2, dl, dd, da)
             ctx.update(dlogits=dl, ddeltas=dd, danchor_wh=da)
         elif training and compute_loss:
             matched, labels = sampling.rpn_match(targets["gt_boxes"], targets["gt_count"], anchors, N,
@@ -135,6 +137,8 @@ class GuassianRPN(nn.Module):
         N = ctx["N"]
         rows = N * feat.H * (feat.W + 1)
         dev = feat.t.device
+        if ar.precision == "f16x3":
+            return self._backward_x3(ctx, g_cls, g_loc)
         dhead = torch.empty(rows, 128, dtype=torch.float16, device=dev)
         call("ptb200_pack_grad2_f16", ctx["dlogits"], A, ctx["ddeltas"], A * 8, g_cls, g_loc, S, rows, 128, dhead)
         p = "proposal_generator.rpn_head."
@@ -145,6 +149,33 @@ class GuassianRPN(nn.Module):
         ops.conv3x3_wgrad(dzt, feat, ar.gview(p + "conv.weight").view(C, 9 * C), scale=inv,
                           bias_out=ar.gview(p + "conv.bias"))
         dfeat = ops.conv3x3(dzt, ar.dgrad_half["rpn_conv"], None, aux=feat.t)
+        if ctx.get("danchor_wh") is not None:
+            call("ptb200_axpy_dev", g_loc, 1.0, ctx["danchor_wh"],
+                 ar.gview("proposal_generator.anchor_generator.anchor_0"), A * 2)
+        return dfeat
+
+    def _backward_x3(self, ctx, g_cls, g_loc):
+        """f16x3 precision: same chain over triples; returns d(loss)/d(feat) as an UN-masked fp32 tensor
+        [N, H*(W+1), C] (scaled by the loss scale; the ReLU mask of the backbone output is applied when the RPN and
+        ROI paths are summed)."""
+        ar = self.arena
+        C, A = ar.C, ar.A
+        S = self.loss_scale
+        inv = 1.0 / S
+        feat, t = ctx["feat"], ctx["t"]
+        N = ctx["N"]
+        rows = N * feat.H * (feat.W + 1)
+        dhead = ops.pack_grad2_x3(ctx["dlogits"], A, ctx["ddeltas"], A * 8, g_cls, g_loc, S, rows, 128)
+        p = "proposal_generator.rpn_head."
+        ops.wgrad_x3(dhead.view(1, rows, 384), t.t.view(1, rows, 3 * C), ar.gview(p + "_heads.weight"), m_total=128,
+                     n_total=C, scale=inv, bias_out=ar.gview(p + "_heads.bias"))
+        wd3, alpha = ar.dgrad_x3["rpn_heads"]
+        dzt = ops.gemm_tn_x3(dhead.view(1, rows, 384), wd3, alpha, epi=ops.EPI_SPLIT3_MASK, aux=t.t.view(1, rows, 3 * C))
+        dzt = ops.FlatAct(dzt.view(N, -1, 3 * C), feat.H, feat.W)
+        ops.conv3x3_wgrad_x3(dzt, feat, ar.gview(p + "conv.weight").view(C, 9 * C), C, C, scale=inv,
+                             bias_out=ar.gview(p + "conv.bias"))
+        wd3, alpha = ar.dgrad_x3["rpn_conv"]
+        dfeat = ops.conv3x3_dgrad_x3(dzt, wd3, alpha)
         if ctx.get("danchor_wh") is not None:
             call("ptb200_axpy_dev", g_loc, 1.0, ctx["danchor_wh"],
                  ar.gview("proposal_generator.anchor_generator.anchor_0"), A * 2)

@@ -48,7 +48,7 @@ class GuassianROIHead(nn.Module):
         return x0, h1.view(rows, -1), h2.view(rows, -1), scores, deltas
 
     def _box_head_x3(self, feat, rois, counts, cap):
-        """Split-fp16 parity precision of the box head (forward only)."""
+        """Split-fp16 fp32-equivalent precision of the box head."""
         ar = self.arena
         x0 = ops.roi_align_fwd_x3(feat, rois, counts, cap, self.pooler_scale, self.pooler_resolution)
         rows = x0.shape[0]
@@ -105,6 +105,8 @@ class GuassianROIHead(nn.Module):
         dev = ctx["x0"].device
         fc = ar.fc_dim
         seg = (ctx["counts"], ctx["cap"])
+        if ar.precision == "f16x3":
+            return self._backward_x3(ctx, g_cls, g_box)
         dpred = torch.empty(rows, 128, dtype=torch.float16, device=dev)
         call("ptb200_pack_grad2_f16", ctx["dscores"], K + 1, ctx["ddeltas"], 8 * K, g_cls, g_box, S, rows, 128, dpred)
         p = "roi_heads.box_predictor."
@@ -121,3 +123,34 @@ class GuassianROIHead(nn.Module):
         dx0 = ops.gemm_tn(dz1, ar.dgrad_half["fc1"], epi=ops.EPI_BIAS, seg=seg)
         return ops.roi_align_bwd(dx0.view(rows, fin), ctx["feat"], ctx["rois"], ctx["counts"], ctx["cap"],
                                  self.pooler_scale, self.pooler_resolution)
+
+    def _backward_x3(self, ctx, g_cls, g_box):
+        """f16x3 precision of `backward` (the reference's fp32 autograd): saved activations and output gradients are
+        triples, the fc1 data gradient is stored in fp32 for the ROIAlign backward."""
+        ar = self.arena
+        K = self.num_classes
+        S = self.loss_scale
+        inv = 1.0 / S
+        rows = ctx["x0"].shape[0]
+        fc = ar.fc_dim
+        seg = (ctx["counts"], ctx["cap"])
+        dpred = ops.pack_grad2_x3(ctx["dscores"], K + 1, ctx["ddeltas"], 8 * K, g_cls, g_box, S, rows, 128)
+        dpred = dpred.view(1, rows, 384)
+        h2, h1, x0 = ctx["h2"].view(1, rows, 3 * fc), ctx["h1"].view(1, rows, 3 * fc), ctx["x0"]
+        fin = x0.shape[1] // 3
+        p = "roi_heads.box_predictor."
+        ops.wgrad_x3(dpred, h2, ar.gview(p + "_heads.weight"), m_total=128, n_total=fc, scale=inv,
+                     bias_out=ar.gview(p + "_heads.bias"), seg=seg)
+        wd3, alpha = ar.dgrad_x3["pred"]
+        dz2 = ops.gemm_tn_x3(dpred, wd3, alpha, epi=ops.EPI_SPLIT3_MASK, aux=h2, seg=seg)
+        p = "roi_heads.box_head."
+        ops.wgrad_x3(dz2, h1, ar.gview(p + "fc2.weight"), m_total=fc, n_total=fc, scale=inv,
+                     bias_out=ar.gview(p + "fc2.bias"), seg=seg)
+        wd3, alpha = ar.dgrad_x3["fc2"]
+        dz1 = ops.gemm_tn_x3(dz2, wd3, alpha, epi=ops.EPI_SPLIT3_MASK, aux=h1, seg=seg)
+        ops.wgrad_x3(dz1, x0.view(1, rows, 3 * fin), ar.gview(p + "fc1.weight").view(fc, fin), m_total=fc, n_total=fin,
+                     scale=inv, bias_out=ar.gview(p + "fc1.bias"), seg=seg)
+        wd3, alpha = ar.dgrad_x3["fc1"]
+        dx0 = ops.gemm_tn_x3(dz1, wd3, alpha, epi=ops.EPI_F32_STORE, seg=seg)
+        return ops.roi_align_bwd_f32(dx0.view(rows, fin), ctx["feat"], ctx["rois"], ctx["counts"], ctx["cap"],
+                                     self.pooler_scale, self.pooler_resolution)

@@ -93,20 +93,29 @@ def conv3x3(x: FlatAct, w_packed, bias, relu=True, aux=None, out=None):
 
 
 # ------------------------------------------------------------------------------------------ f16x3
-# Split-fp16 parity precision (forward only): activations are [hi | lo | hi] triples (3C wide), weights
-# [Wh | Wh | Wl] triples of W * 2^s with alpha = 2^-s (ParamArena.pack_x3). See include/ptb200.h.
-# longest chain of tensor-core accumulations (k-iterations of 64 = 4 MMAs each) before the partial sum is
-# promoted to a round-to-nearest fp32 add: the MMA accumulates with truncation. Measured on B200 with positive
-# operands (tests/dev/x3_diag.py): mean signed error -2.4e-4 for one chain over K = 3 x 25088, -2.7e-6 / -1.2e-6 /
-# -4.8e-7 / -1.8e-7 with chunks of 8 / 4 / 2 / 1 k-iterations; the bias compounds through the 16 stacked layers.
-X3_MAX_K_ITERS = [2]
+# Split-fp16 fp32-equivalent precision (forward and backward): activations / output gradients are [hi | lo | hi]
+# triples (3C wide), weights [Wh | Wh | Wl] triples of W * 2^s with alpha = 2^-s (ParamArena.pack_x3). See
+# include/ptb200.h. The tensor core accumulates with truncation (measured on B200 with positive operands,
+# tests/dev/x3_diag.py: mean signed error -2.4e-4 for one chain over K = 3 x 25088, -2.7e-6 / -1.2e-6 / -4.8e-7 /
+# -1.8e-7 with chunks of 8 / 4 / 2 / 1 k-iterations of 64); the kernel promotes its TMEM partial sums to fp32
+# registers every X3_CHUNK[0] k-iterations (round 1 did this with split-K atomics through HBM).
+X3_CHUNK = [4]
+EPI_SPLIT3_MASK, EPI_F32_STORE = 7, 8
+
+
+def _x3_bn(n_total):
+    for bn in (256, 128, 64):
+        if n_total % bn == 0:
+            return bn
+    raise ValueError(f"f16x3 GEMM: n_total={n_total} is not a multiple of 64")
 
 
 def gemm_tn_x3(A3, B3, alpha, *, taps=1, shifts=None, bn=None, epi=EPI_SPLIT3_RELU, bias=None, w_valid=0, wp=0,
-               split=0, n_valid=0, n_total=None, seg=None, ksplit=None):
+               split=0, n_valid=0, n_total=None, seg=None, ksplit=None, aux=None):
     """A3: [batch, rows, 3K] fp16 triples; B3: [n_rows, taps*3K]. Returns the output triples
-    [batch, rows, 3*n_total] or (d0, d1) fp32 for EPI_F32_SPLIT. ksplit=None chooses the K chunking from
-    X3_MAX_K_ITERS (triple epilogues only)."""
+    [batch, rows, 3*n_total] (SPLIT3* epilogues; aux = forward activation triples for EPI_SPLIT3_MASK), an fp32
+    [batch, rows, n_total] tensor (EPI_F32_STORE) or (d0, d1) fp32 for EPI_F32_SPLIT. ksplit=None: split the
+    reduction over CTAs only for skinny problems (fc1 forward)."""
     batch, rows, lda = A3.shape
     k3 = B3.shape[1] // taps
     assert k3 == lda and k3 % 3 == 0
@@ -114,35 +123,47 @@ def gemm_tn_x3(A3, B3, alpha, *, taps=1, shifts=None, bn=None, epi=EPI_SPLIT3_RE
     alloc = torch.zeros if seg is not None else torch.empty
     if n_total is None:
         n_total = B3.shape[0]
+    dev = A3.device
+    if epi == EPI_F32_SPLIT:
+        d0 = alloc(batch, rows, split, dtype=torch.float32, device=dev)
+        d1 = alloc(batch, rows, n_valid - split, dtype=torch.float32, device=dev)
+        call("ptb200_gemm_tn_f16x3", A3, batch, rows, k3, lda, rows * lda, taps, shifts, B3, n_total, bn or n_total,
+             epi, bias, 0 if bias is None else bias.numel(), None, 0, 0, w_valid, wp, d0, split, d1, n_valid - split,
+             split, n_valid, GEMM_MAX_CTAS[0], 1, seg_counts, seg_cap, float(alpha), None, 0)
+        return d0, d1
     if bn is None:
-        bn = 256
-        while n_total % bn:
-            bn //= 2
-    out = d0 = d1 = None
-    ld_d = dbs = 0
+        bn = _x3_bn(n_total)
+    nb = 0 if bias is None else bias.numel()
     if ksplit is None:
-        k_iters = taps * (k3 // 64)
-        ksplit = (k_iters + X3_MAX_K_ITERS[0] - 1) // X3_MAX_K_ITERS[0] if epi in (EPI_SPLIT3_RELU, EPI_SPLIT3) else 1
+        ksplit = 1
+        if epi in (EPI_SPLIT3_RELU, EPI_SPLIT3):
+            tiles = ((rows + 127) // 128) * batch * (n_total // bn)
+            k_iters = taps * (k3 // 64)
+            if 2 * tiles <= 148 and k_iters >= 128:
+                ksplit = max(1, min(148 // tiles, k_iters // 32))
     if ksplit > 1:
         assert epi in (EPI_SPLIT3_RELU, EPI_SPLIT3)
-        acc = torch.zeros(batch, rows, n_total, dtype=torch.float32, device=A3.device)
+        acc = torch.zeros(batch, rows, n_total, dtype=torch.float32, device=dev)
         call("ptb200_gemm_tn_f16x3", A3, batch, rows, k3, lda, rows * lda, taps, shifts, B3, n_total, bn, EPI_ATOMIC,
              None, 0, None, 0, 0, 0, 0, acc, n_total, None, 0, 0, n_total, GEMM_MAX_CTAS[0], ksplit, seg_counts,
-             seg_cap, 1.0)
-        out = torch.empty(batch, rows, 3 * n_total, dtype=torch.float16, device=A3.device)
+             seg_cap, 1.0, None, X3_CHUNK[0])
+        out = torch.empty(batch, rows, 3 * n_total, dtype=torch.float16, device=dev)
         call("ptb200_bias_act_split3_f16", acc, bias, 1 if epi == EPI_SPLIT3_RELU else 0, float(alpha), batch * rows,
              n_total, wp, w_valid, out)
         return out
-    if epi == EPI_F32_SPLIT:
-        d0 = alloc(batch, rows, split, dtype=torch.float32, device=A3.device)
-        d1 = alloc(batch, rows, n_valid - split, dtype=torch.float32, device=A3.device)
-    else:
-        out = alloc(batch, rows, 3 * n_total, dtype=torch.float16, device=A3.device)
-        ld_d, dbs = 3 * n_total, rows * 3 * n_total
-    call("ptb200_gemm_tn_f16x3", A3, batch, rows, k3, lda, rows * lda, taps, shifts, B3, n_total, bn, epi, bias,
-         0 if bias is None else bias.numel(), out, ld_d, dbs, w_valid, wp, d0, split, d1, n_valid - split, split,
-         n_valid, GEMM_MAX_CTAS[0], 1, seg_counts, seg_cap, float(alpha))
-    return (d0, d1) if epi == EPI_F32_SPLIT else out
+    if epi == EPI_F32_STORE:
+        d0 = alloc(batch, rows, n_total, dtype=torch.float32, device=dev)
+        call("ptb200_gemm_tn_f16x3", A3, batch, rows, k3, lda, rows * lda, taps, shifts, B3, n_total, bn, epi, bias,
+             nb, None, 0, 0, w_valid, wp, d0, n_total, None, 0, 0, n_total, GEMM_MAX_CTAS[0], 1, seg_counts, seg_cap,
+             float(alpha), None, X3_CHUNK[0])
+        return d0
+    assert epi in (EPI_SPLIT3_RELU, EPI_SPLIT3, EPI_SPLIT3_MASK)
+    assert (aux is not None) == (epi == EPI_SPLIT3_MASK)
+    out = alloc(batch, rows, 3 * n_total, dtype=torch.float16, device=dev)
+    call("ptb200_gemm_tn_f16x3", A3, batch, rows, k3, lda, rows * lda, taps, shifts, B3, n_total, bn, epi, bias, nb,
+         out, 3 * n_total, rows * 3 * n_total, w_valid, wp, None, 0, None, 0, 0, n_total, GEMM_MAX_CTAS[0], 1,
+         seg_counts, seg_cap, float(alpha), aux, X3_CHUNK[0])
+    return out
 
 
 def conv3x3_x3(x: FlatAct, w3, alpha, bias):
@@ -205,6 +226,66 @@ def wgrad(G, X, out, *, taps=1, shifts=None, scale=1.0, ksplit=0, m_total=None, 
 
 def conv3x3_wgrad(dy: FlatAct, x: FlatAct, out, scale=1.0, bias_out=None):
     return wgrad(dy.t, x.t, out, taps=9, shifts=_shifts(x.W + 1), scale=scale, bias_out=bias_out)
+
+
+def wgrad_x3(G3, X3, out, *, m_total, n_total, taps=1, shifts=None, scale=1.0, bias_out=None, seg=None):
+    """f16x3 weight gradient: G3 [batch, rows, 3*m_total] / X3 [batch, rows, 3*n_total] triples;
+    out += scale * (Gh'Xh + Gl'Xh + Gh'Xl) as three passes of the MN-major tcgen05 kernel over column slices of the
+    triples (the fp32 red.add accumulation into `out` is round-to-nearest); bias_out += scale * colsum(Gh + Gl)."""
+    batch, rows, ldg = G3.shape
+    ldx = X3.shape[2]
+    assert ldg == 3 * m_total and ldx == 3 * n_total
+    bn = 256
+    while n_total % bn:
+        bn //= 2
+    tiles = taps * (m_total // 128) * (n_total // bn)
+    chunks = ((rows + 63) // 64) * batch
+    # one wave of CTAs, and reduction chains of at most 128 chunks (512 truncating MMAs) per CTA
+    ksplit = max(1, min(max(148 // tiles, (chunks + 127) // 128), max(1, chunks // 8)))
+    sc, cap = (seg[0], seg[1]) if seg else (None, 0)
+    Gh, Gl = G3[:, :, :m_total], G3[:, :, m_total:2 * m_total]
+    Xh, Xl = X3[:, :, :n_total], X3[:, :, n_total:2 * n_total]
+    for g, x, b in ((Gh, Xh, bias_out), (Gl, Xh, bias_out), (Gh, Xl, None)):
+        call("ptb200_gemm_wgrad_f16", g, ldg, rows * ldg, x, ldx, rows * ldx, batch, rows, m_total, n_total, taps,
+             shifts, out, taps * n_total, float(scale), ksplit, b, sc, cap)
+    return out
+
+
+def conv3x3_wgrad_x3(dy: FlatAct, x: FlatAct, out, cout, cin, scale=1.0, bias_out=None):
+    return wgrad_x3(dy.t, x.t, out, m_total=cout, n_total=cin, taps=9, shifts=_shifts(x.W + 1), scale=scale,
+                    bias_out=bias_out)
+
+
+def conv3x3_dgrad_x3(dz: FlatAct, wd3, alpha, aux=None):
+    """Data gradient of a 3x3 conv in f16x3: aux (forward input triples) selects the fused ReLU backward and a
+    triple result; without aux the result is an fp32 [N, rows, Cin] tensor (consumed by the max-pool backward)."""
+    Wp = dz.W + 1
+    if aux is not None:
+        o = gemm_tn_x3(dz.t, wd3, alpha, taps=9, shifts=_shifts(Wp), epi=EPI_SPLIT3_MASK, aux=aux, w_valid=dz.W, wp=Wp)
+        return FlatAct(o, dz.H, dz.W)
+    return gemm_tn_x3(dz.t, wd3, alpha, taps=9, shifts=_shifts(Wp), epi=EPI_F32_STORE, w_valid=dz.W, wp=Wp)
+
+
+def maxpool2x2_relu_bwd_x3(x: FlatAct, dpooled_f32):
+    N, _, C3 = x.t.shape
+    dz = torch.empty_like(x.t)
+    call("ptb200_maxpool2x2_relu_bwd_f16x3", x.t, dpooled_f32, dz, N, x.H, x.W, C3 // 3)
+    return FlatAct(dz, x.H, x.W)
+
+
+def pack_grad2_x3(d0, n0, d1, n1, g0, g1, lscale, rows, ld=128):
+    out = torch.empty(rows, 3 * ld, dtype=torch.float16, device=d0.device)
+    call("ptb200_pack_grad2_f16x3", d0, n0, d1, n1, g0, g1, float(lscale), rows, ld, out)
+    return out
+
+
+def roi_align_bwd_f32(dout_f32, feat_like: FlatAct, rois, counts, cap, scale, pooled):
+    N, rows, C3 = feat_like.t.shape
+    C = C3 // 3
+    dfeat = torch.zeros(N, rows, C, dtype=torch.float32, device=dout_f32.device)
+    call("ptb200_roi_align_bwd_f32", dout_f32, N, feat_like.H, feat_like.W, C, rois, counts, cap, float(scale), pooled,
+         dfeat)
+    return dfeat
 
 
 # ------------------------------------------------------------------------------------------ elementwise

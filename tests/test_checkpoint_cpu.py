@@ -220,3 +220,38 @@ def test_untrusted_pickles_are_refused(tmp_path):
     ck.load(str(tmp_path / "zoo.pth"), trusted=True)  # numpy arrays become tensors (_convert_ndarray_to_tensor)
     assert torch.equal(ck.model.state_dict()["roi_heads.box_head.fc2.bias"], m.state_dict()["roi_heads.box_head.fc2.bias"])
     assert isinstance(np.zeros(1), np.ndarray)
+
+
+def test_optimizer_entry_is_interchangeable_with_torch_sgd(tmp_path):
+    """The `optimizer` entry travels both ways (trainer.py:104-111 saves torch SGD's state_dict): what this trainer
+    writes loads into a torch.optim.SGD built over the reference's parameter order, and a state_dict written by
+    torch SGD (integer keys, no names) loads into the momentum arena by position, shapes checked."""
+    student = _CpuDetector(seed=2)
+    student.arena.momentum.copy_(torch.randn(student.arena.momentum.numel(), generator=torch.Generator().manual_seed(3)))
+    student.arena.load_momentum_state_dict(student.arena.momentum_state_dict())  # zero the padding
+    st = C.ArenaSGDState(_Trainer(student, 7)).state_dict()
+    order = C.reference_trainable_order(student.arena)
+    assert len(order) == 33 and order[20:24] == ["proposal_generator.rpn_head.objectness_logits.weight",
+                                                  "proposal_generator.rpn_head.objectness_logits.bias",
+                                                  "proposal_generator.rpn_head.anchor_deltas.weight",
+                                                  "proposal_generator.rpn_head.anchor_deltas.bias"]
+    sd = student.state_dict()
+    params = [torch.nn.Parameter(sd[n].clone()) for n in order]
+    opt = torch.optim.SGD([{"params": [p]} for p in params], lr=0.01, momentum=0.9, weight_decay=1e-4)
+    torch.save({"optimizer": st}, tmp_path / "o.pth")
+    opt.load_state_dict(torch.load(tmp_path / "o.pth", weights_only=True)["optimizer"])  # torch accepts the entry
+    msd = student.arena.momentum_state_dict()
+    for p, n in zip(params, order):
+        assert torch.equal(opt.state[p]["momentum_buffer"], msd[n]), n
+    # ... and back: a file written by torch SGD alone
+    ref_written = opt.state_dict()
+    assert set(ref_written) == {"state", "param_groups"}
+    other = _CpuDetector(seed=9)
+    C.ArenaSGDState(_Trainer(other, 0)).load_state_dict(ref_written)
+    assert torch.equal(other.arena.momentum, student.arena.momentum)
+    # a mismatching parameter count is refused instead of silently zeroing the momentum
+    bad = {"state": {}, "param_groups": ref_written["param_groups"][:-1]}
+    with pytest.raises(ValueError):
+        C.ArenaSGDState(_Trainer(other, 0)).load_state_dict(bad)
+    with pytest.raises(ValueError):
+        C.ArenaSGDState(_Trainer(other, 0)).load_state_dict({"foo": 1})

@@ -237,3 +237,83 @@ def test_cuda_graph_step_matches_eager(cuda, concurrent):
             tol = t_rpn if "rpn" in k else t_roi
             assert abs(a[k] - b[k]) <= tol * max(abs(a[k]), 1e-3), (k, a[k], b[k])
             assert b[k] == b[k]
+
+
+def test_graph_step_without_host_sync_sees_each_steps_own_ground_truth(cuda):
+    """The host runs ahead of the device in graph mode (a replay is launched in microseconds): the pinned staging of
+    ground truth / resize geometry must not be rewritten while an earlier step's host->device copy is still queued.
+    With lr = 0 the weights never change, so every step's supervised losses are a function of THAT step's inputs only:
+    the graphed trainer, driven WITHOUT any host synchronisation and with different ground truth every step, must
+    reproduce the eager trainer's per-step losses."""
+    from oracle import pt_oracle as O
+    from probabilisticteacher_b200.config import c2f_config
+    from probabilisticteacher_b200.engine.trainer import PTrainer
+    cfg = c2f_config()
+    cfg.UNSUPNET.BURN_UP_STEP = 0
+    cfg.SOLVER.BASE_LR = 0.0
+    cfg.SOLVER.WEIGHT_DECAY = 0.0
+    unl = O.synthetic_batch(2, H, W, K, 2, labelled=False)
+    labs = [O.synthetic_batch(2, H, W, K, 100 + s, boxes_per_image=1 + (3 * s) % 7) for s in range(8)]
+
+    def loader():
+        s = 0
+        while True:
+            lab = labs[s % len(labs)]
+            yield _to_inst(lab), _to_inst(lab), _to_inst(unl), _to_inst(unl)
+            s += 1
+    g = torch.Generator().manual_seed(7)
+    R = (H // 16) * (W // 16) * 9
+    pr = {"rpn": (torch.rand(4, R, generator=g).to(cuda), torch.rand(4, R, generator=g).to(cuda)),
+          "roi": (torch.rand(4, 2016, generator=g).to(cuda), torch.rand(4, 2016, generator=g).to(cuda))}
+    hist = []
+    for use_graph in (False, True):
+        tr = PTrainer(cfg, loader(), device=cuda, seed=3, use_cuda_graph=use_graph, graph_warmup=1, gt_capacity=16)
+        tr.model.prio_override = pr
+        rec = []
+        for step in range(8):
+            losses = tr.step()
+            rec.append({k: v.clone() for k, v in losses.items() if k.endswith("_sup")})  # stream-ordered copy, no sync
+        torch.cuda.synchronize()
+        assert (tr._graph is not None) == use_graph
+        hist.append([{k: float(v) for k, v in r.items()} for r in rec])
+    for s, (a, b) in enumerate(zip(*hist)):
+        for k in a:
+            assert abs(a[k] - b[k]) <= 1e-4 * max(abs(a[k]), 1e-3), (s, k, a[k], b[k])
+    # the inputs really differ from step to step
+    assert len({round(h["loss_rpn_loc_sup"], 5) for h in hist[0]}) >= 6
+
+
+@pytest.mark.parametrize("concurrent", [False, True])
+def test_graph_step_honours_teacher_update_iter(cuda, concurrent):
+    """pt/engine/trainer.py:296-298: the teacher is refreshed only when (iter - BURN_UP_STEP) % TEACHER_UPDATE_ITER
+    == 0. The captured step reads the keep rate from device memory (1.0 on the other iterations: bit-exact no-op)."""
+    from oracle import pt_oracle as O
+    from probabilisticteacher_b200.config import c2f_config
+    from probabilisticteacher_b200.engine.trainer import PTrainer
+    cfg = c2f_config()
+    cfg.UNSUPNET.BURN_UP_STEP = 0
+    cfg.UNSUPNET.TEACHER_UPDATE_ITER = 2
+    cfg.UNSUPNET.EMA_KEEP_RATE = 0.9
+    lab = O.synthetic_batch(2, H, W, K, 1)
+    unl = O.synthetic_batch(2, H, W, K, 2, labelled=False)
+
+    def loader():
+        while True:
+            yield _to_inst(lab), _to_inst(lab), _to_inst(unl), _to_inst(unl)
+    tr = PTrainer(cfg, loader(), device=cuda, seed=3, use_cuda_graph=True, graph_warmup=1, gt_capacity=16,
+                  concurrent=concurrent)
+    for it in range(7):
+        t_before = tr.model_teacher.arena.data.clone()
+        s_before = tr.model.arena.data.clone()
+        tr.step()
+        torch.cuda.synchronize()
+        t_after = tr.model_teacher.arena.data
+        if it == 0:
+            assert torch.equal(t_after, s_before)                      # iter == BURN_UP_STEP: copy (eager step)
+        elif it % 2 == 0:
+            expect = 0.9 * t_before + (1 - 0.9) * s_before
+            assert float((t_after - expect).abs().max()) <= 1e-6, it
+            assert not torch.equal(t_after, t_before)
+        else:
+            assert torch.equal(t_after, t_before), it                   # skipped: untouched bit for bit
+    assert tr._graph is not None

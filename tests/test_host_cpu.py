@@ -62,10 +62,16 @@ def test_structures():
 
 
 def test_lr_schedule():
-    from probabilisticteacher_b200.engine.trainer import warmup_multistep_lr
-    assert abs(warmup_multistep_lr(0.016, 0, (30000,), 0.1, 0.001, 400) - 0.016 * 0.001) < 1e-12
-    assert abs(warmup_multistep_lr(0.016, 400, (30000,), 0.1, 0.001, 400) - 0.016) < 1e-12
-    assert abs(warmup_multistep_lr(0.016, 30000, (30000,), 0.1, 0.001, 400) - 0.0016) < 1e-12
+    """The schedule `PTrainer._optimizer_step` evaluates (solver.lr_at_iter) at the c2f config's corner points."""
+    from probabilisticteacher_b200.config import c2f_config
+    from probabilisticteacher_b200.solver import lr_at_iter
+    cfg = c2f_config()
+    cfg.SOLVER.BASE_LR, cfg.SOLVER.STEPS, cfg.SOLVER.GAMMA = 0.016, (30000,), 0.1
+    cfg.SOLVER.WARMUP_FACTOR, cfg.SOLVER.WARMUP_ITERS, cfg.SOLVER.WARMUP_METHOD = 0.001, 400, "linear"
+    cfg.SOLVER.LR_SCHEDULER_NAME = "WarmupMultiStepLR"
+    assert abs(lr_at_iter(cfg, 0) - 0.016 * 0.001) < 1e-12
+    assert abs(lr_at_iter(cfg, 400) - 0.016) < 1e-12
+    assert abs(lr_at_iter(cfg, 30000) - 0.0016) < 1e-12
 
 
 def test_state_dict_layout_conversion():
@@ -153,12 +159,14 @@ def test_arena_segments_are_128_byte_aligned():
 
 def test_k2c_config_and_lr_schedule():
     from probabilisticteacher_b200.config import c2f_config, k2c_config
-    from probabilisticteacher_b200.engine.trainer import warmup_multistep_lr
+    from probabilisticteacher_b200.solver import lr_at_iter
     c, k = c2f_config(), k2c_config()
     assert k.MODEL.ROI_HEADS.NUM_CLASSES == 1 and c.MODEL.ROI_HEADS.NUM_CLASSES == 8
     assert k.UNSUPNET.TAU == c.UNSUPNET.TAU == [0.5, 0.5]
     # detectron2 WarmupMultiStepLR (linear warm-up from WARMUP_FACTOR over WARMUP_ITERS, x GAMMA at each step)
-    lr = lambda it: warmup_multistep_lr(0.016, it, (30000,), 0.1, 0.001, 400)  # noqa: E731
+    c.SOLVER.BASE_LR, c.SOLVER.STEPS, c.SOLVER.GAMMA = 0.016, (30000,), 0.1
+    c.SOLVER.WARMUP_FACTOR, c.SOLVER.WARMUP_ITERS, c.SOLVER.WARMUP_METHOD = 0.001, 400, "linear"
+    lr = lambda it: lr_at_iter(c, it)  # noqa: E731
     assert abs(lr(0) - 0.016 * 0.001) < 1e-12
     assert abs(lr(200) - 0.016 * (0.001 * 0.5 + 0.5)) < 1e-12
     assert lr(400) == 0.016 and lr(29999) == 0.016

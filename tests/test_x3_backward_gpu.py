@@ -1,0 +1,341 @@
+"""GPU: the f16x3 (fp32-equivalent) BACKWARD -- kernels against fp64 autograd, then the parameter gradients of the
+supervised and unsupervised branches against the CPU oracle's fp32 autograd at the tolerance `north_star` states
+(1e-3 relative), on shared proposals (pt/engine/trainer.py:383-386 runs the reference's backward in fp32).
+
+Relative error of a tensor = max |got - ref| / max |ref| (the measure of tests/test_e2e_gpu.py, where the fp16-operand
+mode is held to 5e-2)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-3
+
+
+def _rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def _flat3(x_nchw):
+    """NCHW fp32 -> f16x3 FlatAct triples."""
+    from probabilisticteacher_b200 import ops
+    N, C, H, W = x_nchw.shape
+    xf = torch.zeros(N, H, W + 1, C, device=x_nchw.device)
+    xf[:, :, :W] = x_nchw.permute(0, 2, 3, 1)
+    return ops.FlatAct(ops.split3_pack(xf, C).view(N, H * (W + 1), 3 * C), H, W)
+
+
+def _unflat3(a, C):
+    from probabilisticteacher_b200 import ops
+    N = a.t.shape[0]
+    return ops.split3_unpack(a.t, C).view(N, a.H, a.W + 1, C)[:, :, :a.W].permute(0, 3, 1, 2)
+
+
+# ------------------------------------------------------------------------------------------ kernels
+@pytest.mark.parametrize("rows,K,N", [(300, 256, 128), (1000, 512, 256), (77, 1024, 64), (260, 3200, 512)])
+def test_promote_gemm_epilogues_vs_fp64(cuda, rows, K, N):
+    from probabilisticteacher_b200 import ops
+    g = torch.Generator().manual_seed(rows + K)
+    A = (torch.randn(rows, K, generator=g) * 3).to(cuda)
+    Wt = (torch.randn(N, K, generator=g) * 0.02).to(cuda)
+    bias = torch.randn(N, generator=g).to(cuda)
+    fwd = torch.randn(rows, N, generator=g).to(cuda)  # "forward activation" whose sign gates the ReLU backward
+    A3 = ops.split3_pack(A, K, 1.0, 0).view(1, rows, 3 * K)
+    W3 = ops.split3_pack(Wt, K, 4096.0, 1)
+    ref = A.double() @ Wt.double().t()
+    # fp32 store (+ bias)
+    o = ops.gemm_tn_x3(A3, W3, 1.0 / 4096.0, epi=ops.EPI_F32_STORE, bias=bias)
+    assert _rel(o[0], ref + bias.double()) < 2e-6
+    # masked triple
+    f3 = ops.split3_pack(fwd, N, 1.0, 0).view(1, rows, 3 * N)
+    o3 = ops.gemm_tn_x3(A3, W3, 1.0 / 4096.0, epi=ops.EPI_SPLIT3_MASK, aux=f3)
+    om = ops.split3_unpack(o3, N)
+    refm = torch.where(fwd.double() > 0, ref, torch.zeros_like(ref))
+    assert _rel(om, refm) < 2e-6
+    assert bool(((om == 0) == (refm == 0)).all())
+    # split-K partials reduced with atomics, then the finisher
+    o3 = ops.gemm_tn_x3(A3, W3, 1.0 / 4096.0, epi=ops.EPI_SPLIT3_RELU, bias=bias, ksplit=3)
+    assert _rel(ops.split3_unpack(o3, N), (ref + bias.double()).clamp_min(0)) < 2e-6
+    # segment skipping: rows beyond the live count of each segment that fall in dead 128-row tiles stay zero
+    if rows == 1000:
+        counts = torch.tensor([130, 0, 7, 250], dtype=torch.int32, device=cuda)
+        o = ops.gemm_tn_x3(A3, W3, 1.0 / 4096.0, epi=ops.EPI_F32_STORE, seg=(counts, 250))
+        for s, c in enumerate(counts.tolist()):
+            assert _rel(o[0, s * 250:s * 250 + c], ref[s * 250:s * 250 + c]) < 2e-6 if c else True
+        assert float(o[0, 256:384].abs().max()) == 0.0  # tile [256, 384) holds no live row: skipped, stays zero
+
+
+def test_promotion_removes_the_truncation_bias(cuda):
+    """Positive operands over a long reduction (fc1: K = 25088): one tensor-core accumulation chain is biased by
+    ~ -2e-4 (truncating adds); promoting every 4 k-iterations keeps the signed error below 5e-6."""
+    from probabilisticteacher_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    rows, K, N = 256, 25088, 256
+    A = torch.rand(rows, K, generator=g).to(cuda) + 0.5
+    Wt = (torch.rand(N, K, generator=g) * 0.01 + 0.005).to(cuda)
+    A3 = ops.split3_pack(A, K, 1.0, 0).view(1, rows, 3 * K)
+    W3 = ops.split3_pack(Wt, K, 2.0 ** 18, 1)
+    ref = A.double() @ Wt.double().t()
+    o = ops.gemm_tn_x3(A3, W3, 2.0 ** -18, epi=ops.EPI_F32_STORE)[0].double()
+    signed = float(((o - ref) / ref).mean())
+    print("mean signed relative error with promotion:", signed)
+    assert abs(signed) < 5e-6
+    old = ops.X3_CHUNK[0]
+    try:
+        ops.X3_CHUNK[0] = 100000  # one chain
+        o1 = ops.gemm_tn_x3(A3, W3, 2.0 ** -18, epi=ops.EPI_F32_STORE)[0].double()
+    finally:
+        ops.X3_CHUNK[0] = old
+    signed1 = float(((o1 - ref) / ref).mean())
+    print("single chain:", signed1)
+    assert signed1 < -5e-5
+
+
+@pytest.mark.parametrize("Cin,Cout,H,W,pooled", [(128, 256, 24, 38, False), (256, 256, 25, 37, True), (512, 512, 12, 17, False)])
+def test_conv_backward_x3_vs_fp64(cuda, Cin, Cout, H, W, pooled):
+    """Data gradient (ReLU mask fused, or fp32 out + max-pool/ReLU backward) and weight / bias gradients of one
+    VGG layer against fp64 autograd."""
+    from probabilisticteacher_b200 import ops
+    g = torch.Generator().manual_seed(Cin + H)
+    Hi, Wi = (2 * H + 1, 2 * W) if pooled else (H, W)   # odd height: the fringe row gets no gradient
+    x_pre = torch.randn(2, Cin, Hi, Wi, generator=g).double()          # pre-activation of the PREVIOUS layer
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) * (2.0 / (9 * Cout)) ** 0.5).double()
+    gy = (torch.randn(2, Cout, H, W, generator=g) * 0.01).double()     # gradient w.r.t. this layer's pre-activation
+    x_pre.requires_grad_(True)
+    w.requires_grad_(True)
+    a = F.relu(x_pre)
+    xin = F.max_pool2d(a, 2, 2) if pooled else a
+    y = F.conv2d(xin, w, None, padding=1)
+    y.backward(gy)
+    dx_ref, dw_ref, db_ref = x_pre.grad, w.grad, gy.sum((0, 2, 3))
+
+    S = 1024.0
+    a3 = _flat3(a.detach().float().to(cuda))
+    xin3 = _flat3(xin.detach().float().to(cuda))
+    dz3 = _flat3((gy * S).float().to(cuda))
+    wk = w.detach().float().permute(0, 2, 3, 1).contiguous().to(cuda)   # [Cout][ky][kx][Cin]
+    wd3 = torch.empty(Cin, 9 * 3 * Cout, dtype=torch.float16, device=cuda)
+    from probabilisticteacher_b200._lib import call
+    call("ptb200_transpose_pack_f16x3", wk, wd3, Cout, Cin, 9, 1, 4096.0)
+    if pooled:
+        dp = ops.conv3x3_dgrad_x3(dz3, wd3, 1.0 / 4096.0)
+        dx3 = ops.maxpool2x2_relu_bwd_x3(a3, dp)
+    else:
+        dx3 = ops.conv3x3_dgrad_x3(dz3, wd3, 1.0 / 4096.0, aux=xin3.t)
+    dx = _unflat3(dx3, Cin) / S
+    assert _rel(dx, dx_ref) < 5e-6
+    assert float(ops.split3_unpack(dx3.t, Cin).view(2, Hi, Wi + 1, Cin)[:, :, Wi].abs().max()) == 0.0
+    gw = torch.zeros(Cout, 9 * Cin, device=cuda)
+    gb = torch.zeros(Cout, device=cuda)
+    ops.conv3x3_wgrad_x3(dz3, xin3, gw, Cout, Cin, scale=1.0 / S, bias_out=gb)
+    assert _rel(gw.view(Cout, 3, 3, Cin).permute(0, 3, 1, 2), dw_ref) < 5e-6
+    assert _rel(gb, db_ref) < 5e-6
+
+
+def test_fc_backward_x3_with_segments_vs_fp64(cuda):
+    from probabilisticteacher_b200 import ops
+    from probabilisticteacher_b200._lib import call
+    g = torch.Generator().manual_seed(11)
+    cap, nseg, K, N = 200, 3, 1024, 1024
+    rows = cap * nseg
+    counts = torch.tensor([200, 37, 0], dtype=torch.int32, device=cuda)
+    live = torch.zeros(rows, dtype=torch.bool)
+    for s, c in enumerate(counts.tolist()):
+        live[s * cap:s * cap + c] = True
+    x = torch.randn(rows, K, generator=g).double() * live[:, None]
+    w = (torch.randn(N, K, generator=g) * 0.03).double()
+    gy = (torch.randn(rows, N, generator=g) * 0.01).double() * live[:, None]
+    x.requires_grad_(True)
+    w.requires_grad_(True)
+    y = F.relu(x) @ w.t()
+    y.backward(gy)
+    S = 1024.0
+    h3 = ops.split3_pack(F.relu(x.detach()).float().to(cuda), K).view(1, rows, 3 * K)
+    g3 = ops.split3_pack((gy * S).float().to(cuda), N).view(1, rows, 3 * N)
+    wd3 = torch.empty(K, 3 * N, dtype=torch.float16, device=cuda)
+    call("ptb200_transpose_pack_f16x3", w.detach().float().to(cuda), wd3, N, K, 1, 0, 2048.0)
+    seg = (counts, cap)
+    dz3 = ops.gemm_tn_x3(g3, wd3, 1.0 / 2048.0, epi=ops.EPI_SPLIT3_MASK, aux=h3, seg=seg)
+    dz = ops.split3_unpack(dz3, K) / S
+    assert _rel(dz[live.to(cuda)], x.grad[live]) < 5e-6
+    gw = torch.zeros(N, K, device=cuda)
+    gb = torch.zeros(N, device=cuda)
+    ops.wgrad_x3(g3, h3, gw, m_total=N, n_total=K, scale=1.0 / S, bias_out=gb, seg=seg)
+    assert _rel(gw, w.grad) < 5e-6
+    assert _rel(gb, gy.sum(0)) < 5e-6
+
+
+def test_pack_grad2_and_add_mask_x3(cuda):
+    from probabilisticteacher_b200 import ops
+    from probabilisticteacher_b200._lib import call
+    g = torch.Generator().manual_seed(2)
+    rows = 333
+    d0 = torch.randn(rows, 9, generator=g).to(cuda)
+    d1 = torch.randn(rows, 72, generator=g).to(cuda)
+    g0 = torch.tensor([0.5], device=cuda)
+    g1 = torch.tensor([2.0], device=cuda)
+    o3 = ops.pack_grad2_x3(d0, 9, d1, 72, g0, g1, 1024.0, rows, 128)
+    o = ops.split3_unpack(o3, 128)
+    ref = torch.zeros(rows, 128, dtype=torch.float64)
+    ref[:, :9] = d0.double().cpu() * 0.5 * 1024
+    ref[:, 9:81] = d1.double().cpu() * 2.0 * 1024
+    assert _rel(o, ref) < 1e-6 and float(o[:, 81:].abs().max()) == 0.0
+    C = 64
+    a = torch.randn(rows, C, generator=g).to(cuda)
+    b = torch.randn(rows, C, generator=g).to(cuda)
+    f = torch.randn(rows, C, generator=g).to(cuda)
+    f3 = ops.split3_pack(f, C)
+    out = torch.empty_like(f3)
+    call("ptb200_add_mask_f16x3", a, b, f3, out, rows, C)
+    refm = torch.where(f > 0, a + b, torch.zeros_like(a))
+    assert _rel(ops.split3_unpack(out, C), refm) < 1e-6
+
+
+# ------------------------------------------------------------------------------------------ model gradients
+H, W, K = 192, 272, 8
+
+
+def _setup(cuda, anchor_gen="DifferentiableAnchorGenerator"):
+    from oracle import pt_oracle as O
+    from probabilisticteacher_b200.config import c2f_config
+    from probabilisticteacher_b200.modeling.meta_arch.rcnn import build_model
+    cfg = c2f_config()
+    cfg.MODEL.ANCHOR_GENERATOR.NAME = anchor_gen
+    model = build_model(cfg, cuda, precision="f16x3")
+    sd = model.init_synthetic(seed=3)
+    model.train()
+    om = O.OracleRCNN(O.OracleCfg(anchor_generator=anchor_gen), seed=0)
+    om.load_ref_state_dict(sd)
+    return O, model, om
+
+
+def _to_inst(batch):
+    from probabilisticteacher_b200.structures import Boxes, FreeInstances
+    out = []
+    for d in batch:
+        nd = dict(d)
+        if "instances" in d:
+            i = d["instances"]
+            nd["instances"] = FreeInstances(i.image_size, gt_boxes=Boxes(i.gt_boxes.tensor.clone()),
+                                            gt_classes=i.gt_classes.clone())
+        out.append(nd)
+    return out
+
+
+class _Sampler:
+    def __init__(self, pr):
+        self.pr = pr
+
+    def prio(self, tag, n):
+        grp, which = tag[0].split("_")
+        return (self.pr[grp][0] if which == "pos" else self.pr[grp][1])[tag[1]].cpu()
+
+
+def _oracle_props(O, model, size):
+    p = model._last_ctx["props"]
+    out = []
+    for n in range(p["boxes"].shape[0]):
+        c = int(p["count"][n])
+        out.append(O.OInst(size, proposal_boxes=O.OBoxes(p["boxes"][n, :c].cpu()),
+                           objectness_logits=p["scores"][n, :c].cpu()))
+    return out
+
+
+def _grad_errors(model, om):
+    kinds = {s.name: s.kind for s in model.arena.segments.values()}
+    og = {k.replace("__", "."): v.grad for k, v in om.named_parameters()}
+    out = {}
+    for name, v, gv, trainable in model.arena.exposed_parameters():
+        if trainable and og.get(name) is not None:
+            g = model.arena._to_ref(kinds.get(name, "mat"), gv, model.arena.C, 7).reshape(og[name].shape)
+            out[name] = (_rel(g, og[name]), float(og[name].abs().max()))
+    return out
+
+
+def _check_grads(model, om, tag):
+    gr = _grad_errors(model, om)
+    worst = max(gr.items(), key=lambda kv: kv[1][0])
+    print(tag, "worst gradient:", worst[0], "rel", worst[1][0], "max|g|", worst[1][1], "of", len(gr), "tensors")
+    for name, (r, m) in gr.items():
+        assert r < TOL, (tag, name, r, m)
+    return gr
+
+
+def test_supervised_branch_grads_1e3(cuda):
+    O, model, om = _setup(cuda)
+    lab = O.synthetic_batch(2, H, W, K, 1)
+    g = torch.Generator().manual_seed(7)
+    R = (H // 16) * (W // 16) * 9
+    L = 2000 + 16
+    pr = {"rpn": (torch.rand(2, R, generator=g).to(cuda), torch.rand(2, R, generator=g).to(cuda)),
+          "roi": (torch.rand(2, L, generator=g).to(cuda), torch.rand(2, L, generator=g).to(cuda))}
+    model.prio_override = pr
+    om.sampler = _Sampler(pr)
+    model.zero_grad()
+    lg, _, _, _ = model(_to_inst(lab), branch="supervised")
+    lo, _, _, _ = om(lab, branch="supervised", proposals_override=_oracle_props(O, model, (H, W)))
+    for k in lo:
+        assert abs(float(lg[k]) - float(lo[k])) <= TOL * abs(float(lo[k])), (k, float(lg[k]), float(lo[k]))
+    (lg["loss_cls"] * 0.7 + lg["loss_box_reg"] * 1.3 + lg["loss_rpn_cls"] + lg["loss_rpn_loc"] * 0.5).backward()
+    (lo["loss_cls"] * 0.7 + lo["loss_box_reg"] * 1.3 + lo["loss_rpn_cls"] + lo["loss_rpn_loc"] * 0.5).backward()
+    torch.cuda.synchronize()
+    gr = _check_grads(model, om, "supervised")
+    assert len(gr) >= 20  # blocks 3-5 (weights + biases), RPN head, box head, predictor
+
+
+def test_unsupervised_branch_grads_1e3(cuda):
+    O, model, om = _setup(cuda)
+    from probabilisticteacher_b200.structures import Boxes, FreeInstances
+    unl = O.synthetic_batch(2, H, W, K, 2, labelled=False)
+    with torch.no_grad():
+        _, _, roih, _ = om(unl, branch="unsup_data_weak")
+    pseudo = [O.OInst(r.image_size, pseudo_boxes=O.OBoxes(r.pred_boxes.tensor), scores_logists=r.scores_logists,
+                      boxes_sigma=r.boxes_sigma) for r in roih]
+    unl_o = [dict(d, instances=p) for d, p in zip(unl, pseudo)]
+    unl_g = [dict(d, instances=FreeInstances(p.image_size, pseudo_boxes=Boxes(p.pseudo_boxes.tensor.to(cuda)),
+                                             scores_logists=p.scores_logists.to(cuda), boxes_sigma=p.boxes_sigma.to(cuda)))
+             for d, p in zip(unl, pseudo)]
+    model.zero_grad()
+    lg, _, _, _ = model(unl_g, branch="unsupervised", danchor=True)
+    lo, _, _, _ = om(unl_o, branch="unsupervised", danchor=True, proposals_override=_oracle_props(O, model, (H, W)))
+    for k in lo:
+        assert abs(float(lg[k]) - float(lo[k])) <= TOL * abs(float(lo[k])), (k, float(lg[k]), float(lo[k]))
+    sum(lg.values()).backward()
+    sum(lo.values()).backward()
+    torch.cuda.synchronize()
+    gr = _check_grads(model, om, "unsupervised")
+    assert gr["proposal_generator.anchor_generator.anchor_0"][1] > 0  # danchor=True reaches the anchor parameter
+
+
+def test_both_branches_accumulate_1e3(cuda):
+    """The trainer's step accumulates the supervised and the unsupervised backward into one gradient arena
+    (trainer.py:364-384: one weighted sum, one backward)."""
+    O, model, om = _setup(cuda)
+    from probabilisticteacher_b200.structures import Boxes, FreeInstances
+    lab = O.synthetic_batch(2, H, W, K, 4)
+    unl = O.synthetic_batch(2, H, W, K, 5, labelled=False)
+    g = torch.Generator().manual_seed(9)
+    R = (H // 16) * (W // 16) * 9
+    pr = {"rpn": (torch.rand(2, R, generator=g).to(cuda), torch.rand(2, R, generator=g).to(cuda)),
+          "roi": (torch.rand(2, 2016, generator=g).to(cuda), torch.rand(2, 2016, generator=g).to(cuda))}
+    model.prio_override = pr
+    om.sampler = _Sampler(pr)
+    with torch.no_grad():
+        _, _, roih, _ = om(unl, branch="unsup_data_weak")
+    pseudo = [O.OInst(r.image_size, pseudo_boxes=O.OBoxes(r.pred_boxes.tensor), scores_logists=r.scores_logists,
+                      boxes_sigma=r.boxes_sigma) for r in roih]
+    unl_o = [dict(d, instances=p) for d, p in zip(unl, pseudo)]
+    unl_g = [dict(d, instances=FreeInstances(p.image_size, pseudo_boxes=Boxes(p.pseudo_boxes.tensor.to(cuda)),
+                                             scores_logists=p.scores_logists.to(cuda), boxes_sigma=p.boxes_sigma.to(cuda)))
+             for d, p in zip(unl, pseudo)]
+    model.zero_grad()
+    ls, _, _, _ = model(_to_inst(lab), branch="supervised")
+    los, _, _, _ = om(lab, branch="supervised", proposals_override=_oracle_props(O, model, (H, W)))
+    lu, _, _, _ = model(unl_g, branch="unsupervised", danchor=True)
+    lou, _, _, _ = om(unl_o, branch="unsupervised", danchor=True, proposals_override=_oracle_props(O, model, (H, W)))
+    (sum(ls.values()) + 2.0 * sum(lu.values())).backward()
+    (sum(los.values()) + 2.0 * sum(lou.values())).backward()
+    torch.cuda.synchronize()
+    _check_grads(model, om, "sup + 2 * unsup")

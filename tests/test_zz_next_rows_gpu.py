@@ -12,12 +12,7 @@
 import pytest
 import torch
 
-# Every test of this module was written AFTER the round's GPU budget was spent: none has run on hardware yet (their
-# oracle / host halves run in the CPU suite). They therefore do not gate the suite: a failure is reported as XFAIL, a
-# pass as XPASS -- the first GPU session of the next round (tools/gpu_first_call.sh) reads that list, fixes what fails
-# and removes this marker.
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="not yet exercised on hardware (written after the round's GPU budget was spent)")]
+pytestmark = pytest.mark.gpu
 
 
 def test_trainer_checkpoint_resume(cuda, tmp_path):
@@ -671,8 +666,15 @@ def test_every_hyper_parameter_away_from_its_default(cuda):
             assert abs(float(lu[k]) - v) <= TOL * abs(v), ("unsup", k, float(lu[k]), v)
 
 
-def test_trainer_hyper_parameters_off_their_defaults(cuda):
-    """Three post-burn-in steps of the B200 `PTrainer` with the trainer-level hyper-parameters away from their defaults
+@pytest.mark.parametrize("precision", ["f16x3", "f16"])
+def test_trainer_hyper_parameters_off_their_defaults(cuda, precision):
+    """(precision="f16x3": every loss of every step, the student's per-tensor updates and the teacher's EMA are held
+    to north_star's 1e-3 against the reference's own trainer. precision="f16": fp16-operand tolerances below; the EMA
+    kernel is then checked exactly against THIS trainer's own student, and against the reference within the share
+    (1 - keep) of the student's deviation that the teacher inherits -- round 1 compared the fp16-mode teacher with the
+    reference at 2e-4 of max|w| and failed on hardware by 3.7e-6 vs 1.6e-6 on bbox_pred.weight, whose weights are
+    ~1e-3: that was the student's fp16-gradient deviation, not the EMA.)
+    Three post-burn-in steps of the B200 `PTrainer` with the trainer-level hyper-parameters away from their defaults
     (loss weights 0.5 / 2.0, EMA keep rate 0.99, TEACHER_UPDATE_ITER 2, momentum 0.8, weight decay 5e-4, lr 0.004)
     against the reference's own trainer (tests/golden/pt_reference_step_oddcfg_golden.pt,
     oracle/make_golden_step_oddcfg.py). Exact: the teacher is the initial student after step 0 and UNCHANGED after
@@ -721,7 +723,9 @@ def test_trainer_hyper_parameters_off_their_defaults(cuda):
     def samples(model):
         return {k: v.detach().reshape(-1).cpu()[idx(v.numel())] for k, v in model.state_dict().items()}
 
-    tr = PTrainer(cfg, loader(), device=cuda, seed=0)
+    tr = PTrainer(cfg, loader(), device=cuda, seed=0, precision=precision)
+    x3 = precision == "f16x3"
+    keep = t["ema_keep_rate"]
     ocfg = O.OracleCfg(num_classes=K)
     sd = {k: v.detach() for k, v in O.OracleRCNN(ocfg, seed=G["seed"]).ref_state_dict().items()}
     sd_t = {k: v.detach() for k, v in O.OracleRCNN(ocfg, seed=G["teacher_seed"]).ref_state_dict().items()}
@@ -737,9 +741,9 @@ def test_trainer_hyper_parameters_off_their_defaults(cuda):
         torch.cuda.synchronize()
         got = {k: float(v) for k, v in losses.items()}
         print("step", it, {k: (round(got[k], 4), round(v, 4)) for k, v in ref["losses"].items()})
-        if it == 0:  # the trainer reports UNWEIGHTED losses (metrics_dict = record_dict, trainer.py:379-381)
+        if it == 0 or x3:  # the trainer reports UNWEIGHTED losses (metrics_dict = record_dict, trainer.py:379-381)
             for k, v in ref["losses"].items():
-                tol = (2e-2 if "rpn" in k else 0.1) if k.endswith("_sup") else 0.3
+                tol = 1e-3 if x3 else ((2e-2 if "rpn" in k else 0.1) if k.endswith("_sup") else 0.3)
                 if not abs(got[k] - v) <= tol * max(abs(v), 1e-3):
                     problems.append((it, k, got[k], v))
         st, te = samples(tr.model), samples(tr.model_teacher)
@@ -751,16 +755,32 @@ def test_trainer_hyper_parameters_off_their_defaults(cuda):
                 assert torch.equal(te[k], teacher_prev[k]), k          # TEACHER_UPDATE_ITER = 2: untouched
         else:
             for k, v in ref["teacher"].items():                        # EMA with keep rate 0.99
+                own = keep * teacher_prev[k].double() + (1.0 - keep) * prev[k].double()   # prev = own student before this step
+                err_own = float((te[k].double() - own).abs().max())
+                assert err_own <= 1e-9 + 2e-7 * float(v.abs().max()), (k, err_own)        # the EMA kernel itself (fp32)
+                dev = float((prev[k] - prev_ref[k]).abs().max())                          # own student vs reference student
                 err = float((te[k] - v).abs().max())
-                assert err <= 1e-6 + 2e-4 * float(v.abs().max()), (k, err)
+                assert err <= 1e-7 + 2e-6 * float(v.abs().max()) + (1.0 - keep) * dev, (k, err, dev)
+                if x3:
+                    assert err <= 1e-7 + 1e-3 * float((v - teacher_prev[k]).abs().max()), (k, err)  # 1e-3 of the EMA's change
             assert any(not torch.equal(te[k], teacher_prev[k]) for k in te)
         teacher_prev = te
         up_g = torch.cat([st[k] - prev[k] for k in sorted(st)])
         up_r = torch.cat([ref["student"][k] - prev_ref[k] for k in sorted(st)])
         cos = float(torch.dot(up_g, up_r) / (up_g.norm() * up_r.norm()))
         ratio = float(up_g.norm() / up_r.norm())
-        print("   update cosine", round(cos, 4), "norm ratio", round(ratio, 4))
-        if not (cos > (0.99 if it == 0 else 0.97) and (0.95 if it == 0 else 0.9) < ratio < (1.05 if it == 0 else 1.1)):
+        print("   update cosine", round(cos, 6), "norm ratio", round(ratio, 6))
+        if x3:
+            worst = ("", 0.0)
+            for k in sorted(st):
+                du, dr = st[k] - prev[k], ref["student"][k] - prev_ref[k]
+                if float(dr.abs().max()) > 0.0:
+                    e = float((du - dr).abs().max() / dr.abs().max())
+                    worst = (k, e) if e > worst[1] else worst
+            print("   worst per-tensor update error", worst)
+            if worst[1] > 1e-3:
+                problems.append(("update_x3", it) + worst)
+        elif not (cos > (0.99 if it == 0 else 0.97) and (0.95 if it == 0 else 0.9) < ratio < (1.05 if it == 0 else 1.1)):
             problems.append(("update", it, cos, ratio))
         prev, prev_ref = st, ref["student"]
     assert not problems, problems

@@ -1,7 +1,14 @@
 import ctypes, os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from probabilisticteacher_b200._lib import lib
-L = lib()
+import subprocess
+# the probe is NOT part of libptb200.so: it is compiled here, next to the product's tensor-map helper
+_root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_csrc = os.path.join(_root, "probabilisticteacher_b200", "csrc")
+_so = os.path.join(_root, "tools", "_exp_rowshift.so")
+subprocess.check_call(["/usr/local/cuda/bin/nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17",
+                       "-Xcompiler", "-fPIC", "-shared", "-cudart", "static", "-I", _csrc,
+                       os.path.join(_root, "tools", "exp_rowshift.cu"), os.path.join(_csrc, "gemm_tn.cu"), "-o", _so])
+L = ctypes.CDLL(_so)
 dev = torch.device("cuda:0")
 g = torch.Generator().manual_seed(0)
 A = torch.randn(136, 64, generator=g).half().to(dev)
