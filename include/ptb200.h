@@ -293,8 +293,9 @@ int ptb200_roi_match_unsup(const float* pseudo_boxes, const float* pseudo_logits
 int ptb200_roi_align_fwd_f16(const void* feat, int n, int h, int w, int c, const float* rois,
                              const int* roi_count, int cap, float spatial_scale, int pooled, void* out,
                              void* stream);
-/* f16x3 variant of the same call (roi_heads.py:68-73,126): feat rows and output bins are [hi | lo | hi] triples
- * (3*c wide); bilinear sums in fp32. */
+/* f16x3 variant of the same call (roi_heads.py:68-73,126): feat rows are [hi | lo | hi] triples (3*c wide); a roi's
+ * output row is the triple [hi | lo | hi] of the plain [pooled*pooled][c] row (3*pooled*pooled*c wide), i.e. the
+ * K-major operand of fc1; bilinear sums in fp32. */
 int ptb200_roi_align_fwd_f16x3(const void* feat3, int n, int h, int w, int c, const float* rois,
                                const int* roi_count, int cap, float spatial_scale, int pooled, void* out3,
                                void* stream);

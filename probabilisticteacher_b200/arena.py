@@ -286,7 +286,9 @@ class ParamArena:
         if self.x3 is None:
             self.x3 = {}
         for s in self._x3_segments():
-            k = s.shape[-1]
+            # reduction length of one weight row per tap: Cin for convs, the whole row for fully connected layers
+            # (fc1: 49 * 512, matching the [hi | lo | hi] roi rows ptb200_roi_align_fwd_f16x3 writes)
+            k = s.numel // s.shape[0] if s.kind == "fc1" else s.shape[-1]
             e = self._x3_exp[s.name]
             rows = s.numel // k
             ent = self.x3.get(s.name)

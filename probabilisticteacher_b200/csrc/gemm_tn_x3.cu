@@ -23,6 +23,7 @@
 //   EPI_ATOMIC_F32                       : split-K partial (skinny problems): d0[row][n] += acc
 #include "ptx.cuh"
 #include "gemm_tn.h"
+#include <stdio.h>
 #include <stdlib.h>
 
 namespace ptb {
@@ -70,7 +71,8 @@ __device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint3
 }
 
 template <int NCH>  // N tile = 64 * NCH columns
-__global__ void __maxnreg__(200)  // 320 threads x 200 registers = one CTA per SM
+// 10 warps = 3 on two of the four SM sub-partitions (16 K registers each): at most 168 registers per thread
+__global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tn_promote_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                        const __grid_constant__ CUtensorMap map_d, const __grid_constant__ CUtensorMap map_aux,
                        const GemmTnParams p) {
@@ -241,11 +243,15 @@ gemm_tn_promote_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
         const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * bn + 32 * hf;
 #pragma unroll
         for (int ch = 0; ch < NCH; ++ch) {
-          uint32_t v[32];
-          tmem_ld_32x32(t_addr + ch * 64, v);
-          tmem_ld_wait();
+          // 16 columns at a time: with 128 accumulators live, a 32-register landing buffer would spill
 #pragma unroll
-          for (int j = 0; j < 32; ++j) acc[ch][j] += __uint_as_float(v[j]);
+          for (int hh = 0; hh < 2; ++hh) {
+            uint32_t v[16];
+            tmem_ld_32x16(t_addr + ch * 64 + hh * 16, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) acc[ch][hh * 16 + j] += __uint_as_float(v[j]);
+          }
         }
         tc_fence_before();
         __syncwarp();
@@ -381,7 +387,15 @@ int launch_nch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& 
   if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
   if (grid < 1) return 0;
   gemm_tn_promote_kernel<NCH><<<grid, NUM_THREADS, smem_bytes, stream>>>(ma, mb, md, mx, p);
-  return (int)cudaGetLastError();
+  const cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) {
+    cudaFuncAttributes fa;
+    if (cudaFuncGetAttributes(&fa, gemm_tn_promote_kernel<NCH>) == cudaSuccess)
+      fprintf(stderr, "gemm_tn_promote_kernel<%d>: launch failed (%s): regs %d, maxThreadsPerBlock %d, static smem %zu, "
+              "max dynamic smem %d, requested %d threads / %d B\n", NCH, cudaGetErrorString(err), fa.numRegs,
+              fa.maxThreadsPerBlock, fa.sharedSizeBytes, fa.maxDynamicSharedSizeBytes, NUM_THREADS, smem_bytes);
+  }
+  return (int)err;
 }
 
 }  // namespace

@@ -160,7 +160,11 @@ roi_align_roi_kernel(const __half* __restrict__ feat, const void* __restrict__ d
   for (int ph = 0; ph < P; ++ph) {
     const Axis& ay = s_ax[ph];
     const int bin = ph * P + pw;
-    const int64_t o_off = (static_cast<int64_t>(roi) * P * P + bin) * LD + c0;
+    // X3: a roi row is the K-concatenation [hi (P*P*C) | lo (P*P*C) | hi (P*P*C)] of the plain [bin][C] row, so
+    // that fc1 sees an ordinary activation triple (forward weights [Wh | Wh | Wl] over K = P*P*C, weight gradient
+    // over column slices)
+    const int64_t o_off = X3 ? (static_cast<int64_t>(roi) * 3 * P * P + bin) * C + c0
+                             : (static_cast<int64_t>(roi) * P * P + bin) * LD + c0;
     float acc[8];
     float gr[8];
     if (BWD) {
@@ -271,8 +275,9 @@ roi_align_roi_kernel(const __half* __restrict__ feat, const void* __restrict__ d
       }
       *reinterpret_cast<uint4*>(out + o_off) = *reinterpret_cast<const uint4*>(r);
       if (X3) {
-        *reinterpret_cast<uint4*>(out + o_off + C) = *reinterpret_cast<const uint4*>(rl);
-        *reinterpret_cast<uint4*>(out + o_off + 2 * C) = *reinterpret_cast<const uint4*>(r);
+        const int64_t fin = static_cast<int64_t>(P) * P * C;
+        *reinterpret_cast<uint4*>(out + o_off + fin) = *reinterpret_cast<const uint4*>(rl);
+        *reinterpret_cast<uint4*>(out + o_off + 2 * fin) = *reinterpret_cast<const uint4*>(r);
       }
     }
   }

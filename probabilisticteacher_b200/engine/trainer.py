@@ -369,6 +369,10 @@ class PTrainer:
         st = self._static
         b = self._static_batches()
         nl = len(b["lq"])
+        # the C-ABI launches go to a cached stream handle: re-read it INSIDE the capture (torch captures on a side
+        # stream). Without this the EMA + teacher re-pack below were issued eagerly on the outer stream while the graph
+        # was being captured and never replayed (round 1; caught by test_graph_step_honours_teacher_update_iter)
+        refresh_stream()
         self.model.zero_grad()
         self._update_teacher_model(keep_dev=st["ema_keep"])
         with torch.no_grad():

@@ -311,8 +311,11 @@ def test_graph_step_honours_teacher_update_iter(cuda, concurrent):
         if it == 0:
             assert torch.equal(t_after, s_before)                      # iter == BURN_UP_STEP: copy (eager step)
         elif it % 2 == 0:
-            expect = 0.9 * t_before + (1 - 0.9) * s_before
-            assert float((t_after - expect).abs().max()) <= 1e-6, it
+            expect = 0.9 * t_before.double() + (1 - 0.9) * s_before.double()
+            # fp32 rounding of the two products (anchor parameters are ~500; the terms may cancel)
+            bound = 1e-6 * (0.9 * t_before.double().abs() + 0.1 * s_before.double().abs()) + 1e-12
+            worst = float(((t_after.double() - expect).abs() / bound).max())
+            assert worst <= 1.0, (it, worst)
             assert not torch.equal(t_after, t_before)
         else:
             assert torch.equal(t_after, t_before), it                   # skipped: untouched bit for bit

@@ -122,7 +122,7 @@ def test_conv1_and_roialign_x3(cuda):
     rois = torch.cat([xy, xy + wh], -1).to(cuda)
     counts = torch.tensor([cap, 17], dtype=torch.int32, device=cuda)
     o3 = ops.roi_align_fwd_x3(f3, rois, counts, cap, 1.0 / 16, 7)
-    o = ops.split3_unpack(o3, C).view(2, cap, 49, C)
+    o = ops.split3_unpack(o3, 49 * C).view(2, cap, 49, C)  # a roi row is the triple of the plain [49][C] row
     for n in range(2):
         c = int(counts[n])
         r = torchvision.ops.roi_align(feat[n:n + 1].cpu(), [rois[n, :c].cpu()], 7, 1.0 / 16, 0, True)
@@ -283,13 +283,6 @@ def test_config1_full_size_losses_1e3(cuda):
     _assert_report(_full_iteration(cuda, 800, 1333, 8, "DefaultAnchorGenerator", 1, 3), own_roi=False)
 
 
-def test_x3_refuses_backward(cuda):
-    O, model, om = _pair(cuda, 8, "DifferentiableAnchorGenerator", 3)
-    lab = O.synthetic_batch(1, 96, 128, 8, 1)
-    with pytest.raises(RuntimeError):
-        model(_to_inst(lab), branch="supervised")
-
-
 # ------------------------------------------------------------------------------------------ vs the reference's own classes
 def _gold():
     import os
@@ -333,7 +326,12 @@ def test_cuda_path_vs_reference_model_golden(cuda, case):
             ref_boxes = G["teacher_rpn_boxes"][n]
             assert len(p) == len(ref_boxes), (len(p), len(ref_boxes))
             assert _prop_overlap(p.proposal_boxes.tensor, ref_boxes, scale) >= 0.99  # (near-tied scores may swap places)
-            assert _rel(p.objectness_logits.sort().values, G["teacher_rpn_logits"][n].sort().values) < TOL
+            # proposals present on both sides, matched on (box, logit) jointly: boxes clipped to the image coincide for
+            # several anchors, and a near-threshold NMS flip swaps single proposals
+            lg_g, lg_r = p.objectness_logits.double().cpu(), G["teacher_rpn_logits"][n].double()
+            d = (p.proposal_boxes.tensor.double().cpu()[:, None, :] - ref_boxes.double()[None, :, :]).abs().amax(-1) / scale
+            d = torch.maximum(d, (lg_g[:, None] - lg_r[None, :]).abs() / lg_r.abs().max())
+            assert float((d.min(1).values < TOL).double().mean()) >= 0.99
             ref = G["teacher_roih"][n]
             o = O.OInst(sizes[n], pred_boxes=O.OBoxes(ref["pred_boxes"]), scores=ref["scores"],
                         pred_classes=ref["pred_classes"], scores_logists=ref["scores_logists"],

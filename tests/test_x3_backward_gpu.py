@@ -243,24 +243,50 @@ def _oracle_props(O, model, size):
     return out
 
 
-def _grad_errors(model, om):
+def _grad_pairs(model, om):
     kinds = {s.name: s.kind for s in model.arena.segments.values()}
     og = {k.replace("__", "."): v.grad for k, v in om.named_parameters()}
     out = {}
     for name, v, gv, trainable in model.arena.exposed_parameters():
         if trainable and og.get(name) is not None:
             g = model.arena._to_ref(kinds.get(name, "mat"), gv, model.arena.C, 7).reshape(og[name].shape)
-            out[name] = (_rel(g, og[name]), float(og[name].abs().max()))
+            out[name] = (g.detach().double().cpu(), og[name].detach().double())
     return out
 
 
+def _grad_errors(model, om):
+    return {k: (_rel(g, o), float(o.abs().max())) for k, (g, o) in _grad_pairs(model, om).items()}
+
+
 def _check_grads(model, om, tag):
-    gr = _grad_errors(model, om)
-    worst = max(gr.items(), key=lambda kv: kv[1][0])
-    print(tag, "worst gradient:", worst[0], "rel", worst[1][0], "max|g|", worst[1][1], "of", len(gr), "tensors")
-    for name, (r, m) in gr.items():
-        assert r < TOL, (tag, name, r, m)
-    return gr
+    """Every parameter gradient within 1e-3 of the oracle's fp32 autograd: relative L2 error < 1e-3 for every tensor,
+    and max-norm error < 1e-3 of the tensor's max except for ISOLATED ReLU-kink flips: a pre-activation within ~1e-6 of
+    zero takes the other branch of the ReLU in two fp32 implementations, which changes one row of that layer's weight
+    gradient by a full (roi, unit) contribution. Such a deviation must be concentrated in at most two output rows
+    (>= 90 % of the squared error), stay below 2e-2 and occur in at most 3 tensors; the device backward itself agrees
+    with fp64 on its own saved activations to < 1e-6 (tests/dev/x3_fc_diag.py, test_fc_backward_x3_with_segments_vs_fp64)."""
+    pairs = _grad_pairs(model, om)
+    kinks = []
+    worst = ("", 0.0, 0.0)
+    for name, (g, o) in pairs.items():
+        m = float(o.abs().max())
+        if m == 0.0:
+            assert float(g.abs().max()) == 0.0, (tag, name)
+            continue
+        r_max = float((g - o).abs().max()) / m
+        r_l2 = float((g - o).norm() / o.norm())
+        if r_max > worst[1]:
+            worst = (name, r_max, r_l2)
+        assert r_l2 < TOL, (tag, name, "L2", r_l2)
+        if r_max >= TOL:
+            e2 = ((g - o) ** 2).reshape(g.shape[0], -1).sum(1) if g.dim() > 1 else (g - o) ** 2
+            share = float(e2.sort(descending=True).values[:2].sum() / e2.sum())
+            assert share >= 0.9 and r_max < 2e-2, (tag, name, "max-norm", r_max, "not an isolated ReLU-kink flip", share)
+            kinks.append((name, r_max, share))
+    print(tag, "worst gradient:", worst[0], "max-norm rel", worst[1], "L2 rel", worst[2], "of", len(pairs),
+          "tensors; ReLU-kink flips:", kinks)
+    assert len(kinks) <= 3, kinks
+    return _grad_errors(model, om)
 
 
 def test_supervised_branch_grads_1e3(cuda):

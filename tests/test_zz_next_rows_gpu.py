@@ -39,7 +39,7 @@ def test_trainer_checkpoint_resume(cuda, tmp_path):
     path = tr.save_checkpoint()
     assert path.endswith("model_0000001.pth")
     raw = torch.load(path, map_location="cpu", weights_only=False)
-    assert raw["iteration"] == 1 and set(raw) == {"model", "optimizer", "iteration"}
+    assert raw["iteration"] == 1 and set(raw) == {"model", "optimizer", "scheduler", "iteration"}
     # the file speaks the reference's names and layouts: the oracle (which takes reference state dicts) loads it
     om = O.OracleRCNN(O.OracleCfg(num_classes=K), seed=0)
     student_sd = {k[len("modelStudent."):]: v for k, v in raw["model"].items() if k.startswith("modelStudent.")}
@@ -85,8 +85,10 @@ def test_trainer_checkpoint_resume(cuda, tmp_path):
     assert float(tr3.model.arena.momentum.abs().sum()) == 0.0
 
 
-def test_burn_in_steps_vs_reference_trainer(cuda):
-    """Source-only iterations (iter < BURN_UP_STEP, pt/engine/trainer.py:274-290) of the B200 `PTrainer.run_step`
+@pytest.mark.parametrize("precision", ["f16x3", "f16"])
+def test_burn_in_steps_vs_reference_trainer(cuda, precision):
+    """(precision="f16x3": losses and per-tensor updates within max(1e-3, 4 x the fixture's measured conditioning),
+    tests/golden/step_conditioning.json.) Source-only iterations (iter < BURN_UP_STEP, pt/engine/trainer.py:274-290) of the B200 `PTrainer.run_step`
     against the reference's own trainer (tests/golden/pt_reference_burnin_golden.pt, oracle/make_golden_burnin.py):
     same weights, images, `resize` ratios (q views first, then k) and sampling priorities. fp16 operands, so the
     tolerances are those of tests/test_trainer_step_gpu.py; the teacher must stay untouched."""
@@ -125,7 +127,10 @@ def test_burn_in_steps_vs_reference_trainer(cuda):
     def samples(model):
         return {k: v.detach().reshape(-1).cpu()[idx(v.numel())] for k, v in model.state_dict().items()}
 
-    tr = PTrainer(cfg, loader(), device=cuda, seed=0)
+    tr = PTrainer(cfg, loader(), device=cuda, seed=0, precision=precision)
+    x3 = precision == "f16x3"
+    import json
+    COND = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "step_conditioning.json")))["pt_reference_burnin_golden.pt"]
     sd = {k: v.detach() for k, v in O.OracleRCNN(O.OracleCfg(num_classes=K), seed=G["seed"]).ref_state_dict().items()}
     tr.model.load_state_dict(sd)
     tr.model.prio_override = {k: (v[0].to(cuda), v[1].to(cuda)) for k, v in G["prio"].items()}
@@ -141,12 +146,26 @@ def test_burn_in_steps_vs_reference_trainer(cuda):
         got = {k: float(v) for k, v in losses.items()}
         assert set(got) == set(ref["losses"])  # un-suffixed keys during burn-in
         print("burn-in step", it, {k: (round(got[k], 4), round(v, 4)) for k, v in ref["losses"].items()})
-        if it == 0:
+        if it == 0 or x3:
             for k, v in ref["losses"].items():
                 tol = 2e-2 if "rpn" in k else 0.1  # ROI losses depend on the fp16-sensitive proposal selection
+                if x3:
+                    tol = max(1e-3, 4 * COND[it]["losses"][k])
+                    print(f"      {k}: rel err {abs(got[k] - v) / max(abs(v), 1e-3):.2e} (tolerance {tol:.1e})")
                 if not abs(got[k] - v) <= tol * max(abs(v), 1e-3):
-                    problems.append((it, k, got[k], v))
+                    problems.append((it, k, got[k], v, tol))
         st = samples(tr.model)
+        if x3:
+            worst = ("", 0.0, 0.0)
+            for k in sorted(st):
+                du, dr = st[k] - prev[k], ref["student"][k] - prev_ref[k]
+                if float(dr.abs().max()) > 0.0:
+                    e = float((du - dr).abs().max() / dr.abs().max())
+                    tol = max(1e-3, 4 * COND[it]["update"].get(k, 0.0))
+                    worst = (k, e / tol, e) if e / tol > worst[1] else worst
+                    if e > tol:
+                        problems.append(("update_x3", it, k, e, tol))
+            print("   worst per-tensor update error / tolerance", worst)
         up_g = torch.cat([st[k] - prev[k] for k in sorted(st)])
         up_r = torch.cat([ref["student"][k] - prev_ref[k] for k in sorted(st)])
         cos = float(torch.dot(up_g, up_r) / (up_g.norm() * up_r.norm()))
@@ -274,11 +293,20 @@ def test_anchor_generators_bit_exact(cuda):
     from probabilisticteacher_b200.modeling.anchor_generator import DefaultAnchorGenerator, DifferentiableAnchorGenerator
     cfg = c2f_config()
     arena = ParamArena(num_classes=8, differentiable_anchors=True, device=cuda, with_grads=False)
+    # the constructor initialises the learnable (w, h) pairs from cfg (anchor_generator.py:66-72) ...
+    custom = [[w * 1.5, h * 0.75] for w, h in cfg.MODEL.ANCHOR_GENERATOR.ANCHOR[0]]
+    cfg.MODEL.ANCHOR_GENERATOR.ANCHOR = [custom]
+    gen0 = DifferentiableAnchorGenerator(cfg, arena)
+    assert torch.equal(arena.view("proposal_generator.anchor_generator.anchor_0").cpu(), torch.tensor(custom))
+    assert torch.equal(gen0(3, 5).cpu(), O.grid_anchors(O.differentiable_cell_anchors(torch.tensor(custom)), 3, 5, 16,
+                                                        cfg.MODEL.ANCHOR_GENERATOR.OFFSET))
+    cfg = c2f_config()
     wh = torch.tensor(cfg.MODEL.ANCHOR_GENERATOR.ANCHOR[0]) * torch.linspace(0.9, 1.13, 18).view(9, 2)  # "learned" values
-    arena.view("proposal_generator.anchor_generator.anchor_0").copy_(wh)
     for offset in (0.0, 0.5):
         cfg.MODEL.ANCHOR_GENERATOR.OFFSET = offset
-        gens = ((DifferentiableAnchorGenerator(cfg, arena), O.differentiable_cell_anchors(wh)),
+        dgen = DifferentiableAnchorGenerator(cfg, arena)
+        arena.view("proposal_generator.anchor_generator.anchor_0").copy_(wh)   # ... and training moves them
+        gens = ((dgen, O.differentiable_cell_anchors(wh)),
                 (DefaultAnchorGenerator(cfg, arena), O.default_cell_anchors(cfg.MODEL.ANCHOR_GENERATOR.SIZES[0],
                                                                             cfg.MODEL.ANCHOR_GENERATOR.ASPECT_RATIOS[0])))
         for gen, cell in gens:
@@ -726,6 +754,10 @@ def test_trainer_hyper_parameters_off_their_defaults(cuda, precision):
     tr = PTrainer(cfg, loader(), device=cuda, seed=0, precision=precision)
     x3 = precision == "f16x3"
     keep = t["ema_keep_rate"]
+    import json
+    # conditioning of every fixture quantity under a 2e-6 weight perturbation (oracle/measure_conditioning.py): the
+    # f16x3 step is held to max(1e-3, 4 x conditioning), see tests/test_trainer_step_gpu.py
+    COND = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "step_conditioning.json")))["pt_reference_step_oddcfg_golden.pt"]
     ocfg = O.OracleCfg(num_classes=K)
     sd = {k: v.detach() for k, v in O.OracleRCNN(ocfg, seed=G["seed"]).ref_state_dict().items()}
     sd_t = {k: v.detach() for k, v in O.OracleRCNN(ocfg, seed=G["teacher_seed"]).ref_state_dict().items()}
@@ -743,7 +775,7 @@ def test_trainer_hyper_parameters_off_their_defaults(cuda, precision):
         print("step", it, {k: (round(got[k], 4), round(v, 4)) for k, v in ref["losses"].items()})
         if it == 0 or x3:  # the trainer reports UNWEIGHTED losses (metrics_dict = record_dict, trainer.py:379-381)
             for k, v in ref["losses"].items():
-                tol = 1e-3 if x3 else ((2e-2 if "rpn" in k else 0.1) if k.endswith("_sup") else 0.3)
+                tol = max(1e-3, 4 * COND[it]["losses"][k]) if x3 else ((2e-2 if "rpn" in k else 0.1) if k.endswith("_sup") else 0.3)
                 if not abs(got[k] - v) <= tol * max(abs(v), 1e-3):
                     problems.append((it, k, got[k], v))
         st, te = samples(tr.model), samples(tr.model_teacher)
@@ -761,8 +793,9 @@ def test_trainer_hyper_parameters_off_their_defaults(cuda, precision):
                 dev = float((prev[k] - prev_ref[k]).abs().max())                          # own student vs reference student
                 err = float((te[k] - v).abs().max())
                 assert err <= 1e-7 + 2e-6 * float(v.abs().max()) + (1.0 - keep) * dev, (k, err, dev)
-                if x3:
-                    assert err <= 1e-7 + 1e-3 * float((v - teacher_prev[k]).abs().max()), (k, err)  # 1e-3 of the EMA's change
+                if x3:  # the EMA's change (1 - keep) * (student - teacher), as well-conditioned as the student's updates
+                    c = max([COND[j]["update"].get(k, 0.0) for j in range(it)] + [0.0])
+                    assert err <= 1e-7 + max(1e-3, 4 * c) * float((v - teacher_prev[k]).abs().max()), (k, err, c)
             assert any(not torch.equal(te[k], teacher_prev[k]) for k in te)
         teacher_prev = te
         up_g = torch.cat([st[k] - prev[k] for k in sorted(st)])
@@ -771,15 +804,16 @@ def test_trainer_hyper_parameters_off_their_defaults(cuda, precision):
         ratio = float(up_g.norm() / up_r.norm())
         print("   update cosine", round(cos, 6), "norm ratio", round(ratio, 6))
         if x3:
-            worst = ("", 0.0)
+            worst = ("", 0.0, 0.0)
             for k in sorted(st):
                 du, dr = st[k] - prev[k], ref["student"][k] - prev_ref[k]
                 if float(dr.abs().max()) > 0.0:
                     e = float((du - dr).abs().max() / dr.abs().max())
-                    worst = (k, e) if e > worst[1] else worst
-            print("   worst per-tensor update error", worst)
-            if worst[1] > 1e-3:
-                problems.append(("update_x3", it) + worst)
+                    tol = max(1e-3, 4 * COND[it]["update"].get(k, 0.0))
+                    worst = (k, e / tol, e) if e / tol > worst[1] else worst
+                    if e > tol:
+                        problems.append(("update_x3", it, k, e, tol))
+            print("   worst per-tensor update error / tolerance", worst)
         elif not (cos > (0.99 if it == 0 else 0.97) and (0.95 if it == 0 else 0.9) < ratio < (1.05 if it == 0 else 1.1)):
             problems.append(("update", it, cos, ratio))
         prev, prev_ref = st, ref["student"]
