@@ -119,99 +119,136 @@ class ClockSampler:
 
 # ------------------------------------------------------------------------------------------ roofline profiler
 class GemmProfiler:
-    """Times every launch of the tcgen05 GEMM kernels with CUDA events on the launching stream and
-    books the algorithmic FLOPs (2*MACs)."""
+    """Times every launch of the tcgen05 GEMM kernels with CUDA events on the launching stream, over SEVERAL eager
+    steps run back to back after the warm-up (per-step sums; the median step is reported), and books FLOPs per
+    launch (2 * MACs the tensor cores execute):
+      * `ptb200_gemm_tn_f16` / `ptb200_gemm_tn_f16x3`: 2 * batch * rows * K * taps * N. In the f16x3 precision K is
+        the 3x-wide triple, i.e. the three fp16 products per fp32-equivalent MAC are booked as executed work;
+      * `ptb200_gemm_wgrad_f16`: 2 * batch * rows * M * N * taps (the f16x3 weight gradient is three such launches);
+      * GEMMs over fixed-capacity roi buffers (segment mode) book their LIVE rows, read back from the device-side
+        counts after the profiled steps, not the buffer capacity (dead 128-row tiles are skipped by the kernels)."""
+    GEMMS = ("ptb200_gemm_tn_f16", "ptb200_gemm_tn_f16x3", "ptb200_gemm_wgrad_f16")
 
     def __init__(self):
-        self.records = []
-        self.shapes = []
-        self.other = []
+        self.step = 0
+        self.gemm = []    # (step, name, flops_per_row, rows_or_None, seg_counts, seg_cap, e0, e1, shape)
+        self.other = []   # (step, name, e0, e1, extra)
 
-    def dump(self, path):
-        rows = []
-        for (name, flops, e0, e1), sh in zip(self.records, self.shapes):
-            ms = e0.elapsed_time(e1)
-            rows.append({"kind": sh[0], "shape": sh[1:], "ms": ms, "tflops": flops / ms / 1e9})
-        os.makedirs(os.path.dirname(path), exist_ok=True)
-        json.dump(rows, open(path, "w"))
+    def next_step(self):
+        self.step += 1
 
     def begin(self, name, args):
         import torch
-        if name == "ptb200_gemm_tn_f16":
-            batch, rows, k, taps, n_total = args[1], args[2], args[3], args[6], args[9]
-            n_valid = args[25] if args[11] in (2, 4) else n_total
-            flops = 2.0 * batch * rows * k * taps * n_valid
-        elif name == "ptb200_gemm_wgrad_f16":
-            batch, rows, m, n, taps = args[6], args[7], args[8], args[9], args[10]
-            flops = 2.0 * batch * rows * m * n * taps
-        else:
-            # every other entry point: time only (reported as kernels_ms_per_step); ROIAlign also books its
-            # algorithmic bytes = live rois x 7 x 7 x C x 2 B (the K-major fc1 operand written / read once)
-            e0 = torch.cuda.Event(enable_timing=True)
-            e1 = torch.cuda.Event(enable_timing=True)
-            e0.record()
-            extra = None
-            if name in ("ptb200_roi_align_fwd_f16", "ptb200_roi_align_bwd_f16"):
-                extra = (args[6], args[7], args[9] * args[9] * args[4] * 2)  # counts tensor, cap, bytes per roi
-            self.other.append((name, e0, e1, extra))
-            return ("other", None, e0, e1)
         e0 = torch.cuda.Event(enable_timing=True)
         e1 = torch.cuda.Event(enable_timing=True)
+        if name == "ptb200_gemm_tn_f16" or name == "ptb200_gemm_tn_f16x3":
+            batch, rows, k, taps, n_total, epi = args[1], args[2], args[3], args[6], args[9], args[11]
+            x3 = name.endswith("x3")
+            n_valid = args[24 if x3 else 25] if epi == 2 else n_total
+            seg_counts, seg_cap = (args[27], args[28]) if x3 else (args[28], args[29])
+            per_row = 2.0 * k * taps * n_valid
+            rec = (self.step, name, per_row, batch * rows, seg_counts, seg_cap, e0, e1,
+                   ("tn_x3" if x3 else "tn", batch, rows, k, taps, n_total, args[10], epi))
+            e0.record()
+            self.gemm.append(rec)
+            return rec
+        if name == "ptb200_gemm_wgrad_f16":
+            batch, rows, m, n, taps = args[6], args[7], args[8], args[9], args[10]
+            rec = (self.step, name, 2.0 * m * n * taps, batch * rows, args[17], args[18], e0, e1,
+                   ("wgrad", batch, rows, m, n, taps, 0, 0))
+            e0.record()
+            self.gemm.append(rec)
+            return rec
+        # every other entry point: time only (reported as kernels_ms_per_step); ROIAlign also books its
+        # algorithmic bytes = live rois x 7 x 7 x C x bytes per element (the K-major fc1 operand written / read once)
+        extra = None
+        if name.startswith("ptb200_roi_align_"):
+            elt = {"ptb200_roi_align_fwd_f16": 2, "ptb200_roi_align_bwd_f16": 2, "ptb200_roi_align_fwd_f16x3": 6,
+                   "ptb200_roi_align_bwd_f32": 4}[name]
+            extra = (args[6], args[7], args[9] * args[9] * args[4] * elt)  # counts tensor, cap, bytes per roi
+        rec = (self.step, name, e0, e1, extra)
         e0.record()
-        if name == "ptb200_gemm_tn_f16":
-            self.shapes.append(("tn", args[1], args[2], args[3], args[6], args[9], args[10], args[11]))
-        else:
-            self.shapes.append(("wgrad", args[6], args[7], args[8], args[9], args[10], 0, 0))
-        return (name, flops, e0, e1)
+        self.other.append(rec)
+        return rec
 
     def end(self, tok):
         if tok is not None:
-            tok[3].record()
-            if tok[0] != "other":
-                self.records.append(tok)
+            (tok[7] if len(tok) > 5 else tok[3]).record()
 
-    def other_summary(self):
-        """({entry point: ms per step}, ROIAlign {name: (ms, GB/s)})."""
-        ms = {}
-        roi = {}
-        for name, e0, e1, extra in self.other:
-            t = e0.elapsed_time(e1)
-            ms[name] = ms.get(name, 0.0) + t
-            if extra is not None:
-                counts, cap, per_roi = extra
-                live = int(counts.clamp(max=cap).sum()) if counts is not None else 0
-                a = roi.setdefault(name, [0.0, 0.0])
-                a[0] += t
-                a[1] += live * per_roi
-        return ms, {k: {"ms_per_step": v[0], "algorithmic_GBps": v[1] / v[0] / 1e6 if v[0] > 0 else 0.0,
-                        "MB_per_step": v[1] / 1e6} for k, v in roi.items()}
+    @staticmethod
+    def _live_rows(rows, seg_counts, seg_cap):
+        if seg_counts is None:
+            return rows
+        return int(seg_counts.clamp(max=seg_cap).sum())
+
+    def dump(self, path):
+        rows = []
+        for (step, name, per_row, nrows, sc, cap, e0, e1, sh) in self.gemm:
+            ms = e0.elapsed_time(e1)
+            fl = per_row * self._live_rows(nrows, sc, cap)
+            rows.append({"step": step, "kind": sh[0], "shape": sh[1:], "ms": ms, "tflops": fl / ms / 1e9})
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        json.dump(rows, open(path, "w"))
 
     def summary(self):
-        tot_f = {"ptb200_gemm_tn_f16": 0.0, "ptb200_gemm_wgrad_f16": 0.0}
-        tot_t = {"ptb200_gemm_tn_f16": 0.0, "ptb200_gemm_wgrad_f16": 0.0}
-        cnt = {"ptb200_gemm_tn_f16": 0, "ptb200_gemm_wgrad_f16": 0}
-        for name, flops, e0, e1 in self.records:
-            tot_f[name] += flops
-            tot_t[name] += e0.elapsed_time(e1) * 1e-3
-            cnt[name] += 1
-        return tot_f, tot_t, cnt
+        """Per GEMM entry point: FLOPs per step, kernel ms per step (median and min over the profiled steps),
+        launches per step."""
+        steps = sorted({r[0] for r in self.gemm})
+        out = {}
+        for name in self.GEMMS:
+            per_step_ms, per_step_fl, cnt = [], [], 0
+            for s in steps:
+                recs = [r for r in self.gemm if r[0] == s and r[1] == name]
+                cnt = len(recs)
+                per_step_ms.append(sum(r[6].elapsed_time(r[7]) for r in recs))
+                per_step_fl.append(sum(r[2] * self._live_rows(r[3], r[4], r[5]) for r in recs))
+            if not per_step_ms or cnt == 0:
+                continue
+            order = sorted(range(len(per_step_ms)), key=lambda i: per_step_ms[i])
+            med = order[len(order) // 2]
+            out[name] = {"flops_per_step": per_step_fl[med], "ms_median": per_step_ms[med], "ms_min": min(per_step_ms),
+                         "launches_per_step": cnt, "profiled_steps": len(steps)}
+        return out
+
+    def other_summary(self):
+        """({entry point: median ms per step}, ROIAlign {name: ms, algorithmic GB/s})."""
+        steps = sorted({r[0] for r in self.other})
+        names = sorted({r[1] for r in self.other})
+        ms = {}
+        roi = {}
+        for name in names:
+            per = []
+            for s in steps:
+                per.append(sum(r[2].elapsed_time(r[3]) for r in self.other if r[0] == s and r[1] == name))
+            per.sort()
+            ms[name] = per[len(per) // 2]
+            recs = [r for r in self.other if r[1] == name and r[4] is not None]
+            if recs:
+                t = sum(r[2].elapsed_time(r[3]) for r in recs) / len(steps)
+                by = sum(int(r[4][0].clamp(max=r[4][1]).sum()) * r[4][2] if r[4][0] is not None else 0 for r in recs) / len(steps)
+                roi[name] = {"ms_per_step": t, "algorithmic_GBps": by / t / 1e6 if t > 0 else 0.0, "MB_per_step": by / 1e6}
+        return ms, roi
 
 
 # ------------------------------------------------------------------------------------------ CPU oracle leg
-def cpu_oracle_iters_per_s(steps, warmup, pairs=1, H=H_IMG, W=W_IMG):
+def cpu_oracle_iters_per_s(steps, warmup, pairs=1, H=H_IMG, W=W_IMG, num_classes=None, budget_s=None):
     """Times the CPU restatement of the reference step (oracle/pt_oracle.py, all host threads) on a
-    bounded sample: `pairs` source + `pairs` target images per step. Returns (iters/s normalised to a
-    bs=2+2 iteration, cores, sample description)."""
+    bounded sample: `pairs` source + `pairs` target images per step. With budget_s the run is cut short (fewer
+    warm-up / timed steps, at least 2 timed) once it would exceed the budget. Returns (iters/s normalised to a
+    bs=2+2 iteration, cores, sample description, timed steps, warm-up steps)."""
     import torch
     from oracle import pt_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    cfg = O.OracleCfg()
+    cfg = O.OracleCfg() if num_classes is None else O.OracleCfg(num_classes=num_classes)
     student = O.OracleRCNN(cfg, seed=1)
     teacher = O.OracleRCNN(cfg, seed=1)
     opt = O.make_optimizer(student, cfg)
     times = []
-    for s in range(warmup + steps):
+    t_start = time.perf_counter()
+    warm = warmup
+    s = 0
+    while True:
         lq = O.synthetic_batch(pairs, H, W, cfg.num_classes, 1234 + 2 * s)
         lk = [dict(d) for d in lq]
         uq = O.synthetic_batch(pairs, H, W, cfg.num_classes, 1235 + 2 * s, labelled=False)
@@ -219,33 +256,53 @@ def cpu_oracle_iters_per_s(steps, warmup, pairs=1, H=H_IMG, W=W_IMG):
         t0 = time.perf_counter()
         O.run_step(student, teacher, opt, (lq, lk, uq, uk), cfg, [0.75] * pairs, [0.75] * pairs)
         dt = time.perf_counter() - t0
-        if s >= warmup:
+        s += 1
+        if budget_s is not None and s == 1 and (warmup + steps) * dt > budget_s:
+            warm = min(warmup, 1)
+        if s > warm:
             times.append(dt)
+        if len(times) >= steps:
+            break
+        if budget_s is not None and time.perf_counter() - t_start + dt > budget_s and len(times) >= 2:
+            break
     per_step = sum(times) / len(times)
     iters_per_s = (pairs / PAIRS_PER_GPU) / per_step
     sample = (f"{len(times)} oracle step(s) of {pairs} source + {pairs} target 3x{H}x{W} images "
-              f"({per_step:.2f} s/step), scaled to a {PAIRS_PER_GPU}+{PAIRS_PER_GPU} iteration")
-    return iters_per_s, cores, sample
+              f"({per_step:.2f} s/step) on {cores} host threads, scaled to a {PAIRS_PER_GPU}+{PAIRS_PER_GPU} iteration")
+    return iters_per_s, cores, sample, len(times), warm
+
+
+def workload_config(args, world):
+    """The `config` object of the JSON line: identical for this repo's arm and the reference arm."""
+    name = ("KITTI2CitysScape config (configs/pt/final_k2c.yaml, K = 1), " if args.config == "k2c" else
+            "CitysScape2FoggyCityscape config (configs/pt/final_c2f.yaml + train.sh overrides), ")
+    return {"workload": name + f"synthetic 3x{args.height}x{args.width}, {PAIRS_PER_GPU} source + {PAIRS_PER_GPU} target "
+                               "pairs per GPU, full post-burn-in PT iteration",
+            "global_batch": f"{PAIRS_PER_GPU * world}+{PAIRS_PER_GPU * world}", "parallelism": f"dp{world}",
+            "l2": "per-step working set (GBs of activations) is far larger than the 126 MB L2",
+            "value_definition": "iterations/s summed over ranks (each rank runs one 2+2 iteration per step)"}
 
 
 def run_reference(args):
+    """The reference algorithm on the host cores (the CPU oracle port: detectron2 cannot be installed here). Rank 0
+    only. W warm-up + K timed steps as asked, unless that would take more than ~4 minutes: then fewer timed steps
+    (reported in `steps`). Every step is a bounded sample (1 source + 1 target image) of the 2+2 iteration."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    steps = max(1, min(args.steps, 2))
-    warm = min(args.warmup, 1)
-    v, cores, sample = cpu_oracle_iters_per_s(steps, warm, H=args.height, W=args.width)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    v, cores, sample, n_timed, warm = cpu_oracle_iters_per_s(args.steps, args.warmup, 1, args.height, args.width,
+                                                             1 if args.config == "k2c" else None, budget_s=240.0)
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": "iters/s", "n_gpus": args.gpus,
-        "steps": steps, "warmup": warm, "ms_per_step": 1000.0 / v if v > 0 else None, "higher_is_better": True,
+        "steps": n_timed, "warmup": warm, "ms_per_step": 1000.0 / v, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"CitysScape2FoggyCityscape config, synthetic 3x{args.height}x{args.width}, 2 source + "
-                               "2 target per iteration (CPU run on a 1+1 sample, scaled)", "l2": "inputs larger than L2"},
+        "config": workload_config(args, world),
         "cpu_baseline": {"value": v, "unit": "iters/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "detectron2 is not installable here (no package, no network): the reference arm is the CPU "
-                "oracle port of the reference path (oracle/pt_oracle.py), all host threads; steps capped at "
-                f"{steps} timed + {warm} warm-up to stay within minutes",
+        "note": "detectron2 is not installable here (no package, no network): the reference arm is the CPU oracle port "
+                "of the reference path (oracle/pt_oracle.py, pinned to the reference's own trainer by tests/golden), "
+                "one process on all host threads regardless of --gpus",
     }
     print(json.dumps(line))
     return 0
@@ -277,18 +334,178 @@ def timed_steps(trainer, steps, dist, device, read_losses=False, host_sink=None)
     return ms
 
 
+PRECISION_DETAIL = {
+    "f16x3": "split-fp16 operands (hi + lo fp16 pairs, three tcgen05 kind::f16 products per fp32-equivalent MAC, "
+             "partial sums promoted to fp32 registers every 4 k-iterations), forward AND backward: the precision whose "
+             "losses, logits and parameter gradients meet north_star's 1e-3 against the reference's fp32 path "
+             "(tests/test_x3_backward_gpu.py, tests/test_parity_x3_gpu.py); fp32 master weights, losses, optimizer",
+    "f16": "fp16 operands / fp32 accumulate (tcgen05 kind::f16), fp32 master weights, losses and optimizer: "
+           "mixed-precision throughput mode (gradients within 5e-2, NOT within 1e-3 of the fp32 reference)",
+}
+
+
+def run_arm(precision, args, cfg, pool_dev, pool_host, dist, device, world, rank, local, peaks, profile_steps=5):
+    """One precision: device-resident timing, end-to-end timing, clocks over both, then `profile_steps` eager steps
+    with per-kernel CUDA events for the roofline."""
+    import torch
+    from probabilisticteacher_b200 import _lib
+    from probabilisticteacher_b200.engine.trainer import PTrainer
+    H, W = args.height, args.width
+    use_graph = not args.no_cuda_graph
+    warmup = max(args.warmup, 3)
+    trainer = PTrainer(cfg, cycle(pool_dev), device=device, seed=0, use_cuda_graph=use_graph,
+                       concurrent=use_graph and not args.no_concurrent, precision=precision)
+    for _ in range(warmup + (5 if use_graph else 0)):
+        trainer.step()
+    torch.cuda.synchronize()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    ms = timed_steps(trainer, args.steps, dist, device)
+    ms_per_step = ms / args.steps
+    value = world * 1000.0 / ms_per_step
+    # ---- end-to-end: pinned host images in, loss scalars out, every step
+    trainer._data_loader_iter = cycle(pool_host)
+    trainer._prefetched = None
+    host_sink = torch.empty(8, dtype=torch.float32).pin_memory()
+    trainer.step()
+    ms_e2e = timed_steps(trainer, args.steps, dist, device, read_losses=True, host_sink=host_sink)
+    e2e_value = world * 1000.0 * args.steps / ms_e2e
+    clk = clocks.stop() if rank == 0 else None  # sampled over BOTH timed regions
+    h2d = 4 * PAIRS_PER_GPU * 3 * H * W  # label_q, label_k, unlabel_q, unlabel_k uint8 images
+    d2h = 8 * 4
+    # ---- roofline of the dominant kernel (tcgen05 implicit GEMM): eager steps back to back, every kernel timed
+    trainer._data_loader_iter = cycle(pool_dev)
+    trainer._prefetched = None
+    for _ in range(2):
+        trainer.run_step()
+    torch.cuda.synchronize()
+    prof = GemmProfiler()
+    _lib.profiler[0] = prof
+    l1 = _lib.launch_count[0]
+    for _ in range(profile_steps):
+        trainer.run_step()
+        prof.next_step()
+    eager_launches = (_lib.launch_count[0] - l1) // profile_steps
+    torch.cuda.synchronize()
+    _lib.profiler[0] = None
+    gs = prof.summary()
+    other_ms, roi_stats = prof.other_summary()
+    if os.environ.get("PTB_DUMP_GEMM") and rank == 0:
+        prof.dump(os.path.join(ROOT, "gpurun_out", f"gemm_launches_{precision}.json"))
+    peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
+    peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PFLOP/s sustained (of fallback)"
+    tn_name = "ptb200_gemm_tn_f16x3" if precision == "f16x3" else "ptb200_gemm_tn_f16"
+    tn = gs.get(tn_name, {"flops_per_step": 0.0, "ms_median": 0.0, "ms_min": 0.0, "launches_per_step": 0})
+    wg = gs.get("ptb200_gemm_wgrad_f16", {"flops_per_step": 0.0, "ms_median": 0.0, "ms_min": 0.0, "launches_per_step": 0})
+    rest = {k: v for k, v in gs.items() if k not in (tn_name, "ptb200_gemm_wgrad_f16")}   # f16x3: the narrow fp32 heads
+    tn_ms = tn["ms_median"]
+    achieved = tn["flops_per_step"] / tn_ms / 1e9 if tn_ms > 0 else 0.0
+    total_flops = sum(v["flops_per_step"] for v in gs.values())
+    gemm_ms = sum(v["ms_median"] for v in gs.values())
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "r2_gemm_dram_traffic.json")
+    if os.path.exists(tp):  # committed summary of an ncu pass over one step (dram bytes per launch)
+        tj = json.load(open(tp)).get(precision)
+        if tj:
+            traffic = tj.get("dram_bytes_per_launch")
+    roofline = {
+        "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+        "traffic": traffic,
+        "traffic_note": "mean DRAM read+write bytes per launch of the dominant kernel, ncu --set full pass over one "
+                        "step (profiles/r2_gemm_dram_traffic.json); null until captured for this build",
+        "kernel": "gemm_tn_promote_kernel (ptb200_gemm_tn_f16x3)" if precision == "f16x3" else "gemm_tn_kernel (ptb200_gemm_tn_f16)",
+        "launches_per_step": tn["launches_per_step"], "kernel_ms_per_step": tn_ms, "kernel_ms_per_step_min": tn["ms_min"],
+        "timing": f"CUDA events around every launch over {profile_steps} eager steps run back to back after warm-up; "
+                  "median step; segment-mode GEMMs book their live rows",
+        "peak_source": peak_src,
+        "flops_booked": "executed tensor-core FLOPs" + (" = 3 fp16 products per fp32-equivalent MAC (fp32-equivalent "
+                                                        "throughput = achieved / 3)" if precision == "f16x3" else ""),
+        "wgrad_kernel": {"achieved": wg["flops_per_step"] / wg["ms_median"] / 1e9 if wg["ms_median"] > 0 else 0.0,
+                         "kernel_ms_per_step": wg["ms_median"], "launches_per_step": wg["launches_per_step"]},
+        "other_gemm_entry_points": {k: {"ms_per_step": v["ms_median"], "launches_per_step": v["launches_per_step"]}
+                                    for k, v in rest.items()},
+        "step_tflop": total_flops / 1e12,
+        "step_frac": (total_flops / 1e12) / (ms_per_step * 1e-3) / peak_tf if ms_per_step > 0 else 0.0,
+        "step_frac_note": "all GEMM FLOPs of one step / ms_per_step (the timed, graph-replayed step) / peak",
+        "share_of_step": gemm_ms / ms_per_step,
+    }
+    out = {"value": value, "ms_per_step": ms_per_step, "dtype": precision, "dtype_detail": PRECISION_DETAIL[precision],
+           "pairs_per_s": value * PAIRS_PER_GPU,
+           "e2e": {"value": e2e_value, "unit": "iters/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+           "gpu_launches": eager_launches, "clocks": clk, "roofline": roofline,
+           "kernels_ms_per_step": {k.replace("ptb200_", ""): round(v, 4) for k, v in
+                                   sorted(other_ms.items(), key=lambda kv: -kv[1])[:14]},
+           "roialign": roi_stats}
+    del trainer
+    torch.cuda.empty_cache()
+    return out
+
+
+def backbone_microbench(device, peaks, N=1, H=1024, W=2048, reps=9):
+    """BASELINE config 5: VGG16 13-conv stack forward (fused pre-processing + conv1_1, 12 tcgen05 implicit-GEMM convs,
+    4 max-pools) on N x 3 x 1024 x 2048 uint8 images, fp16 operands; L2 flushed between timed runs."""
+    import torch
+    from probabilisticteacher_b200.config import c2f_config
+    from probabilisticteacher_b200.modeling.meta_arch.rcnn import build_model
+    chans = [(3, 64), (64, 64), (64, 128), (128, 128), (128, 256), (256, 256), (256, 256), (256, 512), (512, 512),
+             (512, 512), (512, 512), (512, 512), (512, 512)]
+    fl, h, w = 0.0, H, W
+    for i, (ci, co) in enumerate(chans):
+        fl += 2.0 * h * w * ci * co * 9
+        if i in (1, 3, 6, 9):
+            h, w = h // 2, w // 2
+    fl *= N
+    model = build_model(c2f_config(), device, with_grads=False)
+    model.init_synthetic(0)
+    model.train()
+    g = torch.Generator().manual_seed(1)
+    batch = [{"image": torch.randint(0, 256, (3, H, W), generator=g, dtype=torch.uint8).to(device)} for _ in range(N)]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+
+    def run():
+        act, _, _ = model.preprocess_image(batch)
+        return model.backbone(act, save=False)[0]["vgg_block5"]
+    ts = []
+    with torch.no_grad():
+        for _ in range(3):
+            run()
+        for _ in range(reps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            run()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+    ms = sorted(ts)[len(ts) // 2]
+    sus, burst = peaks.get("bf16_tflops_sustained", 1400.0), peaks.get("bf16_tflops", 1590.0)
+    tf = fl / ms / 1e9
+    del model
+    torch.cuda.empty_cache()
+    return {"workload": f"VGG16 conv stack fwd, {N} x 3x{H}x{W}, fp16 operands (BASELINE config 5)", "ms": ms,
+            "gflop": fl / 1e9, "tflops": tf, "frac_of_sustained_peak": tf / sus, "frac_of_burst_peak": tf / burst,
+            "peak_source": "MEASURED_PEAKS.json (of measured)" if peaks else "fallback 1400 / 1590 TFLOP/s (of fallback)",
+            "l2": "256 MB flush between timed runs", "reps": reps,
+            "tensor_pipe_note": "ncu sm__pipe_tensor_cycles_active of the same stack: profiles/ (r2_backbone_ncu*.txt)"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ptb200", choices=["ptb200", "reference"])
+    ap.add_argument("--precision", default="both", choices=["both", "f16x3", "f16"],
+                    help="f16x3: fp32-equivalent step (meets the 1e-3 parity; the headline); f16: mixed-precision "
+                         "throughput mode; both (default): the headline is f16x3 and the f16 numbers ride along")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cuda-graph", action="store_true")
     ap.add_argument("--no-concurrent", action="store_true")
-    ap.add_argument("--config", default="c2f", choices=["c2f", "k2c"],
+    ap.add_argument("--no-backbone", action="store_true", help="skip the config-5 backbone micro-benchmark")
+    ap.add_argument("--config", default="c2f", choices=["c2f", "k2c", "backbone"],
                     help="c2f: BASELINE configs 2/3 (default, the headline); k2c: config 4 (K = 1; use with "
-                         "--height 600 --width 2000)")
+                         "--height 600 --width 2000); backbone: config 5 only (VGG16 conv stack fwd 3x1024x2048 fp16)")
     ap.add_argument("--height", type=int, default=H_IMG)
     ap.add_argument("--width", type=int, default=W_IMG)
     args = ap.parse_args()
@@ -297,15 +514,32 @@ def main():
 
     import torch
     import torch.distributed as tdist
-    from probabilisticteacher_b200 import _lib
     from probabilisticteacher_b200.config import c2f_config, k2c_config
-    from probabilisticteacher_b200.engine.trainer import PTrainer
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
+    peaks = {}
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk):
+        peaks = json.load(open(pk))
+    if args.config == "backbone":
+        if rank == 0:
+            clocks = ClockSampler(local)
+            clocks.start()
+            bb = backbone_microbench(device, peaks)
+            line = {"metric": "VGG16 3x3 conv stack fwd 3x1024x2048 fp16: TFLOP/s", "value": bb["tflops"], "unit": "TFLOP/s",
+                    "n_gpus": 1, "steps": bb["reps"], "warmup": 3, "ms_per_step": bb["ms"], "higher_is_better": True,
+                    "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+                    "config": {"workload": bb["workload"], "l2": bb["l2"]}, "clocks": clocks.stop(),
+                    "roofline": {"bound": "tensor", "achieved": bb["tflops"], "peak": peaks.get("bf16_tflops_sustained", 1400.0),
+                                 "unit": "TFLOP/s", "frac": bb["frac_of_sustained_peak"], "traffic": None,
+                                 "peak_source": bb["peak_source"]},
+                    "backbone_microbench": bb}
+            print(json.dumps(line))
+        return 0
     dist = None
     if world > 1:
         tdist.init_process_group("nccl", device_id=device)
@@ -315,107 +549,48 @@ def main():
     cfg.UNSUPNET.BURN_UP_STEP = 0  # time the post-burn-in (teacher + student) iteration
     H, W = args.height, args.width
     K = cfg.MODEL.ROI_HEADS.NUM_CLASSES
-
     pool_dev = synthetic_pool(2, PAIRS_PER_GPU, H, W, K, 1234 + 100 * rank, device=device)
     pool_host = synthetic_pool(2, PAIRS_PER_GPU, H, W, K, 1234 + 100 * rank, device=None, pin=True)
-    use_graph = not args.no_cuda_graph
-    trainer = PTrainer(cfg, cycle(pool_dev), device=device, seed=0, use_cuda_graph=use_graph,
-                       concurrent=use_graph and not args.no_concurrent)
 
-    for _ in range(warmup + (5 if use_graph else 0)):
-        trainer.step()
-    torch.cuda.synchronize()
+    precisions = ["f16x3", "f16"] if args.precision == "both" else [args.precision]
+    arms = {}
+    for prec in precisions:
+        arms[prec] = run_arm(prec, args, cfg, pool_dev, pool_host, dist, device, world, rank, local, peaks)
+    head = arms[precisions[0]]
 
-    # ---- device-resident arm
-    clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
-    l0 = _lib.launch_count[0]
-    ms = timed_steps(trainer, args.steps, dist, device)
-    launches = (_lib.launch_count[0] - l0) // args.steps  # eager launches; graph replays are counted below
-    ms_per_step = ms / args.steps
-    value = world * 1000.0 / ms_per_step
-
-    # ---- end-to-end arm: pinned host images in, loss scalars out, every step
-    trainer._data_loader_iter = cycle(pool_host)
-    host_sink = torch.empty(8, dtype=torch.float32).pin_memory()
-    trainer.step()
-    ms_e2e = timed_steps(trainer, args.steps, dist, device, read_losses=True, host_sink=host_sink)
-    e2e_value = world * 1000.0 * args.steps / ms_e2e
-    clk = clocks.stop() if rank == 0 else None  # sampled over BOTH timed regions (device-resident and end-to-end)
-    h2d = 4 * PAIRS_PER_GPU * 3 * H * W  # label_q, label_k, unlabel_q, unlabel_k uint8 images
-    d2h = 8 * 4
-
-    # ---- roofline of the dominant kernel (tcgen05 implicit GEMM), one extra profiled step
-    prof = GemmProfiler()
-    _lib.profiler[0] = prof
-    trainer._data_loader_iter = cycle(pool_dev)
-    l1 = _lib.launch_count[0]
-    trainer.run_step()  # eager: every kernel is launched (and timed) individually
-    eager_launches = _lib.launch_count[0] - l1
-    torch.cuda.synchronize()
-    _lib.profiler[0] = None
-    tot_f, tot_t, cnt = prof.summary()
-    other_ms, roi_stats = prof.other_summary()
-    if os.environ.get("PTB_DUMP_GEMM") and rank == 0:
-        prof.dump(os.path.join(ROOT, "gpurun_out", "gemm_launches.json"))
-    peaks = {}
-    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(pk):
-        peaks = json.load(open(pk))
-    peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
-    peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s sustained"
-    gt = tot_t["ptb200_gemm_tn_f16"]
-    achieved = tot_f["ptb200_gemm_tn_f16"] / gt / 1e12 if gt > 0 else 0.0
-    wt = tot_t["ptb200_gemm_wgrad_f16"]
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "r1_gemm_dram_traffic.json")
-    if os.path.exists(tp):  # committed summary of an ncu pass over one step (dram bytes per launch)
-        tj = json.load(open(tp)).get("void gemm_tn_kernel<0>")
-        if tj:
-            traffic = (tj["dram_read_MB_per_launch"] + tj["dram_write_MB_per_launch"]) * 1e6
-    roofline = {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": achieved / peak_tf, "traffic": traffic,
-                "traffic_note": "mean DRAM read+write bytes per gemm_tn_kernel launch, ncu pass over one step "
-                                "(profiles/r1_gemm_dram_traffic.json)",
-                "kernel": "gemm_tn_kernel",
-                "launches_per_step": cnt["ptb200_gemm_tn_f16"], "kernel_ms_per_step": gt * 1e3,
-                "peak_source": peak_src,
-                "wgrad_kernel": {"achieved": tot_f["ptb200_gemm_wgrad_f16"] / wt / 1e12 if wt > 0 else 0.0,
-                                 "kernel_ms_per_step": wt * 1e3, "launches_per_step": cnt["ptb200_gemm_wgrad_f16"]},
-                "share_of_step": (gt + wt) * 1e3 / ms_per_step}
-
+    bb = None
+    if rank == 0 and world == 1 and not args.no_backbone:
+        bb = backbone_microbench(device, peaks)
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, cores, sample = cpu_oracle_iters_per_s(1, 0)
+        v, cores, sample, _, _ = cpu_oracle_iters_per_s(2, 1, H=H, W=W, num_classes=1 if args.config == "k2c" else None)
         cpu_baseline = {"value": v, "unit": "iters/s", "cores": cores, "kind": "port", "sample": sample}
 
     if rank == 0:
+        use_graph = not args.no_cuda_graph
         line = {
-            "metric": METRIC, "value": value, "unit": "iters/s", "n_gpus": world, "steps": args.steps,
-            "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "fp16",
-            "dtype_detail": "fp16 operands / fp32 accumulate (tcgen05 kind::f16), fp32 master weights, losses and "
-                            "optimizer; the reference runs fp32 with AMP off",
-            "data": "synthetic",
-            "config": {"workload": ("KITTI2CitysScape config (configs/pt/final_k2c.yaml, K = 1), " if args.config == "k2c" else
-                                    "CitysScape2FoggyCityscape config (configs/pt/final_c2f.yaml + train.sh overrides), ") +
-                                   f"synthetic 3x{H}x{W}, {PAIRS_PER_GPU} source + {PAIRS_PER_GPU} target pairs per GPU, "
-                                   "full post-burn-in PT iteration",
-                       "global_batch": f"{PAIRS_PER_GPU * world}+{PAIRS_PER_GPU * world}",
-                       "parallelism": f"dp{world}",
-                       "l2": "per-step working set (GBs of activations) is far larger than the 126 MB L2",
-                       "value_definition": "iterations/s summed over ranks (each rank runs one 2+2 iteration per step)"},
-            "pairs_per_s": value * PAIRS_PER_GPU,
-            "e2e": {"value": e2e_value, "unit": "iters/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": eager_launches, "cuda_graph": use_graph, "concurrent_branches": use_graph and not args.no_concurrent,
-            "gpu_launches_note": "kernels of libptb200.so per step (counted on an eager step; in CUDA-graph mode the "
+            "metric": METRIC, "value": head["value"], "unit": "iters/s", "n_gpus": world, "steps": args.steps,
+            "warmup": warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": head["dtype"], "dtype_detail": head["dtype_detail"], "data": "synthetic",
+            "config": workload_config(args, world),
+            "pairs_per_s": head["pairs_per_s"], "e2e": head["e2e"], "gpu_launches": head["gpu_launches"],
+            "cuda_graph": use_graph, "concurrent_branches": use_graph and not args.no_concurrent,
+            "gpu_launches_note": "kernels of libptb200.so per step (counted on eager steps; in CUDA-graph mode the "
                                  "same kernels are replayed from the captured graph)",
-            "clocks": clk, "roofline": roofline, "cpu_baseline": cpu_baseline,
-            "kernels_ms_per_step": {k.replace("ptb200_", ""): round(v, 4) for k, v in
-                                    sorted(other_ms.items(), key=lambda kv: -kv[1])[:12]},
-            "roialign": roi_stats,
+            "clocks": head["clocks"], "roofline": head["roofline"], "cpu_baseline": cpu_baseline,
+            "kernels_ms_per_step": head["kernels_ms_per_step"], "roialign": head["roialign"],
         }
+        if len(precisions) > 1:
+            o = arms[precisions[1]]
+            line["mixed_precision_f16"] = {k: o[k] for k in ("value", "ms_per_step", "dtype", "dtype_detail", "pairs_per_s",
+                                                             "e2e", "gpu_launches", "clocks", "roofline",
+                                                             "kernels_ms_per_step", "roialign")}
+            line["mixed_precision_f16"]["unit"] = "iters/s"
+            line["mixed_precision_f16"]["note"] = ("same step, same kernels, fp16 operands: north_star sanctions it as a "
+                                                   "throughput mode; it does NOT meet the 1e-3 gradient parity, so it "
+                                                   "is not the headline")
+        if bb is not None:
+            line["backbone_microbench"] = bb
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

@@ -227,8 +227,10 @@ int ptb200_rpn_topk_decode(const uint32_t* sorted_idx, int64_t idx_stride, const
 
 /* d2 batched_nms -> torchvision nms (proposal_utils.py:140, fast_rcnn.py:104): greedy NMS over the
  * candidates in `order` (descending score); class_mod > 0 restricts suppression to candidates with
- * equal (order value % class_mod). keep_idx holds positions in `order`. mask_scratch needs
- * n * cap * roundup2(ceil(cap/64)) 64-bit words. */
+ * equal (order value % class_mod). keep_idx holds positions in `order`; the scan stops after max_keep survivors
+ * and the suppression bit-mask is only built for the bands of candidate rows the scan reaches. mask_scratch needs
+ * n * wpad + n * band_rows * wpad 64-bit words, wpad = roundup2(ceil(cap/64)), band_rows = 64 * max(first band,
+ * later bands) as computed by ptb200_nms; passing n * (cap + 1) * wpad words is always enough. */
 int ptb200_nms(const float* boxes, int64_t box_stride, const uint32_t* order, int64_t order_stride,
                const int* counts, int n, int cap, float thresh, int class_mod, int max_keep,
                unsigned long long* mask_scratch, int* keep_idx, int* keep_count, void* stream);

@@ -88,7 +88,7 @@ def stream_ptr():
 _keepalive = []
 
 # kernels launched per entry point (default 1); `launch_count[0]` counts launches of OUR kernels.
-KERNELS_PER_CALL = {"ptb200_nms": 2, "ptb200_rpn_match": 2, "ptb200_roi_loss_unsup": 2}
+KERNELS_PER_CALL = {"ptb200_nms": 8, "ptb200_rpn_match": 2, "ptb200_roi_loss_unsup": 2}
 launch_count = [0]
 # optional per-call profiler: set to a callable(name, args) -> context manager (bench.py uses it to
 # time the dominant kernel with CUDA events on the launching stream)

@@ -341,7 +341,13 @@ def nms(boxes, order, counts, thresh, max_keep, class_mod=0):
     counts: int32 [N]. Returns keep_idx [N, max_keep] (positions in `order`), keep_count [N]."""
     N, cap = order.shape
     words = (cap + 63) // 64
-    mask = torch.empty(N * cap * ((words + 1) // 2 * 2), dtype=torch.int64, device=boxes.device)
+    wpad = (words + 1) // 2 * 2
+    # running `removed` vectors + the mask of one band of candidate rows (the first band holds ~1.25 max_keep rows,
+    # the rest of the list is cut into three bands: see ptb200_nms)
+    b0 = min(cap, max(1024, max_keep + max_keep // 4))
+    b0 = (b0 + 63) // 64
+    band = max(b0, max(1, (words - b0 + 2) // 3))
+    mask = torch.empty(N * wpad + N * band * 64 * wpad, dtype=torch.int64, device=boxes.device)
     keep_idx = torch.zeros(N, max_keep, dtype=I32, device=boxes.device)
     keep_count = torch.zeros(N, dtype=I32, device=boxes.device)
     call("ptb200_nms", boxes, boxes.shape[1], order, cap, counts, N, cap, float(thresh), class_mod, max_keep, mask,
