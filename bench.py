@@ -152,9 +152,11 @@ class GemmProfiler:
             e0.record()
             self.gemm.append(rec)
             return rec
-        if name == "ptb200_gemm_wgrad_f16":
+        if name == "ptb200_gemm_wgrad_f16" or name == "ptb200_gemm_wgrad_f16x3":
             batch, rows, m, n, taps = args[6], args[7], args[8], args[9], args[10]
-            rec = (self.step, name, 2.0 * m * n * taps, batch * rows, args[17], args[18], e0, e1,
+            mult = 3.0 if name.endswith("x3") else 1.0   # Gh'Xh + Gl'Xh + Gh'Xl
+            name = "ptb200_gemm_wgrad_f16"
+            rec = (self.step, name, mult * 2.0 * m * n * taps, batch * rows, args[17], args[18], e0, e1,
                    ("wgrad", batch, rows, m, n, taps, 0, 0))
             e0.record()
             self.gemm.append(rec)

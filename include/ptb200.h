@@ -98,6 +98,16 @@ int ptb200_gemm_wgrad_f16(const void* G, int64_t ldg, int64_t g_batch_stride, co
                           float scale, int ksplit, float* bias_out, const int* seg_counts, int seg_cap,
                           void* stream);
 
+/* f16x3 (fp32-equivalent) weight gradient, the reference's fp32 autograd of the same layers
+ * (pt/engine/trainer.py:383-386 through vgg.py:45-53, rpn.py:44-55, roi_heads.py:127-128, fast_rcnn.py:157-169):
+ * G3 [batch][rows][3*m_total] and X3 [batch][rows][3*n_total] are [hi | lo | hi] triples (ldg / ldx = their row
+ * pitches); out += scale * (Gh'Xh + Gl'Xh + Gh'Xl) in ONE launch (a pipeline stage holds the hi and lo tiles of
+ * both operands), bias_out += scale * colsum(Gh + Gl). Other arguments as ptb200_gemm_wgrad_f16. */
+int ptb200_gemm_wgrad_f16x3(const void* G3, int64_t ldg, int64_t g_batch_stride, const void* X3, int64_t ldx,
+                            int64_t x_batch_stride, int batch, int rows, int m_total, int n_total, int taps,
+                            const int* shifts_host, float* out, int64_t ld_out, float scale, int ksplit,
+                            float* bias_out, const int* seg_counts, int seg_cap, void* stream);
+
 /* ---- image / activation helpers ---------------------------------------------------------------- */
 
 /* d2 GeneralizedRCNN.preprocess_image (called at pt/modeling/meta_arch/rcnn.py:38-43): uint8 CHW
@@ -120,6 +130,15 @@ int ptb200_conv1_u8_f16(const uint8_t* images, const int* hw_dev, int n, int hma
 int ptb200_conv1_u8_f16x3(const uint8_t* images, const int* hw_dev, int n, int hmax, int wmax,
                           int64_t image_stride, const float* mean3_host, const float* std3_host,
                           const float* w_f32, const float* bias, void* out_f16x3, void* stream);
+
+/* Tensor-core version of the same fused call (rcnn.py:38-43 + vgg.py:45-53,65-72) in the f16x3 precision: raw pixel
+ * values (exact in fp16) are the A operand, [p | p], against wpack3 = fp16 [64][64] rows
+ * [Wh(27) 0(5) | Wl(27) 0(5)] of w / std * 2^s (alpha = 2^-s); the mean enters through bias_table = fp32 [10][64]:
+ * rows 0..8 = S_t[co] = sum_c w[co][t][c] / std_c * mean_c, row 9 = bias - sum_t S_t (pixels with taps outside their
+ * image add the S_t of the absent taps back: zero padding of the NORMALISED image, as d2 ImageList pads). */
+int ptb200_conv1_u8_f16x3_tc(const uint8_t* images, const int* hw_dev, int n, int hmax, int wmax,
+                             int64_t image_stride, const void* wpack3_f16, const float* bias_table, float alpha,
+                             void* out_f16x3, void* stream);
 
 /* PTrainer.resize (pt/engine/trainer.py:557-590) for one CHW uint8 image: bilinear down-scale to
  * (dh, dw) pasted at (x1, y1) on a canvas filled with int(pixel_mean). */

@@ -9,7 +9,7 @@ import os
 import re
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libptb200.so")
+LIB_PATH = os.environ.get("PTB200_LIB") or os.path.join(_HERE, "libptb200.so")  # (PTB200_LIB: A/B builds in tools/)
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "ptb200.h")
 
 _lib = None

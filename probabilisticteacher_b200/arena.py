@@ -92,6 +92,11 @@ class ParamArena:
         self.x3 = None
         self._x3_exp = None
         self.dgrad_x3 = None
+        # pixel statistics of the model (set by GuassianGeneralizedRCNN): the f16x3 first conv folds them into its
+        # weight / bias operands
+        self.pixel_mean = (103.530, 116.280, 123.675)
+        self.pixel_std = (1.0, 1.0, 1.0)
+        self.conv1_x3 = None  # (wpack3 fp16 [64][64], bias table fp32 [10][64], alpha)
         if with_grads:
             n = self.total - self.trainable_start
             self.grads = torch.zeros(n, dtype=torch.float32, device=self.device)
@@ -218,6 +223,7 @@ class ParamArena:
                 src = sd[name].to(self.device, torch.float32)
                 v.copy_(self._from_ref(kinds.get(name, "mat"), src, v))
         self._x3_exp = None  # new weights: new f16x3 scales
+        self._conv1_dirty = True
         self.pack()
         return missing, [k for k in sd if k not in known]
 
@@ -251,11 +257,47 @@ class ParamArena:
         numbers and the hi halves keep an 8x margin to the fp16 maximum while training moves the weights. ONE host
         sync (all maxima are reduced on the device first); called on the first pack and after load_state_dict."""
         segs = self._x3_segments()
-        m = torch.stack([self.view(s.name).abs().max() for s in segs]).tolist()
+        w1 = self.view(self.conv_specs[0][0] + ".weight")  # first conv: w / std (see _pack_conv1_x3)
+        std = self._pixel_stats()[1].float()
+        m = torch.stack([self.view(s.name).abs().max() for s in segs] + [(w1 / std).abs().max()]).tolist()
         self._x3_exp = {}
-        for s, mx in zip(segs, m):
+        for name, mx in zip([s.name for s in segs] + ["__conv1__"], m):
             e = math.floor(math.log2(8192.0 / mx)) if mx > 0 and math.isfinite(mx) else 0
-            self._x3_exp[s.name] = max(-24, min(24, e))
+            self._x3_exp[name] = max(-24, min(24, e))
+
+    def _pixel_stats(self):
+        """(mean, std) as fp64 device tensors, cached: no host -> device copy once they exist (CUDA-graph capture)."""
+        key = (tuple(self.pixel_mean), tuple(self.pixel_std))
+        c = getattr(self, "_pix_cache", None)
+        if c is None or c[0] != key:
+            c = (key, torch.tensor(self.pixel_mean, dtype=torch.float64, device=self.device),
+                 torch.tensor(self.pixel_std, dtype=torch.float64, device=self.device))
+            self._pix_cache = c
+        return c[1], c[2]
+
+    def _pack_conv1_x3(self):
+        """Operands of ptb200_conv1_u8_f16x3_tc: raw pixels are exact in fp16, so only the weights are split --
+        rows [Wh(27) 0(5) | Wl(27) 0(5)] of w / std * 2^e -- and the mean goes into a bias table: rows 0..8 hold
+        S_t[co] = sum_c w[co][t][c] / std_c * mean_c, row 9 = bias - sum_t S_t (evaluated in fp64). A handful of
+        small device ops, no host sync."""
+        name = self.conv_specs[0][0]
+        e = self._x3_exp["__conv1__"]
+        w = self.view(name + ".weight").view(64, 9, 3).double()
+        mean, std = self._pixel_stats()
+        wp = w / std.view(1, 1, 3)
+        ws = (wp * (2.0 ** e)).float().view(64, 27)
+        wh = ws.half()
+        wl = (ws - wh.float()).half()
+        if self.conv1_x3 is None:
+            self.conv1_x3 = (torch.zeros(64, 64, dtype=torch.float16, device=self.device),
+                             torch.zeros(10, 64, dtype=torch.float32, device=self.device), 0.0)
+        pack, table, _ = self.conv1_x3
+        pack[:, :27] = wh
+        pack[:, 32:59] = wl
+        S = (wp * mean.view(1, 1, 3)).sum(-1)  # [64][9]
+        table[:9] = S.t().float()
+        table[9] = (self.view(name + ".bias").double() - S.sum(1)).float()
+        self.conv1_x3 = (pack, table, 2.0 ** (-e))
 
     # data-gradient operands: arena segment -> (key, rows = Cout, cols = Cin, taps, flip)
     def _x3_dgrad_specs(self):
@@ -285,6 +327,11 @@ class ParamArena:
             self.refresh_x3_scales()
         if self.x3 is None:
             self.x3 = {}
+        # the first conv is frozen (FREEZE_AT >= 1): the student's operands only change when weights are loaded; the
+        # teacher's follow the EMA (they differ from the student's until the first copy step)
+        if self.conv1_x3 is None or self.grads is None or getattr(self, "_conv1_dirty", True):
+            self._pack_conv1_x3()
+            self._conv1_dirty = False
         for s in self._x3_segments():
             # reduction length of one weight row per tap: Cin for convs, the whole row for fully connected layers
             # (fc1: 49 * 512, matching the [hi | lo | hi] roi rows ptb200_roi_align_fwd_f16x3 writes)

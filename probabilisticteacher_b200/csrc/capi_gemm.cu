@@ -120,3 +120,13 @@ extern "C" int ptb200_gemm_wgrad_f16(const void* G, int64_t ldg, int64_t g_batch
                            n_total, taps, shifts, out, ld_out, scale, ksplit, bias_out, seg_counts, seg_cap,
                            static_cast<cudaStream_t>(stream));
 }
+
+extern "C" int ptb200_gemm_wgrad_f16x3(const void* G3, int64_t ldg, int64_t g_batch_stride, const void* X3,
+                                       int64_t ldx, int64_t x_batch_stride, int batch, int rows, int m_total,
+                                       int n_total, int taps, const int* shifts, float* out, int64_t ld_out,
+                                       float scale, int ksplit, float* bias_out, const int* seg_counts, int seg_cap,
+                                       void* stream) {
+  return gemm_wgrad_launch(G3, ldg, g_batch_stride, X3, ldx, x_batch_stride, batch, rows, m_total, n_total, taps,
+                           shifts, out, ld_out, scale, ksplit, bias_out, seg_counts, seg_cap,
+                           static_cast<cudaStream_t>(stream), true);
+}

@@ -188,19 +188,27 @@ struct C1Ctl {
   uint32_t pad;
 };
 
+// X3 = f16x3 (fp32-equivalent) precision, by EXACTNESS rather than by splitting the activation: a raw pixel value
+// (0..255) is exactly representable in fp16, so the A tile carries the raw bytes twice, [p | p] (K = 2 x 32), against
+// B = [Wh | Wl], the hi / lo fp16 halves of w / std * 2^s; the mean enters through the bias:
+//   sum_t w'_t (p_t - mean) = sum_t w'_t p_t - sum_{t in image} w'_t mean   (taps outside the image contribute 0),
+// so interior pixels use bias_int = b - sum_t S_t, S_t[co] = sum_c w'[co][t][c] mean_c, and border pixels add the S_t of
+// their absent taps back (`bias` = fp32 [10][64]: S_0..S_8, bias_int; computed in fp64 by ParamArena.pack_x3). Output:
+// [hi | lo | hi] triples (192 wide). Replaces the fp32 CUDA-core kernel of csrc/split3.cu (3.9 ms per step).
+template <bool X3>
 __global__ void __launch_bounds__(C1_THREADS, 1)
 conv1_u8_tc_kernel(const uint8_t* __restrict__ img, const int* __restrict__ hw, int N, int Hmax, int Wmax,
                    int64_t img_stride, float m0, float m1, float m2, float is0, float is1, float is2,
-                   const __half* __restrict__ wpack /* [64][32] */, const float* __restrict__ bias,
-                   const __grid_constant__ CUtensorMap map_d) {
+                   const __half* __restrict__ wpack /* [64][32], X3: [64][64] */, const float* __restrict__ bias,
+                   float alpha, const __grid_constant__ CUtensorMap map_d) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
   uint8_t* a_tiles = smem;                              // 2 x 16 KB
   uint8_t* b_tile = a_tiles + 2 * C1_A_BYTES;           // 8 KB
-  uint8_t* staging = b_tile + C1_B_BYTES;               // 2 x 16 KB
-  float* bias_s = reinterpret_cast<float*>(staging + 2 * C1_STG_BYTES);
-  C1Ctl* ctl = reinterpret_cast<C1Ctl*>(bias_s + 64);
+  uint8_t* staging = b_tile + C1_B_BYTES;               // 2 x 16 KB (X3: 2 x (hi, lo) = 4 x 16 KB)
+  float* bias_s = reinterpret_cast<float*>(staging + (X3 ? 4 : 2) * C1_STG_BYTES);  // [64], X3: [10][64]
+  C1Ctl* ctl = reinterpret_cast<C1Ctl*>(bias_s + (X3 ? 640 : 64));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int Wp = Wmax + 1;
@@ -219,12 +227,13 @@ conv1_u8_tc_kernel(const uint8_t* __restrict__ img, const int* __restrict__ hw, 
     fence_mbar_init();
   }
   // weights -> K-major SWIZZLE_128B B tile (row n, 16-byte chunk c at position c ^ (n & 7)); k >= 32 unused
-  for (int i = threadIdx.x; i < 64 * 4; i += blockDim.x) {
-    const int n = i >> 2, c = i & 3;
+  constexpr int kChunks = X3 ? 8 : 4;  // 16-byte chunks of a weight row that carry data
+  for (int i = threadIdx.x; i < 64 * kChunks; i += blockDim.x) {
+    const int n = i / kChunks, c = i % kChunks;
     *reinterpret_cast<uint4*>(b_tile + n * 128 + ((c ^ (n & 7)) << 4)) =
-        *reinterpret_cast<const uint4*>(wpack + n * 32 + c * 8);
+        *reinterpret_cast<const uint4*>(wpack + n * (8 * kChunks) + c * 8);
   }
-  if (threadIdx.x < 64) bias_s[threadIdx.x] = bias[threadIdx.x];
+  for (int i = threadIdx.x; i < (X3 ? 640 : 64); i += blockDim.x) bias_s[i] = bias[i];
   fence_proxy_async_smem();
   if (warp == 0) {
     tmem_alloc(&ctl->tmem_base, 128);
@@ -252,6 +261,10 @@ conv1_u8_tc_kernel(const uint8_t* __restrict__ img, const int* __restrict__ hw, 
         const uint64_t db = umma_desc_sw128(b_addr, 16, 1024);
         umma_f16_ss(tmem_u + s * 64, da, db, idesc, 0u);
         umma_f16_ss(tmem_u + s * 64, da + 2, db + 2, idesc, 1u);
+        if (X3) {  // second half of K: the same pixels against the lo halves of the weights
+          umma_f16_ss(tmem_u + s * 64, da + 4, db + 4, idesc, 1u);
+          umma_f16_ss(tmem_u + s * 64, da + 6, db + 6, idesc, 1u);
+        }
         umma_commit(&ctl->a_empty[s]);
         umma_commit(&ctl->tmem_full[s]);
       }
@@ -297,8 +310,8 @@ conv1_u8_tc_kernel(const uint8_t* __restrict__ img, const int* __restrict__ hw, 
         const int64_t plane = static_cast<int64_t>(h) * w;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-          const float mean = c == 0 ? m0 : (c == 1 ? m1 : m2);
-          const float istd = c == 0 ? is0 : (c == 1 ? is1 : is2);
+          const float mean = X3 ? 0.f : (c == 0 ? m0 : (c == 1 ? m1 : m2));     // X3: raw pixel values (exact in fp16)
+          const float istd = X3 ? 1.f : (c == 0 ? is0 : (c == 1 ? is1 : is2));
           const uint8_t* bc = b0 + c * plane;
 #pragma unroll
           for (int dy = 0; dy < 3; ++dy) {
@@ -318,8 +331,8 @@ conv1_u8_tc_kernel(const uint8_t* __restrict__ img, const int* __restrict__ hw, 
             if (yy < 0 || yy >= h) continue;
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-              const float mean = c == 0 ? m0 : (c == 1 ? m1 : m2);
-              const float istd = c == 0 ? is0 : (c == 1 ? is1 : is2);
+              const float mean = X3 ? 0.f : (c == 0 ? m0 : (c == 1 ? m1 : m2));
+              const float istd = X3 ? 1.f : (c == 0 ? is0 : (c == 1 ? is1 : is2));
               const uint8_t* rowp = ib + (static_cast<int64_t>(c) * h + yy) * w;
 #pragma unroll
               for (int dx = 0; dx < 3; ++dx) {
@@ -345,9 +358,11 @@ conv1_u8_tc_kernel(const uint8_t* __restrict__ img, const int* __restrict__ hw, 
       mbar_wait(&ctl->a_empty[grp], ph ^ 1);   // the MMAs that read this stage two tiles ago are done
       uint8_t* rowp = a_tile + r * 128;
 #pragma unroll
-      for (int c = 0; c < 4; ++c)
-        *reinterpret_cast<uint4*>(rowp + ((c ^ (r & 7)) << 4)) =
-            make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+      for (int c = 0; c < 4; ++c) {
+        const uint4 q4 = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+        *reinterpret_cast<uint4*>(rowp + ((c ^ (r & 7)) << 4)) = q4;
+        if (X3) *reinterpret_cast<uint4*>(rowp + (((c + 4) ^ (r & 7)) << 4)) = q4;   // [p | p]
+      }
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&ctl->a_full[grp]);
@@ -365,7 +380,7 @@ conv1_u8_tc_kernel(const uint8_t* __restrict__ img, const int* __restrict__ hw, 
       const uint32_t ph = (it >> 1) & 1;
       const int n = tile / m_tiles;
       const int row0 = (tile - n * m_tiles) * 128;
-      uint8_t* stg = staging + s * C1_STG_BYTES;
+      uint8_t* stg = staging + s * (X3 ? 2 : 1) * C1_STG_BYTES;
       // the TMA store that read this staging buffer two tiles ago must have drained
       if (ew == 0 && elect_one()) tma_store_wait_read<1>();
       named_bar_sync(1, 256);
@@ -380,6 +395,45 @@ conv1_u8_tc_kernel(const uint8_t* __restrict__ img, const int* __restrict__ hw, 
       const int row = row0 + r;
       const bool live = row < rows && (row % Wp) < Wmax;
       uint8_t* rowp = stg + r * 128;
+      if (X3) {
+        // per-pixel bias: interior pixels use bias_int (table row 9); a pixel with taps outside ITS image adds the
+        // mean terms of the absent taps back (table rows 0..8)
+        const int y = row / Wp, x = row - y * Wp;
+        const int h = hw[2 * n], w = hw[2 * n + 1];
+        const bool interior = x >= 1 && x + 1 < w && y >= 1 && y + 1 < h;
+        uint8_t* rowl = rowp + C1_STG_BYTES;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int jj = 4 * hf + j;
+          float f[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[j * 8 + e]) * alpha + bias_s[9 * 64 + jj * 8 + e];
+          if (!interior) {
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+              const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
+              if (yy < 0 || yy >= h || xx < 0 || xx >= w) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) f[e] += bias_s[t * 64 + jj * 8 + e];
+              }
+            }
+          }
+          uint4 oh, ol;
+          uint32_t* ohp = reinterpret_cast<uint32_t*>(&oh);
+          uint32_t* olp = reinterpret_cast<uint32_t*>(&ol);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float a = live ? fmaxf(f[2 * e], 0.f) : 0.f, b = live ? fmaxf(f[2 * e + 1], 0.f) : 0.f;
+            const __half2 hh = __floats2half2_rn(a, b);
+            const float2 hf2 = __half22float2(hh);
+            const __half2 ll = __floats2half2_rn(a - hf2.x, b - hf2.y);
+            ohp[e] = *reinterpret_cast<const uint32_t*>(&hh);
+            olp[e] = *reinterpret_cast<const uint32_t*>(&ll);
+          }
+          *reinterpret_cast<uint4*>(rowp + ((jj ^ (r & 7)) << 4)) = oh;
+          *reinterpret_cast<uint4*>(rowl + ((jj ^ (r & 7)) << 4)) = ol;
+        }
+      } else {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int jj = 4 * hf + j;
@@ -400,10 +454,15 @@ conv1_u8_tc_kernel(const uint8_t* __restrict__ img, const int* __restrict__ hw, 
         if (!live) o = make_uint4(0, 0, 0, 0);
         *reinterpret_cast<uint4*>(rowp + ((jj ^ (r & 7)) << 4)) = o;
       }
+      }
       fence_proxy_async_smem();
       named_bar_sync(1, 256);
       if (ew == 0 && elect_one()) {
         tma_store_3d(&map_d, stg, 0, row0, n);
+        if (X3) {
+          tma_store_3d(&map_d, stg + C1_STG_BYTES, 64, row0, n);
+          tma_store_3d(&map_d, stg, 128, row0, n);
+        }
         tma_store_commit();
       }
     }
@@ -435,7 +494,7 @@ extern "C" int ptb200_conv1_u8_f16(const uint8_t* images, const int* hw_dev, int
     const int smem_bytes = 2 * C1_A_BYTES + C1_B_BYTES + 2 * C1_STG_BYTES + 64 * 4 + (int)sizeof(C1Ctl) + 1024;
     static bool configured = false;
     if (!configured) {
-      cudaError_t e = cudaFuncSetAttribute(conv1_u8_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      cudaError_t e = cudaFuncSetAttribute(conv1_u8_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            smem_bytes);
       if (e != cudaSuccess) return (int)e;
       configured = true;
@@ -449,9 +508,10 @@ extern "C" int ptb200_conv1_u8_f16(const uint8_t* images, const int* hw_dev, int
     const int64_t tiles = ((rows + 127) / 128) * n;
     const int grid = tiles < sms ? (int)tiles : sms;
     if (grid < 1) return 0;
-    conv1_u8_tc_kernel<<<grid, C1_THREADS, smem_bytes, static_cast<cudaStream_t>(stream)>>>(
+    conv1_u8_tc_kernel<false><<<grid, C1_THREADS, smem_bytes, static_cast<cudaStream_t>(stream)>>>(
         images, hw_dev, n, hmax, wmax, image_stride, mean3_host[0], mean3_host[1], mean3_host[2],
-        1.f / std3_host[0], 1.f / std3_host[1], 1.f / std3_host[2], static_cast<const __half*>(wpack_f16), bias, md);
+        1.f / std3_host[0], 1.f / std3_host[1], 1.f / std3_host[2], static_cast<const __half*>(wpack_f16), bias, 1.f,
+        md);
     return static_cast<int>(cudaGetLastError());
   }
   const int64_t tiles = static_cast<int64_t>(n) * hmax * ((wmax + 1 + 31) / 32);
@@ -461,5 +521,37 @@ extern "C" int ptb200_conv1_u8_f16(const uint8_t* images, const int* hw_dev, int
       images, hw_dev, n, hmax, wmax, image_stride, mean3_host[0], mean3_host[1], mean3_host[2],
       1.f / std3_host[0], 1.f / std3_host[1], 1.f / std3_host[2], static_cast<const __half*>(wpack_f16), bias,
       static_cast<__half*>(out_f16));
+  return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int ptb200_conv1_u8_f16x3_tc(const uint8_t* images, const int* hw_dev, int n, int hmax, int wmax,
+                                        int64_t image_stride, const void* wpack3_f16, const float* bias_table,
+                                        float alpha, void* out_f16x3, void* stream) {
+  const int64_t rows = static_cast<int64_t>(hmax) * (wmax + 1);
+  CUtensorMap md;
+  uint64_t dims[3] = {192, (uint64_t)rows, (uint64_t)n};
+  uint64_t str[2] = {384, (uint64_t)rows * 384};
+  uint32_t box[3] = {64, 128, 1};
+  if (ptb::make_tmap_f16(&md, out_f16x3, 3, dims, str, box)) return 1501;
+  const int smem_bytes = 2 * C1_A_BYTES + C1_B_BYTES + 4 * C1_STG_BYTES + 640 * 4 + (int)sizeof(C1Ctl) + 1024;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv1_u8_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         smem_bytes);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  const int64_t tiles = ((rows + 127) / 128) * n;
+  const int grid = tiles < sms ? (int)tiles : sms;
+  if (grid < 1) return 0;
+  conv1_u8_tc_kernel<true><<<grid, C1_THREADS, smem_bytes, static_cast<cudaStream_t>(stream)>>>(
+      images, hw_dev, n, hmax, wmax, image_stride, 0.f, 0.f, 0.f, 1.f, 1.f, 1.f, static_cast<const __half*>(wpack3_f16),
+      bias_table, alpha, md);
   return static_cast<int>(cudaGetLastError());
 }

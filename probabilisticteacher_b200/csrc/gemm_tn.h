@@ -83,6 +83,6 @@ int gemm_tn_promote_launch(const GemmTnArgs& a, int chunk, cudaStream_t stream);
 int gemm_wgrad_launch(const void* G, int64_t ldg, int64_t g_batch_stride, const void* X, int64_t ldx,
                       int64_t x_batch_stride, int batch, int rows, int m_total, int n_total, int taps,
                       const int* shifts, float* out, int64_t ld_out, float scale, int ksplit, float* bias_out,
-                      const int* seg_counts, int seg_cap, cudaStream_t stream);
+                      const int* seg_counts, int seg_cap, cudaStream_t stream, bool x3 = false);
 
 }  // namespace ptb

@@ -68,6 +68,11 @@ __device__ __forceinline__ bool chunk_live(const int* __restrict__ seg_counts, i
   return false;
 }
 
+// X3 = f16x3 (fp32-equivalent) precision: G and X are [hi | lo | hi] triples; a stage holds the hi AND lo tiles of both
+// operands and the accumulator receives Gh'Xh + Gl'Xh + Gh'Xl (12 MMAs per 64-row chunk instead of 4). One fused
+// launch instead of three passes of the plain kernel over column slices: a stage moves 2x the bytes for 3x the
+// MMAs, which lifts the kernel off its L2 -> shared-memory bound (48 KB per 512 tensor cycles at BN = 256).
+template <bool X3>
 __global__ void __launch_bounds__(WG_THREADS, 2)
 gemm_wgrad_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant__ CUtensorMap map_x,
                   const WgParams p) {
@@ -77,7 +82,8 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_consta
   const int bn = p.bn;
   const int a_bytes = (WG_BM / 64) * WG_BLK_BYTES;  // 16 KB
   const int b_bytes = (bn / 64) * WG_BLK_BYTES;
-  const int stage_bytes = a_bytes + b_bytes;
+  // stage layout: [Gh][Gl (X3)][Xh][Xl (X3)]
+  const int stage_bytes = (X3 ? 2 : 1) * (a_bytes + b_bytes);
   WgCtl* ctl = reinterpret_cast<WgCtl*>(smem + p.stages * stage_bytes);
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -142,10 +148,14 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_consta
         mbar_wait(&ctl->empty[s], ph ^ 1);
         if (elect_one()) {
           uint8_t* sa = smem + s * stage_bytes;
-          uint8_t* sb = sa + a_bytes;
+          uint8_t* sb = sa + (X3 ? 2 : 1) * a_bytes;
           mbar_arrive_expect_tx(&ctl->full[s], stage_bytes);
           tma_load_4d(sa, &map_g, &ctl->full[s], 0, r0, mt * (WG_BM / 64), b);
           tma_load_4d(sb, &map_x, &ctl->full[s], 0, r0 + shift, nt * (bn / 64), b);
+          if (X3) {  // the lo halves: channel blocks [m_total/64, 2 m_total/64) and [n_total/64, 2 n_total/64)
+            tma_load_4d(sa + a_bytes, &map_g, &ctl->full[s], 0, r0, p.m_total / 64 + mt * (WG_BM / 64), b);
+            tma_load_4d(sb + b_bytes, &map_x, &ctl->full[s], 0, r0 + shift, p.n_total / 64 + nt * (bn / 64), b);
+          }
         }
         __syncwarp();
         if (++s == p.stages) {
@@ -163,7 +173,7 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_consta
         mbar_wait(&ctl->full[s], ph);
         tc_fence_after();
         const uint32_t a_addr = __shfl_sync(0xffffffffu, smem_u32(smem + s * stage_bytes), 0);
-        const uint32_t b_addr = __shfl_sync(0xffffffffu, a_addr + a_bytes, 0);
+        const uint32_t b_addr = __shfl_sync(0xffffffffu, a_addr + (X3 ? 2 : 1) * a_bytes, 0);
         if (elect_one()) {
           // MN-major SW128: LBO = stride between 64-channel blocks, SBO = stride between 8-row groups
           const uint64_t da = umma_desc_sw128(a_addr, WG_BLK_BYTES, 1024);
@@ -173,6 +183,14 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_consta
             // 16 reduction rows = 2048 B further into each block
             umma_f16_ss(tmem_base_u, da + (2048 >> 4) * k, db + (2048 >> 4) * k, idesc,
                         (ki > 0 || k > 0) ? 1u : 0u);
+          }
+          if (X3) {
+            const uint64_t dal = umma_desc_sw128(a_addr + a_bytes, WG_BLK_BYTES, 1024);   // Gl
+            const uint64_t dbl = umma_desc_sw128(b_addr + b_bytes, WG_BLK_BYTES, 1024);   // Xl
+#pragma unroll
+            for (int k = 0; k < WG_BK / 16; ++k) umma_f16_ss(tmem_base_u, dal + (2048 >> 4) * k, db + (2048 >> 4) * k, idesc, 1u);
+#pragma unroll
+            for (int k = 0; k < WG_BK / 16; ++k) umma_f16_ss(tmem_base_u, da + (2048 >> 4) * k, dbl + (2048 >> 4) * k, idesc, 1u);
           }
           umma_commit(&ctl->empty[s]);
           if (ki == k_iters - 1) umma_commit(&ctl->acc_full);
@@ -201,15 +219,19 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_consta
           mbar_wait(&ctl->full[s], ph);
           const uint8_t* g = smem + s * stage_bytes + blk * WG_BLK_BYTES + (col & 7) * 2;
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            const int kr0 = half_ * 32 + i, kr1 = kr0 + 1;
-            const __half2 a = *reinterpret_cast<const __half2*>(g + kr0 * 128 + (((col >> 3) ^ (kr0 & 7)) << 4));
-            const __half2 b = *reinterpret_cast<const __half2*>(g + kr1 * 128 + (((col >> 3) ^ (kr1 & 7)) << 4));
-            const float2 fa = __half22float2(a), fb = __half22float2(b);
-            s0 += fa.x;
-            s1 += fa.y;
-            s2 += fb.x;
-            s3 += fb.y;
+          for (int part = 0; part < (X3 ? 2 : 1); ++part) {  // X3: Gh then Gl (sum of both = the fp32 gradient)
+            const uint8_t* gp = g + part * a_bytes;
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              const int kr0 = half_ * 32 + i, kr1 = kr0 + 1;
+              const __half2 a = *reinterpret_cast<const __half2*>(gp + kr0 * 128 + (((col >> 3) ^ (kr0 & 7)) << 4));
+              const __half2 b = *reinterpret_cast<const __half2*>(gp + kr1 * 128 + (((col >> 3) ^ (kr1 & 7)) << 4));
+              const float2 fa = __half22float2(a), fb = __half22float2(b);
+              s0 += fa.x;
+              s1 += fa.y;
+              s2 += fb.x;
+              s3 += fb.y;
+            }
           }
           __syncwarp();
           if (lane == 0) mbar_arrive(&ctl->empty[s]);
@@ -253,12 +275,13 @@ static int g_wg_sms = 0;
 int gemm_wgrad_launch(const void* G, int64_t ldg, int64_t g_batch_stride, const void* X, int64_t ldx,
                       int64_t x_batch_stride, int batch, int rows, int m_total, int n_total, int taps,
                       const int* shifts, float* out, int64_t ld_out, float scale, int ksplit, float* bias_out,
-                      const int* seg_counts, int seg_cap, cudaStream_t stream) {
+                      const int* seg_counts, int seg_cap, cudaStream_t stream, bool x3) {
   if (seg_counts != nullptr && (batch != 1 || seg_cap <= 0)) return 1103;
   if (m_total % WG_BM != 0 || n_total % 64 != 0 || taps < 1 || taps > 9) return 1101;
-  int bn = 256;
+  int bn = 256;  // (x3 stages hold hi + lo tiles of both operands: 96 KB per stage at BN = 256, two stages)
   while (n_total % bn != 0) bn >>= 1;
   if (bn < 64) return 1102;
+  if (x3 && (ldg < 3 * m_total || ldx < 3 * n_total)) return 1104;
   if (g_wg_sms == 0) {
     int dev = 0;
     cudaGetDevice(&dev);
@@ -266,13 +289,13 @@ int gemm_wgrad_launch(const void* G, int64_t ldg, int64_t g_batch_stride, const 
   }
   CUtensorMap mg, mx;
   {
-    uint64_t dims[4] = {64, (uint64_t)rows, (uint64_t)(m_total / 64), (uint64_t)batch};
+    uint64_t dims[4] = {64, (uint64_t)rows, (uint64_t)((x3 ? 3 : 1) * m_total / 64), (uint64_t)batch};
     uint64_t str[3] = {(uint64_t)ldg * 2, 128, (uint64_t)g_batch_stride * 2};
     uint32_t box[4] = {64, WG_BK, (uint32_t)(WG_BM / 64), 1};
     if (make_tmap_f16(&mg, G, 4, dims, str, box)) return 1110;
   }
   {
-    uint64_t dims[4] = {64, (uint64_t)rows, (uint64_t)(n_total / 64), (uint64_t)batch};
+    uint64_t dims[4] = {64, (uint64_t)rows, (uint64_t)((x3 ? 3 : 1) * n_total / 64), (uint64_t)batch};
     uint64_t str[3] = {(uint64_t)ldx * 2, 128, (uint64_t)x_batch_stride * 2};
     uint32_t box[4] = {64, WG_BK, (uint32_t)(bn / 64), 1};
     if (make_tmap_f16(&mx, X, 4, dims, str, box)) return 1111;
@@ -300,7 +323,7 @@ int gemm_wgrad_launch(const void* G, int64_t ldg, int64_t g_batch_stride, const 
     if (ksplit < 1) ksplit = 1;
   }
   p.ksplit = ksplit;
-  const int stage_bytes = (WG_BM / 64 + bn / 64) * WG_BLK_BYTES;
+  const int stage_bytes = (x3 ? 2 : 1) * (WG_BM / 64 + bn / 64) * WG_BLK_BYTES;
   int stages = (232448 - 2048) / stage_bytes;
   if (stages > 8) stages = 8;
   static int stage_cap = -1;  // experiment knob: PTB200_WG_STAGES=2 lets two CTAs share an SM
@@ -312,17 +335,21 @@ int gemm_wgrad_launch(const void* G, int64_t ldg, int64_t g_batch_stride, const 
   // many tiles with a short reduction (fc1: 784 tiles x 63 chunks): two 2-stage CTAs per SM, so that one CTA's
   // prologue / red.add epilogue overlaps the other's main loop (fc1 wgrad 229 -> 160 us); long reductions
   // (conv layers) keep the deep single-CTA pipeline
-  if (stage_cap == 0 && tiles * ksplit >= 2 * g_wg_sms && total_chunks / ksplit <= 128 && stages > 2) stages = 2;
+  if (!x3 && stage_cap == 0 && tiles * ksplit >= 2 * g_wg_sms && total_chunks / ksplit <= 128 && stages > 2) stages = 2;
   p.stages = stages;
   const int smem_bytes = stages * stage_bytes + (int)sizeof(WgCtl) + 1024;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_wgrad_kernel,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    cudaError_t e = cudaFuncSetAttribute(gemm_wgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(gemm_wgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
-  gemm_wgrad_kernel<<<tiles * ksplit, WG_THREADS, smem_bytes, stream>>>(mg, mx, p);
+  if (x3)
+    gemm_wgrad_kernel<true><<<tiles * ksplit, WG_THREADS, smem_bytes, stream>>>(mg, mx, p);
+  else
+    gemm_wgrad_kernel<false><<<tiles * ksplit, WG_THREADS, smem_bytes, stream>>>(mg, mx, p);
   return (int)cudaGetLastError();
 }
 

@@ -62,6 +62,8 @@ class GuassianGeneralizedRCNN(nn.Module):
         if precision not in ("f16", "f16x3"):
             raise ValueError(f"unknown precision {precision!r}")
         self.arena.precision = precision
+        self.arena.pixel_mean = tuple(float(x) for x in cfg.MODEL.PIXEL_MEAN)
+        self.arena.pixel_std = tuple(float(x) for x in cfg.MODEL.PIXEL_STD)
         self.loss_scale = float(loss_scale)
         self.backbone = BACKBONE_REGISTRY.get(cfg.MODEL.BACKBONE.NAME)(cfg, self.arena, self.loss_scale)
         anchor_gen = ANCHOR_GENERATOR_REGISTRY.get(cfg.MODEL.ANCHOR_GENERATOR.NAME)(cfg, self.arena)
@@ -162,8 +164,14 @@ class GuassianGeneralizedRCNN(nn.Module):
         hw_i, img_hw = cached
         name0 = self.arena.conv_specs[0][0]
         if self.arena.precision == "f16x3":
-            act = ops.conv1_u8_x3(batch.view(len(imgs), -1), hw_i, H, W, self._mean, self._std,
-                                  self.arena.view(name0 + ".weight").view(64, 27), self.arena.view(name0 + ".bias"))
+            if ops.X3_CONV1_TC[0]:
+                if self.arena.conv1_x3 is None:
+                    self.arena.pack_x3(dgrad=self.arena.dgrad_half is not None)
+                pack, table, alpha = self.arena.conv1_x3
+                act = ops.conv1_u8_x3_tc(batch.view(len(imgs), -1), hw_i, H, W, pack, table, alpha)
+            else:  # fp32 CUDA-core version (cross-check)
+                act = ops.conv1_u8_x3(batch.view(len(imgs), -1), hw_i, H, W, self._mean, self._std,
+                                      self.arena.view(name0 + ".weight").view(64, 27), self.arena.view(name0 + ".bias"))
             return act, sizes, img_hw
         act = ops.conv1_u8(batch.view(len(imgs), -1), hw_i, H, W, self._mean, self._std, self.arena.conv1_half,
                            self.arena.view(name0 + ".bias"))

@@ -100,6 +100,7 @@ def conv3x3(x: FlatAct, w_packed, bias, relu=True, aux=None, out=None):
 # -1.8e-7 with chunks of 8 / 4 / 2 / 1 k-iterations of 64); the kernel promotes its TMEM partial sums to fp32
 # registers every X3_CHUNK[0] k-iterations (round 1 did this with split-K atomics through HBM).
 X3_CHUNK = [4]
+X3_FUSED_WGRAD = [True]  # False: three passes of ptb200_gemm_wgrad_f16 over column slices (tests compare both)
 EPI_SPLIT3_MASK, EPI_F32_STORE = 7, 8
 
 
@@ -197,6 +198,18 @@ def conv1_u8_x3(images_u8, hw, hmax, wmax, mean, std, w_f32, bias):
     return FlatAct(out, hmax, wmax)
 
 
+X3_CONV1_TC = [True]  # False: the fp32 CUDA-core first conv of csrc/split3.cu (tests compare both)
+
+
+def conv1_u8_x3_tc(images_u8, hw, hmax, wmax, wpack3, bias_table, alpha):
+    """Tensor-core f16x3 first conv (raw pixels are exact in fp16; see ParamArena._pack_conv1_x3)."""
+    N = hw.shape[0]
+    out = torch.empty(N, hmax * (wmax + 1), 192, dtype=torch.float16, device=images_u8.device)
+    call("ptb200_conv1_u8_f16x3_tc", images_u8, hw, N, hmax, wmax, images_u8.stride(0), wpack3, bias_table, float(alpha),
+         out)
+    return FlatAct(out, hmax, wmax)
+
+
 def maxpool2x2_x3(x: FlatAct):
     N, _, C3 = x.t.shape
     Ho, Wo = x.H // 2, x.W // 2
@@ -240,9 +253,14 @@ def wgrad_x3(G3, X3, out, *, m_total, n_total, taps=1, shifts=None, scale=1.0, b
         bn //= 2
     tiles = taps * (m_total // 128) * (n_total // bn)
     chunks = ((rows + 63) // 64) * batch
-    # one wave of CTAs, and reduction chains of at most 128 chunks (512 truncating MMAs) per CTA
+    # one wave of CTAs, and reduction chains of at most 128 chunks (3 x 512 truncating MMAs) per CTA
     ksplit = max(1, min(max(148 // tiles, (chunks + 127) // 128), max(1, chunks // 8)))
     sc, cap = (seg[0], seg[1]) if seg else (None, 0)
+    if X3_FUSED_WGRAD[0]:
+        call("ptb200_gemm_wgrad_f16x3", G3, ldg, rows * ldg, X3, ldx, rows * ldx, batch, rows, m_total, n_total, taps,
+             shifts, out, taps * n_total, float(scale), ksplit, bias_out, sc, cap)
+        return out
+    # three passes of the plain kernel over column slices of the triples (kept as the cross-check of the fused kernel)
     Gh, Gl = G3[:, :, :m_total], G3[:, :, m_total:2 * m_total]
     Xh, Xl = X3[:, :, :n_total], X3[:, :, n_total:2 * n_total]
     for g, x, b in ((Gh, Xh, bias_out), (Gl, Xh, bias_out), (Gh, Xl, None)):

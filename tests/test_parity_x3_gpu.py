@@ -110,6 +110,32 @@ def test_conv1_and_roialign_x3(cuda):
     xin = img.double() - torch.tensor(mean, dtype=torch.float64).view(1, 3, 1, 1)
     ref = F.relu(F.conv2d(xin, w.double(), b.double(), padding=1)).permute(0, 2, 3, 1)
     assert _rel(y[:, :, :W], ref) < 1e-5
+    # the tensor-core version (raw pixels as exact fp16 operands, mean folded into a per-pixel bias): two images of
+    # DIFFERENT sizes on one canvas (taps outside an image are zeros of the NORMALISED image), non-unit std
+    from probabilisticteacher_b200.arena import ParamArena
+    ar = ParamArena(device=cuda, with_grads=False)
+    ar.precision = "f16x3"
+    ar.pixel_mean, ar.pixel_std = tuple(mean), (57.375, 57.12, 58.395)
+    n0 = ar.conv_specs[0][0]
+    ar.view(n0 + ".weight").copy_(w.permute(0, 2, 3, 1).to(cuda))
+    ar.view(n0 + ".bias").copy_(b.to(cuda))
+    ar.refresh_x3_scales()
+    ar._pack_conv1_x3()
+    h2, w2 = H - 9, W - 14
+    img2 = torch.randint(0, 256, (3, h2, w2), generator=g, dtype=torch.uint8)
+    flat = torch.zeros(2, 3 * H * W, dtype=torch.uint8)
+    flat[0] = img[0].reshape(-1)
+    flat[1, :img2.numel()] = img2.reshape(-1)
+    hw2 = torch.tensor([[H, W], [h2, w2]], dtype=torch.int32, device=cuda)
+    y3 = ops.conv1_u8_x3_tc(flat.to(cuda), hw2, H, W, *ar.conv1_x3)
+    y = ops.split3_unpack(y3.t, 64).view(2, H, W + 1, 64)
+    std = torch.tensor(ar.pixel_std, dtype=torch.float64).view(1, 3, 1, 1)
+    canvas = torch.zeros(2, 3, H, W, dtype=torch.float64)   # normalised images, zero padded to the batch size
+    canvas[0] = (img[0].double() - torch.tensor(mean, dtype=torch.float64).view(3, 1, 1)) / std[0]
+    canvas[1, :, :h2, :w2] = (img2.double() - torch.tensor(mean, dtype=torch.float64).view(3, 1, 1)) / std[0]
+    ref = F.relu(F.conv2d(canvas, w.double(), b.double(), padding=1)).permute(0, 2, 3, 1)
+    assert _rel(y[:, :, :W], ref) < 1e-5
+    assert float(y[:, :, W].abs().max()) == 0.0
     # ROIAlign over triples vs torchvision on the fp32 feature map
     C, Hf, Wf = 64, 20, 31
     feat = (torch.randn(2, C, Hf, Wf, generator=g) * 5).to(cuda)
@@ -331,7 +357,8 @@ def test_cuda_path_vs_reference_model_golden(cuda, case):
             lg_g, lg_r = p.objectness_logits.double().cpu(), G["teacher_rpn_logits"][n].double()
             d = (p.proposal_boxes.tensor.double().cpu()[:, None, :] - ref_boxes.double()[None, :, :]).abs().amax(-1) / scale
             d = torch.maximum(d, (lg_g[:, None] - lg_r[None, :]).abs() / lg_r.abs().max())
-            assert float((d.min(1).values < TOL).double().mean()) >= 0.99
+            unmatched = int((d.min(1).values >= TOL).sum())
+            assert unmatched <= max(1, len(lg_g) // 100), (unmatched, len(lg_g))   # (lists of ~40 proposals: one flip)
             ref = G["teacher_roih"][n]
             o = O.OInst(sizes[n], pred_boxes=O.OBoxes(ref["pred_boxes"]), scores=ref["scores"],
                         pred_classes=ref["pred_classes"], scores_logists=ref["scores_logists"],

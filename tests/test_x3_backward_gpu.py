@@ -127,11 +127,16 @@ def test_conv_backward_x3_vs_fp64(cuda, Cin, Cout, H, W, pooled):
     dx = _unflat3(dx3, Cin) / S
     assert _rel(dx, dx_ref) < 5e-6
     assert float(ops.split3_unpack(dx3.t, Cin).view(2, Hi, Wi + 1, Cin)[:, :, Wi].abs().max()) == 0.0
-    gw = torch.zeros(Cout, 9 * Cin, device=cuda)
-    gb = torch.zeros(Cout, device=cuda)
-    ops.conv3x3_wgrad_x3(dz3, xin3, gw, Cout, Cin, scale=1.0 / S, bias_out=gb)
-    assert _rel(gw.view(Cout, 3, 3, Cin).permute(0, 3, 1, 2), dw_ref) < 5e-6
-    assert _rel(gb, db_ref) < 5e-6
+    for fused in (True, False):
+        ops.X3_FUSED_WGRAD[0] = fused
+        try:
+            gw = torch.zeros(Cout, 9 * Cin, device=cuda)
+            gb = torch.zeros(Cout, device=cuda)
+            ops.conv3x3_wgrad_x3(dz3, xin3, gw, Cout, Cin, scale=1.0 / S, bias_out=gb)
+        finally:
+            ops.X3_FUSED_WGRAD[0] = True
+        assert _rel(gw.view(Cout, 3, 3, Cin).permute(0, 3, 1, 2), dw_ref) < 5e-6, fused
+        assert _rel(gb, db_ref) < 5e-6, fused
 
 
 def test_fc_backward_x3_with_segments_vs_fp64(cuda):
@@ -160,11 +165,16 @@ def test_fc_backward_x3_with_segments_vs_fp64(cuda):
     dz3 = ops.gemm_tn_x3(g3, wd3, 1.0 / 2048.0, epi=ops.EPI_SPLIT3_MASK, aux=h3, seg=seg)
     dz = ops.split3_unpack(dz3, K) / S
     assert _rel(dz[live.to(cuda)], x.grad[live]) < 5e-6
-    gw = torch.zeros(N, K, device=cuda)
-    gb = torch.zeros(N, device=cuda)
-    ops.wgrad_x3(g3, h3, gw, m_total=N, n_total=K, scale=1.0 / S, bias_out=gb, seg=seg)
-    assert _rel(gw, w.grad) < 5e-6
-    assert _rel(gb, gy.sum(0)) < 5e-6
+    for fused in (True, False):   # one fused launch (hi + lo tiles per stage) / three passes over column slices
+        ops.X3_FUSED_WGRAD[0] = fused
+        try:
+            gw = torch.zeros(N, K, device=cuda)
+            gb = torch.zeros(N, device=cuda)
+            ops.wgrad_x3(g3, h3, gw, m_total=N, n_total=K, scale=1.0 / S, bias_out=gb, seg=seg)
+        finally:
+            ops.X3_FUSED_WGRAD[0] = True
+        assert _rel(gw, w.grad) < 5e-6, fused
+        assert _rel(gb, gy.sum(0)) < 5e-6, fused
 
 
 def test_pack_grad2_and_add_mask_x3(cuda):
