@@ -99,7 +99,12 @@ class ParamArena:
         self.conv1_x3 = None  # (wpack3 fp16 [64][64], bias table fp32 [10][64], alpha)
         if with_grads:
             n = self.total - self.trainable_start
-            self.grads = torch.zeros(n, dtype=torch.float32, device=self.device)
+            # the gradient arena is followed by a small fp32 metrics tail: the 8 loss scalars of the step ride on the
+            # gradient all-reduce (the reference averages its logged metrics over ranks, pt/engine/trainer.py:394-429)
+            self.METRICS_TAIL = 16
+            self.grads_ext = torch.zeros(n + self.METRICS_TAIL, dtype=torch.float32, device=self.device)
+            self.grads = self.grads_ext[:n]
+            self.metrics_tail = self.grads_ext[n:]
             self.momentum = torch.zeros(n, dtype=torch.float32, device=self.device)
             self.dgrad_half = {}
         else:

@@ -171,12 +171,39 @@ class PTrainer:
         t.pack()
 
     # ------------------------------------------------------------------ clip + SGD (trainer.py:383-386,592-603)
+    METRIC_KEYS = ("loss_cls_sup", "loss_box_reg_sup", "loss_rpn_cls_sup", "loss_rpn_loc_sup", "loss_cls_unsup",
+                   "loss_box_reg_unsup", "loss_rpn_cls_unsup", "loss_rpn_loc_unsup")
+
+    def _stash_metrics(self, losses):
+        """Writes the step's loss scalars into the metrics tail of the gradient buffer (device copy, no sync) so that
+        they are summed over ranks by the gradient all-reduce."""
+        a = self.model.arena
+        keys = [k for k in self.METRIC_KEYS if k in losses] or sorted(losses)
+        self._metric_keys = keys
+        a.metrics_tail.zero_()
+        a.metrics_tail[:len(keys)].copy_(torch.stack([losses[k].detach().reshape(()).float() for k in keys]))
+
+    def reduced_metrics(self):
+        """The last step's losses averaged over the data-parallel ranks -- what the reference's `_write_metrics` logs
+        on rank 0 (`comm.gather` + mean, pt/engine/trainer.py:394-429). Device tensors; reading them synchronises."""
+        a = self.model.arena
+        keys = getattr(self, "_metric_keys", None)
+        if not keys:
+            return {}
+        vals = a.metrics_tail[:len(keys)] * dp.pre_scale()
+        return {k: vals[i] for i, k in enumerate(keys)}
+
     def _optimizer_step(self, clip_norm=10.0, reduced=False):
         a = self.model.arena
         n = a.grads.numel()
         pre = dp.pre_scale()  # SUM all-reduce, 1/world folded into the clip / SGD kernels: DDP's gradient averaging
+        if self.last_losses:
+            self._stash_metrics(self.last_losses)
         if not reduced:
-            dp.allreduce_grads(a.grads, bucket_elems=n)  # one collective over the whole arena (no-op at world 1)
+            # one collective over the whole arena + metrics tail (no-op at world 1)
+            dp.allreduce_grads(a.grads_ext, bucket_elems=a.grads_ext.numel())
+        elif self.world > 1:
+            dist.all_reduce(a.metrics_tail)
         lr = lr_at_iter(self.cfg, self.iter)  # pt/solver/build.py: WarmupMultiStepLR unless the config says otherwise
         call("ptb200_grad_sumsq", a.grads, n, pre, self._sumsq)
         call("ptb200_clip_sgd_step", a.data[a.trainable_start:], a.grads, a.momentum, n, float(lr),
@@ -226,8 +253,8 @@ class PTrainer:
                         raise NotImplementedError
         losses = sum(loss_dict.values())
         losses.backward()
-        self._optimizer_step(10.0)
         self.last_losses = {k: v.detach() for k, v in record_dict.items()}
+        self._optimizer_step(10.0)
         self.iter += 1
         return self.last_losses
 

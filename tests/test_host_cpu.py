@@ -100,6 +100,26 @@ for w in works:
 assert len(works) == 4
 mean = g * dp.pre_scale()
 assert torch.allclose(mean, torch.arange(100000, dtype=torch.float32) * 1.5)
+# the trainer's path: ONE collective over [gradient arena | 16-float metrics tail]; the tail carries the step's 8 loss
+# scalars, whose cross-rank mean is what the reference logs (pt/engine/trainer.py:394-429)
+from probabilisticteacher_b200.engine.trainer import PTrainer
+class _Arena: pass
+class _Model: pass
+tr = PTrainer.__new__(PTrainer)
+tr.model = _Model(); tr.model.arena = _Arena()
+a = tr.model.arena
+a.grads_ext = torch.zeros(1000 + 16); a.grads = a.grads_ext[:1000]; a.metrics_tail = a.grads_ext[1000:]
+a.grads.fill_(float(rank + 1))
+losses = {k: torch.tensor(float(i + 1) * (rank + 1)) for i, k in enumerate(PTrainer.METRIC_KEYS)}
+tr._stash_metrics(losses)
+works = dp.allreduce_grads(a.grads_ext, bucket_elems=a.grads_ext.numel(), async_op=True)
+assert len(works) == 1
+works[0].wait()
+m = tr.reduced_metrics()
+assert list(m) == list(PTrainer.METRIC_KEYS)
+for i, k in enumerate(PTrainer.METRIC_KEYS):
+    assert abs(float(m[k]) - 1.5 * (i + 1)) < 1e-6, (k, float(m[k]))
+assert bool((a.grads == 3.0).all())
 dist.destroy_process_group()
 print("ok")
 '''

@@ -26,15 +26,35 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
-    H, W, steps = 320, 480, 8
+    import argparse
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--height", type=int, default=320)
+    ap.add_argument("--width", type=int, default=480)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--precision", default="f16x3", choices=["f16x3", "f16"])
+    args = ap.parse_args()
+    H, W, steps = args.height, args.width, args.steps
     cfg = c2f_config()
     cfg.UNSUPNET.BURN_UP_STEP = 0
     pool = synthetic_pool(2, 2, H, W, 8, 1234 + 100 * rank, device=dev)
-    tr = PTrainer(cfg, cycle(pool), device=dev, seed=0, use_cuda_graph=True, concurrent=True)
+    tr = PTrainer(cfg, cycle(pool), device=dev, seed=0, use_cuda_graph=True, concurrent=True, precision=args.precision)
     for _ in range(steps):
         tr.step()
     torch.cuda.synchronize()
     ok = True
+    # cross-rank metric reduction (pt/engine/trainer.py:394-429): the losses that rode on the gradient all-reduce
+    # must be the mean over ranks of every rank's own losses
+    keys = sorted(tr.last_losses)
+    mine = torch.stack([tr.last_losses[k].reshape(()).float() for k in keys])
+    allv = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(allv, mine)
+    mean = torch.stack(allv).double().mean(0)
+    red = tr.reduced_metrics()
+    got = torch.stack([red[k].reshape(()).double() for k in keys])
+    merr = float(((got - mean).abs() / mean.abs().clamp_min(1e-6)).max())
+    if rank == 0:
+        print(f"{args.precision} {H}x{W}: reduced metrics vs mean of the {world} ranks' losses: max rel err {merr:.2e}")
+    ok = ok and merr < 1e-5
     for name, arena in (("student", tr.model.arena), ("teacher", tr.model_teacher.arena)):
         mine = arena.data
         ref = mine.clone()
