@@ -511,6 +511,12 @@ def main():
     ap.add_argument("--height", type=int, default=H_IMG)
     ap.add_argument("--width", type=int, default=W_IMG)
     args = ap.parse_args()
+    # stdout carries exactly ONE line (the JSON): library chatter written to file descriptor 1 (NCCL prints its
+    # version there) is sent to stderr instead
+    sys.stdout.flush()
+    out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = out
     if args.impl == "reference":
         return run_reference(args)
 
