@@ -364,6 +364,26 @@ int ptb200_roi_loss_unsup(const float* scores, const float* deltas, const float*
 
 int ptb200_axpy_dev(const float* alpha_dev, float scale, const float* x, float* y, int n, void* stream);
 
+/* ---- input pipeline: strong augmentation on the device ----------------------------- */
+
+/* The per-pixel operations of `build_strong_augmentation` (pt/data/detection_utils.py:38-60: torchvision ColorJitter /
+ * RandomGrayscale on a PIL image, Solarize of pt/data/transforms/augmentation_impl.py:40-53), bit-exact with Pillow's
+ * Image.blend / Image.convert arithmetic, over a planar uint8 image [3][h][w]. ops_host[i] in {0 brightness,
+ * 1 contrast, 2 saturation, 3 hue, 4 grayscale (3 equal channels), 5 solarize(128)}; factors_host[i] = the blend factor
+ * (ops 0-2) or the uint8 hue shift np.uint8(hue_factor * 255) (op 3). A contrast op must be the FIRST of its call: its
+ * degenerate image is the mean luma of the image at that point of the chain, read from gray_sum_in (sum of the luma of
+ * the input, written by the previous call through gray_sum_out; may be NULL when not needed). in == out is allowed. */
+int ptb200_aug_pointwise_u8(const uint8_t* in, uint8_t* out, int h, int w, int n_ops, const int* ops_host,
+                            const float* factors_host, const unsigned long long* gray_sum_in,
+                            unsigned long long* gray_sum_out, void* stream);
+
+/* PIL ImageFilter.GaussianBlur as the reference's GaussianBlur applies it (pt/data/transforms/augmentation_impl.py:22-37):
+ * `passes` box-blur passes along x then along y with the 8.24 fixed-point weights ww (full taps) / fw (the two
+ * fractional outer taps) of libImaging/BoxBlur.c and edge extension; planes x [h][w] uint8, tmp = scratch of the
+ * same size. (radius, ww, fw) from the Gaussian sigma: probabilisticteacher_b200/data_aug.py. */
+int ptb200_aug_boxblur_u8(const uint8_t* in, uint8_t* tmp, uint8_t* out, int planes, int h, int w, int radius,
+                          int ww, int fw, int passes, void* stream);
+
 /* ---- optimiser arena ------------------------------------------------------------------------------ */
 
 /* pt/engine/trainer.py:431-449: teacher = keep * teacher + (1 - keep) * student over the flat arena. */
