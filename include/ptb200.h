@@ -384,6 +384,18 @@ int ptb200_aug_pointwise_u8(const uint8_t* in, uint8_t* out, int h, int w, int n
 int ptb200_aug_boxblur_u8(const uint8_t* in, uint8_t* tmp, uint8_t* out, int planes, int h, int w, int radius,
                           int ww, int fw, int passes, void* stream);
 
+/* Weak augmentation of the same mapper (d2 v0.5 `utils.build_augmentation`: ResizeShortestEdge + RandomFlip, used at
+ * pt/data/dataset_mapper.py:67,104-106): one pass of Pillow's `Image.resize(..., BILINEAR)` (libImaging/Resample.c,
+ * 8 bpc) along x (along_x = 1: in_h == out_h) or y over planes x [in_h][in_w] uint8; bounds_dev int32 [out][2] = (first
+ * input index, tap count), coeffs_dev int32 [out][ksize] = 22-bit fixed-point coefficients (computed on the host as
+ * precompute_coeffs / normalize_coeffs_8bpc do: probabilisticteacher_b200/data_aug.py). A resize is the x pass
+ * followed by the y pass, each rounded to uint8. */
+int ptb200_aug_resample_u8(const uint8_t* in, uint8_t* out, int planes, int in_h, int in_w, int out_h, int out_w,
+                           int along_x, const int* bounds_dev, const int* coeffs_dev, int ksize, void* stream);
+
+/* d2 HFlipTransform.apply_image of RandomFlip(horizontal): out[.., x] = in[.., w - 1 - x]. */
+int ptb200_aug_hflip_u8(const uint8_t* in, uint8_t* out, int planes, int h, int w, void* stream);
+
 /* ---- optimiser arena ------------------------------------------------------------------------------ */
 
 /* pt/engine/trainer.py:431-449: teacher = keep * teacher + (1 - keep) * student over the flat arena. */

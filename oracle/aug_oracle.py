@@ -232,3 +232,95 @@ def strong_augment(img, p):
     if p.solarize:
         out = solarize(out, 128)
     return out
+
+
+# ------------------------------------------------------------------------------------------ weak augmentation
+# detectron2 v0.5 (un-vendored): `utils.build_augmentation` = ResizeShortestEdge(MIN_SIZE_TRAIN, MAX_SIZE_TRAIN,
+# MIN_SIZE_TRAIN_SAMPLING) + RandomFlip(horizontal), used by the reference's mapper at pt/data/dataset_mapper.py:67,104-106.
+# Their image arithmetic is Pillow's `Image.resize(..., BILINEAR)` (libImaging/Resample.c) and a column reversal; the
+# resize is restated here and pinned to the installed Pillow (tests/test_aug_oracle_cpu.py); the size rule and the box
+# transforms restate d2's data/transforms/{augmentation_impl,transform}.py.
+_PRECISION_BITS = 32 - 8 - 2
+
+
+def resample_coeffs(in_size, out_size):
+    """Resample.c precompute_coeffs + normalize_coeffs_8bpc for the bilinear (triangle) filter over the whole axis:
+    (bounds [out, 2] = (first input index, tap count), coefficients [out, ksize] in 22-bit fixed point)."""
+    scale = in_size / out_size
+    fscale = max(scale, 1.0)
+    support = 1.0 * fscale
+    ksize = int(math.ceil(support)) * 2 + 1
+    bounds = np.zeros((out_size, 2), np.int64)
+    kk = np.zeros((out_size, ksize), np.int64)
+    ss = 1.0 / fscale
+    for xx in range(out_size):
+        center = (xx + 0.5) * scale
+        xmin = max(int(center - support + 0.5), 0)
+        xmax = min(int(center + support + 0.5), in_size) - xmin
+        w = []
+        for x in range(xmax):
+            a = abs((x + xmin - center + 0.5) * ss)
+            w.append(1.0 - a if a < 1.0 else 0.0)
+        ww = sum(w)
+        if ww != 0.0:
+            w = [v / ww for v in w]
+        for x, v in enumerate(w):
+            kk[xx, x] = int(-0.5 + v * (1 << _PRECISION_BITS)) if v < 0 else int(0.5 + v * (1 << _PRECISION_BITS))
+        bounds[xx] = (xmin, xmax)
+    return bounds, kk
+
+
+def resample_1d(img, out_size, axis):
+    a = np.moveaxis(img, axis, 0).astype(np.int64)
+    bounds, kk = resample_coeffs(a.shape[0], out_size)
+    out = np.zeros((out_size,) + a.shape[1:], np.int64)
+    for xx in range(out_size):
+        xmin, xmax = bounds[xx]
+        ss = np.full(a.shape[1:], 1 << (_PRECISION_BITS - 1), np.int64)
+        for x in range(xmax):
+            ss += a[xmin + x] * kk[xx, x]
+        out[xx] = np.clip(ss >> _PRECISION_BITS, 0, 255)
+    return np.moveaxis(out.astype(np.uint8), 0, axis)
+
+
+def resize_bilinear(img, new_h, new_w):
+    """PIL Image.resize((new_w, new_h), BILINEAR) of a uint8 image: horizontal pass, then vertical pass, each with
+    uint8 output."""
+    out = img
+    if new_w != img.shape[1]:
+        out = resample_1d(out, new_w, 1)
+    if new_h != img.shape[0]:
+        out = resample_1d(out, new_h, 0)
+    return out
+
+
+def shortest_edge_size(h, w, size, max_size):
+    """d2 v0.5 ResizeShortestEdge.get_transform: output (h, w) for a sampled short-edge `size`."""
+    scale = size * 1.0 / min(h, w)
+    if h < w:
+        newh, neww = size, scale * w
+    else:
+        newh, neww = scale * h, size
+    if max(newh, neww) > max_size:
+        scale = max_size * 1.0 / max(newh, neww)
+        newh = newh * scale
+        neww = neww * scale
+    return int(newh + 0.5), int(neww + 0.5)
+
+
+def weak_augment(img, boxes, size, max_size, flip):
+    """ResizeShortestEdge + RandomFlip(horizontal) applied to an image [H, W, 3] and XYXY boxes [n, 4] (float64 as d2's
+    apply_box, clipped to the image as transform_instance_annotations does)."""
+    h, w = img.shape[:2]
+    nh, nw = shortest_edge_size(h, w, size, max_size)
+    out = resize_bilinear(img, nh, nw)
+    b = np.asarray(boxes, dtype=np.float64).copy().reshape(-1, 4)
+    b[:, 0::2] *= nw * 1.0 / w
+    b[:, 1::2] *= nh * 1.0 / h
+    if flip:
+        out = out[:, ::-1].copy()
+        x1 = nw - b[:, 2]
+        x2 = nw - b[:, 0]
+        b[:, 0], b[:, 2] = x1, x2
+    b = np.minimum(b.clip(min=0), [nw, nh, nw, nh])
+    return out, b

@@ -209,6 +209,41 @@ __global__ void aug_boxblur_cols_kernel(const uint8_t* __restrict__ in, uint8_t*
     for (int y = ry; y < H; y += nry) out[base + static_cast<int64_t>(y) * W + x0 + cx] = a[cx * Hp + y];
 }
 
+// One pass of Pillow's ImagingResample (libImaging/Resample.c, 8 bits per channel) along x or y of a planar image:
+// out[o] = clip8((2^21 + sum_j in[xmin_o + j] * kk[o][j]) >> 22) with the per-output tap window (bounds) and 22-bit
+// fixed-point coefficients precomputed on the host exactly as precompute_coeffs / normalize_coeffs_8bpc do.
+__global__ void aug_resample_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, int planes, int in_h,
+                                    int in_w, int out_h, int out_w, int along_x, const int* __restrict__ bounds,
+                                    const int* __restrict__ kk, int ksize) {
+  const int64_t total = static_cast<int64_t>(planes) * out_h * out_w;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int x = static_cast<int>(i % out_w);
+    const int64_t r = i / out_w;
+    const int y = static_cast<int>(r % out_h);
+    const int pl = static_cast<int>(r / out_h);
+    const int o = along_x ? x : y;
+    const int xmin = bounds[2 * o], cnt = bounds[2 * o + 1];
+    const int* k = kk + static_cast<int64_t>(o) * ksize;
+    const uint8_t* src = in + static_cast<int64_t>(pl) * in_h * in_w + (along_x ? static_cast<int64_t>(y) * in_w + xmin
+                                                                               : static_cast<int64_t>(xmin) * in_w + x);
+    const int stride = along_x ? 1 : in_w;
+    int ss = 1 << 21;
+    for (int j = 0; j < cnt; ++j) ss += static_cast<int>(src[static_cast<int64_t>(j) * stride]) * k[j];
+    ss >>= 22;
+    out[i] = static_cast<uint8_t>(ss < 0 ? 0 : (ss > 255 ? 255 : ss));
+  }
+}
+
+__global__ void aug_hflip_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, int64_t rows, int w) {
+  const int64_t total = rows * w;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int x = static_cast<int>(i % w);
+    out[i] = in[i - x + (w - 1 - x)];
+  }
+}
+
 inline int grid_for(int64_t n) {
   int64_t g = (n + 255) / 256;
   if (g > 148 * 16) g = 148 * 16;
@@ -259,5 +294,21 @@ extern "C" int ptb200_aug_boxblur_u8(const uint8_t* in, uint8_t* tmp, uint8_t* o
   dim3 grid((w + 31) / 32, planes);
   aug_boxblur_cols_kernel<<<grid, 256, smem_c, STREAM>>>(tmp, out, h, w, radius, static_cast<uint32_t>(ww),
                                                         static_cast<uint32_t>(fw), passes);
+  return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int ptb200_aug_resample_u8(const uint8_t* in, uint8_t* out, int planes, int in_h, int in_w, int out_h,
+                                      int out_w, int along_x, const int* bounds_dev, const int* coeffs_dev, int ksize,
+                                      void* stream) {
+  if ((along_x && in_h != out_h) || (!along_x && in_w != out_w) || ksize < 1) return 1608;
+  const int64_t total = static_cast<int64_t>(planes) * out_h * out_w;
+  aug_resample_kernel<<<grid_for(total), 256, 0, STREAM>>>(in, out, planes, in_h, in_w, out_h, out_w, along_x,
+                                                          bounds_dev, coeffs_dev, ksize);
+  return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int ptb200_aug_hflip_u8(const uint8_t* in, uint8_t* out, int planes, int h, int w, void* stream) {
+  const int64_t rows = static_cast<int64_t>(planes) * h;
+  aug_hflip_kernel<<<grid_for(rows * w), 256, 0, STREAM>>>(in, out, rows, w);
   return static_cast<int>(cudaGetLastError());
 }

@@ -144,3 +144,126 @@ def two_crop(image_weak, strong_augmentation):
     """`DatasetMapperTwoCropSeparate.__call__`'s last step (dataset_mapper.py:159-172) for a device image: returns
     (strongly augmented image, weakly augmented image), both uint8 [3, H, W]."""
     return strong_augmentation(image_weak), image_weak
+
+
+# ------------------------------------------------------------------------------------------ weak augmentation
+# d2 v0.5 `utils.build_augmentation(cfg, is_train)` = [ResizeShortestEdge(MIN_SIZE_TRAIN, MAX_SIZE_TRAIN, sampling),
+# RandomFlip(horizontal)] as the reference's mapper uses it (pt/data/dataset_mapper.py:67,104-106). The image ops run
+# on the device, bit-exact with Pillow's bilinear `Image.resize`; sizes, decisions and the box transform stay on the host.
+_PRECISION_BITS = 32 - 8 - 2
+_coeff_cache = {}
+
+
+def resample_coeffs(in_size, out_size):
+    """Pillow's precompute_coeffs + normalize_coeffs_8bpc for the bilinear filter (libImaging/Resample.c): int32
+    bounds [out, 2] and 22-bit fixed-point coefficients [out, ksize]."""
+    key = (in_size, out_size)
+    hit = _coeff_cache.get(key)
+    if hit is not None:
+        return hit
+    scale = in_size / out_size
+    fscale = max(scale, 1.0)
+    support = 1.0 * fscale
+    ksize = int(np.ceil(support)) * 2 + 1
+    xx = np.arange(out_size, dtype=np.float64)
+    center = (xx + 0.5) * scale
+    xmin = np.maximum((center - support + 0.5).astype(np.int64), 0)
+    xmax = np.minimum((center + support + 0.5).astype(np.int64), in_size) - xmin
+    j = np.arange(ksize, dtype=np.float64)[None, :]
+    a = np.abs((j + xmin[:, None] - center[:, None] + 0.5) * (1.0 / fscale))
+    w = np.where((a < 1.0) & (j < xmax[:, None]), 1.0 - a, 0.0)
+    ww = w.sum(1, keepdims=True)
+    w = np.where(ww != 0.0, w / np.where(ww != 0.0, ww, 1.0), w)
+    kk = np.where(w < 0, (-0.5 + w * (1 << _PRECISION_BITS)).astype(np.int64), (0.5 + w * (1 << _PRECISION_BITS)).astype(np.int64))
+    kk = np.where(j < xmax[:, None], kk, 0)
+    out = (np.stack([xmin, xmax], 1).astype(np.int32), kk.astype(np.int32), ksize)
+    if len(_coeff_cache) < 64:
+        _coeff_cache[key] = out
+    return out
+
+
+def resize_bilinear(image, new_h, new_w):
+    """PIL `Image.resize((new_w, new_h), BILINEAR)` of a uint8 CUDA image [3, H, W]."""
+    _, H, W = image.shape
+    cur = image.contiguous()
+    dev = image.device
+    if new_w != W:
+        b, k, ks = resample_coeffs(W, new_w)
+        out = torch.empty(3, H, new_w, dtype=torch.uint8, device=dev)
+        call("ptb200_aug_resample_u8", cur, out, 3, H, W, H, new_w, 1, torch.from_numpy(b).to(dev), torch.from_numpy(k).to(dev), ks)
+        cur = out
+    if new_h != H:
+        b, k, ks = resample_coeffs(H, new_h)
+        out = torch.empty(3, new_h, cur.shape[2], dtype=torch.uint8, device=dev)
+        call("ptb200_aug_resample_u8", cur, out, 3, H, cur.shape[2], new_h, cur.shape[2], 0, torch.from_numpy(b).to(dev),
+             torch.from_numpy(k).to(dev), ks)
+        cur = out
+    return cur
+
+
+def shortest_edge_size(h, w, size, max_size):
+    """d2 v0.5 ResizeShortestEdge.get_transform."""
+    scale = size * 1.0 / min(h, w)
+    if h < w:
+        newh, neww = size, scale * w
+    else:
+        newh, neww = scale * h, size
+    if max(newh, neww) > max_size:
+        scale = max_size * 1.0 / max(newh, neww)
+        newh = newh * scale
+        neww = neww * scale
+    return int(newh + 0.5), int(neww + 0.5)
+
+
+class WeakAugmentation:
+    """ResizeShortestEdge(short_edge_length, max_size, sample_style) + RandomFlip(prob, horizontal) on a uint8 CUDA
+    image [3, H, W] and its XYXY boxes. Decisions come from numpy's global RNG in d2's order (np.random.choice /
+    randint for the size, then np.random.uniform for the flip)."""
+
+    def __init__(self, short_edge_length=(600,), max_size=1200, sample_style="choice", flip_prob=0.5, is_train=True):
+        self.short_edge_length = tuple(short_edge_length)
+        self.max_size = max_size
+        self.is_range = sample_style == "range"
+        self.flip_prob = flip_prob if is_train else 0.0
+
+    def sample(self):
+        if self.is_range:
+            size = int(np.random.randint(self.short_edge_length[0], self.short_edge_length[1] + 1))
+        else:
+            size = int(np.random.choice(self.short_edge_length))
+        flip = bool(np.random.uniform() < self.flip_prob) if self.flip_prob > 0 else False
+        return size, flip
+
+    def apply(self, image, boxes, size, flip):
+        _, H, W = image.shape
+        nh, nw = shortest_edge_size(H, W, size, self.max_size) if size != 0 else (H, W)
+        out = resize_bilinear(image, nh, nw)
+        b = np.asarray(boxes.detach().cpu() if torch.is_tensor(boxes) else boxes, dtype=np.float64).reshape(-1, 4).copy()
+        b[:, 0::2] *= nw * 1.0 / W
+        b[:, 1::2] *= nh * 1.0 / H
+        if flip:
+            flipped = torch.empty_like(out)
+            call("ptb200_aug_hflip_u8", out, flipped, 3, nh, nw)
+            out = flipped
+            x1, x2 = nw - b[:, 2], nw - b[:, 0]
+            b[:, 0], b[:, 2] = x1, x2
+        b = np.minimum(b.clip(min=0), [nw, nh, nw, nh])   # transform_instance_annotations clips to the image
+        return out, torch.from_numpy(b).to(torch.float32)
+
+    def __call__(self, image, boxes):
+        size, flip = self.sample()
+        return self.apply(image, boxes, size, flip)
+
+
+def map_two_crop(image, boxes, classes, weak, strong):
+    """`DatasetMapperTwoCropSeparate.__call__` (pt/data/dataset_mapper.py:88-172) for an image that is already on the
+    device: weak augmentation of image + boxes, then the strong augmentation of the weak image; returns the
+    (strong, weak) pair of dataset dicts the paired loader consumes (both carry the same instances)."""
+    from .structures import Boxes, FreeInstances
+    img_w, b = weak(image, boxes)
+    h, w = img_w.shape[-2:]
+    keep = (b[:, 2] > b[:, 0]) & (b[:, 3] > b[:, 1])    # utils.filter_empty_instances
+    inst = FreeInstances((h, w), gt_boxes=Boxes(b[keep]), gt_classes=torch.as_tensor(classes)[keep])
+    strong_img = strong(img_w)
+    return ({"image": strong_img, "height": h, "width": w, "instances": inst},
+            {"image": img_w, "height": h, "width": w, "instances": inst})

@@ -84,3 +84,42 @@ def test_decision_sampling_matches_the_oracle_sampler(cuda):
             assert getattr(a, k) == getattr(b, k), (seed, k)
     with pytest.raises(ValueError):
         StrongAugmentation.apply(torch.zeros(3, 4, 4, dtype=torch.uint8), aug.sample())   # no CPU path
+
+
+@pytest.mark.parametrize("H,W,size,max_size", [(1024, 2048, 600, 1200), (375, 500, 600, 1200), (500, 375, 800, 1333),
+                                               (37, 53, 64, 100), (600, 1200, 600, 1200), (90, 60, 45, 1000)])
+def test_weak_augmentation_bit_exact_vs_oracle(cuda, H, W, size, max_size):
+    """ResizeShortestEdge + RandomFlip on the device == the oracle (pinned to Pillow's bilinear resize on the CPU)."""
+    from oracle import aug_oracle as A
+    from probabilisticteacher_b200.data_aug import WeakAugmentation
+    rs = np.random.RandomState(H + W)
+    img = rs.randint(0, 256, (H, W, 3)).astype(np.uint8)
+    boxes = np.stack([rs.uniform(0, W / 2, 5), rs.uniform(0, H / 2, 5), rs.uniform(W / 2, W, 5), rs.uniform(H / 2, H, 5)], 1)
+    aug = WeakAugmentation((size,), max_size)
+    for flip in (False, True):
+        want_img, want_b = A.weak_augment(img, boxes, size, max_size, flip)
+        got, b = aug.apply(_chw(img, cuda), torch.from_numpy(boxes), size, flip)
+        torch.cuda.synchronize()
+        assert np.array_equal(_hwc(got), want_img)
+        assert np.allclose(b.numpy(), want_b.astype(np.float32), rtol=0, atol=1e-4)
+
+
+def test_two_crop_mapper_on_device(cuda):
+    """The (strong, weak) pair of DatasetMapperTwoCropSeparate: same instances on both, strong = aug(weak image)."""
+    from oracle import aug_oracle as A
+    from probabilisticteacher_b200.data_aug import StrongAugmentation, WeakAugmentation, map_two_crop
+    rs = np.random.RandomState(0)
+    img = rs.randint(0, 256, (120, 200, 3)).astype(np.uint8)
+    boxes = torch.tensor([[10.0, 20.0, 100.0, 90.0], [50.0, 5.0, 50.0, 80.0]])   # the second is empty -> filtered
+    np.random.seed(3); torch.manual_seed(3); random.seed(3)
+    strong, weak = map_two_crop(_chw(img, cuda), boxes, [1, 2], WeakAugmentation((60, 75), 110), StrongAugmentation())
+    np.random.seed(3)
+    size = int(np.random.choice((60, 75)))
+    flip = bool(np.random.uniform() < 0.5)
+    want_img, want_b = A.weak_augment(img, boxes.numpy().astype(np.float64), size, 110, flip)
+    assert np.array_equal(_hwc(weak["image"]), want_img)
+    assert len(weak["instances"]) == 1 and weak["instances"] is strong["instances"]
+    assert np.allclose(weak["instances"].gt_boxes.tensor.cpu().numpy(), want_b[:1].astype(np.float32), atol=1e-4)
+    torch.manual_seed(3); random.seed(3)
+    p = A.sample_params()
+    assert np.array_equal(_hwc(strong["image"]), A.strong_augment(want_img, p))
