@@ -60,8 +60,10 @@ int ptb200_gemm_tn_f16(const void* A, int batch, int rows, int k_per_tap, int64_
  * accumulators (round to nearest) while the next chunk runs.
  * Epilogues: PTB200_EPI_SPLIT3_{RELU_,}F16 (D3 is [batch][rows][3*n_total]); PTB200_EPI_SPLIT3_MASK_F16 (ReLU
  * backward fused into a data-gradient GEMM: aux3 = the forward activation triples, same geometry as D3);
- * PTB200_EPI_F32_STORE (fp32 d0[row][n], ld0 = row pitch); PTB200_EPI_ATOMIC_F32 with ksplit > 1 (skinny
- * problems, finished by ptb200_bias_act_split3_f16); PTB200_EPI_F32_SPLIT (narrow fp32 heads, single chain).
+ * PTB200_EPI_F32_STORE (fp32 d0[row][n], ld0 = row pitch; with ksplit > 1 -- skinny
+ * problems -- d0 is [ksplit][batch][rows][ld0], one partial sum per K split, finished in a fixed order by
+ * ptb200_bias_act_split3_f16: no atomics, the forward is bit-reproducible); PTB200_EPI_ATOMIC_F32 with ksplit > 1
+ * (red.add partial sums); PTB200_EPI_F32_SPLIT (narrow fp32 heads, single chain).
  * bn must be 64, 128 or 256 except for PTB200_EPI_F32_SPLIT. */
 int ptb200_gemm_tn_f16x3(const void* A3, int batch, int rows, int k3_per_tap, int64_t lda,
                          int64_t a_batch_stride, int taps, const int* shifts_host, const void* B3,
@@ -71,11 +73,11 @@ int ptb200_gemm_tn_f16x3(const void* A3, int batch, int rows, int k3_per_tap, in
                          float alpha, const void* aux3, int chunk, void* stream);
 
 /* Bias + ReLU of the same layers (pt/modeling/backbone/vgg.py:65-72, the box head of roi_heads.py:127-128) applied to
- * the fp32 partial sums of a K-chunked f16x3 GEMM:
- * out3 = triple(act(alpha * in + bias)), fp32 [rows][n] -> fp16 [rows][3n]; wp > 0: rows with
- * (row % wp) >= w_valid are written as zero (pad column of the flat activation layout). */
-int ptb200_bias_act_split3_f16(const float* in, const float* bias, int relu, float alpha, int64_t rows, int n,
-                               int wp, int w_valid, void* out3, void* stream);
+ * the fp32 partial sums of a split-K f16x3 GEMM:
+ * out3 = triple(act(alpha * sum_s in[s] + bias)), fp32 [slices][rows][n] added in slice order -> fp16 [rows][3n];
+ * wp > 0: rows with (row % wp) >= w_valid are written as zero (pad column of the flat activation layout). */
+int ptb200_bias_act_split3_f16(const float* in, int slices, const float* bias, int relu, float alpha, int64_t rows,
+                               int n, int wp, int w_valid, void* out3, void* stream);
 
 /* Operand preparation that has no counterpart in the reference (it feeds fp32 tensors to cuDNN / cuBLAS at
  * vgg.py:45-53, rpn.py:96, fast_rcnn.py:157-169 directly):

@@ -40,9 +40,24 @@ constexpr int STAGING_BYTES = BM * 128;
 constexpr int NUM_THREADS = 320;  // TMA warp, MMA warp, 8 epilogue warps
 constexpr int EPI_THREADS = 256;
 
+// ROWWIN (3x3 convs with N <= 128, where streaming one A box per tap makes the tile L2-BANDWIDTH bound: conv1_2 in
+// f16x3 pulled 432 KB of A per 128-pixel tile through L2, 10 TB/s against a ~12 TB/s LTS cap, tensor pipe 31 %): the
+// A ring holds 136-row windows (rows p0 + (ky-1)*Wp - 1 ...) shared by the three horizontal taps of a filter row --
+// the taps are UMMA descriptors offset by kx*128 B, SWIZZLE_128B being a function of absolute shared-memory address
+// bits (tools/exp_rowshift.cu) -- and the B tiles travel through a ring of their own (one tile per tap and K chunk),
+// so a slot is recycled as soon as its 4 MMAs retire: 2.8x fewer A bytes through L2.
+constexpr int WIN_ROWS = 136;
+constexpr int WIN_BYTES = WIN_ROWS * 128;  // 17 * 1024
+constexpr int RW_MAX_A = 4;
+constexpr int RW_MAX_B = 16;
+
 struct Ctl {
   uint64_t full[8];
   uint64_t empty[8];
+  uint64_t full_a[RW_MAX_A];
+  uint64_t empty_a[RW_MAX_A];
+  uint64_t full_b[RW_MAX_B];
+  uint64_t empty_b[RW_MAX_B];
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
   uint64_t aux_full;
@@ -70,7 +85,7 @@ __device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint3
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
-template <int NCH>  // N tile = 64 * NCH columns
+template <int NCH, bool ROWWIN>  // N tile = 64 * NCH columns
 // 10 warps = 3 on two of the four SM sub-partitions (16 K registers each): at most 168 registers per thread
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tn_promote_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
@@ -79,10 +94,14 @@ gemm_tn_promote_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr int bn = 64 * NCH;
   constexpr int stage_bytes = A_STAGE_BYTES + bn * BK * 2;
-  const int stages = p.stages;
+  constexpr int b_tile_bytes = bn * BK * 2;
+  const int stages = p.stages;      // ROWWIN: slots of the A-window ring
+  const int b_slots = p.b_resident;  // ROWWIN: slots of the B-tile ring (the field is otherwise unused here)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  uint8_t* staging = smem + stages * stage_bytes;  // two 16 KB buffers: hi chunk, lo chunk
+  uint8_t* ring_b = smem + stages * WIN_BYTES;  // ROWWIN only
+  // two 16 KB buffers: hi chunk, lo chunk
+  uint8_t* staging = ROWWIN ? ring_b + b_slots * b_tile_bytes : smem + stages * stage_bytes;
   float* bias_s = reinterpret_cast<float*>(staging + 2 * STAGING_BYTES);
   Ctl* ctl = reinterpret_cast<Ctl*>(bias_s + 256);
 
@@ -95,7 +114,7 @@ gemm_tn_promote_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
   const int ksplit = p.ksplit;
   const int num_tiles = tiles_per_batch * p.batch * ksplit;
   const int k_chunks = p.k_per_tap / BK;
-  const int k_iters_total = k_chunks * p.taps;
+  const int k_iters_total = k_chunks * (ROWWIN ? 3 : p.taps);  // ROWWIN: one k-iteration = a filter row's 3 taps
   const int chunk = p.chunk;
 
   constexpr uint32_t tmem_cols = 2 * bn < 32 ? 32 : 2 * bn;  // 128 / 256 / 512: powers of two
@@ -104,9 +123,20 @@ gemm_tn_promote_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
     if (p.epi != EPI_F32_STORE && p.epi != EPI_ATOMIC_F32) tma_prefetch_desc(&map_d);
-    for (int i = 0; i < stages; ++i) {
-      mbar_init(&ctl->full[i], 1);
-      mbar_init(&ctl->empty[i], 1);
+    if (ROWWIN) {
+      for (int i = 0; i < stages; ++i) {
+        mbar_init(&ctl->full_a[i], 1);
+        mbar_init(&ctl->empty_a[i], 1);
+      }
+      for (int i = 0; i < b_slots; ++i) {
+        mbar_init(&ctl->full_b[i], 1);
+        mbar_init(&ctl->empty_b[i], 1);
+      }
+    } else {
+      for (int i = 0; i < stages; ++i) {
+        mbar_init(&ctl->full[i], 1);
+        mbar_init(&ctl->empty[i], 1);
+      }
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&ctl->tmem_full[i], 1);
@@ -129,6 +159,8 @@ gemm_tn_promote_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
     if (elect_one()) {
       int s = 0;
       uint32_t ph = 0;
+      int sb = 0;
+      uint32_t phb = 0;
       for (int work = blockIdx.x; work < num_tiles; work += gridDim.x) {
         const int ks = work % ksplit;
         const int tile = work / ksplit;
@@ -142,6 +174,27 @@ gemm_tn_promote_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
         const int ki0 = (k_iters_total * ks) / ksplit, ki1 = (k_iters_total * (ks + 1)) / ksplit;
         for (int ki = ki0; ki < ki1; ++ki) {
           const int t = ki / k_chunks, kc = ki - t * k_chunks;
+          if (ROWWIN) {
+            // t = filter row ky: the window starts one pixel left of the kx = 0 tap
+            mbar_wait(&ctl->empty_a[s], ph ^ 1);
+            mbar_arrive_expect_tx(&ctl->full_a[s], WIN_BYTES);
+            tma_load_3d(smem + s * WIN_BYTES, &map_a, &ctl->full_a[s], kc * BK, row0 + (t - 1) * p.wp - 1, b);
+            if (++s == stages) {
+              s = 0;
+              ph ^= 1;
+            }
+            for (int kx = 0; kx < 3; ++kx) {
+              mbar_wait(&ctl->empty_b[sb], phb ^ 1);
+              mbar_arrive_expect_tx(&ctl->full_b[sb], b_tile_bytes);
+              tma_load_2d(ring_b + sb * b_tile_bytes, &map_b, &ctl->full_b[sb], (t * 3 + kx) * p.k_per_tap + kc * BK,
+                          n0);
+              if (++sb == b_slots) {
+                sb = 0;
+                phb ^= 1;
+              }
+            }
+            continue;
+          }
           mbar_wait(&ctl->empty[s], ph ^ 1);
           uint8_t* sa = smem + s * stage_bytes;
           uint8_t* sb = sa + A_STAGE_BYTES;
@@ -160,6 +213,8 @@ gemm_tn_promote_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
     const uint32_t idesc = umma_idesc_f16(BM, bn, 0, 0);
     int s = 0;
     uint32_t ph = 0;
+    int sb = 0;
+    uint32_t phb = 0;
     int it = 0;  // accumulator-stage use counter: one per CHUNK
     const uint32_t tmem_base_u = __shfl_sync(0xffffffffu, tmem_base, 0);
     for (int work = blockIdx.x; work < num_tiles; work += gridDim.x) {
@@ -179,6 +234,36 @@ gemm_tn_promote_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
         tc_fence_after();
         const uint32_t d_tmem = tmem_base_u + as * bn;
         for (int ki = 0; ki < kn; ++ki) {
+          if (ROWWIN) {
+            mbar_wait(&ctl->full_a[s], ph);
+            const uint64_t da = umma_desc_sw128(smem_u32(smem + s * WIN_BYTES), 16, 1024);
+            for (int kx = 0; kx < 3; ++kx) {
+              mbar_wait(&ctl->full_b[sb], phb);
+              tc_fence_after();
+              if (elect_one()) {
+                const uint64_t dax = da + (128 >> 4) * kx;  // one pixel row further
+                const uint64_t db = umma_desc_sw128(smem_u32(ring_b + sb * b_tile_bytes), 16, 1024);
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k)
+                  umma_f16_ss(d_tmem, dax + 2 * k, db + 2 * k, idesc, (ki > 0 || kx > 0 || k > 0) ? 1u : 0u);
+                umma_commit(&ctl->empty_b[sb]);
+                if (kx == 2) {
+                  umma_commit(&ctl->empty_a[s]);
+                  if (ki == kn - 1) umma_commit(&ctl->tmem_full[as]);
+                }
+              }
+              __syncwarp();
+              if (++sb == b_slots) {
+                sb = 0;
+                phb ^= 1;
+              }
+            }
+            if (++s == stages) {
+              s = 0;
+              ph ^= 1;
+            }
+            continue;
+          }
           mbar_wait(&ctl->full[s], ph);
           tc_fence_after();
           if (elect_one()) {
@@ -276,7 +361,8 @@ gemm_tn_promote_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
         }
       } else if (p.epi == EPI_F32_STORE) {
         if (row < p.rows) {
-          float* orow = p.d0 + (static_cast<size_t>(b) * p.rows + row) * p.ld0 + n0 + 32 * hf;
+          // ksplit > 1: one slice [batch][rows][ld0] per K split (summed in a fixed order by the finishing kernel)
+          float* orow = p.d0 + ((static_cast<size_t>(ks) * p.batch + b) * p.rows + row) * p.ld0 + n0 + 32 * hf;
 #pragma unroll
           for (int ch = 0; ch < NCH; ++ch)
 #pragma unroll
@@ -363,20 +449,32 @@ gemm_tn_promote_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
 
 int g_num_sms = 0;
 
-template <int NCH>
+template <int NCH, bool ROWWIN>
 int launch_nch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& md, const CUtensorMap& mx,
                GemmTnParams& p, int max_ctas, cudaStream_t stream) {
   constexpr int bn = 64 * NCH;
   constexpr int stage_bytes = A_STAGE_BYTES + bn * BK * 2;
   const int fixed = 2 * STAGING_BYTES + 256 * 4 + (int)sizeof(Ctl) + 1024;
-  int stages = (232448 - fixed) / stage_bytes;
-  if (stages > 8) stages = 8;
-  if (stages < 2) return 1005;
-  p.stages = stages;
-  const int smem_bytes = stages * stage_bytes + fixed;
+  int smem_bytes;
+  if (ROWWIN) {
+    // A-window ring + B-tile ring: the B ring takes what 3 (N = 128) / 4 (N = 64) windows leave
+    const int a_slots = NCH == 1 ? 4 : 3;
+    int b_slots = (232448 - fixed - a_slots * WIN_BYTES) / (bn * BK * 2);
+    if (b_slots > RW_MAX_B) b_slots = RW_MAX_B;
+    if (b_slots < 6) return 1005;
+    p.stages = a_slots;
+    p.b_resident = b_slots;
+    smem_bytes = a_slots * WIN_BYTES + b_slots * bn * BK * 2 + fixed;
+  } else {
+    int stages = (232448 - fixed) / stage_bytes;
+    if (stages > 8) stages = 8;
+    if (stages < 2) return 1005;
+    p.stages = stages;
+    smem_bytes = stages * stage_bytes + fixed;
+  }
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tn_promote_kernel<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(gemm_tn_promote_kernel<NCH, ROWWIN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          232448);
     if (e != cudaSuccess) return (int)e;
     configured = true;
@@ -386,11 +484,11 @@ int launch_nch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& 
   int grid = num_tiles < g_num_sms ? num_tiles : g_num_sms;
   if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
   if (grid < 1) return 0;
-  gemm_tn_promote_kernel<NCH><<<grid, NUM_THREADS, smem_bytes, stream>>>(ma, mb, md, mx, p);
+  gemm_tn_promote_kernel<NCH, ROWWIN><<<grid, NUM_THREADS, smem_bytes, stream>>>(ma, mb, md, mx, p);
   const cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) {
     cudaFuncAttributes fa;
-    if (cudaFuncGetAttributes(&fa, gemm_tn_promote_kernel<NCH>) == cudaSuccess)
+    if (cudaFuncGetAttributes(&fa, gemm_tn_promote_kernel<NCH, ROWWIN>) == cudaSuccess)
       fprintf(stderr, "gemm_tn_promote_kernel<%d>: launch failed (%s): regs %d, maxThreadsPerBlock %d, static smem %zu, "
               "max dynamic smem %d, requested %d threads / %d B\n", NCH, cudaGetErrorString(err), fa.numRegs,
               fa.maxThreadsPerBlock, fa.sharedSizeBytes, fa.maxDynamicSharedSizeBytes, NUM_THREADS, smem_bytes);
@@ -409,7 +507,7 @@ int gemm_tn_promote_launch(const GemmTnArgs& a, int chunk, cudaStream_t stream) 
   const bool f32_out = a.epi == EPI_F32_STORE || a.epi == EPI_ATOMIC_F32;
   const bool triple = a.epi == EPI_SPLIT3_RELU_F16 || a.epi == EPI_SPLIT3_F16 || a.epi == EPI_SPLIT3_MASK_F16;
   if (!f32_out && !triple) return 1021;
-  if (a.ksplit > 1 && a.epi != EPI_ATOMIC_F32) return 1007;
+  if (a.ksplit > 1 && a.epi != EPI_ATOMIC_F32 && !(a.epi == EPI_F32_STORE && a.bias == nullptr)) return 1007;
   if (a.seg_counts != nullptr && (a.batch != 1 || a.seg_cap <= 0)) return 1008;
   if (a.epi == EPI_SPLIT3_MASK_F16 && a.aux == nullptr) return 1009;
   if (f32_out && a.d0 == nullptr) return 1009;
@@ -418,11 +516,22 @@ int gemm_tn_promote_launch(const GemmTnArgs& a, int chunk, cudaStream_t stream) 
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
   }
+  // row-window mode: 3x3 tap pattern over the flattened rows, narrow N tile (the L2-bound case), whole-K tiles
+  static int rowwin_opt = -1, rw_chunk = 0;
+  if (rowwin_opt < 0) {
+    const char* e = getenv("PTB200_X3_ROWWIN");
+    rowwin_opt = (e == nullptr) ? 1 : atoi(e);
+    const char* c = getenv("PTB200_X3_RW_CHUNK");
+    rw_chunk = c ? atoi(c) : 0;
+  }
+  bool rowwin = rowwin_opt != 0 && a.taps == 9 && a.wp > 0 && a.bn <= 128 && a.ksplit <= 1 && a.seg_counts == nullptr;
+  if (rowwin)
+    for (int t = 0; t < 9; ++t) rowwin = rowwin && a.shifts[t] == (t / 3 - 1) * a.wp + (t % 3 - 1);
   CUtensorMap ma, mb, md, mx;
   {
     uint64_t dims[3] = {(uint64_t)a.k_per_tap, (uint64_t)a.rows, (uint64_t)a.batch};
     uint64_t str[2] = {(uint64_t)a.lda * 2, (uint64_t)a.a_batch_stride * 2};
-    uint32_t box[3] = {BK, BM, 1};
+    uint32_t box[3] = {BK, (uint32_t)(rowwin ? WIN_ROWS : BM), 1};
     if (make_tmap_f16(&ma, a.A, 3, dims, str, box)) return 1010;
   }
   {
@@ -476,10 +585,19 @@ int gemm_tn_promote_launch(const GemmTnArgs& a, int chunk, cudaStream_t stream) 
     chunk_env = e ? atoi(e) : 0;
   }
   p.chunk = chunk_env > 0 ? chunk_env : (chunk > 0 ? chunk : 4);
+  if (rowwin) {
+    // a row-window k-iteration issues 12 MMAs (3 taps x 64 columns of K). One promotion per 3 k-iterations: chains of
+    // 36 truncating tensor-core accumulations (16 in the per-tap kernel at chunk 4) over K <= 3456 -- measured on
+    // B200 at full size, conv1_2: chunk 1 / 3 / 9 = 0.681 / 0.609 / 0.592 ms per 2 images (per-tap kernel 0.725) at
+    // 2.5e-7 / 8.6e-7 / 2.1e-6 relative error against fp64
+    p.chunk = rw_chunk > 0 ? rw_chunk : 3;
+    return a.bn == 64 ? launch_nch<1, true>(ma, mb, md, mx, p, a.max_ctas, stream)
+                      : launch_nch<2, true>(ma, mb, md, mx, p, a.max_ctas, stream);
+  }
   switch (a.bn) {
-    case 64: return launch_nch<1>(ma, mb, md, mx, p, a.max_ctas, stream);
-    case 128: return launch_nch<2>(ma, mb, md, mx, p, a.max_ctas, stream);
-    default: return launch_nch<4>(ma, mb, md, mx, p, a.max_ctas, stream);
+    case 64: return launch_nch<1, false>(ma, mb, md, mx, p, a.max_ctas, stream);
+    case 128: return launch_nch<2, false>(ma, mb, md, mx, p, a.max_ctas, stream);
+    default: return launch_nch<4, false>(ma, mb, md, mx, p, a.max_ctas, stream);
   }
 }
 

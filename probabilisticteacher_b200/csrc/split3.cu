@@ -185,10 +185,12 @@ conv1_u8_x3_kernel(const uint8_t* __restrict__ img, const int* __restrict__ hw, 
   }
 }
 
-// Finishes a K-chunked f16x3 GEMM (fp32 partial sums reduced with red.add): x = act(alpha * in + bias) -> triple.
+// Finishes a split-K f16x3 GEMM: `slices` fp32 partial sums [slices][rows][n] (one per K split, written by
+// EPI_F32_STORE) are added IN A FIXED ORDER -- the forward stays bit-reproducible run to run, which the discrete
+// proposal / pseudo-label decisions downstream need -- then x = act(alpha * sum + bias) -> triple.
 // wp > 0: rows with (row % wp) >= w_valid (the pad column of the flat activation layout) are written as zero.
-__global__ void bias_act_split3_kernel(const float* __restrict__ in, const float* __restrict__ bias, int relu,
-                                       float alpha, int64_t rows, int n, int wp, int w_valid,
+__global__ void bias_act_split3_kernel(const float* __restrict__ in, int slices, const float* __restrict__ bias,
+                                       int relu, float alpha, int64_t rows, int n, int wp, int w_valid,
                                        __half* __restrict__ out) {
   const int n4 = n / 4;
   const int64_t total4 = rows * n4;
@@ -196,7 +198,14 @@ __global__ void bias_act_split3_kernel(const float* __restrict__ in, const float
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const int64_t r = i / n4;
     const int c = static_cast<int>(i - r * n4) * 4;
-    const float4 v4 = reinterpret_cast<const float4*>(in)[i];
+    float4 v4 = reinterpret_cast<const float4*>(in)[i];
+    for (int sl = 1; sl < slices; ++sl) {
+      const float4 w4 = reinterpret_cast<const float4*>(in)[sl * total4 + i];
+      v4.x += w4.x;
+      v4.y += w4.y;
+      v4.z += w4.z;
+      v4.w += w4.w;
+    }
     float v[4] = {v4.x, v4.y, v4.z, v4.w};
     const bool live = wp <= 0 || static_cast<int>(r % wp) < w_valid;
     __align__(8) __half h[4], l[4];
@@ -401,11 +410,11 @@ extern "C" int ptb200_conv1_u8_f16x3(const uint8_t* images, const int* hw_dev, i
   return static_cast<int>(cudaGetLastError());
 }
 
-extern "C" int ptb200_bias_act_split3_f16(const float* in, const float* bias, int relu, float alpha, int64_t rows,
-                                          int n, int wp, int w_valid, void* out3, void* stream) {
-  if (n % 4 != 0) return 1203;
-  bias_act_split3_kernel<<<grid_for(rows * n / 4), kThreads, 0, STREAM>>>(in, bias, relu, alpha, rows, n, wp, w_valid,
-                                                                         static_cast<__half*>(out3));
+extern "C" int ptb200_bias_act_split3_f16(const float* in, int slices, const float* bias, int relu, float alpha,
+                                          int64_t rows, int n, int wp, int w_valid, void* out3, void* stream) {
+  if (n % 4 != 0 || slices < 1) return 1203;
+  bias_act_split3_kernel<<<grid_for(rows * n / 4), kThreads, 0, STREAM>>>(in, slices, bias, relu, alpha, rows, n, wp,
+                                                                         w_valid, static_cast<__half*>(out3));
   return static_cast<int>(cudaGetLastError());
 }
 

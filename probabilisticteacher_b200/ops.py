@@ -144,13 +144,17 @@ def gemm_tn_x3(A3, B3, alpha, *, taps=1, shifts=None, bn=None, epi=EPI_SPLIT3_RE
                 ksplit = max(1, min(148 // tiles, k_iters // 32))
     if ksplit > 1:
         assert epi in (EPI_SPLIT3_RELU, EPI_SPLIT3)
-        acc = torch.zeros(batch, rows, n_total, dtype=torch.float32, device=dev)
-        call("ptb200_gemm_tn_f16x3", A3, batch, rows, k3, lda, rows * lda, taps, shifts, B3, n_total, bn, EPI_ATOMIC,
+        # one fp32 slice per K split, added in a fixed order by the finishing kernel: no atomics in the forward, so
+        # the discrete decisions downstream (top-k, NMS, pseudo-label thresholds) are reproducible run to run.
+        # Segment mode skips dead tiles: their rows must read as zero
+        acc = (torch.zeros if seg_counts is not None else torch.empty)(ksplit, batch, rows, n_total, dtype=torch.float32,
+                                                                       device=dev)
+        call("ptb200_gemm_tn_f16x3", A3, batch, rows, k3, lda, rows * lda, taps, shifts, B3, n_total, bn, EPI_F32_STORE,
              None, 0, None, 0, 0, 0, 0, acc, n_total, None, 0, 0, n_total, GEMM_MAX_CTAS[0], ksplit, seg_counts,
              seg_cap, 1.0, None, X3_CHUNK[0])
         out = torch.empty(batch, rows, 3 * n_total, dtype=torch.float16, device=dev)
-        call("ptb200_bias_act_split3_f16", acc, bias, 1 if epi == EPI_SPLIT3_RELU else 0, float(alpha), batch * rows,
-             n_total, wp, w_valid, out)
+        call("ptb200_bias_act_split3_f16", acc, ksplit, bias, 1 if epi == EPI_SPLIT3_RELU else 0, float(alpha),
+             batch * rows, n_total, wp, w_valid, out)
         return out
     if epi == EPI_F32_STORE:
         d0 = alloc(batch, rows, n_total, dtype=torch.float32, device=dev)

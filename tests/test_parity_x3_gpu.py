@@ -70,7 +70,8 @@ def test_gemm_x3_vs_fp64(cuda, rows, K, N):
     assert _rel(torch.cat([d0[0], d1[0]], 1), ref[:, :N - 7]) < 1e-5
 
 
-@pytest.mark.parametrize("Cin,Cout,H,W", [(64, 64, 40, 51), (128, 256, 25, 38), (512, 512, 12, 17)])
+@pytest.mark.parametrize("Cin,Cout,H,W", [(64, 64, 40, 51), (128, 256, 25, 38), (512, 512, 12, 17),
+                                          (64, 128, 33, 47), (128, 128, 21, 130), (64, 64, 3, 300)])
 def test_conv_x3_vs_fp64(cuda, Cin, Cout, H, W):
     from probabilisticteacher_b200 import ops
     g = torch.Generator().manual_seed(Cin + H)
@@ -237,8 +238,16 @@ def _full_iteration(cuda, H, W, K, anchor_gen, n_img, seed):
 
     def both(batch_g, batch_o, branch, tag, **kw):
         lg, _, _, _ = model(batch_g, branch=branch, **kw)
-        lo, _, _, _ = om(batch_o, branch=branch, **kw)
-        ls, _, _, _ = om(batch_o, branch=branch, proposals_override=_oracle_props(O, model, (H, W)), **kw)
+        tr = {}
+        lo, _, _, _ = om(batch_o, branch=branch, trace=tr, **kw)
+        gp = _oracle_props(O, model, (H, W))
+        ls, _, _, _ = om(batch_o, branch=branch, proposals_override=gp, **kw)
+        # do both sides hand the SAME proposal set to their ROI stage? (one near-threshold NMS pair or one near-tied
+        # score at the top-k boundary is enough to change it, and with it the sampled rois)
+        rep[f"{tag}/same_proposals"] = all(
+            len(a.proposal_boxes) == len(b.proposal_boxes)
+            and _prop_overlap(a.proposal_boxes.tensor, b.proposal_boxes.tensor, scale) == 1.0
+            for a, b in zip(gp, tr["proposals"]))
         for k in lo:
             rep[f"{tag}/own/{k}"] = (float(lg[k]), float(lo[k]))
             rep[f"{tag}/shared/{k}"] = (float(lg[k]), float(ls[k]))
@@ -286,11 +295,20 @@ def _assert_report(rep, own_roi=True):
                 assert all(x < TOL for x in d["worst_own"].values()), d
                 if own_roi:
                     assert d["n_prop_g"] == d["n_prop_o"], d
+        elif k.endswith("/same_proposals"):
+            continue
         else:
             a, b = v
-            if "/own/" in k and not own_roi and "rpn" not in k:
-                continue  # reported, not asserted: see _full_iteration
-            assert abs(a - b) <= TOL * max(abs(b), 1e-6), (k, a, b)
+            tol = TOL
+            if "/own/" in k and "rpn" not in k:
+                if not own_roi:
+                    continue  # reported, not asserted: see _full_iteration
+                if not rep[k.split("/")[0] + "/same_proposals"]:
+                    # the two sides' proposal LISTS differ by a discrete flip (a pair within ~1e-7 of the NMS threshold
+                    # in this fixture: measured 179 vs 180 proposals), so their ROI stages sample different rois:
+                    # the 1e-3 statement for the ROI losses is the "shared" row; "own" is bounded, not matched
+                    tol = 2e-2
+            assert abs(a - b) <= tol * max(abs(b), 1e-6), (k, a, b)
 
 
 def test_full_iteration_losses_1e3_small(cuda):
