@@ -461,7 +461,7 @@ int launch_nch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& 
     const int a_slots = NCH == 1 ? 4 : 3;
     int b_slots = (232448 - fixed - a_slots * WIN_BYTES) / (bn * BK * 2);
     if (b_slots > RW_MAX_B) b_slots = RW_MAX_B;
-    if (b_slots < 6) return 1005;
+    if (b_slots < 4) return 1005;
     p.stages = a_slots;
     p.b_resident = b_slots;
     smem_bytes = a_slots * WIN_BYTES + b_slots * bn * BK * 2 + fixed;
@@ -524,7 +524,9 @@ int gemm_tn_promote_launch(const GemmTnArgs& a, int chunk, cudaStream_t stream) 
     const char* c = getenv("PTB200_X3_RW_CHUNK");
     rw_chunk = c ? atoi(c) : 0;
   }
-  bool rowwin = rowwin_opt != 0 && a.taps == 9 && a.wp > 0 && a.bn <= 128 && a.ksplit <= 1 && a.seg_counts == nullptr;
+  // (PTB200_X3_ROWWIN = 2 restricts it to the N <= 128 layers)
+  bool rowwin = rowwin_opt != 0 && a.taps == 9 && a.wp > 0 && (a.bn <= 128 || rowwin_opt == 1) && a.ksplit <= 1 &&
+                a.seg_counts == nullptr;
   if (rowwin)
     for (int t = 0; t < 9; ++t) rowwin = rowwin && a.shifts[t] == (t / 3 - 1) * a.wp + (t % 3 - 1);
   CUtensorMap ma, mb, md, mx;
@@ -590,9 +592,11 @@ int gemm_tn_promote_launch(const GemmTnArgs& a, int chunk, cudaStream_t stream) 
     // 36 truncating tensor-core accumulations (16 in the per-tap kernel at chunk 4) over K <= 3456 -- measured on
     // B200 at full size, conv1_2: chunk 1 / 3 / 9 = 0.681 / 0.609 / 0.592 ms per 2 images (per-tap kernel 0.725) at
     // 2.5e-7 / 8.6e-7 / 2.1e-6 relative error against fp64
-    p.chunk = rw_chunk > 0 ? rw_chunk : 3;
-    return a.bn == 64 ? launch_nch<1, true>(ma, mb, md, mx, p, a.max_ctas, stream)
-                      : launch_nch<2, true>(ma, mb, md, mx, p, a.max_ctas, stream);
+    // N = 256: a k-iteration is 1536 tensor cycles, one promotion per k-iteration costs nothing (chains of 12 MMAs)
+    p.chunk = rw_chunk > 0 ? rw_chunk : (a.bn == 256 ? 1 : 3);
+    return a.bn == 64    ? launch_nch<1, true>(ma, mb, md, mx, p, a.max_ctas, stream)
+           : a.bn == 128 ? launch_nch<2, true>(ma, mb, md, mx, p, a.max_ctas, stream)
+                         : launch_nch<4, true>(ma, mb, md, mx, p, a.max_ctas, stream);
   }
   switch (a.bn) {
     case 64: return launch_nch<1, false>(ma, mb, md, mx, p, a.max_ctas, stream);

@@ -8,7 +8,8 @@ from probabilisticteacher_b200 import ops
 
 dev = torch.device("cuda:0")
 g = torch.Generator().manual_seed(0)
-for (Cin, Cout, H, W, n) in [(64, 64, 800, 1333, 2), (64, 128, 400, 666, 2), (128, 128, 400, 666, 2), (128, 256, 200, 333, 2)]:
+for (Cin, Cout, H, W, n) in [(64, 64, 800, 1333, 2), (64, 128, 400, 666, 2), (128, 128, 400, 666, 2), (128, 256, 200, 333, 2), (256, 256, 200, 333, 2),
+                           (256, 512, 100, 167, 2), (512, 512, 100, 167, 2), (512, 512, 50, 84, 4)]:
     x = (torch.randn(n, Cin, H, W, generator=g).abs()).to(dev)
     w = (torch.randn(Cout, Cin, 3, 3, generator=g) * (2.0 / (9 * Cout)) ** 0.5).to(dev)
     b = torch.randn(Cout, generator=g).to(dev)
