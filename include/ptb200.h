@@ -36,7 +36,9 @@ extern "C" {
  *   pt/modeling/proposal_generator/rpn.py:96 (RPN head), pt/modeling/roi_heads/roi_heads.py:127-128
  *   (box head), pt/modeling/roi_heads/fast_rcnn.py:157-169 (predictor), and their data-gradients.
  * Rows outside [0, rows) read as zero (conv zero padding). ksplit > 1 (with PTB200_EPI_ATOMIC_F32)
- * splits the reduction across CTAs for skinny problems (fc1 forward). seg_counts (may be NULL, batch == 1):
+ * splits the reduction across CTAs for skinny problems (fc1 forward): with split == 0 the partial sums are
+ * added into d0 with fp32 atomics; with split == 1 d0 is [ksplit][batch][rows][ld0] and every K split stores its
+ * own slice (ptb200_bias_act_cast_f16 adds them in a fixed order: a bit-reproducible forward). seg_counts (may be NULL, batch == 1):
  * rows form segments of seg_cap rows of which only the first seg_counts[s] are live (fixed-capacity roi
  * buffers); 128-row tiles without a live row are skipped and their outputs left untouched. */
 int ptb200_gemm_tn_f16(const void* A, int batch, int rows, int k_per_tap, int64_t lda,
@@ -199,9 +201,10 @@ int ptb200_pack_grad2_f16(const float* d0, int n0, const float* d1, int n1, cons
 int ptb200_pack_grad2_f16x3(const float* d0, int n0, const float* d1, int n1, const float* g0, const float* g1,
                             float lscale, int64_t rows, int ld, void* out3, void* stream);
 
-/* Finishes a split-K GEMM (fc1 of the box head, roi_heads.py:127-128): out = half(act(in + bias)). */
-int ptb200_bias_act_cast_f16(const float* in, const float* bias, int relu, int64_t rows, int n, void* out,
-                             void* stream);
+/* Finishes a split-K GEMM (fc1 of the box head, roi_heads.py:127-128): out = half(act(sum_s in[s] + bias)),
+ * in = fp32 [slices][rows][n] added in slice order. */
+int ptb200_bias_act_cast_f16(const float* in, int slices, const float* bias, int relu, int64_t rows, int n,
+                             void* out, void* stream);
 
 /* out = half(a + scale * b): autograd's accumulation of two gradient paths into one tensor (the RPN and ROI
  * branches both consume `features["vgg_block5"]`, pt/modeling/meta_arch/rcnn.py:45-61). */

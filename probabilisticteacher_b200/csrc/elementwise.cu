@@ -335,14 +335,22 @@ __global__ void resize_paste_u8_kernel(const uint8_t* __restrict__ src, uint8_t*
   }
 }
 
-// out[r][c] = half(act(in[r][c] + bias[c])) : finishes a split-K GEMM whose partials were reduced in fp32
-__global__ void bias_act_cast_kernel(const float* __restrict__ in, const float* __restrict__ bias, int relu,
-                                     int64_t rows, int n, __half* __restrict__ out) {
+// out[r][c] = half(act(sum_s in[s][r][c] + bias[c])) : finishes a split-K GEMM; the `slices` fp32 partial sums are
+// added in slice order (fixed, so the forward is bit-reproducible)
+__global__ void bias_act_cast_kernel(const float* __restrict__ in, int slices, const float* __restrict__ bias,
+                                     int relu, int64_t rows, int n, __half* __restrict__ out) {
   const int64_t total4 = rows * n / 4;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total4;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const int c = static_cast<int>((i * 4) % n);
     float4 v = reinterpret_cast<const float4*>(in)[i];
+    for (int sl = 1; sl < slices; ++sl) {
+      const float4 w = reinterpret_cast<const float4*>(in)[sl * total4 + i];
+      v.x += w.x;
+      v.y += w.y;
+      v.z += w.z;
+      v.w += w.w;
+    }
     if (bias != nullptr) {
       v.x += bias[c];
       v.y += bias[c + 1];
@@ -456,10 +464,10 @@ extern "C" int ptb200_resize_paste_u8_dev(const uint8_t* src, uint8_t* dst, int 
   return LAUNCH_OK();
 }
 
-extern "C" int ptb200_bias_act_cast_f16(const float* in, const float* bias, int relu, int64_t rows, int n, void* out,
-                                        void* stream) {
-  if (n % 4 != 0) return 1203;
-  bias_act_cast_kernel<<<grid_for(rows * n / 4), kThreads, 0, STREAM>>>(in, bias, relu, rows, n,
+extern "C" int ptb200_bias_act_cast_f16(const float* in, int slices, const float* bias, int relu, int64_t rows, int n,
+                                        void* out, void* stream) {
+  if (n % 4 != 0 || slices < 1) return 1203;
+  bias_act_cast_kernel<<<grid_for(rows * n / 4), kThreads, 0, STREAM>>>(in, slices, bias, relu, rows, n,
                                                                        static_cast<__half*>(out));
   return LAUNCH_OK();
 }

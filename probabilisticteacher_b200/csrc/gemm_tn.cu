@@ -267,12 +267,20 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * bn;
 
       if (p.epi == EPI_ATOMIC_F32) {
-        float* orow = p.d0 + (static_cast<size_t>(b) * p.rows + row) * p.ld0 + n0;
+        // split == 1 ("slices"): every K split owns a slice [batch][rows][ld0] of d0 and stores its partial sum; the
+        // finishing kernel adds the slices in a fixed order (a bit-reproducible forward). Otherwise fp32 red.add.
+        const bool slices = p.split != 0;
+        const int ks = work % ksplit;
+        float* orow = p.d0 + ((static_cast<size_t>(slices ? ks : 0) * p.batch + b) * p.rows + row) * p.ld0 + n0;
         for (int c0 = 32 * hf; c0 < bn; c0 += 64) {
           uint32_t v[32];
           tmem_ld_32x32(t_addr + c0, v);
           tmem_ld_wait();
-          if (row < p.rows) {
+          if (row < p.rows && slices) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<uint4*>(orow + c0 + 4 * j) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          } else if (row < p.rows) {
 #pragma unroll
             for (int j = 0; j < 8; ++j)
               asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(orow + c0 + 4 * j),

@@ -85,7 +85,10 @@ __device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint3
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
-template <int NCH, bool ROWWIN>  // N tile = 64 * NCH columns
+// MH = 2 (row-window mode, N <= 128): a CTA tile is TWO 128-row halves that share every B tile (the filter slice of
+// a tap is read from L2 once per 256 pixels; B was 60-75 % of the L2 bytes of these layers), each half with its own
+// pair of TMEM accumulator stages and its own fp32 register accumulators.
+template <int NCH, bool ROWWIN, int MH>  // N tile = 64 * NCH columns, M tile = 128 * MH rows
 // 10 warps = 3 on two of the four SM sub-partitions (16 K registers each): at most 168 registers per thread
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tn_promote_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
@@ -95,11 +98,13 @@ gemm_tn_promote_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
   constexpr int bn = 64 * NCH;
   constexpr int stage_bytes = A_STAGE_BYTES + bn * BK * 2;
   constexpr int b_tile_bytes = bn * BK * 2;
+  static_assert(MH == 1 || (ROWWIN && NCH <= 2), "two M halves: row-window mode, N <= 128");
+  constexpr int a_slot_bytes = MH * WIN_BYTES;  // ROWWIN
   const int stages = p.stages;      // ROWWIN: slots of the A-window ring
   const int b_slots = p.b_resident;  // ROWWIN: slots of the B-tile ring (the field is otherwise unused here)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  uint8_t* ring_b = smem + stages * WIN_BYTES;  // ROWWIN only
+  uint8_t* ring_b = smem + stages * a_slot_bytes;  // ROWWIN only
   // two 16 KB buffers: hi chunk, lo chunk
   uint8_t* staging = ROWWIN ? ring_b + b_slots * b_tile_bytes : smem + stages * stage_bytes;
   float* bias_s = reinterpret_cast<float*>(staging + 2 * STAGING_BYTES);
@@ -108,7 +113,8 @@ gemm_tn_promote_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  const int m_tiles = (p.rows + BM - 1) / BM;
+  constexpr int BMT = BM * MH;
+  const int m_tiles = (p.rows + BMT - 1) / BMT;
   const int n_tiles = p.n_total / bn;
   const int tiles_per_batch = m_tiles * n_tiles;
   const int ksplit = p.ksplit;
@@ -117,7 +123,7 @@ gemm_tn_promote_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
   const int k_iters_total = k_chunks * (ROWWIN ? 3 : p.taps);  // ROWWIN: one k-iteration = a filter row's 3 taps
   const int chunk = p.chunk;
 
-  constexpr uint32_t tmem_cols = 2 * bn < 32 ? 32 : 2 * bn;  // 128 / 256 / 512: powers of two
+  constexpr uint32_t tmem_cols = 2 * MH * bn < 32 ? 32 : 2 * MH * bn;  // 128 / 256 / 512: powers of two
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&map_a);
@@ -168,7 +174,7 @@ gemm_tn_promote_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
         const int rem = tile - b * tiles_per_batch;
         const int mt = rem / n_tiles;
         const int nt = rem - mt * n_tiles;
-        const int row0 = mt * BM;
+        const int row0 = mt * BMT;
         const int n0 = nt * bn;
         if (!tile_live(p.seg_counts, p.seg_cap, row0, p.rows)) continue;
         const int ki0 = (k_iters_total * ks) / ksplit, ki1 = (k_iters_total * (ks + 1)) / ksplit;
@@ -177,8 +183,11 @@ gemm_tn_promote_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
           if (ROWWIN) {
             // t = filter row ky: the window starts one pixel left of the kx = 0 tap
             mbar_wait(&ctl->empty_a[s], ph ^ 1);
-            mbar_arrive_expect_tx(&ctl->full_a[s], WIN_BYTES);
-            tma_load_3d(smem + s * WIN_BYTES, &map_a, &ctl->full_a[s], kc * BK, row0 + (t - 1) * p.wp - 1, b);
+            mbar_arrive_expect_tx(&ctl->full_a[s], a_slot_bytes);
+#pragma unroll
+            for (int h = 0; h < MH; ++h)
+              tma_load_3d(smem + s * a_slot_bytes + h * WIN_BYTES, &map_a, &ctl->full_a[s], kc * BK,
+                          row0 + h * BM + (t - 1) * p.wp - 1, b);
             if (++s == stages) {
               s = 0;
               ph ^= 1;
@@ -221,7 +230,7 @@ gemm_tn_promote_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
       if (p.seg_counts != nullptr) {
         const int tile_ = work / ksplit;
         const int mt_ = (tile_ % tiles_per_batch) / n_tiles;
-        if (!tile_live(p.seg_counts, p.seg_cap, mt_ * BM, p.rows)) continue;
+        if (!tile_live(p.seg_counts, p.seg_cap, mt_ * BMT, p.rows)) continue;
       }
       const int ks = work % ksplit;
       const int k_iters = (k_iters_total * (ks + 1)) / ksplit - (k_iters_total * ks) / ksplit;
@@ -232,20 +241,23 @@ gemm_tn_promote_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
         ++it;
         mbar_wait(&ctl->tmem_empty[as], aph ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base_u + as * bn;
+        const uint32_t d_tmem = tmem_base_u + as * (MH * bn);
         for (int ki = 0; ki < kn; ++ki) {
           if (ROWWIN) {
             mbar_wait(&ctl->full_a[s], ph);
-            const uint64_t da = umma_desc_sw128(smem_u32(smem + s * WIN_BYTES), 16, 1024);
+            const uint64_t da = umma_desc_sw128(smem_u32(smem + s * a_slot_bytes), 16, 1024);
             for (int kx = 0; kx < 3; ++kx) {
               mbar_wait(&ctl->full_b[sb], phb);
               tc_fence_after();
               if (elect_one()) {
-                const uint64_t dax = da + (128 >> 4) * kx;  // one pixel row further
                 const uint64_t db = umma_desc_sw128(smem_u32(ring_b + sb * b_tile_bytes), 16, 1024);
 #pragma unroll
-                for (int k = 0; k < BK / 16; ++k)
-                  umma_f16_ss(d_tmem, dax + 2 * k, db + 2 * k, idesc, (ki > 0 || kx > 0 || k > 0) ? 1u : 0u);
+                for (int h = 0; h < MH; ++h) {
+                  const uint64_t dax = da + (h * WIN_BYTES >> 4) + (128 >> 4) * kx;  // half h, one pixel row further
+#pragma unroll
+                  for (int k = 0; k < BK / 16; ++k)
+                    umma_f16_ss(d_tmem + h * bn, dax + 2 * k, db + 2 * k, idesc, (ki > 0 || kx > 0 || k > 0) ? 1u : 0u);
+                }
                 umma_commit(&ctl->empty_b[sb]);
                 if (kx == 2) {
                   umma_commit(&ctl->empty_a[s]);
@@ -300,7 +312,7 @@ gemm_tn_promote_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
       const int rem = tile - b * tiles_per_batch;
       const int mt = rem / n_tiles;
       const int nt = rem - mt * n_tiles;
-      const int row0 = mt * BM;
+      const int row0 = mt * BMT;
       const int n0 = nt * bn;
       if (!tile_live(p.seg_counts, p.seg_cap, row0, p.rows)) continue;
       const int k_iters = (k_iters_total * (ks + 1)) / ksplit - (k_iters_total * ks) / ksplit;
@@ -313,11 +325,13 @@ gemm_tn_promote_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
         staged_n0 = n0;
       }
 
-      float acc[NCH][32];
+      // accumulator group g = (M half h, 64-column chunk ch), g = h * NCH + ch: TMEM columns g * 64 of a stage
+      constexpr int G = MH * NCH;
+      float acc[G][32];
 #pragma unroll
-      for (int ch = 0; ch < NCH; ++ch)
+      for (int g = 0; g < G; ++g)
 #pragma unroll
-        for (int j = 0; j < 32; ++j) acc[ch][j] = 0.f;
+        for (int j = 0; j < 32; ++j) acc[g][j] = 0.f;
 
       for (int kb = 0; kb < k_iters; kb += chunk) {
         const int as = it & 1;
@@ -325,17 +339,17 @@ gemm_tn_promote_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
         ++it;
         mbar_wait(&ctl->tmem_full[as], aph);
         tc_fence_after();
-        const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * bn + 32 * hf;
+        const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * (MH * bn) + 32 * hf;
 #pragma unroll
-        for (int ch = 0; ch < NCH; ++ch) {
+        for (int g = 0; g < G; ++g) {
           // 16 columns at a time: with 128 accumulators live, a 32-register landing buffer would spill
 #pragma unroll
           for (int hh = 0; hh < 2; ++hh) {
             uint32_t v[16];
-            tmem_ld_32x16(t_addr + ch * 64 + hh * 16, v);
+            tmem_ld_32x16(t_addr + g * 64 + hh * 16, v);
             tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 16; ++j) acc[ch][hh * 16 + j] += __uint_as_float(v[j]);
+            for (int j = 0; j < 16; ++j) acc[g][hh * 16 + j] += __uint_as_float(v[j]);
           }
         }
         tc_fence_before();
@@ -343,38 +357,40 @@ gemm_tn_promote_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
         if (lane == 0) mbar_arrive(&ctl->tmem_empty[as]);
       }
 
-      const int row = row0 + r;
-      bool row_live = row < p.rows;
-      if (p.wp > 0) row_live = row_live && ((row % p.wp) < p.w_valid);
-
       if (p.epi == EPI_ATOMIC_F32) {
-        if (row < p.rows) {
-          float* orow = p.d0 + (static_cast<size_t>(b) * p.rows + row) * p.ld0 + n0 + 32 * hf;
 #pragma unroll
-          for (int ch = 0; ch < NCH; ++ch)
+        for (int g = 0; g < G; ++g) {
+          const int row = row0 + (g / NCH) * BM + r;
+          if (row < p.rows) {
+            float* orow = p.d0 + (static_cast<size_t>(b) * p.rows + row) * p.ld0 + n0 + (g % NCH) * 64 + 32 * hf;
 #pragma unroll
             for (int j = 0; j < 8; ++j)
-              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(orow + ch * 64 + 4 * j),
-                           "f"(acc[ch][4 * j]), "f"(acc[ch][4 * j + 1]), "f"(acc[ch][4 * j + 2]),
-                           "f"(acc[ch][4 * j + 3])
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(orow + 4 * j), "f"(acc[g][4 * j]),
+                           "f"(acc[g][4 * j + 1]), "f"(acc[g][4 * j + 2]), "f"(acc[g][4 * j + 3])
                            : "memory");
+          }
         }
       } else if (p.epi == EPI_F32_STORE) {
-        if (row < p.rows) {
-          // ksplit > 1: one slice [batch][rows][ld0] per K split (summed in a fixed order by the finishing kernel)
-          float* orow = p.d0 + ((static_cast<size_t>(ks) * p.batch + b) * p.rows + row) * p.ld0 + n0 + 32 * hf;
 #pragma unroll
-          for (int ch = 0; ch < NCH; ++ch)
+        for (int g = 0; g < G; ++g) {
+          const int row = row0 + (g / NCH) * BM + r;
+          bool row_live = row < p.rows;
+          if (p.wp > 0) row_live = row_live && ((row % p.wp) < p.w_valid);
+          if (row < p.rows) {
+            // ksplit > 1: one slice [batch][rows][ld0] per K split (summed in a fixed order by the finishing kernel)
+            float* orow = p.d0 + ((static_cast<size_t>(ks) * p.batch + b) * p.rows + row) * p.ld0 + n0 +
+                          (g % NCH) * 64 + 32 * hf;
+            const float* bs = bias_s + (g % NCH) * 64 + 32 * hf;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               float4 o;
-              const float* bs = bias_s + ch * 64 + 32 * hf + 4 * j;
-              o.x = row_live ? acc[ch][4 * j] * p.alpha + bs[0] : 0.f;
-              o.y = row_live ? acc[ch][4 * j + 1] * p.alpha + bs[1] : 0.f;
-              o.z = row_live ? acc[ch][4 * j + 2] * p.alpha + bs[2] : 0.f;
-              o.w = row_live ? acc[ch][4 * j + 3] * p.alpha + bs[3] : 0.f;
-              *reinterpret_cast<float4*>(orow + ch * 64 + 4 * j) = o;
+              o.x = row_live ? acc[g][4 * j] * p.alpha + bs[4 * j] : 0.f;
+              o.y = row_live ? acc[g][4 * j + 1] * p.alpha + bs[4 * j + 1] : 0.f;
+              o.z = row_live ? acc[g][4 * j + 2] * p.alpha + bs[4 * j + 2] : 0.f;
+              o.w = row_live ? acc[g][4 * j + 3] * p.alpha + bs[4 * j + 3] : 0.f;
+              *reinterpret_cast<float4*>(orow + 4 * j) = o;
             }
+          }
         }
       } else {
         // triple output: hi chunk in staging buffer 0, lo chunk in buffer 1, three TMA stores per 64 columns
@@ -383,15 +399,19 @@ gemm_tn_promote_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
         const bool masked = p.epi == EPI_SPLIT3_MASK_F16;
         const bool relu = p.epi == EPI_SPLIT3_RELU_F16;
 #pragma unroll
-        for (int ch = 0; ch < NCH; ++ch) {
-          const int c0 = ch * 64;
+        for (int g = 0; g < G; ++g) {
+          const int c0 = (g % NCH) * 64;
+          const int rowg0 = row0 + (g / NCH) * BM;
+          const int row = rowg0 + r;
+          bool row_live = row < p.rows;
+          if (p.wp > 0) row_live = row_live && ((row % p.wp) < p.w_valid);
           if (warp == 2 && elect_one()) tma_store_wait_read<0>();
           named_bar_sync(1, EPI_THREADS);
           if (masked) {
             if (warp == 2 && elect_one()) {  // forward activation (hi, lo) tiles land in the staging buffers
               mbar_arrive_expect_tx(&ctl->aux_full, 2 * STAGING_BYTES);
-              tma_load_3d(staging, &map_aux, &ctl->aux_full, n0 + c0, row0, b);
-              tma_load_3d(staging + STAGING_BYTES, &map_aux, &ctl->aux_full, p.n_total + n0 + c0, row0, b);
+              tma_load_3d(staging, &map_aux, &ctl->aux_full, n0 + c0, rowg0, b);
+              tma_load_3d(staging + STAGING_BYTES, &map_aux, &ctl->aux_full, p.n_total + n0 + c0, rowg0, b);
             }
             mbar_wait(&ctl->aux_full, aux_ph);
             aux_ph ^= 1u;
@@ -404,7 +424,7 @@ gemm_tn_promote_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
             float f[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-              f[e] = acc[ch][j * 8 + e] * p.alpha + bias_s[c0 + jj * 8 + e];
+              f[e] = acc[g][j * 8 + e] * p.alpha + bias_s[c0 + jj * 8 + e];
               if (relu) f[e] = fmaxf(f[e], 0.f);
               if (!row_live) f[e] = 0.f;
             }
@@ -429,10 +449,11 @@ gemm_tn_promote_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
           }
           fence_proxy_async_smem();
           named_bar_sync(1, EPI_THREADS);
-          if (warp == 2 && elect_one()) {
-            tma_store_3d(&map_d, staging, n0 + c0, row0, b);
-            tma_store_3d(&map_d, staging + STAGING_BYTES, p.n_total + n0 + c0, row0, b);
-            tma_store_3d(&map_d, staging, 2 * p.n_total + n0 + c0, row0, b);
+          // (a half that starts beyond the last row has nothing to store: the box would lie outside the tensor)
+          if (warp == 2 && rowg0 < p.rows && elect_one()) {
+            tma_store_3d(&map_d, staging, n0 + c0, rowg0, b);
+            tma_store_3d(&map_d, staging + STAGING_BYTES, p.n_total + n0 + c0, rowg0, b);
+            tma_store_3d(&map_d, staging, 2 * p.n_total + n0 + c0, rowg0, b);
             tma_store_commit();
           }
         }
@@ -449,7 +470,7 @@ gemm_tn_promote_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
 
 int g_num_sms = 0;
 
-template <int NCH, bool ROWWIN>
+template <int NCH, bool ROWWIN, int MH>
 int launch_nch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& md, const CUtensorMap& mx,
                GemmTnParams& p, int max_ctas, cudaStream_t stream) {
   constexpr int bn = 64 * NCH;
@@ -458,13 +479,13 @@ int launch_nch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& 
   int smem_bytes;
   if (ROWWIN) {
     // A-window ring + B-tile ring: the B ring takes what 3 (N = 128) / 4 (N = 64) windows leave
-    const int a_slots = NCH == 1 ? 4 : 3;
-    int b_slots = (232448 - fixed - a_slots * WIN_BYTES) / (bn * BK * 2);
+    const int a_slots = (NCH == 1 && MH == 1) ? 4 : 3;
+    int b_slots = (232448 - fixed - a_slots * MH * WIN_BYTES) / (bn * BK * 2);
     if (b_slots > RW_MAX_B) b_slots = RW_MAX_B;
     if (b_slots < 4) return 1005;
     p.stages = a_slots;
     p.b_resident = b_slots;
-    smem_bytes = a_slots * WIN_BYTES + b_slots * bn * BK * 2 + fixed;
+    smem_bytes = a_slots * MH * WIN_BYTES + b_slots * bn * BK * 2 + fixed;
   } else {
     int stages = (232448 - fixed) / stage_bytes;
     if (stages > 8) stages = 8;
@@ -474,21 +495,21 @@ int launch_nch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& 
   }
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tn_promote_kernel<NCH, ROWWIN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(gemm_tn_promote_kernel<NCH, ROWWIN, MH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          232448);
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
-  const int m_tiles = (p.rows + BM - 1) / BM;
+  const int m_tiles = (p.rows + BM * MH - 1) / (BM * MH);
   const int num_tiles = m_tiles * (p.n_total / bn) * p.batch * p.ksplit;
   int grid = num_tiles < g_num_sms ? num_tiles : g_num_sms;
   if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
   if (grid < 1) return 0;
-  gemm_tn_promote_kernel<NCH, ROWWIN><<<grid, NUM_THREADS, smem_bytes, stream>>>(ma, mb, md, mx, p);
+  gemm_tn_promote_kernel<NCH, ROWWIN, MH><<<grid, NUM_THREADS, smem_bytes, stream>>>(ma, mb, md, mx, p);
   const cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) {
     cudaFuncAttributes fa;
-    if (cudaFuncGetAttributes(&fa, gemm_tn_promote_kernel<NCH, ROWWIN>) == cudaSuccess)
+    if (cudaFuncGetAttributes(&fa, gemm_tn_promote_kernel<NCH, ROWWIN, MH>) == cudaSuccess)
       fprintf(stderr, "gemm_tn_promote_kernel<%d>: launch failed (%s): regs %d, maxThreadsPerBlock %d, static smem %zu, "
               "max dynamic smem %d, requested %d threads / %d B\n", NCH, cudaGetErrorString(err), fa.numRegs,
               fa.maxThreadsPerBlock, fa.sharedSizeBytes, fa.maxDynamicSharedSizeBytes, NUM_THREADS, smem_bytes);
@@ -594,14 +615,22 @@ int gemm_tn_promote_launch(const GemmTnArgs& a, int chunk, cudaStream_t stream) 
     // 2.5e-7 / 8.6e-7 / 2.1e-6 relative error against fp64
     // N = 256: a k-iteration is 1536 tensor cycles, one promotion per k-iteration costs nothing (chains of 12 MMAs)
     p.chunk = rw_chunk > 0 ? rw_chunk : (a.bn == 256 ? 1 : 3);
-    return a.bn == 64    ? launch_nch<1, true>(ma, mb, md, mx, p, a.max_ctas, stream)
-           : a.bn == 128 ? launch_nch<2, true>(ma, mb, md, mx, p, a.max_ctas, stream)
-                         : launch_nch<4, true>(ma, mb, md, mx, p, a.max_ctas, stream);
+    static int mh_opt = -1;
+    if (mh_opt < 0) {
+      const char* e = getenv("PTB200_X3_MH");
+      mh_opt = e ? atoi(e) : 2;
+    }
+    if (a.bn == 256) return launch_nch<4, true, 1>(ma, mb, md, mx, p, a.max_ctas, stream);
+    if (mh_opt == 2 && a.rows > 2 * BM)
+      return a.bn == 64 ? launch_nch<1, true, 2>(ma, mb, md, mx, p, a.max_ctas, stream)
+                        : launch_nch<2, true, 2>(ma, mb, md, mx, p, a.max_ctas, stream);
+    return a.bn == 64 ? launch_nch<1, true, 1>(ma, mb, md, mx, p, a.max_ctas, stream)
+                      : launch_nch<2, true, 1>(ma, mb, md, mx, p, a.max_ctas, stream);
   }
   switch (a.bn) {
-    case 64: return launch_nch<1, false>(ma, mb, md, mx, p, a.max_ctas, stream);
-    case 128: return launch_nch<2, false>(ma, mb, md, mx, p, a.max_ctas, stream);
-    default: return launch_nch<4, false>(ma, mb, md, mx, p, a.max_ctas, stream);
+    case 64: return launch_nch<1, false, 1>(ma, mb, md, mx, p, a.max_ctas, stream);
+    case 128: return launch_nch<2, false, 1>(ma, mb, md, mx, p, a.max_ctas, stream);
+    default: return launch_nch<4, false, 1>(ma, mb, md, mx, p, a.max_ctas, stream);
   }
 }
 

@@ -59,12 +59,13 @@ def gemm_tn(A, B, *, taps=1, shifts=None, bn=None, epi=EPI_BIAS, bias=None, out=
     if ksplit > 1:
         # skinny problem: split the reduction over CTAs, reduce partials in fp32, then bias/act/cast
         assert epi in (EPI_BIAS_RELU, EPI_BIAS) and aux is None
-        acc = torch.zeros(batch, rows, n_total, dtype=torch.float32, device=A.device)
+        # (one slice per K split, added in a fixed order: no atomics in the forward; dead segment tiles read as zero)
+        acc = alloc(ksplit, batch, rows, n_total, dtype=torch.float32, device=A.device)
         call("ptb200_gemm_tn_f16", A, batch, rows, k, lda, rows * lda, taps, shifts, B, n_total, bn, EPI_ATOMIC, None,
-             0, None, 0, 0, None, 0, 0, acc, n_total, None, 0, 0, n_total, GEMM_MAX_CTAS[0], ksplit, seg_counts, seg_cap)
+             0, None, 0, 0, None, 0, 0, acc, n_total, None, 0, 1, n_total, GEMM_MAX_CTAS[0], ksplit, seg_counts, seg_cap)
         if out is None:
             out = torch.empty(batch, rows, n_total, dtype=torch.float16, device=A.device)
-        call("ptb200_bias_act_cast_f16", acc, bias, 1 if epi == EPI_BIAS_RELU else 0, batch * rows, n_total, out)
+        call("ptb200_bias_act_cast_f16", acc, ksplit, bias, 1 if epi == EPI_BIAS_RELU else 0, batch * rows, n_total, out)
         return out
     if epi == EPI_F32_SPLIT:
         if d0 is None:
