@@ -38,8 +38,15 @@ def main():
     cfg.UNSUPNET.BURN_UP_STEP = 0
     pool = synthetic_pool(2, 2, H, W, 8, 1234 + 100 * rank, device=dev)
     tr = PTrainer(cfg, cycle(pool), device=dev, seed=0, use_cuda_graph=True, concurrent=True, precision=args.precision)
-    for _ in range(steps):
+    trace = os.environ.get("PTB200_TRACE_STEPS", "0") == "1"
+    if trace:  # a hung run dumps every thread's Python stack and exits on its own
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ.get("PTB200_TRACE_TIMEOUT", "70")), exit=True)
+    for i in range(steps):
         tr.step()
+        if trace:
+            torch.cuda.synchronize()
+            print(f"[rank {rank}] step {i} done", file=sys.stderr, flush=True)
     torch.cuda.synchronize()
     ok = True
     # cross-rank metric reduction (pt/engine/trainer.py:394-429): the losses that rode on the gradient all-reduce
