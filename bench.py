@@ -439,6 +439,7 @@ def run_arm(precision, args, cfg, pool_dev, pool_host, dist, device, world, rank
            "kernels_ms_per_step": {k.replace("ptb200_", ""): round(v, 4) for k, v in
                                    sorted(other_ms.items(), key=lambda kv: -kv[1])[:14]},
            "roialign": roi_stats}
+    trainer.release_graphs()
     del trainer
     torch.cuda.empty_cache()
     return out
@@ -493,6 +494,9 @@ def backbone_microbench(device, peaks, N=1, H=1024, W=2048, reps=9):
 
 
 def main():
+    if os.environ.get("PTB200_WATCHDOG_S"):  # experiments: a hung run dumps every thread's stack and exits by itself
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ["PTB200_WATCHDOG_S"]), exit=True)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)

@@ -1,10 +1,13 @@
 """Data-parallel plumbing (one process per GPU, torch.distributed): parameter broadcast at start-up
 (`pt/engine/trainer.py:491-496`, DDP `_sync_params_and_buffers`) and the per-step gradient all-reduce
-that torch DDP performs for the reference (`trainer.py:92-95,384`): ONE SUM all-reduce over the flat fp32 gradient
-arena issued after the step's backward (`bucket_elems` can cut it into several collectives; the trainer uses one),
-with the step's loss scalars riding in a 16-float tail of the same buffer (the reference's cross-rank metric mean,
-`trainer.py:394-429`). The 1/world averaging is folded into the clip/SGD kernel (`pre_scale`). The collective is NOT
-overlapped with the backward: the in-graph variant of round 1 dead-locked at full size."""
+that torch DDP performs for the reference (`trainer.py:92-95,384`): SUM all-reduce over the flat fp32 gradient
+arena, with the step's loss scalars riding in a 16-float tail of the same buffer (the reference's cross-rank metric
+mean, `trainer.py:394-429`). The 1/world averaging is folded into the clip/SGD kernel (`pre_scale`).
+Eager steps issue ONE collective after the backward (`allreduce_grads`; `bucket_elems` can cut it into several). The
+CUDA-graph step of `engine/trainer.py` (`_graph_body_concurrent`) issues two buckets inside the graph: everything
+behind the VGG backbone as soon as both student passes have finished their head backward (overlapping the backbone
+backward), the backbone bucket after the join; the metrics tail follows eagerly. A graph that holds captured NCCL
+kernels must be released before `dist.destroy_process_group()` (`PTrainer.release_graphs`)."""
 import torch
 import torch.distributed as dist
 

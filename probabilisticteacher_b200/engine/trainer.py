@@ -65,12 +65,14 @@ class PTrainer:
         self._prefetched = None
         self._slot = 0
         self._grads_reduced = False
-        # EXPERIMENTAL, off by default (PTB200_OVERLAP_ALLREDUCE=1): world > 1 + concurrent graph step, all-reduce
-        # the head gradients inside the graph while the backbone backward runs. tools/check_ddp.py passes with it
-        # on 2 GPUs at 320x480 (bit-identical replicas), but bench.py at 3x800x1333 hangs with it (round 1, cause
-        # not found: NCCL kernels co-scheduled with one-CTA-per-SM persistent GEMMs are the suspect). The default
-        # is the single eager all-reduce after the graph (0.4 ms of 14.7 ms at 2 GPUs).
-        self.overlap_allreduce = os.environ.get("PTB200_OVERLAP_ALLREDUCE", "0") == "1"
+        # world > 1 + concurrent graph step: the gradients behind the VGG backbone (29.3 M of 43.8 M floats) are
+        # all-reduced INSIDE the graph on a communication stream while the backbone backward still runs, the backbone
+        # bucket after the join (torch DDP's bucketed overlap, pt/engine/trainer.py:92-95). Round 1 recorded a "hang at
+        # full size": every step ran, the process then blocked in dist.destroy_process_group() because the live graph
+        # still held captured NCCL kernels -- call release_graphs() before tearing the process group down (bench.py and
+        # tools/check_ddp.py do). Measured (profiles/r2b_allreduce_overlap_ab.json): 8 GPUs 37.18 -> 36.94 ms (f16x3),
+        # 14.74 -> 14.69 ms (f16); nothing at 2 GPUs. PTB200_OVERLAP_ALLREDUCE=0 selects the single eager all-reduce.
+        self.overlap_allreduce = os.environ.get("PTB200_OVERLAP_ALLREDUCE", "1") == "1"
         self.concurrent_gemm_ctas = int(os.environ.get("PTB200_GEMM_CTAS", "0"))  # 0 = one CTA per SM
 
     # ------------------------------------------------------------------ pseudo-labelling (trainer.py:179-257)
@@ -628,6 +630,20 @@ class PTrainer:
             dist.broadcast(self.model.arena.momentum, src=0)
         # the captured graph holds no parameter values (it reads the arenas), so it stays valid
         return self.start_iter
+
+    def release_graphs(self):
+        """Drops the captured step graph (and what it keeps alive). Call before `dist.destroy_process_group()` when the
+        graph holds captured NCCL kernels (in-graph gradient all-reduce): tearing the communicator down under a live
+        graph blocks inside destroy_process_group (measured: every step of tools/check_ddp.py passed at 800x1333 and
+        the process then hung there -- the "hang at full size" of round 1)."""
+        import gc
+        torch.cuda.synchronize(self.device)
+        self._graph = None
+        self._graph_losses = None
+        self._keep = None
+        self._prefetched = None
+        gc.collect()
+        torch.cuda.synchronize(self.device)
 
     def step(self):
         if self.use_cuda_graph and self.iter > self.cfg.UNSUPNET.BURN_UP_STEP:

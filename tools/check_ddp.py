@@ -84,6 +84,7 @@ def main():
         print(f"all-reduce(SUM) vs all-gather reference: max abs err {err:.3e}")
         print("losses (rank 0):", {k: round(float(v), 5) for k, v in tr.last_losses.items()})
         print("DDP CHECK", "PASSED" if ok and err < 1e-5 else "FAILED")
+    tr.release_graphs()
     dist.destroy_process_group()
     return 0 if ok else 1
 
