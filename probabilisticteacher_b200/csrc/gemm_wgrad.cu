@@ -17,9 +17,7 @@
 namespace ptb {
 
 static constexpr int WG_BM = 128;   // output-channel tile (UMMA M)
-static constexpr int WG_BK = 64;    // reduction rows per stage
 static constexpr int WG_THREADS = 192;
-static constexpr int WG_BLK_BYTES = WG_BK * 128;  // one [64 rows][64 ch] box
 
 struct WgCtl {
   uint64_t full[8];
@@ -56,10 +54,10 @@ __device__ __forceinline__ void tma_load_4d(void* smem, const CUtensorMap* m, ui
       : "memory");
 }
 
-__device__ __forceinline__ bool chunk_live(const int* __restrict__ seg_counts, int seg_cap, int r0, int rows) {
+__device__ __forceinline__ bool chunk_live(const int* __restrict__ seg_counts, int seg_cap, int r0, int rows, int bk) {
   if (seg_counts == nullptr) return true;
   int r = r0;
-  const int rend = min(r0 + WG_BK, rows);
+  const int rend = min(r0 + bk, rows);
   while (r < rend) {
     const int n = r / seg_cap;
     if (r - n * seg_cap < min(seg_counts[n], seg_cap)) return true;
@@ -72,15 +70,19 @@ __device__ __forceinline__ bool chunk_live(const int* __restrict__ seg_counts, i
 // operands and the accumulator receives Gh'Xh + Gl'Xh + Gh'Xl (12 MMAs per 64-row chunk instead of 4). One fused
 // launch instead of three passes of the plain kernel over column slices: a stage moves 2x the bytes for 3x the
 // MMAs, which lifts the kernel off its L2 -> shared-memory bound (48 KB per 512 tensor cycles at BN = 256).
-template <bool X3>
+// WG_BK = reduction rows per stage (one [WG_BK rows][64 ch] box per 64-channel block): 64 for the fp16 kernel; the X3
+// kernel runs 32-row stages -- four 48 KB stages instead of two of 96 KB, same bytes in flight but every load is
+// issued a stage-time earlier (measured per step: 7.83 -> 7.24 ms, 1 152 -> 1 243 TFLOP/s; PTB200_WG_BK=64 restores).
+template <bool X3, int WG_BK>
 __global__ void __launch_bounds__(WG_THREADS, 2)
 gemm_wgrad_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant__ CUtensorMap map_x,
                   const WgParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
+  constexpr int WG_BLK_BYTES = WG_BK * 128;  // one [WG_BK rows][64 ch] box
   const int bn = p.bn;
-  const int a_bytes = (WG_BM / 64) * WG_BLK_BYTES;  // 16 KB
+  const int a_bytes = (WG_BM / 64) * WG_BLK_BYTES;  // 16 KB at WG_BK = 64
   const int b_bytes = (bn / 64) * WG_BLK_BYTES;
   // stage layout: [Gh][Gl (X3)][Xh][Xl (X3)]
   const int stage_bytes = (X3 ? 2 : 1) * (a_bytes + b_bytes);
@@ -109,7 +111,7 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_consta
   int k_iters = c_end - c_begin;
   if (p.seg_counts != nullptr) {  // count the live chunks of this CTA's range (every role does the same)
     k_iters = 0;
-    for (int c = c_begin; c < c_end; ++c) k_iters += chunk_live(p.seg_counts, p.seg_cap, c * WG_BK, p.rows) ? 1 : 0;
+    for (int c = c_begin; c < c_end; ++c) k_iters += chunk_live(p.seg_counts, p.seg_cap, c * WG_BK, p.rows, WG_BK) ? 1 : 0;
   }
 
   uint32_t tmem_cols = 32;
@@ -144,7 +146,7 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_consta
       for (int c = c_begin; c < c_end; ++c) {
         const int b = c / chunks_per_img;
         const int r0 = (c - b * chunks_per_img) * WG_BK;
-        if (!chunk_live(p.seg_counts, p.seg_cap, r0, p.rows)) continue;
+        if (!chunk_live(p.seg_counts, p.seg_cap, r0, p.rows, WG_BK)) continue;
         mbar_wait(&ctl->empty[s], ph ^ 1);
         if (elect_one()) {
           uint8_t* sa = smem + s * stage_bytes;
@@ -222,8 +224,8 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_consta
           for (int part = 0; part < (X3 ? 2 : 1); ++part) {  // X3: Gh then Gl (sum of both = the fp32 gradient)
             const uint8_t* gp = g + part * a_bytes;
 #pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              const int kr0 = half_ * 32 + i, kr1 = kr0 + 1;
+            for (int i = 0; i < WG_BK / 2; i += 2) {
+              const int kr0 = half_ * (WG_BK / 2) + i, kr1 = kr0 + 1;
               const __half2 a = *reinterpret_cast<const __half2*>(gp + kr0 * 128 + (((col >> 3) ^ (kr0 & 7)) << 4));
               const __half2 b = *reinterpret_cast<const __half2*>(gp + kr1 * 128 + (((col >> 3) ^ (kr1 & 7)) << 4));
               const float2 fa = __half22float2(a), fb = __half22float2(b);
@@ -278,7 +280,7 @@ int gemm_wgrad_launch(const void* G, int64_t ldg, int64_t g_batch_stride, const 
                       const int* seg_counts, int seg_cap, cudaStream_t stream, bool x3) {
   if (seg_counts != nullptr && (batch != 1 || seg_cap <= 0)) return 1103;
   if (m_total % WG_BM != 0 || n_total % 64 != 0 || taps < 1 || taps > 9) return 1101;
-  int bn = 256;  // (x3 stages hold hi + lo tiles of both operands: 96 KB per stage at BN = 256, two stages)
+  int bn = 256;  // (x3 stages hold hi + lo tiles of both operands: 48 KB per 32-row stage at BN = 256, four stages)
   while (n_total % bn != 0) bn >>= 1;
   if (bn < 64) return 1102;
   if (x3 && (ldg < 3 * m_total || ldx < 3 * n_total)) return 1104;
@@ -287,17 +289,24 @@ int gemm_wgrad_launch(const void* G, int64_t ldg, int64_t g_batch_stride, const 
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&g_wg_sms, cudaDevAttrMultiProcessorCount, dev);
   }
+  static int bk_opt = -1;
+  if (bk_opt < 0) {
+    const char* e = getenv("PTB200_WG_BK");
+    bk_opt = (e && atoi(e) == 64) ? 64 : 32;
+  }
+  const int WG_BK = x3 ? bk_opt : 64;
+  const int WG_BLK_BYTES = WG_BK * 128;
   CUtensorMap mg, mx;
   {
     uint64_t dims[4] = {64, (uint64_t)rows, (uint64_t)((x3 ? 3 : 1) * m_total / 64), (uint64_t)batch};
     uint64_t str[3] = {(uint64_t)ldg * 2, 128, (uint64_t)g_batch_stride * 2};
-    uint32_t box[4] = {64, WG_BK, (uint32_t)(WG_BM / 64), 1};
+    uint32_t box[4] = {64, (uint32_t)WG_BK, (uint32_t)(WG_BM / 64), 1};
     if (make_tmap_f16(&mg, G, 4, dims, str, box)) return 1110;
   }
   {
     uint64_t dims[4] = {64, (uint64_t)rows, (uint64_t)((x3 ? 3 : 1) * n_total / 64), (uint64_t)batch};
     uint64_t str[3] = {(uint64_t)ldx * 2, 128, (uint64_t)x_batch_stride * 2};
-    uint32_t box[4] = {64, WG_BK, (uint32_t)(bn / 64), 1};
+    uint32_t box[4] = {64, (uint32_t)WG_BK, (uint32_t)(bn / 64), 1};
     if (make_tmap_f16(&mx, X, 4, dims, str, box)) return 1111;
   }
   WgParams p;
@@ -318,7 +327,8 @@ int gemm_wgrad_launch(const void* G, int64_t ldg, int64_t g_batch_stride, const 
   const int total_chunks = ((rows + WG_BK - 1) / WG_BK) * batch;
   if (ksplit <= 0) {
     ksplit = g_wg_sms / tiles;                       // aim at one full wave of CTAs
-    const int max_split = (total_chunks + 31) / 32;  // at least 32 k-iterations per CTA
+    const int per_cta = 2048 / WG_BK;                          // at least 2048 reduction rows per CTA
+    const int max_split = (total_chunks + per_cta - 1) / per_cta;
     if (ksplit > max_split) ksplit = max_split;
     if (ksplit < 1) ksplit = 1;
   }
@@ -340,16 +350,20 @@ int gemm_wgrad_launch(const void* G, int64_t ldg, int64_t g_batch_stride, const 
   const int smem_bytes = stages * stage_bytes + (int)sizeof(WgCtl) + 1024;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_wgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    cudaError_t e = cudaFuncSetAttribute(gemm_wgrad_kernel<false, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
     if (e != cudaSuccess) return (int)e;
-    e = cudaFuncSetAttribute(gemm_wgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    e = cudaFuncSetAttribute(gemm_wgrad_kernel<true, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(gemm_wgrad_kernel<true, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
-  if (x3)
-    gemm_wgrad_kernel<true><<<tiles * ksplit, WG_THREADS, smem_bytes, stream>>>(mg, mx, p);
+  if (x3 && WG_BK == 32)
+    gemm_wgrad_kernel<true, 32><<<tiles * ksplit, WG_THREADS, smem_bytes, stream>>>(mg, mx, p);
+  else if (x3)
+    gemm_wgrad_kernel<true, 64><<<tiles * ksplit, WG_THREADS, smem_bytes, stream>>>(mg, mx, p);
   else
-    gemm_wgrad_kernel<false><<<tiles * ksplit, WG_THREADS, smem_bytes, stream>>>(mg, mx, p);
+    gemm_wgrad_kernel<false, 64><<<tiles * ksplit, WG_THREADS, smem_bytes, stream>>>(mg, mx, p);
   return (int)cudaGetLastError();
 }
 
