@@ -414,8 +414,9 @@ def run_arm(precision, args, cfg, pool_dev, pool_host, dist, device, world, rank
     roofline = {
         "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
         "traffic": traffic,
-        "traffic_note": "mean DRAM read+write bytes per launch of the dominant kernel, ncu --set full pass over one "
-                        "step (profiles/r2_gemm_dram_traffic.json); null until captured for this build",
+        "traffic_note": "mean DRAM read+write bytes per launch of the dominant kernel, ncu dram__bytes_{read,write}.sum "
+                        "over every launch of one eager step (profiles/r2_gemm_dram_traffic.json, "
+                        "profiles/r2b_gemm_launches_f16x3.json)",
         "kernel": "gemm_tn_promote_kernel (ptb200_gemm_tn_f16x3)" if precision == "f16x3" else "gemm_tn_kernel (ptb200_gemm_tn_f16)",
         "launches_per_step": tn["launches_per_step"], "kernel_ms_per_step": tn_ms, "kernel_ms_per_step_min": tn["ms_min"],
         "timing": f"CUDA events around every launch over {profile_steps} eager steps run back to back after warm-up; "
