@@ -93,7 +93,10 @@ def test_promotion_removes_the_truncation_bias(cuda):
     assert signed1 < -5e-5
 
 
-@pytest.mark.parametrize("Cin,Cout,H,W,pooled", [(128, 256, 24, 38, False), (256, 256, 25, 37, True), (512, 512, 12, 17, False)])
+@pytest.mark.parametrize("Cin,Cout,H,W,pooled", [(128, 256, 24, 38, False), (256, 256, 25, 37, True), (512, 512, 12, 17, False),
+                                                 # data gradients with N = Cin <= 128: the 256-row row-window tiles with the
+                                                 # ReLU-mask and the fp32 epilogues (VGG blocks 1-2 when they are not frozen)
+                                                 (64, 128, 31, 45, False), (128, 128, 20, 33, True), (64, 128, 9, 300, False)])
 def test_conv_backward_x3_vs_fp64(cuda, Cin, Cout, H, W, pooled):
     """Data gradient (ReLU mask fused, or fp32 out + max-pool/ReLU backward) and weight / bias gradients of one
     VGG layer against fp64 autograd."""
