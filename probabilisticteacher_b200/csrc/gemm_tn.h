@@ -43,6 +43,7 @@ struct GemmTnParams {
   const int* seg_counts;  // optional: rows are [segments][seg_cap], only the first seg_counts[s] rows of a
   int seg_cap;            // segment are live; 128-row tiles without any live row are skipped entirely
   int chunk = 0;          // gemm_tn_x3.cu: k-iterations (of 64) per fp32 promotion of the TMEM partial sums
+  int hi_share = 0;       // gemm_tn_x3.cu row-window mode: one `hi` A window serves the Wh AND the Wl products
 };
 
 struct GemmTnArgs {

@@ -45,7 +45,10 @@ constexpr int EPI_THREADS = 256;
 // A ring holds 136-row windows (rows p0 + (ky-1)*Wp - 1 ...) shared by the three horizontal taps of a filter row --
 // the taps are UMMA descriptors offset by kx*128 B, SWIZZLE_128B being a function of absolute shared-memory address
 // bits (tools/exp_rowshift.cu) -- and the B tiles travel through a ring of their own (one tile per tap and K chunk),
-// so a slot is recycled as soon as its 4 MMAs retire: 2.8x fewer A bytes through L2.
+// so a slot is recycled as soon as its 4 MMAs retire: 2.8x fewer A bytes through L2. With hi_share the k-iterations of
+// a filter row are (hi_j, lo_j) pairs: the `hi` window of channel chunk j is loaded ONCE and multiplied with the Wh
+// tiles (K chunk j) and the Wl tiles (K chunk 2C/64 + j) -- the [hi | lo | hi] triple holds it twice --, the `lo`
+// window with the second Wh copy: a third fewer A bytes again.
 constexpr int WIN_ROWS = 136;
 constexpr int WIN_BYTES = WIN_ROWS * 128;  // 17 * 1024
 constexpr int RW_MAX_A = 4;
@@ -120,7 +123,10 @@ gemm_tn_promote_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
   const int ksplit = p.ksplit;
   const int num_tiles = tiles_per_batch * p.batch * ksplit;
   const int k_chunks = p.k_per_tap / BK;
-  const int k_iters_total = k_chunks * (ROWWIN ? 3 : p.taps);  // ROWWIN: one k-iteration = a filter row's 3 taps
+  // ROWWIN: one k-iteration = a filter row's 3 taps over one A window; hi_share: 2 windows (hi, lo) per channel chunk
+  const bool hi_share = ROWWIN && p.hi_share != 0;
+  const int kc3 = k_chunks / 3;
+  const int k_iters_total = ROWWIN ? 3 * (hi_share ? 2 * kc3 : k_chunks) : k_chunks * p.taps;
   const int chunk = p.chunk;
 
   constexpr uint32_t tmem_cols = 2 * MH * bn < 32 ? 32 : 2 * MH * bn;  // 128 / 256 / 512: powers of two
@@ -179,9 +185,16 @@ gemm_tn_promote_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
         if (!tile_live(p.seg_counts, p.seg_cap, row0, p.rows)) continue;
         const int ki0 = (k_iters_total * ks) / ksplit, ki1 = (k_iters_total * (ks + 1)) / ksplit;
         for (int ki = ki0; ki < ki1; ++ki) {
-          const int t = ki / k_chunks, kc = ki - t * k_chunks;
+          int t = ki / k_chunks, kc = ki - t * k_chunks;
           if (ROWWIN) {
             // t = filter row ky: the window starts one pixel left of the kx = 0 tap
+            int kc_b2 = -1;  // hi_share, hi window: second B chunk (the Wl tiles)
+            if (hi_share) {
+              t = ki / (2 * kc3);
+              const int rr = ki - t * 2 * kc3, j = rr >> 1;
+              kc = (rr & 1) ? kc3 + j : j;
+              if (!(rr & 1)) kc_b2 = 2 * kc3 + j;
+            }
             mbar_wait(&ctl->empty_a[s], ph ^ 1);
             mbar_arrive_expect_tx(&ctl->full_a[s], a_slot_bytes);
 #pragma unroll
@@ -193,13 +206,15 @@ gemm_tn_promote_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
               ph ^= 1;
             }
             for (int kx = 0; kx < 3; ++kx) {
-              mbar_wait(&ctl->empty_b[sb], phb ^ 1);
-              mbar_arrive_expect_tx(&ctl->full_b[sb], b_tile_bytes);
-              tma_load_2d(ring_b + sb * b_tile_bytes, &map_b, &ctl->full_b[sb], (t * 3 + kx) * p.k_per_tap + kc * BK,
-                          n0);
-              if (++sb == b_slots) {
-                sb = 0;
-                phb ^= 1;
+              for (int g = 0; g < (kc_b2 >= 0 ? 2 : 1); ++g) {
+                mbar_wait(&ctl->empty_b[sb], phb ^ 1);
+                mbar_arrive_expect_tx(&ctl->full_b[sb], b_tile_bytes);
+                tma_load_2d(ring_b + sb * b_tile_bytes, &map_b, &ctl->full_b[sb],
+                            (t * 3 + kx) * p.k_per_tap + (g == 0 ? kc : kc_b2) * BK, n0);
+                if (++sb == b_slots) {
+                  sb = 0;
+                  phb ^= 1;
+                }
               }
             }
             continue;
@@ -246,7 +261,10 @@ gemm_tn_promote_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
           if (ROWWIN) {
             mbar_wait(&ctl->full_a[s], ph);
             const uint64_t da = umma_desc_sw128(smem_u32(smem + s * a_slot_bytes), 16, 1024);
-            for (int kx = 0; kx < 3; ++kx) {
+            // hi_share: even k-iterations of a tile hold a `hi` window that meets two B tiles per tap (Wh, Wl)
+            const int nb = (hi_share && !((kb + ki) & 1)) ? 6 : 3;
+            for (int bt = 0; bt < nb; ++bt) {
+              const int kx = nb == 6 ? bt >> 1 : bt;
               mbar_wait(&ctl->full_b[sb], phb);
               tc_fence_after();
               if (elect_one()) {
@@ -256,10 +274,10 @@ gemm_tn_promote_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
                   const uint64_t dax = da + (h * WIN_BYTES >> 4) + (128 >> 4) * kx;  // half h, one pixel row further
 #pragma unroll
                   for (int k = 0; k < BK / 16; ++k)
-                    umma_f16_ss(d_tmem + h * bn, dax + 2 * k, db + 2 * k, idesc, (ki > 0 || kx > 0 || k > 0) ? 1u : 0u);
+                    umma_f16_ss(d_tmem + h * bn, dax + 2 * k, db + 2 * k, idesc, (ki > 0 || bt > 0 || k > 0) ? 1u : 0u);
                 }
                 umma_commit(&ctl->empty_b[sb]);
-                if (kx == 2) {
+                if (bt == nb - 1) {
                   umma_commit(&ctl->empty_a[s]);
                   if (ki == kn - 1) umma_commit(&ctl->tmem_full[as]);
                 }
@@ -614,7 +632,17 @@ int gemm_tn_promote_launch(const GemmTnArgs& a, int chunk, cudaStream_t stream) 
     // B200 at full size, conv1_2: chunk 1 / 3 / 9 = 0.681 / 0.609 / 0.592 ms per 2 images (per-tap kernel 0.725) at
     // 2.5e-7 / 8.6e-7 / 2.1e-6 relative error against fp64
     // N = 256: a k-iteration is 1536 tensor cycles, one promotion per k-iteration costs nothing (chains of 12 MMAs)
-    p.chunk = rw_chunk > 0 ? rw_chunk : (a.bn == 256 ? 1 : 3);
+    static int hs_opt = -1;
+    if (hs_opt < 0) {
+      const char* e = getenv("PTB200_X3_HISHARE");
+      hs_opt = e ? atoi(e) : 1;
+    }
+    p.hi_share = hs_opt != 0 ? 1 : 0;
+    // hi_share: a (hi, lo) pair of k-iterations is 24 + 12 MMAs: promote per pair at N <= 128, per window at N = 256
+    if (p.hi_share)
+      p.chunk = rw_chunk > 0 ? rw_chunk : (a.bn == 256 ? 1 : 2);
+    else
+      p.chunk = rw_chunk > 0 ? rw_chunk : (a.bn == 256 ? 1 : 3);
     static int mh_opt = -1;
     if (mh_opt < 0) {
       const char* e = getenv("PTB200_X3_MH");
