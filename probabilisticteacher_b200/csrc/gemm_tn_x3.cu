@@ -48,7 +48,10 @@ constexpr int EPI_THREADS = 256;
 // so a slot is recycled as soon as its 4 MMAs retire: 2.8x fewer A bytes through L2. With hi_share the k-iterations of
 // a filter row are (hi_j, lo_j) pairs: the `hi` window of channel chunk j is loaded ONCE and multiplied with the Wh
 // tiles (K chunk j) and the Wl tiles (K chunk 2C/64 + j) -- the [hi | lo | hi] triple holds it twice --, the `lo`
-// window with the second Wh copy: a third fewer A bytes again.
+// window with the second Wh copy: a third fewer A bytes again. hi_share == 2 ("pair mode") goes one step further: a
+// k-iteration is the PAIR (hi_j, lo_j) of windows, both resident, and every Wh tile is loaded once for both of them
+// (the [Wh | Wh | Wl] triple holds it twice): 6 instead of 9 B tiles per pair, a third fewer B bytes -- B is the
+// larger part of the L2 traffic at N = 256.
 constexpr int WIN_ROWS = 136;
 constexpr int WIN_BYTES = WIN_ROWS * 128;  // 17 * 1024
 constexpr int RW_MAX_A = 4;
@@ -124,9 +127,10 @@ gemm_tn_promote_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
   const int num_tiles = tiles_per_batch * p.batch * ksplit;
   const int k_chunks = p.k_per_tap / BK;
   // ROWWIN: one k-iteration = a filter row's 3 taps over one A window; hi_share: 2 windows (hi, lo) per channel chunk
-  const bool hi_share = ROWWIN && p.hi_share != 0;
+  const bool hi_share = ROWWIN && p.hi_share == 1;
+  const bool pair_mode = ROWWIN && p.hi_share == 2;
   const int kc3 = k_chunks / 3;
-  const int k_iters_total = ROWWIN ? 3 * (hi_share ? 2 * kc3 : k_chunks) : k_chunks * p.taps;
+  const int k_iters_total = ROWWIN ? 3 * (pair_mode ? kc3 : hi_share ? 2 * kc3 : k_chunks) : k_chunks * p.taps;
   const int chunk = p.chunk;
 
   constexpr uint32_t tmem_cols = 2 * MH * bn < 32 ? 32 : 2 * MH * bn;  // 128 / 256 / 512: powers of two
@@ -186,6 +190,33 @@ gemm_tn_promote_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
         const int ki0 = (k_iters_total * ks) / ksplit, ki1 = (k_iters_total * (ks + 1)) / ksplit;
         for (int ki = ki0; ki < ki1; ++ki) {
           int t = ki / k_chunks, kc = ki - t * k_chunks;
+          if (ROWWIN && pair_mode) {
+            t = ki / kc3;
+            const int j = ki - t * kc3;
+            for (int part = 0; part < 2; ++part) {  // the hi window(s), then the lo window(s): two consecutive A slots
+              mbar_wait(&ctl->empty_a[s], ph ^ 1);
+              mbar_arrive_expect_tx(&ctl->full_a[s], a_slot_bytes);
+#pragma unroll
+              for (int h = 0; h < MH; ++h)
+                tma_load_3d(smem + s * a_slot_bytes + h * WIN_BYTES, &map_a, &ctl->full_a[s], (part ? kc3 + j : j) * BK,
+                            row0 + h * BM + (t - 1) * p.wp - 1, b);
+              if (++s == stages) {
+                s = 0;
+                ph ^= 1;
+              }
+            }
+            for (int bt = 0; bt < 6; ++bt) {  // per tap: the Wh tile (for hi and lo), then the Wl tile (for hi)
+              mbar_wait(&ctl->empty_b[sb], phb ^ 1);
+              mbar_arrive_expect_tx(&ctl->full_b[sb], b_tile_bytes);
+              tma_load_2d(ring_b + sb * b_tile_bytes, &map_b, &ctl->full_b[sb],
+                          (t * 3 + (bt >> 1)) * p.k_per_tap + ((bt & 1) ? 2 * kc3 + j : j) * BK, n0);
+              if (++sb == b_slots) {
+                sb = 0;
+                phb ^= 1;
+              }
+            }
+            continue;
+          }
           if (ROWWIN) {
             // t = filter row ky: the window starts one pixel left of the kx = 0 tap
             int kc_b2 = -1;  // hi_share, hi window: second B chunk (the Wl tiles)
@@ -258,6 +289,55 @@ gemm_tn_promote_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
         tc_fence_after();
         const uint32_t d_tmem = tmem_base_u + as * (MH * bn);
         for (int ki = 0; ki < kn; ++ki) {
+          if (ROWWIN && pair_mode) {
+            const int s_hi = s;
+            const uint32_t ph_hi = ph;
+            if (++s == stages) {
+              s = 0;
+              ph ^= 1;
+            }
+            const int s_lo = s;
+            const uint32_t ph_lo = ph;
+            if (++s == stages) {
+              s = 0;
+              ph ^= 1;
+            }
+            mbar_wait(&ctl->full_a[s_hi], ph_hi);
+            mbar_wait(&ctl->full_a[s_lo], ph_lo);
+            const uint64_t da_hi = umma_desc_sw128(smem_u32(smem + s_hi * a_slot_bytes), 16, 1024);
+            const uint64_t da_lo = umma_desc_sw128(smem_u32(smem + s_lo * a_slot_bytes), 16, 1024);
+            for (int bt = 0; bt < 6; ++bt) {
+              const int kx = bt >> 1;
+              mbar_wait(&ctl->full_b[sb], phb);
+              tc_fence_after();
+              if (elect_one()) {
+                const uint64_t db = umma_desc_sw128(smem_u32(ring_b + sb * b_tile_bytes), 16, 1024);
+#pragma unroll
+                for (int h = 0; h < MH; ++h) {
+                  const uint64_t off = (h * WIN_BYTES >> 4) + (128 >> 4) * kx;  // half h, one pixel row further
+#pragma unroll
+                  for (int k = 0; k < BK / 16; ++k)
+                    umma_f16_ss(d_tmem + h * bn, da_hi + off + 2 * k, db + 2 * k, idesc, (ki > 0 || bt > 0 || k > 0) ? 1u : 0u);
+                  if (!(bt & 1)) {  // a Wh tile also meets the lo window
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) umma_f16_ss(d_tmem + h * bn, da_lo + off + 2 * k, db + 2 * k, idesc, 1u);
+                  }
+                }
+                umma_commit(&ctl->empty_b[sb]);
+                if (bt == 5) {
+                  umma_commit(&ctl->empty_a[s_hi]);
+                  umma_commit(&ctl->empty_a[s_lo]);
+                  if (ki == kn - 1) umma_commit(&ctl->tmem_full[as]);
+                }
+              }
+              __syncwarp();
+              if (++sb == b_slots) {
+                sb = 0;
+                phb ^= 1;
+              }
+            }
+            continue;
+          }
           if (ROWWIN) {
             mbar_wait(&ctl->full_a[s], ph);
             const uint64_t da = umma_desc_sw128(smem_u32(smem + s * a_slot_bytes), 16, 1024);
@@ -497,10 +577,11 @@ int launch_nch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& 
   int smem_bytes;
   if (ROWWIN) {
     // A-window ring + B-tile ring: the B ring takes what 3 (N = 128) / 4 (N = 64) windows leave
-    const int a_slots = (NCH == 1 && MH == 1) ? 4 : 3;
+    // pair mode needs the hi and the lo slot of a pair resident together: one more slot where it fits
+    const int a_slots = ((NCH == 1 && MH == 1) || (p.hi_share == 2 && MH == 1)) ? 4 : 3;
     int b_slots = (232448 - fixed - a_slots * MH * WIN_BYTES) / (bn * BK * 2);
     if (b_slots > RW_MAX_B) b_slots = RW_MAX_B;
-    if (b_slots < 4) return 1005;
+    if (b_slots < 3) return 1005;
     p.stages = a_slots;
     p.b_resident = b_slots;
     smem_bytes = a_slots * MH * WIN_BYTES + b_slots * bn * BK * 2 + fixed;
@@ -632,14 +713,20 @@ int gemm_tn_promote_launch(const GemmTnArgs& a, int chunk, cudaStream_t stream) 
     // B200 at full size, conv1_2: chunk 1 / 3 / 9 = 0.681 / 0.609 / 0.592 ms per 2 images (per-tap kernel 0.725) at
     // 2.5e-7 / 8.6e-7 / 2.1e-6 relative error against fp64
     // N = 256: a k-iteration is 1536 tensor cycles, one promotion per k-iteration costs nothing (chains of 12 MMAs)
-    static int hs_opt = -1;
-    if (hs_opt < 0) {
+    static int hs_opt = -2;
+    if (hs_opt == -2) {
       const char* e = getenv("PTB200_X3_HISHARE");
-      hs_opt = e ? atoi(e) : 1;
+      hs_opt = e ? atoi(e) : -1;
     }
-    p.hi_share = hs_opt != 0 ? 1 : 0;
-    // hi_share: a (hi, lo) pair of k-iterations is 24 + 12 MMAs: promote per pair at N <= 128, per window at N = 256
-    if (p.hi_share)
+    // default: pair mode at N = 256 (B is two thirds of its L2 bytes), hi sharing at N <= 128 (the 256-row tiles leave
+    // room for three A slots only, and a pair needs two of them: the B ring would drain at every pair boundary).
+    // PTB200_X3_HISHARE = 0 / 1 / 2: off / hi sharing everywhere / pair mode everywhere
+    p.hi_share = hs_opt < 0 ? (a.bn == 256 ? 2 : 1) : hs_opt;
+    // hi_share: a (hi, lo) pair of k-iterations is 24 + 12 MMAs: promote per pair at N <= 128, per window at N = 256;
+    // pair mode (2): one k-iteration IS the pair (36 MMAs per accumulator), promoted every time
+    if (p.hi_share == 2)
+      p.chunk = rw_chunk > 0 ? rw_chunk : 1;
+    else if (p.hi_share)
       p.chunk = rw_chunk > 0 ? rw_chunk : (a.bn == 256 ? 1 : 2);
     else
       p.chunk = rw_chunk > 0 ? rw_chunk : (a.bn == 256 ? 1 : 3);
