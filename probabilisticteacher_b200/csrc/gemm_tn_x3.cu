@@ -577,8 +577,8 @@ int launch_nch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& 
   int smem_bytes;
   if (ROWWIN) {
     // A-window ring + B-tile ring: the B ring takes what 3 (N = 128) / 4 (N = 64) windows leave
-    // pair mode needs the hi and the lo slot of a pair resident together: one more slot where it fits
-    const int a_slots = ((NCH == 1 && MH == 1) || (p.hi_share == 2 && MH == 1)) ? 4 : 3;
+    // pair mode needs the hi and the lo slot of a pair resident together: four slots = two pairs
+    const int a_slots = ((NCH == 1 && MH == 1) || p.hi_share == 2) ? 4 : 3;
     int b_slots = (232448 - fixed - a_slots * MH * WIN_BYTES) / (bn * BK * 2);
     if (b_slots > RW_MAX_B) b_slots = RW_MAX_B;
     if (b_slots < 3) return 1005;
@@ -718,10 +718,10 @@ int gemm_tn_promote_launch(const GemmTnArgs& a, int chunk, cudaStream_t stream) 
       const char* e = getenv("PTB200_X3_HISHARE");
       hs_opt = e ? atoi(e) : -1;
     }
-    // default: pair mode at N = 256 (B is two thirds of its L2 bytes), hi sharing at N <= 128 (the 256-row tiles leave
-    // room for three A slots only, and a pair needs two of them: the B ring would drain at every pair boundary).
-    // PTB200_X3_HISHARE = 0 / 1 / 2: off / hi sharing everywhere / pair mode everywhere
-    p.hi_share = hs_opt < 0 ? (a.bn == 256 ? 2 : 1) : hs_opt;
+    // default: pair mode (measured against hi sharing, ms per 2 images: 512->512 conv 0.350 -> 0.329, conv1_2 0.528 ->
+    // 0.504 with four A slots -- with three, the B ring drained at every pair boundary and conv1_2 ran at 0.571).
+    // PTB200_X3_HISHARE = 0 / 1 / 2: off / hi sharing / pair mode
+    p.hi_share = hs_opt < 0 ? 2 : hs_opt;
     // hi_share: a (hi, lo) pair of k-iterations is 24 + 12 MMAs: promote per pair at N <= 128, per window at N = 256;
     // pair mode (2): one k-iteration IS the pair (36 MMAs per accumulator), promoted every time
     if (p.hi_share == 2)
