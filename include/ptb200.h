@@ -57,7 +57,8 @@ int ptb200_gemm_tn_f16(const void* A, int batch, int rows, int k_per_tap, int64_
  * tensor-core main loop accumulates hi*Wh + lo*Wh + hi*Wl in fp32 (the lo*Wl term, 2^-22 relative, is
  * dropped). alpha = 2^-s is applied to the accumulator before the bias. k3_per_tap = 3 * K.
  * The tensor core adds into its fp32 accumulator with truncation, a bias that grows with the number of chained
- * MMAs; the kernel therefore runs the reduction in chunks of `chunk` k-iterations of 64 (0 = default 4) on
+ * MMAs; the kernel therefore runs the reduction in chunks of `chunk` k-iterations of 64 (0 = default 4; the
+ * row-window / pair modes promote per filter-row pair of windows -- at most 36 chained MMAs -- unless chunk >= 64) on
  * alternating TMEM accumulator stages and its epilogue warps promote every finished chunk into fp32 register
  * accumulators (round to nearest) while the next chunk runs.
  * Epilogues: PTB200_EPI_SPLIT3_{RELU_,}F16 (D3 is [batch][rows][3*n_total]); PTB200_EPI_SPLIT3_MASK_F16 (ReLU

@@ -44,6 +44,7 @@ struct GemmTnParams {
   int seg_cap;            // segment are live; 128-row tiles without any live row are skipped entirely
   int chunk = 0;          // gemm_tn_x3.cu: k-iterations (of 64) per fp32 promotion of the TMEM partial sums
   int hi_share = 0;       // gemm_tn_x3.cu row-window mode: one `hi` A window serves the Wh AND the Wl products
+  int rw_ny = 3, rw_nx = 3;  // gemm_tn_x3.cu pair mode: 3 x 3 taps (conv) or 1 x 1 (plain GEMM through the same rings)
 };
 
 struct GemmTnArgs {

@@ -130,7 +130,12 @@ gemm_tn_promote_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
   const bool hi_share = ROWWIN && p.hi_share == 1;
   const bool pair_mode = ROWWIN && p.hi_share == 2;
   const int kc3 = k_chunks / 3;
-  const int k_iters_total = ROWWIN ? 3 * (pair_mode ? kc3 : hi_share ? 2 * kc3 : k_chunks) : k_chunks * p.taps;
+  // pair mode also runs plain GEMMs (rw_ny = rw_nx = 1: the fc layers) through the A / B rings: the same sharing of the
+  // hi window and of the Wh tile applies to any [hi | lo | hi] x [Wh | Wh | Wl] contraction
+  const int rw_ny = pair_mode ? p.rw_ny : 3, rw_nx = pair_mode ? p.rw_nx : 3;
+  const int rw_row_shift = rw_nx == 3 ? -1 : 0;       // the window starts one pixel left of the kx = 0 tap
+  const int rw_dy = rw_ny == 3 ? p.wp : 0, rw_y0 = rw_ny == 3 ? 1 : 0;
+  const int k_iters_total = ROWWIN ? rw_ny * (pair_mode ? kc3 : hi_share ? 2 * kc3 : k_chunks) : k_chunks * p.taps;
   const int chunk = p.chunk;
 
   constexpr uint32_t tmem_cols = 2 * MH * bn < 32 ? 32 : 2 * MH * bn;  // 128 / 256 / 512: powers of two
@@ -199,17 +204,17 @@ gemm_tn_promote_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
 #pragma unroll
               for (int h = 0; h < MH; ++h)
                 tma_load_3d(smem + s * a_slot_bytes + h * WIN_BYTES, &map_a, &ctl->full_a[s], (part ? kc3 + j : j) * BK,
-                            row0 + h * BM + (t - 1) * p.wp - 1, b);
+                            row0 + h * BM + (t - rw_y0) * rw_dy + rw_row_shift, b);
               if (++s == stages) {
                 s = 0;
                 ph ^= 1;
               }
             }
-            for (int bt = 0; bt < 6; ++bt) {  // per tap: the Wh tile (for hi and lo), then the Wl tile (for hi)
+            for (int bt = 0; bt < 2 * rw_nx; ++bt) {  // per tap: the Wh tile (for hi and lo), then the Wl tile (for hi)
               mbar_wait(&ctl->empty_b[sb], phb ^ 1);
               mbar_arrive_expect_tx(&ctl->full_b[sb], b_tile_bytes);
               tma_load_2d(ring_b + sb * b_tile_bytes, &map_b, &ctl->full_b[sb],
-                          (t * 3 + (bt >> 1)) * p.k_per_tap + ((bt & 1) ? 2 * kc3 + j : j) * BK, n0);
+                          (t * rw_nx + (bt >> 1)) * p.k_per_tap + ((bt & 1) ? 2 * kc3 + j : j) * BK, n0);
               if (++sb == b_slots) {
                 sb = 0;
                 phb ^= 1;
@@ -306,7 +311,8 @@ gemm_tn_promote_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
             mbar_wait(&ctl->full_a[s_lo], ph_lo);
             const uint64_t da_hi = umma_desc_sw128(smem_u32(smem + s_hi * a_slot_bytes), 16, 1024);
             const uint64_t da_lo = umma_desc_sw128(smem_u32(smem + s_lo * a_slot_bytes), 16, 1024);
-            for (int bt = 0; bt < 6; ++bt) {
+            const int nbt = 2 * rw_nx;
+            for (int bt = 0; bt < nbt; ++bt) {
               const int kx = bt >> 1;
               mbar_wait(&ctl->full_b[sb], phb);
               tc_fence_after();
@@ -324,7 +330,7 @@ gemm_tn_promote_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
                   }
                 }
                 umma_commit(&ctl->empty_b[sb]);
-                if (bt == 5) {
+                if (bt == nbt - 1) {
                   umma_commit(&ctl->empty_a[s_hi]);
                   umma_commit(&ctl->empty_a[s_lo]);
                   if (ki == kn - 1) umma_commit(&ctl->tmem_full[as]);
@@ -649,6 +655,17 @@ int gemm_tn_promote_launch(const GemmTnArgs& a, int chunk, cudaStream_t stream) 
                 a.seg_counts == nullptr;
   if (rowwin)
     for (int t = 0; t < 9; ++t) rowwin = rowwin && a.shifts[t] == (t / 3 - 1) * a.wp + (t % 3 - 1);
+  // plain GEMMs at N = 256 tiles (fc1 / fc2 and their data gradients; split-K and segment mode included) run through
+  // the same A / B rings in pair mode
+  static int hs_env = -2, plain_opt = 1;
+  if (hs_env == -2) {
+    const char* e = getenv("PTB200_X3_HISHARE");
+    hs_env = e ? atoi(e) : -1;
+    const char* q = getenv("PTB200_X3_PLAIN");  // 0: plain GEMMs keep the per-tap pipeline (A/B)
+    plain_opt = q ? atoi(q) : 1;
+  }
+  const bool plain_pair = plain_opt != 0 && rowwin_opt == 1 && (hs_env < 0 || hs_env == 2) && a.taps == 1 && a.shifts[0] == 0 && a.bn == 256;
+  if (plain_pair) rowwin = true;
   CUtensorMap ma, mb, md, mx;
   {
     uint64_t dims[3] = {(uint64_t)a.k_per_tap, (uint64_t)a.rows, (uint64_t)a.batch};
@@ -722,6 +739,7 @@ int gemm_tn_promote_launch(const GemmTnArgs& a, int chunk, cudaStream_t stream) 
     // 0.504 with four A slots -- with three, the B ring drained at every pair boundary and conv1_2 ran at 0.571).
     // PTB200_X3_HISHARE = 0 / 1 / 2: off / hi sharing / pair mode
     p.hi_share = hs_opt < 0 ? 2 : hs_opt;
+    p.rw_ny = p.rw_nx = plain_pair ? 1 : 3;
     // hi_share: a (hi, lo) pair of k-iterations is 24 + 12 MMAs: promote per pair at N <= 128, per window at N = 256;
     // pair mode (2): one k-iteration IS the pair (36 MMAs per accumulator), promoted every time
     if (p.hi_share == 2)
@@ -730,6 +748,9 @@ int gemm_tn_promote_launch(const GemmTnArgs& a, int chunk, cudaStream_t stream) 
       p.chunk = rw_chunk > 0 ? rw_chunk : (a.bn == 256 ? 1 : 2);
     else
       p.chunk = rw_chunk > 0 ? rw_chunk : (a.bn == 256 ? 1 : 3);
+    // a caller that asks for very long chains (chunk >= 64: the test that demonstrates the truncation bias of a single
+    // tensor-core accumulation chain) gets them in this mode's own k-iteration unit
+    if (chunk >= 64) p.chunk = chunk;
     static int mh_opt = -1;
     if (mh_opt < 0) {
       const char* e = getenv("PTB200_X3_MH");
