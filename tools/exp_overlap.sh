@@ -23,5 +23,6 @@ PY
   grep -n "Timeout\|Error\|error" $out/overlap_${tag}_${n}gpu.err | head -5
 }
 run overlap PTB200_OVERLAP_ALLREDUCE=1
+[ -n "$ONLY_OVERLAP" ] && exit 0
 run eager PTB200_OVERLAP_ALLREDUCE=0
 [ "$n" = "2" ] && run overlap2 PTB200_OVERLAP_ALLREDUCE=1
