@@ -495,9 +495,13 @@ def backbone_microbench(device, peaks, N=1, H=1024, W=2048, reps=9):
 
 
 def main():
-    if os.environ.get("PTB200_WATCHDOG_S"):  # experiments: a hung run dumps every thread's stack and exits by itself
+    # fail-safe: a multi-rank run that hangs (a dead peer, a collective that never completes) dumps every thread's
+    # Python stack and exits by itself instead of holding N GPUs until an outer limit fires. PTB200_WATCHDOG_S sets the
+    # limit in seconds (0 disables); default 1800 s under torchrun, off for single-process runs.
+    wd = os.environ.get("PTB200_WATCHDOG_S", "1800" if int(os.environ.get("WORLD_SIZE", "1")) > 1 else "0")
+    if int(wd) > 0:
         import faulthandler
-        faulthandler.dump_traceback_later(int(os.environ["PTB200_WATCHDOG_S"]), exit=True)
+        faulthandler.dump_traceback_later(int(wd), exit=True)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)

@@ -123,3 +123,16 @@ def test_two_crop_mapper_on_device(cuda):
     torch.manual_seed(3); random.seed(3)
     p = A.sample_params()
     assert np.array_equal(_hwc(strong["image"]), A.strong_augment(want_img, p))
+
+
+def test_device_resize_vs_pillow_directly(cuda):
+    """The device resize against Pillow itself (the library d2's ResizeTransform calls for uint8 images), not only
+    against the oracle's restatement of it."""
+    Image = pytest.importorskip("PIL.Image")
+    from probabilisticteacher_b200.data_aug import resize_bilinear
+    rs = np.random.RandomState(11)
+    for (h, w), (nh, nw) in [((375, 500), (600, 800)), ((1024, 2048), (600, 1200)), ((61, 47), (23, 90))]:
+        img = rs.randint(0, 256, (h, w, 3)).astype(np.uint8)
+        want = np.asarray(Image.fromarray(img).resize((nw, nh), Image.BILINEAR))
+        got = _hwc(resize_bilinear(_chw(img, cuda), nh, nw))
+        assert np.array_equal(got, want), ((h, w), (nh, nw))
