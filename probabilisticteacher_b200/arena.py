@@ -120,6 +120,13 @@ class ParamArena:
         s = self.segments[name]
         return self.half[s.offset:s.offset + s.numel].view(s.shape)
 
+    def head_bucket_start(self):
+        """Offset (in elements of `grads`) where the parameters behind the VGG backbone start: the cut between the two
+        gradient all-reduce buckets of the graph step (engine/trainer.py). Everything from here on -- RPN head, box
+        head, predictor, learnable anchors -- has its final gradient as soon as both student passes have finished their
+        head backward; everything before it is backbone."""
+        return self.segments["proposal_generator.rpn_head.conv.weight"].offset - self.trainable_start
+
     def gview(self, name, flat=None):
         """View of a segment inside a flat buffer laid out like the trainable suffix (default: the gradient arena;
         the momentum arena has the same layout)."""

@@ -518,8 +518,7 @@ class PTrainer:
             # overlap at pt/engine/trainer.py:92-95, with two buckets cut at the arena's natural boundary.)
             self.model.heads_backward_hook = None
             g = self.model.arena.grads
-            cut = self.model.arena.segments["proposal_generator.rpn_head.conv.weight"].offset - \
-                self.model.arena.trainable_start
+            cut = self.model.arena.head_bucket_start()
             assert len(head_events) == 2
             sc = self._comm_stream
             sc.wait_stream(main)

@@ -120,6 +120,16 @@ assert list(m) == list(PTrainer.METRIC_KEYS)
 for i, k in enumerate(PTrainer.METRIC_KEYS):
     assert abs(float(m[k]) - 1.5 * (i + 1)) < 1e-6, (k, float(m[k]))
 assert bool((a.grads == 3.0).all())
+# the graph step's two buckets (engine/trainer.py, _graph_body_concurrent): everything behind the backbone first, the
+# backbone after the join -- together ONE all-reduce of the arena, bit for bit (SUM of two ranks is order-free)
+from probabilisticteacher_b200.arena import ParamArena
+pa = ParamArena(num_classes=8, differentiable_anchors=True, device="cpu", with_grads=True)
+cut = pa.head_bucket_start()
+gen = torch.Generator().manual_seed(100 + rank)
+local = torch.randn(pa.grads.numel(), generator=gen)
+one = local.clone(); dist.all_reduce(one)
+two = local.clone(); dist.all_reduce(two[cut:]); dist.all_reduce(two[:cut])
+assert 0 < cut < two.numel() and torch.equal(one, two)
 dist.destroy_process_group()
 print("ok")
 '''
@@ -136,6 +146,28 @@ def test_data_parallel_plumbing_gloo(tmp_path):
     for p in procs:
         out = p.communicate(timeout=120)[0]
         assert p.returncode == 0 and "ok" in out, out
+
+
+def test_overlap_buckets_partition_the_gradient_arena():
+    """The cut between the two in-graph all-reduce buckets sits exactly at the backbone boundary: every trainable
+    segment before it is a VGG parameter, every segment from it on is not (RPN head, box head, predictor, anchors),
+    and the cut is 128-byte aligned like every segment."""
+    from probabilisticteacher_b200.arena import ParamArena
+    for K, diff in ((8, True), (1, False)):
+        a = ParamArena(num_classes=K, differentiable_anchors=diff, device="cpu", with_grads=True)
+        cut = a.head_bucket_start()
+        assert 0 < cut < a.grads.numel() and cut % 64 == 0
+        n_head = 0
+        for name, s in a.segments.items():
+            if not s.trainable:
+                continue
+            o = s.offset - a.trainable_start
+            if name.startswith("backbone."):
+                assert o + s.numel <= cut, name
+            else:
+                assert o >= cut, name
+                n_head += 1
+        assert n_head >= 8   # rpn conv / heads, fc1, fc2, cls_score, bbox_pred (weights + biases)
 
 
 def test_bucket_bounds():
