@@ -73,7 +73,10 @@ __device__ __forceinline__ bool chunk_live(const int* __restrict__ seg_counts, i
 // WG_BK = reduction rows per stage (one [WG_BK rows][64 ch] box per 64-channel block): 64 for the fp16 kernel; the X3
 // kernel runs 32-row stages -- four 48 KB stages instead of two of 96 KB, same bytes in flight but every load is
 // issued a stage-time earlier (measured per step: 7.83 -> 7.24 ms, 1 152 -> 1 243 TFLOP/s; PTB200_WG_BK=64 restores).
-template <bool X3, int WG_BK>
+// MT = 2 (X3 only, m_total % 256 == 0): a CTA owns TWO 128-channel output tiles (two TMEM accumulators of bn columns)
+// that share every X tile -- a 32-row stage moves 64 KB for 24 MMAs instead of 48 KB for 12: a third fewer bytes
+// through L2 per MMA (ncu: this kernel sat at the ~12 TB/s LTS cap, 12.8 TB/s time-weighted).
+template <bool X3, int WG_BK, int MT>
 __global__ void __launch_bounds__(WG_THREADS, 2)
 gemm_wgrad_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant__ CUtensorMap map_x,
                   const WgParams p) {
@@ -82,7 +85,8 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_consta
                                              ~static_cast<uintptr_t>(1023));
   constexpr int WG_BLK_BYTES = WG_BK * 128;  // one [WG_BK rows][64 ch] box
   const int bn = p.bn;
-  const int a_bytes = (WG_BM / 64) * WG_BLK_BYTES;  // 16 KB at WG_BK = 64
+  constexpr int half_bytes = (WG_BM / 64) * WG_BLK_BYTES;  // one 128-channel G tile: 16 KB at WG_BK = 64
+  const int a_bytes = MT * half_bytes;
   const int b_bytes = (bn / 64) * WG_BLK_BYTES;
   // stage layout: [Gh][Gl (X3)][Xh][Xl (X3)]
   const int stage_bytes = (X3 ? 2 : 1) * (a_bytes + b_bytes);
@@ -91,7 +95,7 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_consta
   const int lane = threadIdx.x & 31;
 
   // tile decode: blockIdx.x = ((tap * m_tiles + mt) * n_tiles + nt) * ksplit + ks
-  const int m_tiles = p.m_total / WG_BM;
+  const int m_tiles = p.m_total / (WG_BM * MT);
   const int n_tiles = p.n_total / bn;
   int id = blockIdx.x;
   const int ks = id % p.ksplit;
@@ -115,7 +119,7 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_consta
   }
 
   uint32_t tmem_cols = 32;
-  while (tmem_cols < static_cast<uint32_t>(bn)) tmem_cols <<= 1;
+  while (tmem_cols < static_cast<uint32_t>(MT * bn)) tmem_cols <<= 1;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&map_g);
@@ -152,10 +156,10 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_consta
           uint8_t* sa = smem + s * stage_bytes;
           uint8_t* sb = sa + (X3 ? 2 : 1) * a_bytes;
           mbar_arrive_expect_tx(&ctl->full[s], stage_bytes);
-          tma_load_4d(sa, &map_g, &ctl->full[s], 0, r0, mt * (WG_BM / 64), b);
+          tma_load_4d(sa, &map_g, &ctl->full[s], 0, r0, mt * (MT * WG_BM / 64), b);
           tma_load_4d(sb, &map_x, &ctl->full[s], 0, r0 + shift, nt * (bn / 64), b);
           if (X3) {  // the lo halves: channel blocks [m_total/64, 2 m_total/64) and [n_total/64, 2 n_total/64)
-            tma_load_4d(sa + a_bytes, &map_g, &ctl->full[s], 0, r0, p.m_total / 64 + mt * (WG_BM / 64), b);
+            tma_load_4d(sa + a_bytes, &map_g, &ctl->full[s], 0, r0, p.m_total / 64 + mt * (MT * WG_BM / 64), b);
             tma_load_4d(sb + b_bytes, &map_x, &ctl->full[s], 0, r0 + shift, p.n_total / 64 + nt * (bn / 64), b);
           }
         }
@@ -178,21 +182,24 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_consta
         const uint32_t b_addr = __shfl_sync(0xffffffffu, a_addr + (X3 ? 2 : 1) * a_bytes, 0);
         if (elect_one()) {
           // MN-major SW128: LBO = stride between 64-channel blocks, SBO = stride between 8-row groups
-          const uint64_t da = umma_desc_sw128(a_addr, WG_BLK_BYTES, 1024);
           const uint64_t db = umma_desc_sw128(b_addr, WG_BLK_BYTES, 1024);
+          const uint64_t dbl = umma_desc_sw128(b_addr + b_bytes, WG_BLK_BYTES, 1024);  // Xl (X3)
 #pragma unroll
-          for (int k = 0; k < WG_BK / 16; ++k) {
-            // 16 reduction rows = 2048 B further into each block
-            umma_f16_ss(tmem_base_u, da + (2048 >> 4) * k, db + (2048 >> 4) * k, idesc,
-                        (ki > 0 || k > 0) ? 1u : 0u);
-          }
-          if (X3) {
-            const uint64_t dal = umma_desc_sw128(a_addr + a_bytes, WG_BLK_BYTES, 1024);   // Gl
-            const uint64_t dbl = umma_desc_sw128(b_addr + b_bytes, WG_BLK_BYTES, 1024);   // Xl
+          for (int h = 0; h < MT; ++h) {  // output tile h: G channel blocks [2h, 2h + 2) of the stage, accumulator h
+            const uint64_t da = umma_desc_sw128(a_addr + h * half_bytes, WG_BLK_BYTES, 1024);
+            const uint32_t d_tmem = tmem_base_u + h * bn;
 #pragma unroll
-            for (int k = 0; k < WG_BK / 16; ++k) umma_f16_ss(tmem_base_u, dal + (2048 >> 4) * k, db + (2048 >> 4) * k, idesc, 1u);
+            for (int k = 0; k < WG_BK / 16; ++k) {
+              // 16 reduction rows = 2048 B further into each block
+              umma_f16_ss(d_tmem, da + (2048 >> 4) * k, db + (2048 >> 4) * k, idesc, (ki > 0 || k > 0) ? 1u : 0u);
+            }
+            if (X3) {
+              const uint64_t dal = umma_desc_sw128(a_addr + a_bytes + h * half_bytes, WG_BLK_BYTES, 1024);  // Gl
 #pragma unroll
-            for (int k = 0; k < WG_BK / 16; ++k) umma_f16_ss(tmem_base_u, da + (2048 >> 4) * k, dbl + (2048 >> 4) * k, idesc, 1u);
+              for (int k = 0; k < WG_BK / 16; ++k) umma_f16_ss(d_tmem, dal + (2048 >> 4) * k, db + (2048 >> 4) * k, idesc, 1u);
+#pragma unroll
+              for (int k = 0; k < WG_BK / 16; ++k) umma_f16_ss(d_tmem, da + (2048 >> 4) * k, dbl + (2048 >> 4) * k, idesc, 1u);
+            }
           }
           umma_commit(&ctl->empty[s]);
           if (ki == k_iters - 1) umma_commit(&ctl->acc_full);
@@ -214,25 +221,30 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_consta
         const int m2 = t & 63, half_ = t >> 6;
         const int colp = 2 * m2;
         const int blk = colp >> 6, col = colp & 63;
-        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        float s0[MT], s1[MT], s2[MT], s3[MT];
+#pragma unroll
+        for (int h = 0; h < MT; ++h) s0[h] = s1[h] = s2[h] = s3[h] = 0.f;
         int s = 0;
         uint32_t ph = 0;
         for (int ki = 0; ki < k_iters; ++ki) {
           mbar_wait(&ctl->full[s], ph);
-          const uint8_t* g = smem + s * stage_bytes + blk * WG_BLK_BYTES + (col & 7) * 2;
 #pragma unroll
-          for (int part = 0; part < (X3 ? 2 : 1); ++part) {  // X3: Gh then Gl (sum of both = the fp32 gradient)
-            const uint8_t* gp = g + part * a_bytes;
+          for (int h = 0; h < MT; ++h) {  // output tile h: channel blocks [2h, 2h + 2) of the staged G tile
+            const uint8_t* g = smem + s * stage_bytes + h * half_bytes + blk * WG_BLK_BYTES + (col & 7) * 2;
 #pragma unroll
-            for (int i = 0; i < WG_BK / 2; i += 2) {
-              const int kr0 = half_ * (WG_BK / 2) + i, kr1 = kr0 + 1;
-              const __half2 a = *reinterpret_cast<const __half2*>(gp + kr0 * 128 + (((col >> 3) ^ (kr0 & 7)) << 4));
-              const __half2 b = *reinterpret_cast<const __half2*>(gp + kr1 * 128 + (((col >> 3) ^ (kr1 & 7)) << 4));
-              const float2 fa = __half22float2(a), fb = __half22float2(b);
-              s0 += fa.x;
-              s1 += fa.y;
-              s2 += fb.x;
-              s3 += fb.y;
+            for (int part = 0; part < (X3 ? 2 : 1); ++part) {  // X3: Gh then Gl (sum of both = the fp32 gradient)
+              const uint8_t* gp = g + part * a_bytes;
+#pragma unroll
+              for (int i = 0; i < WG_BK / 2; i += 2) {
+                const int kr0 = half_ * (WG_BK / 2) + i, kr1 = kr0 + 1;
+                const __half2 a = *reinterpret_cast<const __half2*>(gp + kr0 * 128 + (((col >> 3) ^ (kr0 & 7)) << 4));
+                const __half2 b = *reinterpret_cast<const __half2*>(gp + kr1 * 128 + (((col >> 3) ^ (kr1 & 7)) << 4));
+                const float2 fa = __half22float2(a), fb = __half22float2(b);
+                s0[h] += fa.x;
+                s1[h] += fa.y;
+                s2[h] += fb.x;
+                s3[h] += fb.y;
+              }
             }
           }
           __syncwarp();
@@ -242,23 +254,29 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_consta
             ph ^= 1;
           }
         }
-        atomicAdd(p.bias_out + mt * WG_BM + colp, (s0 + s2) * p.scale);
-        atomicAdd(p.bias_out + mt * WG_BM + colp + 1, (s1 + s3) * p.scale);
+#pragma unroll
+        for (int h = 0; h < MT; ++h) {
+          atomicAdd(p.bias_out + (mt * MT + h) * WG_BM + colp, (s0[h] + s2[h]) * p.scale);
+          atomicAdd(p.bias_out + (mt * MT + h) * WG_BM + colp + 1, (s1[h] + s3[h]) * p.scale);
+        }
       }
       mbar_wait(&ctl->acc_full, 0);
       tc_fence_after();
-      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-      float* orow = p.out + static_cast<int64_t>(mt * WG_BM + r) * p.ld_out +
-                    static_cast<int64_t>(tap) * p.n_total + nt * bn;
-      for (int c0 = 0; c0 < bn; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32(t_addr + c0, v);
-        tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          red_add_v4(orow + c0 + 4 * j, __uint_as_float(v[4 * j]) * p.scale,
-                     __uint_as_float(v[4 * j + 1]) * p.scale, __uint_as_float(v[4 * j + 2]) * p.scale,
-                     __uint_as_float(v[4 * j + 3]) * p.scale);
+      for (int h = 0; h < MT; ++h) {
+        const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + h * bn;
+        float* orow = p.out + static_cast<int64_t>((mt * MT + h) * WG_BM + r) * p.ld_out +
+                      static_cast<int64_t>(tap) * p.n_total + nt * bn;
+        for (int c0 = 0; c0 < bn; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32(t_addr + c0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            red_add_v4(orow + c0 + 4 * j, __uint_as_float(v[4 * j]) * p.scale,
+                       __uint_as_float(v[4 * j + 1]) * p.scale, __uint_as_float(v[4 * j + 2]) * p.scale,
+                       __uint_as_float(v[4 * j + 3]) * p.scale);
+        }
       }
     }
   }
@@ -296,11 +314,19 @@ int gemm_wgrad_launch(const void* G, int64_t ldg, int64_t g_batch_stride, const 
   }
   const int WG_BK = x3 ? bk_opt : 64;
   const int WG_BLK_BYTES = WG_BK * 128;
+  // two output tiles per CTA (see the kernel): f16x3 with 32-row stages, 256 output channels per tile pair and an X
+  // tile of at most 256 columns (2 x 256 TMEM columns). PTB200_WG_MT=1 keeps one tile per CTA.
+  static int mt_opt = -1;
+  if (mt_opt < 0) {
+    const char* e = getenv("PTB200_WG_MT");
+    mt_opt = (e && atoi(e) == 1) ? 1 : 2;
+  }
+  const int MT = (x3 && WG_BK == 32 && mt_opt == 2 && m_total % (2 * WG_BM) == 0) ? 2 : 1;
   CUtensorMap mg, mx;
   {
     uint64_t dims[4] = {64, (uint64_t)rows, (uint64_t)((x3 ? 3 : 1) * m_total / 64), (uint64_t)batch};
     uint64_t str[3] = {(uint64_t)ldg * 2, 128, (uint64_t)g_batch_stride * 2};
-    uint32_t box[4] = {64, (uint32_t)WG_BK, (uint32_t)(WG_BM / 64), 1};
+    uint32_t box[4] = {64, (uint32_t)WG_BK, (uint32_t)(MT * WG_BM / 64), 1};
     if (make_tmap_f16(&mg, G, 4, dims, str, box)) return 1110;
   }
   {
@@ -323,8 +349,11 @@ int gemm_wgrad_launch(const void* G, int64_t ldg, int64_t g_batch_stride, const 
   p.bias_out = bias_out;
   p.seg_counts = seg_counts;
   p.seg_cap = seg_cap;
-  const int tiles = taps * (m_total / WG_BM) * (n_total / bn);
+  const int tiles = taps * (m_total / (WG_BM * MT)) * (n_total / bn);
   const int total_chunks = ((rows + WG_BK - 1) / WG_BK) * batch;
+  // a caller's split count is meant for 128-channel tiles: twice the splits over half as many (double) tiles keeps the
+  // CTA count and the work per CTA
+  if (MT == 2 && ksplit > 0) ksplit = ksplit * 2 <= total_chunks ? ksplit * 2 : ksplit;
   if (ksplit <= 0) {
     ksplit = g_wg_sms / tiles;                       // aim at one full wave of CTAs
     const int per_cta = 2048 / WG_BK;                          // at least 2048 reduction rows per CTA
@@ -333,7 +362,7 @@ int gemm_wgrad_launch(const void* G, int64_t ldg, int64_t g_batch_stride, const 
     if (ksplit < 1) ksplit = 1;
   }
   p.ksplit = ksplit;
-  const int stage_bytes = (x3 ? 2 : 1) * (WG_BM / 64 + bn / 64) * WG_BLK_BYTES;
+  const int stage_bytes = (x3 ? 2 : 1) * (MT * WG_BM / 64 + bn / 64) * WG_BLK_BYTES;
   int stages = (232448 - 2048) / stage_bytes;
   if (stages > 8) stages = 8;
   static int stage_cap = -1;  // experiment knob: PTB200_WG_STAGES=2 lets two CTAs share an SM
@@ -350,20 +379,24 @@ int gemm_wgrad_launch(const void* G, int64_t ldg, int64_t g_batch_stride, const 
   const int smem_bytes = stages * stage_bytes + (int)sizeof(WgCtl) + 1024;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_wgrad_kernel<false, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    cudaError_t e = cudaFuncSetAttribute(gemm_wgrad_kernel<false, 64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
     if (e != cudaSuccess) return (int)e;
-    e = cudaFuncSetAttribute(gemm_wgrad_kernel<true, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    e = cudaFuncSetAttribute(gemm_wgrad_kernel<true, 64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
     if (e != cudaSuccess) return (int)e;
-    e = cudaFuncSetAttribute(gemm_wgrad_kernel<true, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    e = cudaFuncSetAttribute(gemm_wgrad_kernel<true, 32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(gemm_wgrad_kernel<true, 32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
-  if (x3 && WG_BK == 32)
-    gemm_wgrad_kernel<true, 32><<<tiles * ksplit, WG_THREADS, smem_bytes, stream>>>(mg, mx, p);
+  if (x3 && WG_BK == 32 && MT == 2)
+    gemm_wgrad_kernel<true, 32, 2><<<tiles * ksplit, WG_THREADS, smem_bytes, stream>>>(mg, mx, p);
+  else if (x3 && WG_BK == 32)
+    gemm_wgrad_kernel<true, 32, 1><<<tiles * ksplit, WG_THREADS, smem_bytes, stream>>>(mg, mx, p);
   else if (x3)
-    gemm_wgrad_kernel<true, 64><<<tiles * ksplit, WG_THREADS, smem_bytes, stream>>>(mg, mx, p);
+    gemm_wgrad_kernel<true, 64, 1><<<tiles * ksplit, WG_THREADS, smem_bytes, stream>>>(mg, mx, p);
   else
-    gemm_wgrad_kernel<false, 64><<<tiles * ksplit, WG_THREADS, smem_bytes, stream>>>(mg, mx, p);
+    gemm_wgrad_kernel<false, 64, 1><<<tiles * ksplit, WG_THREADS, smem_bytes, stream>>>(mg, mx, p);
   return (int)cudaGetLastError();
 }
 
